@@ -1,0 +1,194 @@
+/* ren_b200.h -- C ABI of libren_b200.so: the B200 (sm_100a) event-NeRF hot path.
+ *
+ * The reference (wengflow/robust-e-nerf) has NO native code and NO FFI: its hot
+ * path is Python calling third-party CUDA extensions (nerfacc, ATen/cuBLAS).
+ * Each entry point below therefore cites the reference *Python* interface whose
+ * arithmetic it replaces; `INTEGRATION.md` shows the ctypes binding a reference
+ * maintainer would add at `RobustENeRF._build_nerf`
+ * (robust_e_nerf/models/robust_e_nerf.py:204-260).
+ *
+ * Conventions
+ *   - All data pointers are DEVICE pointers into caller-owned, contiguous,
+ *     row-major buffers (no allocation, no ownership transfer inside the library).
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *   - Return 0 on success, non-zero REN_E_* otherwise; `ren_last_error()` returns a
+ *     thread-local message.  Nothing throws across the ABI.  No host sync inside.
+ *   - MLP parameters are ONE flat fp32 buffer in the reference's state-dict order
+ *     and `nn.Linear` layout ((out,in) row-major weight, then bias) -- see
+ *     `ren_param_layout`.
+ *   - Samples are laid out dense and ray-major: sample (r, k) at r*K + k, K =
+ *     `ren_samples_per_ray` (an upper bound; dead tail samples are masked).
+ */
+#ifndef REN_B200_H
+#define REN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define REN_ABI_VERSION 1
+
+enum {
+  REN_OK = 0,
+  REN_E_INVALID = 1,     /* bad argument / unsupported configuration */
+  REN_E_CUDA = 2,        /* CUDA runtime error (message has the cudaError string) */
+  REN_E_WORKSPACE = 3,   /* caller-provided workspace / stash too small */
+  REN_E_UNSUPPORTED = 4  /* valid reference configuration this build does not cover */
+};
+
+/* models/nerf.py:17-29 activation tables */
+enum { REN_HIDDEN_SOFTPLUS100 = 0, REN_HIDDEN_RELU = 1 };
+enum { REN_DENSITY_SHIFTED_TRUNC_EXP = 0, REN_DENSITY_SOFTPLUS = 1, REN_DENSITY_SHIFTED_SOFTPLUS = 2 };
+enum { REN_RADIANCE_SOFTPLUS = 0, REN_RADIANCE_SIGMOID = 1 };
+/* models/robust_e_nerf.py:214-218 contraction_type */
+enum { REN_CONTRACT_AABB = 0, REN_CONTRACT_SPHERE = 1, REN_CONTRACT_TANH = 2 };
+/* GEMM engine for the MLP */
+enum {
+  REN_ENGINE_AUTO = 0,    /* tcgen05 when the network shape is covered, else SIMT */
+  REN_ENGINE_SIMT_FP32 = 1, /* fp32 FFMA tiles: parity baseline, any shape */
+  REN_ENGINE_TC_F16X3 = 2,  /* tcgen05 kind::f16, split fp16 hi/lo operands, 3 MMAs (fp32-class accuracy) */
+  REN_ENGINE_TC_F16 = 3     /* tcgen05 kind::f16, single pass (throughput mode; misses the 1e-4 bar) */
+};
+/* loss_metric/loss.py:16-30 error functions */
+enum { REN_ERR_L1 = 0, REN_ERR_MSE = 1, REN_ERR_MAPE = 2 };
+
+/* `VanillaNeRFRadianceField.__init__` (external/mlp.py:247-319) + the
+ * `model.nerf.mlp` YAML block (configs/train/synthetic.yaml:85-96). */
+typedef struct RenFieldDesc {
+  int32_t net_depth;          /* trunk layers (8) */
+  int32_t net_width;          /* trunk width (256), multiple of 16 */
+  int32_t skip_layer;         /* concat encoding after layer i when i%skip==0 && i>0; 0 = none */
+  int32_t net_depth_condition;/* view-conditioned hidden layers (1) */
+  int32_t net_width_condition;/* (128), multiple of 16 */
+  int32_t radiance_dim;       /* C: 1 (monochrome) or 3 (Bayer) */
+  int32_t pos_deg;            /* L_pos (10) -> 3*(1+2L) = 63 features */
+  int32_t dir_deg;            /* L_dir (4)  -> 27 features */
+  int32_t hidden_activation;  /* REN_HIDDEN_* */
+  int32_t density_activation; /* REN_DENSITY_* */
+  int32_t radiance_activation;/* REN_RADIANCE_* */
+  int32_t contraction;        /* REN_CONTRACT_* */
+  float aabb[6];              /* xmin,ymin,zmin,xmax,ymax,zmax (external/mlp.py:269) */
+} RenFieldDesc;
+
+/* `NeRF.__init__` rendering options (models/nerf.py:31-48) as consumed by
+ * `render_image` / nerfacc.ray_marching (external/utils.py:106-119). */
+typedef struct RenRenderDesc {
+  float near_plane;      /* used iff has_near */
+  float far_plane;       /* used iff has_far */
+  float render_step_size;
+  float cone_angle;
+  float early_stop_eps;
+  float alpha_thre;
+  int32_t has_near;
+  int32_t has_far;
+  int32_t stratified;    /* training: t_min += u*step, one u per ray */
+  int32_t engine;        /* REN_ENGINE_* */
+} RenRenderDesc;
+
+int ren_version(void);
+const char* ren_last_error(void);
+
+/* Number of fp32 elements of the flat MLP parameter buffer. */
+int ren_param_count(const RenFieldDesc* f, int64_t* n_params);
+
+/* Layout of the flat buffer: for layer l (state-dict order: base.hidden_layers.0..D-1,
+ * sigma_layer.output_layer, bottleneck_layer.output_layer, rgb_layer.hidden_layers.*,
+ * rgb_layer.output_layer; external/mlp.py:56-76,143-186) writes weight offset, bias
+ * offset, out and in features.  Returns the number of layers via *n_layers; arrays may
+ * be NULL to query the count. */
+int ren_param_layout(const RenFieldDesc* f, int32_t* n_layers, int64_t* w_off, int64_t* b_off,
+                     int32_t* out_features, int32_t* in_features);
+
+/* Upper bound K on samples per ray for the dense layout (host arithmetic only). */
+int ren_samples_per_ray(const RenFieldDesc* f, const RenRenderDesc* r, int32_t* K);
+
+/* Bytes of the activation stash `ren_render_forward` fills when gradients are wanted,
+ * and of the scratch workspace `ren_render_forward` (given has_stash) or
+ * `ren_render_backward` (for_backward != 0) needs. */
+int ren_stash_bytes(const RenFieldDesc* f, const RenRenderDesc* r, int64_t n_rays, int32_t K,
+                    size_t* bytes);
+int ren_workspace_bytes(const RenFieldDesc* f, const RenRenderDesc* r, int64_t n_rays, int32_t K,
+                        int32_t has_stash, int32_t for_backward, size_t* bytes);
+
+/* Replaces `NeRF.forward` (models/nerf.py:230-286) -> `render_image`
+ * (external/utils.py:38-140) -> nerfacc.ray_marching + `rendering`
+ * (external/vol_rendering.py:16-128) -> `VanillaNeRFRadianceField.forward`
+ * (external/mlp.py:350-358).
+ *   rays_o, rays_d  (n_rays,3) f32      jitter (n_rays) f32 in [0,1) or NULL
+ *   params          flat fp32 MLP parameters (ren_param_layout)
+ *   bkgd            (C) f32 background radiance (already soft-plussed) or NULL
+ *   radiance        (n_rays,C) f32  = sum w c + bkgd (1-O)
+ *   opacity         (n_rays)   f32  = sum w
+ *   depth           (n_rays)   f32  = sum w (t0+t1)/2      (NOT yet divided by O+eps)
+ *   n_kept          (n_rays)   i32  samples surviving march + visibility cull
+ *   stash           NULL for no-grad rendering, else ren_stash_bytes() bytes */
+int ren_render_forward(const RenFieldDesc* f, const RenRenderDesc* r, int64_t n_rays, int32_t K,
+                       const float* rays_o, const float* rays_d, const float* jitter,
+                       const float* params, const float* bkgd, float* radiance, float* opacity,
+                       float* depth, int32_t* n_kept, void* stash, size_t stash_bytes,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* Reverse pass of the above (replaces autograd through the same reference files).
+ *   g_radiance (n_rays,C), g_opacity (n_rays), g_depth (n_rays): upstream grads (NULL = 0)
+ *   g_params   flat fp32, ACCUMULATED into (caller zeroes)
+ *   g_bkgd     (C) accumulated, or NULL */
+int ren_render_backward(const RenFieldDesc* f, const RenRenderDesc* r, int64_t n_rays, int32_t K,
+                        const float* rays_o, const float* rays_d, const float* jitter,
+                        const float* params, const float* bkgd, const float* g_radiance,
+                        const float* g_opacity, const float* g_depth, const void* stash,
+                        size_t stash_bytes, float* g_params, float* g_bkgd, void* workspace,
+                        size_t workspace_bytes, void* stream);
+
+/* Replaces `RefractoryPeriod.forward` (models/event_generation_params.py:196-203), the
+ * supervision-timestamp derivation (models/robust_e_nerf.py:322-357),
+ * `LinearTrajectory.forward` (models/trajectories.py:30-91, utils/tensor_ops.py:83-180)
+ * and `NeRF.pixel_params_to_ray` (models/nerf.py:206-228) for the two renders of the
+ * log-intensity-difference loss (and optionally the gradient-loss timestamp).
+ *   position (B,2) f32; start_ts,end_ts (B) i64; nz_* (B) f64 normalised samples
+ *   tau (1) f64 device scalar (refractory period, ns)
+ *   pose_ts (P) i64, pose_pos (P,3) f32, pose_quat (P,4) f32 XYZW; k_inv (9) f32
+ *   n_renders = 2: rays for [diff_start | diff_end]; 3: [grad | diff_start | diff_end]
+ *   out_ts (n_renders,B) f64; out_o,out_d (n_renders,B,3) f32; out_rot (n_renders,B,9) f32 or NULL
+ *   out_ts_diff (B) f64 (the diff interval length), out_start (B) f64 = start_ts + tau */
+int ren_event_rays(int64_t B, const float* position, const int64_t* start_ts,
+                   const int64_t* end_ts, const double* nz_ts_diff, const double* nz_diff_start,
+                   const double* nz_grad_ts, const double* tau, int64_t n_poses,
+                   const int64_t* pose_ts, const float* pose_pos, const float* pose_quat,
+                   const float* k_inv, int32_t n_renders, double* out_ts, float* out_o,
+                   float* out_d, float* out_rot, double* out_ts_diff, double* out_start,
+                   void* stream);
+
+/* Replaces `LinearTrajectory.forward` (models/trajectories.py:30-91) alone: pose at n
+ * timestamps.  ts (n) f64 -> out_pos (n,3) f32, out_rot (n,9) f32 row-major. */
+int ren_trajectory(int64_t n, const double* ts, int64_t n_poses, const int64_t* pose_ts,
+                   const float* pose_pos, const float* pose_quat, float* out_pos, float* out_rot,
+                   void* stream);
+
+/* Replaces `Loss.log_intensity_diff` (loss_metric/loss.py:64-74) on top of
+ * `render_pixels` post-processing (models/robust_e_nerf.py:865-871,432-443):
+ *   I = C + min_modeled_intensity, L = log I, valid = (O0>0)|(O1>0) (all-true with bkgd),
+ *   err = error_fn(L1 - L0, f32(ts_diff * ev_diff/(end-start'))), loss = mean_valid(err).
+ *   c0,c1,o0,o1 (B) f32; ev_diff (B) f32; ts_diff,start,(B) f64; end_ts (B) i64
+ *   out: log_i0, log_i1 (B) f32, loss (1) f32 (unweighted masked mean), n_valid (1) i32,
+ *        g_c0, g_c1 (B) f32 = d loss / d c (NULL to skip), scratch (>= 16 bytes, zeroed inside) */
+int ren_event_diff_loss(int64_t B, int32_t error_fn, int32_t all_valid, float min_modeled_intensity,
+                        const float* c0, const float* c1, const float* o0, const float* o1,
+                        const float* ev_diff, const double* ts_diff, const double* start,
+                        const int64_t* end_ts, float* log_i0, float* log_i1, float* loss,
+                        int32_t* n_valid, float* g_c0, float* g_c1, void* scratch, void* stream);
+
+/* Fused Adam step on a flat fp32 buffer (torch.optim.Adam semantics incl. L2
+ * weight_decay added to the gradient; models/robust_e_nerf.py:800-813).
+ * `step` is the 1-based step count; grad_scale multiplies the gradient first
+ * (1/world after a sum all-reduce). */
+int ren_adam_step(int64_t n, float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
+                  float lr, float beta1, float beta2, float eps, float weight_decay,
+                  float grad_scale, int64_t step, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* REN_B200_H */

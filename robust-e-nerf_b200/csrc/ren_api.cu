@@ -1,0 +1,315 @@
+// ren_api.cu -- C ABI of libren_b200.so (include/ren_b200.h): plan building, argument
+// validation, workspace carving and kernel sequencing.  No allocation, no host sync.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "ren_common.cuh"
+
+// engines
+int ren_simt_launch_fwd(const RenPlan& p, long long n_rays, int K, const float* o, const float* d,
+                        const float* jitter, const float* params, float* stash, float* raw, cudaStream_t st);
+int ren_simt_launch_dgrad(const RenPlan& p, long long S, const float* params, const float* stash,
+                          const float* graw, float* delta, cudaStream_t st);
+int ren_simt_launch_wgrad(const RenPlan& p, long long S, const float* stash, const float* delta,
+                          const float* graw, float* g_params, cudaStream_t st);
+int ren_launch_composite(const RenPlan& p, long long n_rays, int K, const float* o, const float* d,
+                         const float* jitter, const float* raw, const float* bkgd, float* radiance,
+                         float* opacity, float* depth, int* n_kept, cudaStream_t st);
+int ren_launch_composite_bwd(const RenPlan& p, long long n_rays, int K, const float* o, const float* d,
+                             const float* jitter, const float* raw, const float* bkgd,
+                             const float* g_radiance, const float* g_opacity, const float* g_depth,
+                             float* graw, float* g_bkgd, cudaStream_t st);
+// tcgen05 engine (ren_tc.cu)
+int ren_tc_supported(const RenPlan& p);
+size_t ren_tc_workspace_bytes(const RenPlan& p, long long S);
+int ren_tc_launch_fwd(const RenPlan& p, long long n_rays, int K, const float* o, const float* d,
+                      const float* jitter, const float* params, float* stash, float* raw, void* ws,
+                      size_t ws_bytes, cudaStream_t st);
+
+static thread_local char g_err[512] = "";
+
+void ren_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" int ren_version(void) { return REN_ABI_VERSION; }
+extern "C" const char* ren_last_error(void) { return g_err; }
+
+static int validate_field(const RenFieldDesc* f) {
+  if (f == nullptr) { ren_set_error("null RenFieldDesc"); return REN_E_INVALID; }
+  if (f->net_depth < 1 || f->net_depth > REN_MAX_TRUNK) { ren_set_error("net_depth %d outside [1,%d]", f->net_depth, REN_MAX_TRUNK); return REN_E_INVALID; }
+  if (f->net_width < 16 || f->net_width % 16) { ren_set_error("net_width %d must be a positive multiple of 16", f->net_width); return REN_E_INVALID; }
+  if (f->net_depth_condition < 0 || f->net_depth_condition > REN_MAX_COND) { ren_set_error("net_depth_condition %d outside [0,%d]", f->net_depth_condition, REN_MAX_COND); return REN_E_INVALID; }
+  if (f->net_depth_condition > 0 && (f->net_width_condition < 16 || f->net_width_condition % 16)) { ren_set_error("net_width_condition %d must be a positive multiple of 16", f->net_width_condition); return REN_E_INVALID; }
+  if (f->radiance_dim < 1 || f->radiance_dim > 3) { ren_set_error("radiance_dim %d outside [1,3]", f->radiance_dim); return REN_E_INVALID; }
+  if (f->pos_deg < 0 || f->pos_deg > 10 || f->dir_deg < 0 || f->dir_deg > 4) { ren_set_error("encoder degrees (%d,%d) outside [0,10]x[0,4]", f->pos_deg, f->dir_deg); return REN_E_INVALID; }
+  if (f->skip_layer < 0) { ren_set_error("skip_layer must be >= 0 (0 = none)"); return REN_E_INVALID; }
+  if (f->hidden_activation < 0 || f->hidden_activation > 1 || f->density_activation < 0 || f->density_activation > 2 ||
+      f->radiance_activation < 0 || f->radiance_activation > 1 || f->contraction < 0 || f->contraction > 2) {
+    ren_set_error("activation / contraction id out of range");
+    return REN_E_INVALID;
+  }
+  for (int a = 0; a < 3; ++a)
+    if (!(f->aabb[3 + a] > f->aabb[a])) { ren_set_error("aabb max must exceed min on every axis"); return REN_E_INVALID; }
+  return REN_OK;
+}
+
+int ren_build_plan(const RenFieldDesc* f, const RenRenderDesc* r, RenPlan* p) {
+  int rc = validate_field(f);
+  if (rc) return rc;
+  memset(p, 0, sizeof(*p));
+  p->f = *f;
+  if (r) p->r = *r;
+  p->D = f->net_depth; p->CD = f->net_depth_condition;
+  p->W = f->net_width; p->WC = f->net_depth_condition > 0 ? f->net_width_condition : f->net_width;
+  p->C = f->radiance_dim;
+  p->PE = 3 * (1 + 2 * f->pos_deg); p->DE = 3 * (1 + 2 * f->dir_deg);
+  int off = 0, mat = 0;
+  long long moff = 0;
+  int in0 = p->PE, in1 = 0;  // input of the next trunk layer: main width, extra width
+  bool first = true;
+  for (int i = 0; i < p->D; ++i) {
+    RenLayer& L = p->trunk[i];
+    L.K0 = in0; L.K1 = in1; L.src0 = first ? 1 : 0; L.src1 = in1 > 0 ? 1 : 0;
+    L.N = p->W; L.act = 1;
+    L.w_off = off; off += L.N * (L.K0 + L.K1);
+    L.b_off = off; off += L.N;
+    L.mat = mat; p->mat_width[mat] = L.N; p->mat_off[mat] = moff; moff += L.N; ++mat;
+    first = false;
+    in0 = p->W;
+    in1 = (f->skip_layer > 0 && i % f->skip_layer == 0 && i > 0) ? p->PE : 0;
+  }
+  p->hid_K0 = in0; p->hid_K1 = in1;
+  p->sig_w = off; off += p->hid_K0 + p->hid_K1;
+  p->sig_b = off; off += 1;
+  {
+    RenLayer& L = p->bott;
+    L.K0 = p->hid_K0; L.K1 = p->hid_K1; L.src0 = 0; L.src1 = p->hid_K1 > 0 ? 1 : 0;
+    L.N = p->W; L.act = 0;
+    L.w_off = off; off += L.N * (L.K0 + L.K1);
+    L.b_off = off; off += L.N;
+    L.mat = mat; p->mat_width[mat] = L.N; p->mat_off[mat] = moff; moff += L.N; ++mat;
+  }
+  int c0 = p->W, c1 = p->DE;
+  for (int j = 0; j < p->CD; ++j) {
+    RenLayer& L = p->cond[j];
+    L.K0 = c0; L.K1 = c1; L.src0 = 0; L.src1 = c1 > 0 ? 2 : 0;
+    L.N = p->WC; L.act = 1;
+    L.w_off = off; off += L.N * (L.K0 + L.K1);
+    L.b_off = off; off += L.N;
+    L.mat = mat; p->mat_width[mat] = L.N; p->mat_off[mat] = moff; moff += L.N; ++mat;
+    c0 = p->WC; c1 = 0;
+  }
+  p->rgb_w = off; off += p->C * (c0 + c1);
+  p->rgb_b = off; off += p->C;
+  p->n_params = off;
+  p->n_mats = mat;
+  p->act_floats = moff;
+  return REN_OK;
+}
+
+extern "C" int ren_param_count(const RenFieldDesc* f, int64_t* n_params) {
+  RenPlan p;
+  int rc = ren_build_plan(f, nullptr, &p);
+  if (rc) return rc;
+  if (n_params) *n_params = p.n_params;
+  return REN_OK;
+}
+
+extern "C" int ren_param_layout(const RenFieldDesc* f, int32_t* n_layers, int64_t* w_off, int64_t* b_off,
+                                int32_t* out_features, int32_t* in_features) {
+  RenPlan p;
+  int rc = ren_build_plan(f, nullptr, &p);
+  if (rc) return rc;
+  int n = 0;
+  auto put = [&](int wo, int bo, int outf, int inf) {
+    if (w_off) w_off[n] = wo;
+    if (b_off) b_off[n] = bo;
+    if (out_features) out_features[n] = outf;
+    if (in_features) in_features[n] = inf;
+    ++n;
+  };
+  for (int i = 0; i < p.D; ++i) put(p.trunk[i].w_off, p.trunk[i].b_off, p.trunk[i].N, p.trunk[i].K0 + p.trunk[i].K1);
+  put(p.sig_w, p.sig_b, 1, p.hid_K0 + p.hid_K1);
+  put(p.bott.w_off, p.bott.b_off, p.bott.N, p.bott.K0 + p.bott.K1);
+  for (int j = 0; j < p.CD; ++j) put(p.cond[j].w_off, p.cond[j].b_off, p.cond[j].N, p.cond[j].K0 + p.cond[j].K1);
+  put(p.rgb_w, p.rgb_b, p.C, p.CD > 0 ? p.WC : p.W + p.DE);
+  if (n_layers) *n_layers = n;
+  return REN_OK;
+}
+
+static int validate_render(const RenRenderDesc* r) {
+  if (r == nullptr) { ren_set_error("null RenRenderDesc"); return REN_E_INVALID; }
+  if (!(r->render_step_size > 0.f)) { ren_set_error("render_step_size must be > 0"); return REN_E_INVALID; }
+  if (r->cone_angle < 0.f) { ren_set_error("cone_angle must be >= 0"); return REN_E_INVALID; }
+  if (r->engine < 0 || r->engine > 3) { ren_set_error("engine id out of range"); return REN_E_INVALID; }
+  return REN_OK;
+}
+
+extern "C" int ren_samples_per_ray(const RenFieldDesc* f, const RenRenderDesc* r, int32_t* K) {
+  int rc = validate_field(f);
+  if (rc) return rc;
+  rc = validate_render(r);
+  if (rc) return rc;
+  const int cap = 1 << 20;
+  double best = 1e30;
+  if (f->contraction == REN_CONTRACT_AABB) {
+    // marching starts at the box entry: the chord bounds the count (cone steps are only longer)
+    double d2 = 0;
+    for (int a = 0; a < 3; ++a) { double e = (double)f->aabb[3 + a] - f->aabb[a]; d2 += e * e; }
+    best = sqrt(d2) / r->render_step_size + 2.0;
+  }
+  if (r->has_far) {
+    // exact fp32 replay of the device march for the un-jittered ray starting at the near
+    // plane: fl() is monotone, so any jitter / later entry only yields fewer samples.
+    const float t_max = r->far_plane;
+    volatile float t0 = r->has_near ? (r->near_plane > 0.f ? r->near_plane : 0.f) : 0.f;
+    int n = 0;
+    for (;;) {
+      volatile float dt = t0 * r->cone_angle;
+      if (dt < r->render_step_size) dt = r->render_step_size;
+      if (dt > 1e10f) dt = 1e10f;
+      volatile float t1 = t0 + dt;
+      volatile float sum = t0 + t1;
+      volatile float mid = sum * 0.5f;
+      if (!(mid < t_max) || n >= cap) break;
+      ++n;
+      t0 = t1;
+    }
+    if ((double)n < best) best = n;
+  }
+  if (best > 1e29) {
+    ren_set_error("unbounded marching (no far plane, non-aabb contraction) needs the occupancy-grid path");
+    return REN_E_UNSUPPORTED;
+  }
+  if (best >= cap) { ren_set_error("dense sample bound %g too large", best); return REN_E_UNSUPPORTED; }
+  *K = best < 1.0 ? 1 : (int32_t)best;
+  return REN_OK;
+}
+
+static int pick_engine(const RenPlan& p) {
+  int e = p.r.engine;
+  if (e == REN_ENGINE_AUTO) e = ren_tc_supported(p) ? REN_ENGINE_TC_F16X3 : REN_ENGINE_SIMT_FP32;
+  return e;
+}
+
+extern "C" int ren_stash_bytes(const RenFieldDesc* f, const RenRenderDesc* r, int64_t n_rays, int32_t K,
+                               size_t* bytes) {
+  RenPlan p;
+  int rc = ren_build_plan(f, r, &p);
+  if (rc) return rc;
+  if (n_rays < 0 || K < 1) { ren_set_error("bad n_rays/K"); return REN_E_INVALID; }
+  *bytes = sizeof(float) * (size_t)ren_stash_floats(p, (long long)n_rays * K);
+  return REN_OK;
+}
+
+// workspace:
+//   forward : raw [S][1+C] when there is no stash to hold it, + tcgen05 scratch
+//   backward: delta mats [S][act_floats] + graw [S][1+C]
+extern "C" int ren_workspace_bytes(const RenFieldDesc* f, const RenRenderDesc* r, int64_t n_rays, int32_t K,
+                                   int32_t has_stash, int32_t for_backward, size_t* bytes) {
+  RenPlan p;
+  int rc = ren_build_plan(f, r, &p);
+  if (rc) return rc;
+  rc = validate_render(r);
+  if (rc) return rc;
+  if (n_rays < 0 || K < 1) { ren_set_error("bad n_rays/K"); return REN_E_INVALID; }
+  const long long S = (long long)n_rays * K;
+  size_t n;
+  if (for_backward) {
+    n = sizeof(float) * (size_t)((p.act_floats + 1 + p.C) * S);
+  } else {
+    n = (has_stash ? 0 : sizeof(float) * (size_t)((1 + p.C) * S)) + ren_tc_workspace_bytes(p, S);
+  }
+  *bytes = n + 512;
+  return REN_OK;
+}
+
+static inline void* align256(void* p) {
+  return (void*)(((uintptr_t)p + 255) & ~(uintptr_t)255);
+}
+
+extern "C" int ren_render_forward(const RenFieldDesc* f, const RenRenderDesc* r, int64_t n_rays, int32_t K,
+                                  const float* rays_o, const float* rays_d, const float* jitter,
+                                  const float* params, const float* bkgd, float* radiance, float* opacity,
+                                  float* depth, int32_t* n_kept, void* stash, size_t stash_bytes,
+                                  void* workspace, size_t workspace_bytes, void* stream) {
+  RenPlan p;
+  int rc = ren_build_plan(f, r, &p);
+  if (rc) return rc;
+  rc = validate_render(r);
+  if (rc) return rc;
+  if (n_rays < 0 || K < 1) { ren_set_error("bad n_rays/K"); return REN_E_INVALID; }
+  if (n_rays == 0) return REN_OK;
+  if (!rays_o || !rays_d || !params || !radiance || !opacity || !depth || !n_kept) {
+    ren_set_error("ren_render_forward: null pointer argument");
+    return REN_E_INVALID;
+  }
+  if (r->stratified && jitter == nullptr) { ren_set_error("stratified marching needs a jitter buffer"); return REN_E_INVALID; }
+  const long long S = (long long)n_rays * K;
+  cudaStream_t st = (cudaStream_t)stream;
+  float* raw;
+  void* ws = align256(workspace);
+  size_t ws_left = workspace ? workspace_bytes - ((char*)ws - (char*)workspace) : 0;
+  if (stash) {
+    if (stash_bytes < sizeof(float) * (size_t)ren_stash_floats(p, S)) { ren_set_error("stash too small"); return REN_E_WORKSPACE; }
+    raw = (float*)stash + ren_stash_raw(p, S);
+  } else {
+    const size_t need = sizeof(float) * (size_t)((1 + p.C) * S);
+    if (!workspace || ws_left < need) { ren_set_error("workspace too small for raw samples (%zu < %zu)", ws_left, need); return REN_E_WORKSPACE; }
+    raw = (float*)ws;
+    ws = align256((char*)ws + need);
+    ws_left = workspace_bytes - ((char*)ws - (char*)workspace);
+  }
+  const int engine = pick_engine(p);
+  if (engine == REN_ENGINE_SIMT_FP32) {
+    rc = ren_simt_launch_fwd(p, n_rays, K, rays_o, rays_d, jitter, params, (float*)stash, raw, st);
+  } else {
+    if (!ren_tc_supported(p)) { ren_set_error("tcgen05 engine does not cover this network shape"); return REN_E_UNSUPPORTED; }
+    p.r.engine = engine;
+    rc = ren_tc_launch_fwd(p, n_rays, K, rays_o, rays_d, jitter, params, (float*)stash, raw, ws, ws_left, st);
+  }
+  if (rc) return rc;
+  return ren_launch_composite(p, n_rays, K, rays_o, rays_d, jitter, raw, bkgd, radiance, opacity, depth,
+                              n_kept, st);
+}
+
+extern "C" int ren_render_backward(const RenFieldDesc* f, const RenRenderDesc* r, int64_t n_rays, int32_t K,
+                                   const float* rays_o, const float* rays_d, const float* jitter,
+                                   const float* params, const float* bkgd, const float* g_radiance,
+                                   const float* g_opacity, const float* g_depth, const void* stash,
+                                   size_t stash_bytes, float* g_params, float* g_bkgd, void* workspace,
+                                   size_t workspace_bytes, void* stream) {
+  RenPlan p;
+  int rc = ren_build_plan(f, r, &p);
+  if (rc) return rc;
+  rc = validate_render(r);
+  if (rc) return rc;
+  if (n_rays < 0 || K < 1) { ren_set_error("bad n_rays/K"); return REN_E_INVALID; }
+  if (n_rays == 0) return REN_OK;
+  if (!rays_o || !rays_d || !params || !stash || !g_params || !workspace) {
+    ren_set_error("ren_render_backward: null pointer argument");
+    return REN_E_INVALID;
+  }
+  const long long S = (long long)n_rays * K;
+  if (stash_bytes < sizeof(float) * (size_t)ren_stash_floats(p, S)) { ren_set_error("stash too small"); return REN_E_WORKSPACE; }
+  float* ws = (float*)align256(workspace);
+  const size_t ws_left = workspace_bytes - ((char*)ws - (char*)workspace);
+  const size_t need = sizeof(float) * (size_t)((p.act_floats + 1 + p.C) * S);
+  if (ws_left < need) { ren_set_error("workspace too small for backward (%zu < %zu)", ws_left, need); return REN_E_WORKSPACE; }
+  float* delta = ws;
+  float* graw = ws + p.act_floats * S;
+  const float* st_f = (const float*)stash;
+  const float* raw = st_f + ren_stash_raw(p, S);
+  cudaStream_t st = (cudaStream_t)stream;
+  rc = ren_launch_composite_bwd(p, n_rays, K, rays_o, rays_d, jitter, raw, bkgd, g_radiance, g_opacity,
+                                g_depth, graw, g_bkgd, st);
+  if (rc) return rc;
+  rc = ren_simt_launch_dgrad(p, S, params, st_f, graw, delta, st);
+  if (rc) return rc;
+  return ren_simt_launch_wgrad(p, S, st_f, delta, graw, g_params, st);
+}

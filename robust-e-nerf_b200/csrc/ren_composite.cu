@@ -1,0 +1,280 @@
+// ren_composite.cu -- per-ray transmittance compositing, forward and reverse.
+//
+// Replaces nerfacc v0.3.1 `render_visibility` (the no-grad cull inside
+// `ray_marching`, external/utils.py:106-119), `render_weight_from_density` and
+// `accumulate_along_rays` as used by `rendering` (external/vol_rendering.py:82-126).
+// The density cull is evaluated from the SAME field pass (same weights, same samples
+// => same sigma as the reference's extra no-grad trunk pass), so the trunk runs once.
+//
+// One warp per ray: lanes take consecutive samples, the exclusive transmittance sum is a
+// warp scan with a running carry, the early-stop rule is resolved with ballots.
+#include "ren_common.cuh"
+
+struct CompArgs {
+  RenPlan p;
+  long long n_rays;
+  int K;
+  const float* rays_o;
+  const float* rays_d;
+  const float* jitter;
+  const float* raw;      // [S][1+C]
+  const float* bkgd;     // [C] or NULL
+  float* radiance;       // [n_rays][C]
+  float* opacity;        // [n_rays]
+  float* depth;          // [n_rays]
+  int* n_kept;           // [n_rays]
+  // backward only
+  const float* g_radiance;
+  const float* g_opacity;
+  const float* g_depth;
+  float* graw;           // [S][1+C]
+  float* g_bkgd;         // [C] or NULL
+};
+
+__device__ __forceinline__ float warp_incl_scan(float v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    float t = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v += t;
+  }
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Per-sample quantities of one 32-sample block of a ray (lane = sample).
+struct SampleBlk {
+  float t0, t1, sdt, alpha, w, Texcl, dact_s, dact_c[3], c[3];
+  bool alive, keep;
+};
+
+// Walks the ray in blocks of 32 samples.  `Body(k, blk)` is called for every sample index
+// k < K (blk.keep false for culled / dead samples).
+template <typename Body>
+__device__ __forceinline__ void walk_ray(const CompArgs& a, long long r, int lane, Body body) {
+  const RenPlan& p = a.p;
+  const int C1 = 1 + p.C;
+  float o[3], d[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    o[c] = a.rays_o[r * 3 + c];
+    d[c] = a.rays_d[r * 3 + c];
+  }
+  float t_min, t_max;
+  ren_ray_range(p.f, p.r, o, d, a.jitter ? a.jitter[r] : 0.f, &t_min, &t_max);
+  // every lane marches to its own first sample, then strides 32 steps per block
+  float t0, t1;
+  ren_march_to(p.r, t_min, lane, &t0, &t1);
+  float carry_sum = 0.f;    // sum of kept sigma*dt before this block
+  float carry_T = 1.f;      // product of (1-alpha) of kept samples before this block (cull rule)
+  bool stopped = false;
+  for (int kb = 0; kb < a.K; kb += 32) {
+    const int k = kb + lane;
+    SampleBlk b;
+    b.t0 = t0; b.t1 = t1;
+    b.alive = (k < a.K) && ren_alive(t0, t1, t_max);
+    float sraw = -INFINITY;
+    b.c[0] = b.c[1] = b.c[2] = 0.f;
+    b.dact_c[0] = b.dact_c[1] = b.dact_c[2] = 0.f;
+    if (b.alive) {
+      const float* rw = a.raw + (r * a.K + k) * C1;
+      sraw = rw[0];
+      for (int c = 0; c < p.C; ++c) b.c[c] = ren_radiance_act(p.f.radiance_activation, rw[1 + c], &b.dact_c[c]);
+    }
+    float sigma = ren_density_act(p.f.density_activation, sraw, &b.dact_s);
+    if (!b.alive || sraw == -INFINITY) { sigma = 0.f; b.dact_s = 0.f; }
+    const float dt = __fsub_rn(t1, t0);
+    b.sdt = __fmul_rn(sigma, dt);
+    b.alpha = 1.f - expf(-b.sdt);
+    // visibility cull (sequential rule resolved blockwise):
+    //   stopped |= T < eps before each sample; keep = alive & !stopped & !(alpha < thre);
+    //   T *= (1 - alpha) for kept samples.
+    bool cand = b.alive && !(b.alpha < p.r.alpha_thre);
+    // prefix product of (1-alpha) over candidates, assuming no stop inside the block
+    float f = cand ? (1.f - b.alpha) : 1.f;
+    float pp = f;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      float t = __shfl_up_sync(0xffffffffu, pp, off);
+      if (lane >= off) pp *= t;
+    }
+    float Tbefore = __shfl_up_sync(0xffffffffu, pp, 1);
+    if (lane == 0) Tbefore = 1.f;
+    Tbefore *= carry_T;
+    // first lane at which the stop rule fires (T before it < eps); all later lanes are stopped
+    unsigned stopmask = __ballot_sync(0xffffffffu, Tbefore < p.r.early_stop_eps);
+    int first_stop = stopped ? 0 : (stopmask ? (__ffs(stopmask) - 1) : 32);
+    b.keep = cand && (lane < first_stop);
+    if (first_stop < 32) stopped = true;
+    // exclusive sum of kept sigma*dt
+    float sk = b.keep ? b.sdt : 0.f;
+    float incl = warp_incl_scan(sk, lane);
+    float excl = carry_sum + (incl - sk);
+    b.Texcl = expf(-excl);
+    b.w = b.keep ? b.Texcl * (1.f - expf(-b.sdt)) : 0.f;
+    body(k, b);
+    carry_sum += __shfl_sync(0xffffffffu, incl, 31);
+    {
+      // carry_T: product over kept samples of this block
+      float fk = b.keep ? (1.f - b.alpha) : 1.f;
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) fk *= __shfl_xor_sync(0xffffffffu, fk, off);
+      carry_T *= fk;
+    }
+    // advance 32 marching steps
+    for (int i = 0; i < 32; ++i) {
+      t0 = t1;
+      t1 = __fadd_rn(t0, ren_dt(p.r, t0));
+    }
+    if (__ballot_sync(0xffffffffu, b.alive) == 0u) {
+      // the whole block is past t_max: remaining samples are dead too; still let the body
+      // see them (backward must zero their grads)
+      for (int kb2 = kb + 32; kb2 < a.K; kb2 += 32) {
+        SampleBlk z = b;
+        z.alive = false; z.keep = false; z.w = 0.f; z.sdt = 0.f;
+        body(kb2 + lane, z);
+      }
+      break;
+    }
+  }
+}
+
+extern "C" __global__ void __launch_bounds__(128) ren_composite_fwd(const CompArgs a) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const RenPlan& p = a.p;
+  for (long long r = warp; r < a.n_rays; r += n_warps) {
+    float accC[3] = {0.f, 0.f, 0.f}, accO = 0.f, accD = 0.f;
+    int kept = 0;
+    walk_ray(a, r, lane, [&](int k, const SampleBlk& b) {
+      if (b.keep) {
+        for (int c = 0; c < p.C; ++c) accC[c] = fmaf(b.w, b.c[c], accC[c]);
+        accO += b.w;
+        accD = fmaf(b.w, __fmul_rn(__fadd_rn(b.t0, b.t1), 0.5f), accD);
+        kept += 1;
+      }
+    });
+    accO = warp_sum(accO);
+    accD = warp_sum(accD);
+    for (int c = 0; c < p.C; ++c) accC[c] = warp_sum(accC[c]);
+    kept = __reduce_add_sync(0xffffffffu, kept);
+    if (lane == 0) {
+      for (int c = 0; c < p.C; ++c) {
+        float v = accC[c];
+        if (a.bkgd) v = __fadd_rn(v, __fmul_rn(a.bkgd[c], __fsub_rn(1.f, accO)));
+        a.radiance[r * p.C + c] = v;
+      }
+      a.opacity[r] = accO;
+      a.depth[r] = accD;
+      a.n_kept[r] = kept;
+    }
+  }
+}
+
+// Reverse: with G_i = sum_c gC_c (c_i - bkgd_c) + gO + gD tm_i,
+//   dL/dc_i = gC w_i,   dL/ds_i = G_i T_i e^{-s_i} - sum_{j>i kept} G_j w_j   (s = sigma*dt)
+extern "C" __global__ void __launch_bounds__(128) ren_composite_bwd(const CompArgs a) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const RenPlan& p = a.p;
+  const int C1 = 1 + p.C;
+  float gb_acc[3] = {0.f, 0.f, 0.f};
+  for (long long r = warp; r < a.n_rays; r += n_warps) {
+    float gC[3] = {0.f, 0.f, 0.f}, bk[3] = {0.f, 0.f, 0.f};
+    for (int c = 0; c < p.C; ++c) {
+      gC[c] = a.g_radiance ? a.g_radiance[r * p.C + c] : 0.f;
+      bk[c] = a.bkgd ? a.bkgd[c] : 0.f;
+    }
+    const float gO = a.g_opacity ? a.g_opacity[r] : 0.f;
+    const float gD = a.g_depth ? a.g_depth[r] : 0.f;
+    // pass 1: total of G_j w_j and the opacity
+    double tot = 0.0;
+    float accO = 0.f;
+    walk_ray(a, r, lane, [&](int k, const SampleBlk& b) {
+      if (b.keep) {
+        float G = gO + gD * __fmul_rn(__fadd_rn(b.t0, b.t1), 0.5f);
+        for (int c = 0; c < p.C; ++c) G = fmaf(gC[c], b.c[c] - bk[c], G);
+        tot += (double)G * (double)b.w;
+        accO += b.w;
+      }
+    });
+    tot = warp_sum_d(tot);
+    accO = warp_sum(accO);
+    if (a.g_bkgd && a.bkgd)
+      for (int c = 0; c < p.C; ++c) gb_acc[c] += gC[c] * (1.f - accO);  // same on all lanes
+    // pass 2: per-sample grads with a running inclusive prefix of G w
+    double prefix = 0.0;  // sum over samples before this block
+    walk_ray(a, r, lane, [&](int k, const SampleBlk& b) {
+      float G = 0.f;
+      double gw = 0.0;
+      if (b.keep) {
+        G = gO + gD * __fmul_rn(__fadd_rn(b.t0, b.t1), 0.5f);
+        for (int c = 0; c < p.C; ++c) G = fmaf(gC[c], b.c[c] - bk[c], G);
+        gw = (double)G * (double)b.w;
+      }
+      double incl = gw;
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        double t = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= off) incl += t;
+      }
+      const double suffix = tot - (prefix + incl);
+      prefix += __shfl_sync(0xffffffffu, incl, 31);
+      if (k < a.K) {
+        float* g = a.graw + (r * a.K + k) * C1;
+        float gs = 0.f;
+        if (b.keep) {
+          const float dsdt = G * b.Texcl * expf(-b.sdt) - (float)suffix;
+          gs = dsdt * __fsub_rn(b.t1, b.t0) * b.dact_s;
+        }
+        g[0] = gs;
+        for (int c = 0; c < p.C; ++c) g[1 + c] = b.keep ? gC[c] * b.w * b.dact_c[c] : 0.f;
+      }
+    });
+  }
+  if (a.g_bkgd && a.bkgd && lane == 0)
+    for (int c = 0; c < p.C; ++c)
+      if (gb_acc[c] != 0.f) atomicAdd(a.g_bkgd + c, gb_acc[c]);
+}
+
+int ren_launch_composite(const RenPlan& p, long long n_rays, int K, const float* o, const float* d,
+                         const float* jitter, const float* raw, const float* bkgd, float* radiance,
+                         float* opacity, float* depth, int* n_kept, cudaStream_t st) {
+  if (n_rays <= 0) return REN_OK;
+  CompArgs a = {};
+  a.p = p; a.n_rays = n_rays; a.K = K; a.rays_o = o; a.rays_d = d; a.jitter = jitter; a.raw = raw;
+  a.bkgd = bkgd; a.radiance = radiance; a.opacity = opacity; a.depth = depth; a.n_kept = n_kept;
+  long long blocks = (n_rays + 3) / 4;
+  if (blocks > 148 * 64) blocks = 148 * 64;
+  ren_composite_fwd<<<(unsigned)blocks, 128, 0, st>>>(a);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { ren_set_error("composite fwd launch: %s", cudaGetErrorString(e)); return REN_E_CUDA; }
+  return REN_OK;
+}
+
+int ren_launch_composite_bwd(const RenPlan& p, long long n_rays, int K, const float* o, const float* d,
+                             const float* jitter, const float* raw, const float* bkgd,
+                             const float* g_radiance, const float* g_opacity, const float* g_depth,
+                             float* graw, float* g_bkgd, cudaStream_t st) {
+  if (n_rays <= 0) return REN_OK;
+  CompArgs a = {};
+  a.p = p; a.n_rays = n_rays; a.K = K; a.rays_o = o; a.rays_d = d; a.jitter = jitter; a.raw = raw;
+  a.bkgd = bkgd; a.g_radiance = g_radiance; a.g_opacity = g_opacity; a.g_depth = g_depth;
+  a.graw = graw; a.g_bkgd = g_bkgd;
+  long long blocks = (n_rays + 3) / 4;
+  if (blocks > 148 * 64) blocks = 148 * 64;
+  ren_composite_bwd<<<(unsigned)blocks, 128, 0, st>>>(a);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { ren_set_error("composite bwd launch: %s", cudaGetErrorString(e)); return REN_E_CUDA; }
+  return REN_OK;
+}

@@ -1,0 +1,448 @@
+"""`RobustENeRF` task module on top of libren_b200.so -- same constructor, hooks,
+hyper-parameter keys, logged scalars and state-dict keys as the reference's
+`robust_e_nerf.models.robust_e_nerf.RobustENeRF`
+(robust_e_nerf/models/robust_e_nerf.py:16-961), so `scripts/run.py` can instantiate it
+(robust_e_nerf/scripts/run.py:45-63).  Scope: the training hot path;
+validation / test image metrics are out of scope.
+
+A training step is: one `ren_event_rays` launch (refractory correction, supervision
+timestamps, pose lerp/slerp, ray generation for both renders), ONE `ren_render_forward`
+over the concatenated start|end rays, one `ren_event_diff_loss` launch; backward is
+`ren_render_backward`.  The sensor parameters stay tiny PyTorch scalars.
+"""
+import ctypes as C
+import math
+import os
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._pl import LightningModule
+from .nerf import NeRF
+
+
+def _get(cfg, key, default=None):
+    if isinstance(cfg, dict):
+        return cfg.get(key, default)
+    return getattr(cfg, key, default)
+
+
+# ------------------------------------------------------------------ dataset files
+def load_camera_calibration(dataset_directory):
+    """`datasets.Event.load_camera_calibration` (robust_e_nerf/data/datasets.py:15-34,66-80)."""
+    return dict(np.load(os.path.join(dataset_directory, "camera_calibration.npz")))
+
+
+def load_camera_poses(dataset_directory):
+    """`datasets.CameraPose.load_camera_poses` (robust_e_nerf/data/datasets.py:714-727)."""
+    poses = np.load(os.path.join(dataset_directory, "camera_poses.npz"))
+    return {k: torch.tensor(poses[k]) for k in ("T_wc_position", "T_wc_orientation", "T_wc_timestamp")}
+
+
+# ------------------------------------------------------------------ parametrisations
+class Softplus(torch.nn.Module):
+    """utils/modules.py:38-55"""
+
+    def __init__(self, beta=1, threshold=20):
+        super().__init__()
+        self.beta, self.threshold = beta, threshold
+
+    def forward(self, x):
+        return torch.nn.functional.softplus(x, self.beta, self.threshold)
+
+    def right_inverse(self, x):
+        inv = torch.log(torch.exp(self.beta * x) - 1) / self.beta
+        return torch.where(x * self.beta > self.threshold, x, inv)
+
+
+class ScaledShiftedSigmoid(torch.nn.Module):
+    """utils/modules.py:58-74"""
+
+    def __init__(self, low=0, high=1):
+        super().__init__()
+        self.low, self.scale = low, high - low
+
+    def forward(self, x):
+        return self.scale * torch.sigmoid(x / self.scale) + self.low
+
+    def right_inverse(self, x):
+        return self.scale * torch.logit((x - self.low) / self.scale)
+
+
+class ContrastThreshold(torch.nn.Module):
+    """models/event_generation_params.py:8-84 (state-dict key
+    `parametrizations.p2n_contrast_threshold_ratio.original`)."""
+
+    def __init__(self, dataset_directory):
+        super().__init__()
+        calib = load_camera_calibration(dataset_directory)
+        pos = torch.from_numpy(calib["pos_contrast_threshold"])
+        neg = torch.from_numpy(calib["neg_contrast_threshold"])
+        ratio = pos / neg
+        assert ratio > 0
+        self.register_buffer("init_p2n_contrast_threshold_ratio", ratio, persistent=False)
+        self.register_buffer("neg_contrast_threshold", neg, persistent=False)
+        self.p2n_contrast_threshold_ratio = torch.nn.Parameter(ratio.clone())
+        torch.nn.utils.parametrize.register_parametrization(
+            self, "p2n_contrast_threshold_ratio", Softplus(beta=1))
+
+    @property
+    def pos_contrast_threshold(self):
+        return self.p2n_contrast_threshold_ratio * self.neg_contrast_threshold
+
+    @property
+    def mean_contrast_threshold(self):
+        return (self.pos_contrast_threshold + self.neg_contrast_threshold) / 2
+
+    def forward(self, num_pos, num_neg):
+        """Effective log-intensity difference of the event interval (:72-84)."""
+        return num_pos * self.pos_contrast_threshold - num_neg * self.neg_contrast_threshold
+
+
+class RefractoryPeriod(torch.nn.Module):
+    """models/event_generation_params.py:87-203 (f64 parameter, state-dict key
+    `parametrizations._refractory_period.original`)."""
+    MIN_SCALED_SHIFTED_SIGMOID_GRAD_MAGNITUDE = 0.0001
+    REDEFINED_CALIBRATED_REFRACTORY_PERIOD_FACTOR = 0.999
+
+    def __init__(self, dataset_directory):
+        super().__init__()
+        calib = load_camera_calibration(dataset_directory)
+        tau = torch.from_numpy(np.asarray(calib["refractory_period"]))
+        path = os.path.join(dataset_directory, "max_refractory_period.pt")
+        if not os.path.exists(path):
+            raise FileNotFoundError(
+                f"{path}: the cached maximum refractory period is produced by the event "
+                "preprocessing (robust_e_nerf/data/datasets.py:132-187; SURVEY.md section 8f #3)")
+        tau_max = torch.load(path)
+        if not (0 <= tau < tau_max):
+            tau = self.REDEFINED_CALIBRATED_REFRACTORY_PERIOD_FACTOR * tau_max
+        self.register_buffer("init_refractory_period", tau, persistent=False)
+        self.register_buffer("max_refractory_period", tau_max, persistent=False)
+        self.register_buffer(
+            "max_scaled_logit_magnitude",
+            torch.tensor(self.MIN_SCALED_SHIFTED_SIGMOID_GRAD_MAGNITUDE).logit().abs(), persistent=False)
+        self._refractory_period = torch.nn.Parameter(tau.to(torch.float64))
+        torch.nn.utils.parametrize.register_parametrization(
+            self, "_refractory_period", ScaledShiftedSigmoid(low=0, high=tau_max))
+        self.clamp_refractory_period()
+
+    @torch.no_grad()
+    def clamp_refractory_period(self):
+        orig = self.parametrizations._refractory_period.original
+        scaled = orig / self.max_refractory_period
+        clamped = scaled.clamp(min=-self.max_scaled_logit_magnitude, max=self.max_scaled_logit_magnitude)
+        orig.copy_(self.max_refractory_period * clamped)
+
+    @property
+    def refractory_period(self):
+        self.clamp_refractory_period()
+        return self._refractory_period
+
+
+class LinearTrajectory(torch.nn.Module):
+    """models/trajectories.py:8-91: continuous-time pose by lerp + slerp (`ren_trajectory`)."""
+
+    def __init__(self, camera_poses):
+        super().__init__()
+        self.register_buffer("T_wc_timestamp", camera_poses["T_wc_timestamp"].to(torch.int64).contiguous(),
+                             persistent=False)
+        self.register_buffer("T_wc_position", camera_poses["T_wc_position"].float().contiguous(),
+                             persistent=False)
+        self.register_buffer("T_wc_orientation", camera_poses["T_wc_orientation"].float().contiguous(),
+                             persistent=False)
+
+    def forward(self, ts):
+        ts = ts.detach().to(torch.float64).contiguous().reshape(-1)
+        n = ts.numel()
+        pos = torch.empty((n, 3), device=ts.device, dtype=torch.float32)
+        rot = torch.empty((n, 3, 3), device=ts.device, dtype=torch.float32)
+        _lib.check(_lib.load().ren_trajectory(
+            n, _lib.ptr(ts), self.T_wc_timestamp.numel(), _lib.ptr(self.T_wc_timestamp),
+            _lib.ptr(self.T_wc_position), _lib.ptr(self.T_wc_orientation), _lib.ptr(pos), _lib.ptr(rot),
+            _lib.stream_ptr()), "ren_trajectory")
+        return pos, rot
+
+
+# ------------------------------------------------------------------ loss op
+class DiffLossFunction(torch.autograd.Function):
+    """`ren_event_diff_loss`: masked-mean event loss on the two rendered radiances.
+    Differentiable wrt c0, c1 (kernel) and ev_diff (the contrast-threshold path)."""
+
+    @staticmethod
+    def forward(ctx, c0, c1, o0, o1, ev_diff, ts_diff, start, end_ts, error_fn, all_valid, imin):
+        B = c0.numel()
+        dev = c0.device
+        c0, c1, o0, o1 = (t.contiguous().float() for t in (c0, c1, o0, o1))
+        ev_diff = ev_diff.contiguous().float()
+        log_i0 = torch.empty_like(c0)
+        log_i1 = torch.empty_like(c1)
+        g_c0 = torch.empty_like(c0)
+        g_c1 = torch.empty_like(c1)
+        loss = torch.empty((), device=dev, dtype=torch.float32)
+        n_valid = torch.empty((), device=dev, dtype=torch.int32)
+        scratch = torch.empty((2,), device=dev, dtype=torch.float64)
+        _lib.check(_lib.load().ren_event_diff_loss(
+            B, _lib.ERROR_FN[error_fn], int(all_valid), float(imin), _lib.ptr(c0), _lib.ptr(c1),
+            _lib.ptr(o0), _lib.ptr(o1), _lib.ptr(ev_diff), _lib.ptr(ts_diff), _lib.ptr(start),
+            _lib.ptr(end_ts), _lib.ptr(log_i0), _lib.ptr(log_i1), _lib.ptr(loss), _lib.ptr(n_valid),
+            _lib.ptr(g_c0), _lib.ptr(g_c1), _lib.ptr(scratch), _lib.stream_ptr()), "ren_event_diff_loss")
+        ctx.save_for_backward(g_c0, g_c1, c1, ts_diff, start, end_ts)
+        ctx.imin = imin
+        ctx.mark_non_differentiable(log_i0, log_i1, n_valid)
+        return loss, log_i0, log_i1, n_valid
+
+    @staticmethod
+    def backward(ctx, g_loss, _a, _b, _c):
+        g_c0, g_c1, c1, ts_diff, start, end_ts = ctx.saved_tensors
+        g_ev = None
+        if ctx.needs_input_grad[4]:
+            # d loss / d tgt = -(d loss / d L1) with L1 = log(c1 + imin); tgt = ts_diff*ev/(end-start)
+            dl1 = g_c1 * (c1 + ctx.imin)
+            g_ev = (-(dl1.double()) * ts_diff / (end_ts.double() - start)).float() * g_loss
+        return (g_c0 * g_loss, g_c1 * g_loss, None, None, g_ev, None, None, None, None, None, None)
+
+
+# ------------------------------------------------------------------ task module
+class RobustENeRF(LightningModule):
+    INTRINSICS_KEY = "intrinsics"
+    NUM_DIM = 3
+    MAX_NUM_SAMPLES_PER_RAY = 1024                                   # robust_e_nerf.py:19
+    MODEL_COMPONENTS = ["contrast_threshold", "refractory_period", "nerf"]
+
+    def __init__(self, git_head_hash, eval_target, num_nodes, gpus, min_modeled_intensity,
+                 eval_save_pred_intensity_img, checkpoint_filepath, contrast_threshold,
+                 refractory_period, nerf, loss, metric, optimizer, lr_scheduler, dataset_directory,
+                 alpha_over_white_bg, train_eff_ray_sample_batch_size, engine="auto"):
+        super().__init__()
+        assert isinstance(min_modeled_intensity, (int, float)) and min_modeled_intensity > 0
+        for cfg in (contrast_threshold, refractory_period, nerf):
+            assert isinstance(_get(cfg, "load_state_dict"), bool)
+            assert isinstance(_get(cfg, "freeze"), bool)
+        assert isinstance(train_eff_ray_sample_batch_size, int) and train_eff_ray_sample_batch_size > 0
+        if _get(nerf, "freeze"):
+            assert _get(nerf, "load_state_dict")
+        num_gpus = num_nodes * len(gpus)
+        self.train_ray_sample_batch_size = train_eff_ray_sample_batch_size // num_gpus   # :63-66
+        self.eval_save_pred_intensity_img = eval_save_pred_intensity_img
+        self.engine = engine
+
+        calib = load_camera_calibration(dataset_directory)
+        self.has_bayer_filter = str(calib["bayer_pattern"]) != ""
+        self.register_buffer("train_intrinsics_inv",
+                             torch.linalg.inv(torch.from_numpy(calib[self.INTRINSICS_KEY])).float(),
+                             persistent=False)
+        self.render_bkgd = "parameter" if alpha_over_white_bg else None          # :155-159
+        self.save_hyperparameters("git_head_hash", "min_modeled_intensity", "checkpoint_filepath",
+                                  "contrast_threshold", "refractory_period", "nerf", "loss", "metric",
+                                  "optimizer", "lr_scheduler")
+        self.contrast_threshold = ContrastThreshold(dataset_directory)
+        self.refractory_period = RefractoryPeriod(dataset_directory)
+        camera_poses = load_camera_poses(dataset_directory)
+        self.nerf = self._build_nerf(camera_poses, gpus)
+        self.trajectory = LinearTrajectory(camera_poses)
+        self._load_model_component_state_dicts()
+        self._freeze_model_components()
+        lw = _get(loss, "weight")
+        for v in (lw.values() if isinstance(lw, dict) else vars(lw).values()):
+            assert isinstance(v, (int, float)) and v >= 0                         # loss.py:16-20
+        self._opt_state = None
+
+    # -------------------------------------------------------------- builders
+    def _build_nerf(self, camera_poses, gpus):
+        """robust_e_nerf.py:204-260 -- THE drop-in boundary: returns `ren_b200.NeRF`."""
+        cfg = self.hparams["nerf"]
+        aabb = _get(cfg, "aabb")
+        if isinstance(aabb, str) and aabb == "auto":
+            p = camera_poses["T_wc_position"]
+            aabb = torch.cat((p.min(dim=0).values, p.max(dim=0).values)).tolist()
+        step = _get(cfg, "render_step_size")
+        if isinstance(step, str) and step == "auto":
+            ext = torch.tensor(aabb[3:]) - torch.tensor(aabb[:3])
+            step = math.sqrt(self.NUM_DIM) * torch.max(ext).item() / self.MAX_NUM_SAMPLES_PER_RAY
+        arch = _get(cfg, "arch")
+        return NeRF(aabb, _get(cfg, "contraction_type"), _get(cfg, "occ_grid"), _get(cfg, "near_plane"),
+                    _get(cfg, "far_plane"), step, self.render_bkgd, _get(cfg, "cone_angle"),
+                    _get(cfg, "early_stop_eps"), _get(cfg, "alpha_thre"), _get(cfg, "test_chunk_size"),
+                    arch, arch_config=_get(cfg, arch), num_dim=self.NUM_DIM,
+                    radiance_dim=3 if self.has_bayer_filter else 1, engine=self.engine)
+
+    def _load_model_component_state_dicts(self):
+        """robust_e_nerf.py:265-286 + utils/modules.py:16-35 (partial component restore)."""
+        if not any(_get(self.hparams[c], "load_state_dict") for c in self.MODEL_COMPONENTS):
+            return
+        ckpt = torch.load(self.hparams["checkpoint_filepath"], map_location="cpu")
+        for c in self.MODEL_COMPONENTS:
+            if _get(self.hparams[c], "load_state_dict"):
+                prefix = c + "."
+                sub = {k[len(prefix):]: v for k, v in ckpt["state_dict"].items() if k.startswith(prefix)}
+                sub = {k: v for k, v in sub.items() if not k.startswith("occupancy_grid.")}
+                getattr(self, c).load_state_dict(sub)
+
+    def _freeze_model_components(self):
+        for c in self.MODEL_COMPONENTS:
+            if _get(self.hparams[c], "freeze"):
+                for p in getattr(self, c).parameters():
+                    p.requires_grad_(False)
+
+    def forward(self, batch):
+        pass
+
+    # -------------------------------------------------------------- hot path
+    def _loss_cfg(self, group, name):
+        return _get(_get(self.hparams["loss"], group), name)
+
+    def event_rays(self, event, normalized, n_renders=2):
+        """Steps b-d of SURVEY.md section 3.2 + `pixel_params_to_ray` in one launch."""
+        B = event["start_ts"].numel()
+        dev = event["start_ts"].device
+        tau = self.refractory_period.refractory_period.detach().reshape(1).contiguous()
+        out_ts = torch.empty((n_renders, B), device=dev, dtype=torch.float64)
+        out_o = torch.empty((n_renders, B, 3), device=dev, dtype=torch.float32)
+        out_d = torch.empty((n_renders, B, 3), device=dev, dtype=torch.float32)
+        out_rot = torch.empty((n_renders, B, 3, 3), device=dev, dtype=torch.float32)
+        ts_diff = torch.empty((B,), device=dev, dtype=torch.float64)
+        start = torch.empty((B,), device=dev, dtype=torch.float64)
+        tr = self.trajectory
+        c = lambda t: t.contiguous()
+        _lib.check(_lib.load().ren_event_rays(
+            B, _lib.ptr(c(event["position"].float())), _lib.ptr(c(event["start_ts"])),
+            _lib.ptr(c(event["end_ts"])), _lib.ptr(c(normalized["ts_diff"])),
+            _lib.ptr(c(normalized["diff_start_ts"])),
+            _lib.ptr(c(normalized["grad_ts"])) if n_renders == 3 else None, _lib.ptr(tau),
+            tr.T_wc_timestamp.numel(), _lib.ptr(tr.T_wc_timestamp), _lib.ptr(tr.T_wc_position),
+            _lib.ptr(tr.T_wc_orientation), _lib.ptr(c(self.train_intrinsics_inv)), n_renders,
+            _lib.ptr(out_ts), _lib.ptr(out_o), _lib.ptr(out_d), _lib.ptr(out_rot), _lib.ptr(ts_diff),
+            _lib.ptr(start), _lib.stream_ptr()), "ren_event_rays")
+        return dict(ts=out_ts, o=out_o, d=out_d, rot=out_rot, ts_diff=ts_diff, start=start)
+
+    def render_pixels(self, intrinsics_inverse, pixel_position, T_wc_position, T_wc_orientation,
+                      jitter=None):
+        """robust_e_nerf.py:849-885."""
+        o, d = self.nerf.pixel_params_to_ray(intrinsics_inverse, pixel_position, T_wc_position,
+                                              T_wc_orientation)
+        intensity, opacity, depth, spp = self.nerf(o, d, jitter)
+        if intensity.dim() > opacity.dim():
+            intensity = intensity.permute(-1, *range(opacity.dim()))
+        intensity = intensity + self.hparams["min_modeled_intensity"]
+        if self.render_bkgd is None:
+            is_valid = opacity > 0
+        else:
+            is_valid = torch.ones_like(opacity, dtype=torch.bool)
+        depth = depth * torch.sum(d * T_wc_orientation[..., 2], dim=-1)
+        return intensity, opacity, depth, spp, is_valid
+
+    def training_step(self, batch, batch_index, jitter=None):
+        """robust_e_nerf.py:301-517.  `jitter` (optional dict with (B,) tensors `diff_start`,
+        `diff_end`) injects the per-ray stratified offsets (tests / parity runs)."""
+        event = {k: v.squeeze(dim=0) for k, v in batch["event"].items()}
+        normalized = {k: v.squeeze(dim=0) for k, v in batch["normalized"].items()}
+        B = event["start_ts"].numel()
+        for v in normalized.values():
+            assert v.shape[0] == B
+        w_grad = self._loss_cfg("weight", "log_intensity_grad")
+        w_diff = self._loss_cfg("weight", "log_intensity_diff")
+        if w_grad > 0:
+            raise NotImplementedError(
+                "log_intensity_grad loss (tangent-mode render, SURVEY.md section 7.1-5) is not built yet")
+        if not _get(self.hparams["refractory_period"], "freeze"):
+            raise NotImplementedError(
+                "a trainable refractory period needs ray gradients (SURVEY.md App. A9): not built yet")
+        assert w_diff > 0
+        dev = event["start_ts"].device
+        # a: contrast threshold (tiny torch ops on (B,))
+        ev_diff = self.contrast_threshold(event["num_pos"], event["num_neg"])
+        # b-d + raygen
+        rays = self.event_rays(event, normalized, 2)
+        if self.global_step is not None:
+            self.nerf.update_occ_grid(self.global_step, self.trajectory.T_wc_position)   # :375-379
+        # f: both renders in one launch (start rays | end rays)
+        if jitter is None:
+            u = torch.rand((2 * B,), device=dev, dtype=torch.float32)
+        else:
+            u = torch.cat((jitter["diff_start"], jitter["diff_end"])).to(dev, torch.float32)
+        rad, opac, _depth, n_kept = self.nerf.render_raw(rays["o"].reshape(2 * B, 3),
+                                                         rays["d"].reshape(2 * B, 3), u)
+        if self.has_bayer_filter:
+            ch = event["channel_idx"].to(torch.int64).repeat(2).unsqueeze(-1)             # :887-890
+            c = rad.gather(1, ch).squeeze(-1)
+        else:
+            c = rad[:, 0]
+        c0, c1 = c[:B], c[B:]
+        o0, o1 = opac[:B], opac[B:]
+        # h-j: loss
+        loss_raw, log_i0, log_i1, n_valid = DiffLossFunction.apply(
+            c0, c1, o0, o1, ev_diff, rays["ts_diff"], rays["start"], event["end_ts"].contiguous(),
+            self._loss_cfg("error_fn", "log_intensity_diff"), self.render_bkgd is not None,
+            self.hparams["min_modeled_intensity"])
+        mcr = 1 / self.contrast_threshold.mean_contrast_threshold
+        pw = {None: 1.0, "mean_contrast_reciprocal": mcr, "mean_contrast_reciprocal_sq": mcr ** 2}[
+            self._loss_cfg("param_weight", "log_intensity_diff")]
+        mean_loss = pw * loss_raw
+        train_loss = mean_loss * w_diff
+        # i: dynamic batch size (host sync, as in the reference; only with a trainer attached)
+        mean_spp = n_kept.sum() / (2 * B)
+        if self.trainer is not None:
+            mean_spp = self.update_train_batch_size(mean_spp, batch_index)
+        # k: logging
+        self.log("train/loss", train_loss, prog_bar=True)
+        self.log("train/log_intensity_diff", mean_loss)
+        if not _get(self.hparams["contrast_threshold"], "freeze"):
+            self.log("train/p2n_contrast_threshold_ratio", self.contrast_threshold.p2n_contrast_threshold_ratio)
+        self.log("train/batch_size", B)
+        self.log("train/mean_num_samples_per_ray", mean_spp)
+        self.log("train/mean_ray_occ_rate", (n_kept > 0).float().mean())
+        if self.render_bkgd is None:
+            self.log("train/mean_valid_rate", (opac > 0).float().mean())
+        else:
+            self.log("train/mean_valid_rate", torch.ones((), device=dev))
+        self.last = dict(start_log_intensity=log_i0, end_log_intensity=log_i1, n_valid=n_valid,
+                         rays=rays, opacity=opac)
+        return train_loss
+
+    def update_train_batch_size(self, mean_num_samples_per_ray, batch_index):
+        """robust_e_nerf.py:907-950."""
+        m = torch.mean(self.all_gather(mean_num_samples_per_ray.detach().float()))
+        acc = getattr(self.trainer, "accumulate_grad_batches", 1)
+        if acc > 1 and (batch_index % acc) != (acc - 2):
+            return m
+        dm = getattr(self.trainer, "datamodule", None)
+        if dm is not None:
+            new_bs = int(self.train_ray_sample_batch_size / m)
+            dm.train_dataset.batch_size = new_bs
+            for s in dm.train_normalized_sampler.datasets:
+                s.size = new_bs
+        return m
+
+    # -------------------------------------------------------------- optimiser
+    def configure_optimizers(self):
+        """robust_e_nerf.py:782-832: Adam with 4 parameter groups + MultiStepLR."""
+        ct = list(self.contrast_threshold.parameters())
+        rp = list(self.refractory_period.parameters())
+        mlp = [p for n, p in self.named_parameters() if n.startswith("nerf.radiance_field.mlp")]
+        ids = {id(p) for p in ct + rp + mlp}
+        other = [p for p in self.parameters() if id(p) not in ids]
+        opt_cfg = self.hparams["optimizer"]
+        if _get(opt_cfg, "algo") != "adam":
+            raise NotImplementedError
+        lr = _get(opt_cfg, "lr")
+        optimizer = torch.optim.Adam(
+            [{"params": ct, "lr": _get(lr, "contrast_threshold")},
+             {"params": rp, "lr": float(self.refractory_period.max_refractory_period)
+              * _get(_get(opt_cfg, "relative_lr"), "refractory_period")},
+             {"params": mlp, "weight_decay": self._loss_cfg("weight", "nerf_mlp_weight_decay")},
+             {"params": other}], lr=_get(lr, "default"))
+        sch_cfg = self.hparams["lr_scheduler"]
+        if _get(sch_cfg, "algo") != "multi_step_lr":
+            raise NotImplementedError
+        ms = _get(sch_cfg, "multi_step_lr")
+        scheduler = torch.optim.lr_scheduler.MultiStepLR(optimizer, milestones=_get(ms, "milestones"),
+                                                         gamma=_get(ms, "gamma"))
+        return {"optimizer": optimizer,
+                "lr_scheduler": {"scheduler": scheduler, "interval": _get(sch_cfg, "interval")}}
+
+    def validation_step(self, batch, batch_index):
+        raise NotImplementedError("evaluation is out of scope of ren_b200 (SURVEY.md section 8f #2)")
+
+    test_step = validation_step

@@ -1,0 +1,352 @@
+"""`NeRF` -- drop-in for the reference's `robust_e_nerf.models.nerf.NeRF`
+(robust_e_nerf/models/nerf.py:16-286) for `arch: mlp`, backed by libren_b200.so.
+
+Same constructor arguments, same `forward(ray_origin, ray_direction)` ->
+`(radiance, opacity, depth, mean_num_samples_per_ray)`, same `update_occ_grid`,
+`pixel_params_to_ray` and state-dict keys
+(`radiance_field.mlp.base.hidden_layers.{i}.{weight,bias}`, ... -- SURVEY.md section 5), so
+`RobustENeRF._build_nerf` (robust_e_nerf/models/robust_e_nerf.py:204-260) can return it.
+
+All MLP parameters live in ONE flat fp32 buffer (the order `ren_param_layout`
+documents); the named `nn.Parameter`s are views into it, so the C ABI gets a single
+pointer, the gradient is a single vector (one NCCL all-reduce) and Adam is one kernel.
+"""
+import ctypes as C
+import math
+
+import torch
+
+from . import _lib
+
+
+def _contraction_name(contraction_type):
+    if isinstance(contraction_type, str):
+        return contraction_type
+    name = getattr(contraction_type, "name", str(contraction_type))      # nerfacc.ContractionType
+    return {"AABB": "aabb", "UN_BOUNDED_SPHERE": "sphere", "UN_BOUNDED_TANH": "tanh"}[name]
+
+
+def _cfg_get(cfg, key):
+    return cfg[key] if isinstance(cfg, dict) else getattr(cfg, key)
+
+
+class _Holder(torch.nn.Module):
+    """Empty container used to reproduce the reference's module tree / key names."""
+
+
+class _Encoder(torch.nn.Module):
+    def __init__(self, max_deg):
+        super().__init__()
+        # external/mlp.py:217-219: an int64 buffer that is part of the state dict
+        self.register_buffer("scales", torch.tensor([2 ** i for i in range(0, max_deg)]))
+
+
+class RenderFunction(torch.autograd.Function):
+    """ren_render_forward / ren_render_backward as one differentiable op.
+
+    inputs : owner (NeRF), o (B,3), d (B,3), jitter (B)|None, bkgd (C)|None, *params
+    outputs: radiance (B,C), opacity (B), depth_raw (B), n_kept (B) int32
+    Gradients flow to the MLP parameters and `bkgd` (ray gradients are not provided:
+    SURVEY.md App. A9 lists them for the tau-trainable configuration only).
+    """
+
+    @staticmethod
+    def forward(ctx, owner, o, d, jitter, bkgd, *params):
+        lib = _lib.load()
+        if not o.is_cuda:
+            raise RuntimeError("ren_b200 renders on CUDA tensors only (no CPU fallback)")
+        B = o.shape[0]
+        C_ = owner.radiance_dim
+        fdesc, rdesc, K = owner._descs()
+        flat = owner.flat_params()
+        need_grad = any(ctx.needs_input_grad[4:])
+        dev = o.device
+        o = o.contiguous().float()
+        d = d.contiguous().float()
+        if jitter is not None:
+            jitter = jitter.contiguous().float()
+        if bkgd is not None:
+            bkgd = bkgd.contiguous().float()
+        radiance = torch.empty((B, C_), device=dev, dtype=torch.float32)
+        opacity = torch.empty((B,), device=dev, dtype=torch.float32)
+        depth = torch.empty((B,), device=dev, dtype=torch.float32)
+        n_kept = torch.empty((B,), device=dev, dtype=torch.int32)
+        stash = None
+        stash_n = 0
+        if need_grad:
+            stash_n = _lib.stash_bytes(fdesc, rdesc, B, K)
+            stash = torch.empty((stash_n,), device=dev, dtype=torch.uint8)
+        ws_n = _lib.workspace_bytes(fdesc, rdesc, B, K, need_grad, False)
+        ws = torch.empty((ws_n,), device=dev, dtype=torch.uint8)
+        _lib.check(lib.ren_render_forward(
+            C.byref(fdesc), C.byref(rdesc), B, K, _lib.ptr(o), _lib.ptr(d), _lib.ptr(jitter),
+            _lib.ptr(flat), _lib.ptr(bkgd), _lib.ptr(radiance), _lib.ptr(opacity), _lib.ptr(depth),
+            _lib.ptr(n_kept), _lib.ptr(stash), stash_n, _lib.ptr(ws), ws.numel(),
+            _lib.stream_ptr()), "ren_render_forward")
+        if need_grad:
+            ctx.owner = owner
+            ctx.descs = (fdesc, rdesc, K)
+            ctx.save_for_backward(o, d, jitter if jitter is not None else torch.empty(0, device=dev),
+                                  bkgd if bkgd is not None else torch.empty(0, device=dev), stash,
+                                  flat)
+            ctx.has_jitter = jitter is not None
+            ctx.has_bkgd = bkgd is not None
+            ctx.n_params = len(params)
+        ctx.mark_non_differentiable(n_kept)
+        return radiance, opacity, depth, n_kept
+
+    @staticmethod
+    def backward(ctx, g_rad, g_op, g_depth, _g_kept):
+        lib = _lib.load()
+        o, d, jitter, bkgd, stash, flat = ctx.saved_tensors
+        fdesc, rdesc, K = ctx.descs
+        owner = ctx.owner
+        B = o.shape[0]
+        dev = o.device
+        jitter = jitter if ctx.has_jitter else None
+        bkgd = bkgd if ctx.has_bkgd else None
+        g_flat = torch.zeros_like(flat)
+        g_bkgd = torch.zeros_like(bkgd) if bkgd is not None else None
+        ws_n = _lib.workspace_bytes(fdesc, rdesc, B, K, True, True)
+        ws = torch.empty((ws_n,), device=dev, dtype=torch.uint8)
+        cg = lambda t: None if t is None else t.contiguous().float()
+        g_rad, g_op, g_depth = cg(g_rad), cg(g_op), cg(g_depth)
+        _lib.check(lib.ren_render_backward(
+            C.byref(fdesc), C.byref(rdesc), B, K, _lib.ptr(o), _lib.ptr(d), _lib.ptr(jitter),
+            _lib.ptr(flat), _lib.ptr(bkgd), _lib.ptr(g_rad), _lib.ptr(g_op), _lib.ptr(g_depth),
+            _lib.ptr(stash), stash.numel(), _lib.ptr(g_flat), _lib.ptr(g_bkgd), _lib.ptr(ws),
+            ws.numel(), _lib.stream_ptr()), "ren_render_backward")
+        grads = owner._split_flat(g_flat)
+        return (None, None, None, None, g_bkgd) + tuple(grads)
+
+
+class NeRF(torch.nn.Module):
+    """See module docstring.  `arch` must be "mlp" (the 8x256 network the north star
+    names); `arch: ngp` is SURVEY.md section 8(f) #4."""
+
+    HIDDEN_ACTIVATIONS = ("softplus", "relu")                               # models/nerf.py:17-20
+    DENSITY_ACTIVATIONS = ("shifted_trunc_exp", "softplus", "shifted_softplus")   # :21-25
+    RADIANCE_ACTIVATIONS = ("softplus", "sigmoid")                          # :26-29
+
+    def __init__(self, aabb, contraction_type, occ_grid_config, near_plane, far_plane,
+                 render_step_size, render_bkgd, cone_angle, early_stop_eps, alpha_thre,
+                 test_chunk_size, arch, arch_config, num_dim=3, radiance_dim=1,
+                 opacity_eps=1e-10, engine="auto"):
+        super().__init__()
+        # the reference's argument checks (models/nerf.py:52-69)
+        if (near_plane is not None) and (far_plane is not None):
+            assert 0 <= near_plane <= far_plane
+        assert render_step_size > 0
+        assert (render_bkgd is None) or (isinstance(render_bkgd, str) and render_bkgd == "parameter") \
+            or isinstance(render_bkgd, torch.Tensor)
+        assert cone_angle >= 0
+        assert 0 <= early_stop_eps <= 1
+        assert 0 <= alpha_thre <= 1
+        assert test_chunk_size > 0
+        assert num_dim == 3, "ren_b200 renders 3-D scenes"
+        assert radiance_dim > 0
+        assert isinstance(opacity_eps, (int, float)) and opacity_eps > 0
+        if arch != "mlp":
+            raise NotImplementedError(
+                f"arch={arch!r}: ren_b200 implements the `mlp` architecture (SURVEY.md section 8f #4)")
+        if bool(_cfg_get(arch_config, "weight_norm")):
+            raise NotImplementedError("weight_norm=True is not supported by ren_b200")
+
+        self.register_buffer("aabb", torch.tensor(aabb, dtype=torch.float32), persistent=False)
+        self.contraction_type = contraction_type
+        self.contraction = _contraction_name(contraction_type)
+        self.occ_grid_config = occ_grid_config
+        self.near_plane = near_plane
+        self.far_plane = far_plane
+        self.register_buffer("render_step_size", torch.tensor(render_step_size, dtype=torch.float32),
+                             persistent=False)
+        self.cone_angle = cone_angle
+        self.early_stop_eps = early_stop_eps
+        self.alpha_thre = alpha_thre
+        self.test_chunk_size = test_chunk_size
+        self.opacity_eps = opacity_eps
+        self.radiance_dim = radiance_dim
+        self.engine = engine
+
+        # background (models/nerf.py:79-93): softplus-parametrised parameter, buffer or None
+        self._bkgd_mode = None
+        if render_bkgd is None:
+            self.render_bkgd = None
+        elif isinstance(render_bkgd, str):
+            self._bkgd_mode = "parameter"
+            holder = _Holder()
+            holder.render_bkgd = _Holder()
+            holder.render_bkgd.original = torch.nn.Parameter(torch.ones(radiance_dim))
+            self.parametrizations = holder          # key: parametrizations.render_bkgd.original
+        else:
+            self._bkgd_mode = "buffer"
+            self.register_buffer("render_bkgd", render_bkgd, persistent=False)
+
+        g = lambda k: _cfg_get(arch_config, k)
+        self.hidden_activation = g("hidden_activation")
+        self.density_activation = g("density_activation")
+        self.radiance_activation = g("radiance_activation")
+        assert self.hidden_activation in self.HIDDEN_ACTIVATIONS
+        assert self.density_activation in self.DENSITY_ACTIVATIONS
+        assert self.radiance_activation in self.RADIANCE_ACTIVATIONS
+        self._fdesc = _lib.make_field_desc(
+            net_depth=g("net_depth"), net_width=g("net_width"), skip_layer=g("skip_layer"),
+            net_depth_condition=g("net_depth_condition"), net_width_condition=g("net_width_condition"),
+            radiance_dim=radiance_dim, pos_deg=g("pos_encoder_max_deg"),
+            dir_deg=g("view_encoder_max_deg"), hidden_activation=self.hidden_activation,
+            density_activation=self.density_activation, radiance_activation=self.radiance_activation,
+            contraction=self.contraction, aabb=aabb)
+        self._layout = _lib.param_layout(self._fdesc)
+        self._n_params = _lib.param_count(self._fdesc)
+        self._build_tree(g)
+        self._desc_cache = {}
+
+    # ------------------------------------------------------------------ parameters
+    def _build_tree(self, g):
+        """Module tree with the reference's key names (external/mlp.py:143-186,
+        external/mlp.py:266-299); default `nn.Linear` init in construction order so that
+        `torch.manual_seed(s); NeRF(...)` draws the same weights as the reference."""
+        depth, cdepth = g("net_depth"), g("net_depth_condition")
+        names = [f"base.hidden_layers.{i}" for i in range(depth)]
+        names += ["sigma_layer.output_layer", "bottleneck_layer.output_layer"]
+        names += [f"rgb_layer.hidden_layers.{j}" for j in range(cdepth)]
+        names += ["rgb_layer.output_layer"]
+        assert len(names) == len(self._layout)
+        rf = _Holder()
+        rf.register_buffer("aabb", torch.tensor(self.aabb.tolist(), dtype=torch.float32))  # mlp.py:269
+        rf.posi_encoder = _Encoder(g("pos_encoder_max_deg"))
+        rf.view_encoder = _Encoder(g("view_encoder_max_deg"))
+        mlp = _Holder()
+        mlp.base = _Holder()
+        mlp.base.hidden_layers = torch.nn.ModuleList()
+        mlp.sigma_layer = _Holder()
+        mlp.bottleneck_layer = _Holder()
+        mlp.rgb_layer = _Holder()
+        mlp.rgb_layer.hidden_layers = torch.nn.ModuleList()
+        self._linears = []
+        for name, (w_off, b_off, out_f, in_f) in zip(names, self._layout):
+            lin = torch.nn.Linear(in_f, out_f)
+            self._linears.append(lin)
+            if name.startswith("base.hidden_layers"):
+                mlp.base.hidden_layers.append(lin)
+            elif name.startswith("rgb_layer.hidden_layers"):
+                mlp.rgb_layer.hidden_layers.append(lin)
+            else:
+                head, leaf = name.split(".")
+                setattr(getattr(mlp, head), leaf, lin)
+        rf.mlp = mlp
+        self.radiance_field = rf
+        self._flatten()
+
+    def _flatten(self):
+        """(Re)pack every Linear's weight/bias into one flat buffer and re-point the
+        parameters at views of it."""
+        ref = self._linears[0].weight
+        flat = torch.empty((self._n_params,), device=ref.device, dtype=torch.float32)
+        with torch.no_grad():
+            for lin, (w_off, b_off, out_f, in_f) in zip(self._linears, self._layout):
+                flat[w_off:w_off + out_f * in_f].copy_(lin.weight.detach().reshape(-1))
+                flat[b_off:b_off + out_f].copy_(lin.bias.detach())
+                lin.weight.data = flat[w_off:w_off + out_f * in_f].view(out_f, in_f)
+                lin.bias.data = flat[b_off:b_off + out_f]
+        self._flat = flat
+
+    def _views_intact(self):
+        base = self._flat.data_ptr()
+        if self._flat.device != self._linears[0].weight.device:
+            return False
+        for lin, (w_off, b_off, _, _) in zip(self._linears, self._layout):
+            if lin.weight.data_ptr() != base + 4 * w_off or lin.bias.data_ptr() != base + 4 * b_off:
+                return False
+        return True
+
+    def flat_params(self):
+        """The flat fp32 parameter buffer (rebuilt if `.to()` / `load_state_dict` moved
+        the parameters)."""
+        if not self._views_intact():
+            self._flatten()
+        return self._flat
+
+    def mlp_parameters(self):
+        out = []
+        for lin in self._linears:
+            out += [lin.weight, lin.bias]
+        return out
+
+    def _split_flat(self, g_flat):
+        grads = []
+        for (w_off, b_off, out_f, in_f) in self._layout:
+            grads.append(g_flat[w_off:w_off + out_f * in_f].view(out_f, in_f))
+            grads.append(g_flat[b_off:b_off + out_f])
+        return grads
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        self._flatten()
+        return out
+
+    def background(self):
+        """Current background radiance (C,) or None (models/nerf.py:79-93)."""
+        if self._bkgd_mode == "parameter":
+            return torch.nn.functional.softplus(self.parametrizations.render_bkgd.original, beta=1)
+        if self._bkgd_mode == "buffer":
+            return self.render_bkgd
+        return None
+
+    # ------------------------------------------------------------------ rendering
+    def _descs(self):
+        key = (self.training, self.engine)
+        hit = self._desc_cache.get(key)
+        if hit is None:
+            rdesc = _lib.make_render_desc(
+                near_plane=self.near_plane, far_plane=self.far_plane,
+                render_step_size=float(self.render_step_size), cone_angle=self.cone_angle,
+                early_stop_eps=self.early_stop_eps, alpha_thre=self.alpha_thre,
+                stratified=self.training,                    # external/utils.py:115
+                engine=self.engine)
+            K = _lib.samples_per_ray(self._fdesc, rdesc)
+            hit = (self._fdesc, rdesc, K)
+            self._desc_cache[key] = hit
+        return hit
+
+    def update_occ_grid(self, step, T_wc_position):
+        """models/nerf.py:170-204.  The dense marcher treats every cell as occupied
+        (exact for the fixed-N regime of SURVEY.md section 8d); grid skipping is section 8(f) #1."""
+        return None
+
+    @staticmethod
+    def pixel_params_to_ray(intrinsics_inverse, pixel_position, T_wc_position, T_wc_orientation):
+        """models/nerf.py:206-228 (plain torch: a handful of (N,3) ops; the training path
+        uses the fused `ren_event_rays` kernel instead)."""
+        h = torch.cat((pixel_position, torch.ones_like(pixel_position[..., 0].unsqueeze(dim=-1))), dim=-1)
+        ray_direction = (T_wc_orientation @ (intrinsics_inverse @ h.unsqueeze(dim=-1))).squeeze(dim=-1)
+        ray_direction = ray_direction / torch.linalg.vector_norm(ray_direction, dim=-1, keepdim=True)
+        return T_wc_position, ray_direction
+
+    def render_raw(self, o, d, jitter=None):
+        """(radiance (B,C), opacity (B), un-normalised depth (B), n_kept (B) i32)."""
+        if self.training and jitter is None:
+            jitter = torch.rand((o.shape[0],), device=o.device, dtype=torch.float32)
+        if not self.training:
+            jitter = None
+        return RenderFunction.apply(self, o, d, jitter, self.background(), *self.mlp_parameters())
+
+    def forward(self, ray_origin, ray_direction, jitter=None):
+        """models/nerf.py:230-286.  `jitter` (optional, (N,) in [0,1)) injects the per-ray
+        stratified offsets nerfacc draws internally."""
+        lead = ray_origin.shape[:-1]
+        o = ray_origin.reshape(-1, 3)
+        d = ray_direction.reshape(-1, 3)
+        n_rays = o.shape[0]
+        rad, opac, depth, n_kept = [], [], [], []
+        chunk = n_rays if self.training else self.test_chunk_size         # external/utils.py:99-104
+        for i in range(0, max(n_rays, 1), max(chunk, 1)):
+            j = None if jitter is None else jitter.reshape(-1)[i:i + chunk]
+            r, op, dp, nk = self.render_raw(o[i:i + chunk], d[i:i + chunk], j)
+            rad.append(r); opac.append(op); depth.append(dp); n_kept.append(nk)
+        radiance = torch.cat(rad).reshape(*lead, self.radiance_dim).squeeze(dim=-1)
+        opacity = torch.cat(opac).reshape(lead)
+        depth = torch.cat(depth).reshape(lead)
+        depth = depth / (opacity + self.opacity_eps)
+        mean_num_samples_per_ray = torch.cat(n_kept).sum() / n_rays        # device scalar: no host sync
+        return radiance, opacity, depth, mean_num_samples_per_ray

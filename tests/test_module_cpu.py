@@ -1,0 +1,116 @@
+"""Host-side logic of the drop-in modules (no GPU): constructor surface, state-dict key
+names, flat parameter buffer, optimiser groups, loud failure on CPU."""
+import pytest
+import torch
+
+import helpers as H
+from oracle import restatement as R
+
+
+def _model(dataset_dir, name="step_8x256"):
+    g = H.load_golden(name)
+    return g, H.build_product(g, dataset_dir)
+
+
+def test_state_dict_keys_match_reference(built_lib, dataset_dir):
+    _, m = _model(dataset_dir, "step_plumbing")
+    keys = set(m.state_dict().keys())
+    expect = {"contrast_threshold.parametrizations.p2n_contrast_threshold_ratio.original",
+              "refractory_period.parametrizations._refractory_period.original",
+              "nerf.parametrizations.render_bkgd.original", "nerf.radiance_field.aabb",
+              "nerf.radiance_field.posi_encoder.scales", "nerf.radiance_field.view_encoder.scales",
+              "nerf.radiance_field.mlp.sigma_layer.output_layer.weight",
+              "nerf.radiance_field.mlp.sigma_layer.output_layer.bias",
+              "nerf.radiance_field.mlp.bottleneck_layer.output_layer.weight",
+              "nerf.radiance_field.mlp.bottleneck_layer.output_layer.bias",
+              "nerf.radiance_field.mlp.rgb_layer.hidden_layers.0.weight",
+              "nerf.radiance_field.mlp.rgb_layer.hidden_layers.0.bias",
+              "nerf.radiance_field.mlp.rgb_layer.output_layer.weight",
+              "nerf.radiance_field.mlp.rgb_layer.output_layer.bias"}
+    expect |= {f"nerf.radiance_field.mlp.base.hidden_layers.{i}.{w}" for i in range(4) for w in ("weight", "bias")}
+    assert keys == expect
+    sd = m.state_dict()
+    assert sd["refractory_period.parametrizations._refractory_period.original"].dtype == torch.float64
+    assert sd["nerf.radiance_field.posi_encoder.scales"].dtype == torch.int64
+    assert sd["nerf.radiance_field.posi_encoder.scales"].tolist() == [2 ** i for i in range(10)]
+    # golden grads were recorded under the reference's parameter names: same set
+    g = H.load_golden("step_plumbing")
+    assert set(g["grads"].keys()) == {n for n, _ in m.named_parameters()}
+
+
+def test_default_init_equals_reference_init(built_lib, dataset_dir):
+    """torch.manual_seed(s); RobustENeRF(...) draws the reference's weights (external/mlp.py:297-299)."""
+    from ren_b200 import RobustENeRF
+    g = H.load_golden("step_8x256")
+    torch.manual_seed(0)
+    m = RobustENeRF(dataset_directory=dataset_dir, **H.product_config(g))
+    ref = H.golden_params(g)
+    sd = m.state_dict()
+    for k, v in ref.items():
+        assert torch.equal(sd["nerf.radiance_field." + k], v), k
+
+
+def test_flat_parameter_views(built_lib, dataset_dir):
+    _, m = _model(dataset_dir)
+    nerf = m.nerf
+    flat = nerf.flat_params()
+    assert flat.numel() == 595586
+    w = nerf.radiance_field.mlp.base.hidden_layers[3].weight
+    with torch.no_grad():
+        w[5, 7] = 123.0
+    off = nerf._layout[3][0]
+    assert float(nerf.flat_params()[off + 5 * 256 + 7]) == 123.0
+    # .to() / load_state_dict keep the views consistent
+    m2 = m.double().float()
+    assert m2.nerf._views_intact()
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    sd["nerf.radiance_field.mlp.sigma_layer.output_layer.bias"].fill_(0.5)
+    m.load_state_dict(sd)
+    assert float(m.nerf.flat_params()[m.nerf._layout[8][1]]) == 0.5
+
+
+def test_sensor_parametrisations(built_lib, dataset_dir):
+    _, m = _model(dataset_dir)
+    assert abs(float(m.contrast_threshold.p2n_contrast_threshold_ratio) - 1.0) < 1e-6
+    assert abs(float(m.contrast_threshold.mean_contrast_threshold) - 0.25) < 1e-7
+    assert m.refractory_period.refractory_period.dtype == torch.float64
+    assert abs(float(m.refractory_period.refractory_period) - 1000.0) < 1e-6
+    # logit clamp (models/event_generation_params.py:170-185)
+    with torch.no_grad():
+        m.refractory_period.parametrizations._refractory_period.original.fill_(1e9)
+    tau = float(m.refractory_period.refractory_period)
+    assert abs(tau - 50000 * (1 - 1e-4)) < 1e-3
+
+
+def test_optimizer_groups(built_lib, dataset_dir):
+    g, m = _model(dataset_dir, "step_plumbing")
+    cfg = m.configure_optimizers()
+    opt = cfg["optimizer"]
+    assert isinstance(opt, torch.optim.Adam) and len(opt.param_groups) == 4
+    ct, rp, mlp, other = opt.param_groups
+    assert ct["lr"] == 0.1 and rp["lr"] == 50000 * 50 and mlp["lr"] == 0.01
+    assert mlp["weight_decay"] == 1e-6 and ct["weight_decay"] == 0
+    assert len(mlp["params"]) == 2 * (4 + 4) and len(other["params"]) == 1      # bkgd
+    assert cfg["lr_scheduler"]["interval"] == "epoch"
+    assert cfg["lr_scheduler"]["scheduler"].milestones == {20: 1, 30: 1, 36: 1}
+
+
+def test_no_cpu_fallback(built_lib, dataset_dir):
+    """The product path must fail loudly without CUDA (no oracle / torch fallback)."""
+    g, m = _model(dataset_dir)
+    o = torch.zeros(4, 3)
+    d = torch.tensor([[0.0, 0.0, 1.0]]).repeat(4, 1)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m.nerf(o, d, torch.zeros(4))
+    import ren_b200.nerf as nmod, ren_b200.module as mmod, inspect
+    for mod in (nmod, mmod):
+        assert "oracle" not in inspect.getsource(mod)
+
+
+def test_unsupported_configurations_raise(built_lib, dataset_dir):
+    from ren_b200 import NeRF
+    g = H.load_golden("step_8x256")
+    cfg = H.product_config(g)["nerf"]
+    with pytest.raises(NotImplementedError):
+        NeRF(cfg["aabb"], "sphere", cfg["occ_grid"], 0.5, 4.5, 0.03, None, 0.0, 0.0, 0.0, 16384, "ngp",
+             arch_config=cfg["mlp"])
