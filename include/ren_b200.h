@@ -91,6 +91,14 @@ typedef struct RenRenderDesc {
 int ren_version(void);
 const char* ren_last_error(void);
 
+/* Measurement hooks (bench.py): kernels launched by this library so far; optional CUDA-event
+ * timing of every launch on its own stream, summed per kernel kind
+ * (0 field fwd, 1 field dgrad, 2 wgrad, 3 composite fwd, 4 composite bwd, 5 event rays,
+ *  6 loss, 7 adam, 8 weight pack).  `ren_timing_collect` waits for the recorded events. */
+int64_t ren_launch_count(void);
+int ren_timing_enable(int32_t on);
+int ren_timing_collect(int32_t kind, double* total_ms, int64_t* count);
+
 /* Number of fp32 elements of the flat MLP parameter buffer. */
 int ren_param_count(const RenFieldDesc* f, int64_t* n_params);
 

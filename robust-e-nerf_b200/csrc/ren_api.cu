@@ -36,6 +36,59 @@ void ren_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+// ---------------------------------------------------------------- launch accounting
+#include <atomic>
+#include <mutex>
+#include <vector>
+static std::atomic<long long> g_launches{0};
+static std::atomic<int> g_timing{0};
+static std::mutex g_prof_mu;
+struct ProfPair { cudaEvent_t a, b; };
+static std::vector<ProfPair> g_prof[REN_K_COUNT];
+static thread_local cudaEvent_t g_prof_open = nullptr;
+
+void ren_prof_begin(int kind, cudaStream_t st) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (!g_timing.load(std::memory_order_relaxed)) return;
+  cudaEvent_t e;
+  if (cudaEventCreate(&e) != cudaSuccess) return;
+  cudaEventRecord(e, st);
+  g_prof_open = e;
+  (void)kind;
+}
+void ren_prof_end(int kind, cudaStream_t st) {
+  if (!g_timing.load(std::memory_order_relaxed) || g_prof_open == nullptr) return;
+  cudaEvent_t e;
+  if (cudaEventCreate(&e) != cudaSuccess) return;
+  cudaEventRecord(e, st);
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof[kind].push_back({g_prof_open, e});
+  g_prof_open = nullptr;
+}
+
+extern "C" int64_t ren_launch_count(void) { return g_launches.load(); }
+extern "C" int ren_timing_enable(int32_t on) { g_timing.store(on ? 1 : 0); return REN_OK; }
+extern "C" int ren_timing_collect(int32_t kind, double* total_ms, int64_t* count) {
+  if (kind < 0 || kind >= REN_K_COUNT || !total_ms || !count) { ren_set_error("ren_timing_collect: bad arguments"); return REN_E_INVALID; }
+  std::vector<ProfPair> v;
+  {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    v.swap(g_prof[kind]);
+  }
+  double tot = 0;
+  for (auto& p : v) {
+    cudaEventSynchronize(p.b);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, p.a, p.b);
+    tot += ms;
+    cudaEventDestroy(p.a);
+    cudaEventDestroy(p.b);
+  }
+  *total_ms = tot;
+  *count = (int64_t)v.size();
+  return REN_OK;
+}
+
 extern "C" int ren_version(void) { return REN_ABI_VERSION; }
 extern "C" const char* ren_last_error(void) { return g_err; }
 

@@ -256,7 +256,9 @@ int ren_launch_composite(const RenPlan& p, long long n_rays, int K, const float*
   a.bkgd = bkgd; a.radiance = radiance; a.opacity = opacity; a.depth = depth; a.n_kept = n_kept;
   long long blocks = (n_rays + 3) / 4;
   if (blocks > 148 * 64) blocks = 148 * 64;
+  ren_prof_begin(REN_K_COMPOSITE_FWD, st);
   ren_composite_fwd<<<(unsigned)blocks, 128, 0, st>>>(a);
+  ren_prof_end(REN_K_COMPOSITE_FWD, st);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { ren_set_error("composite fwd launch: %s", cudaGetErrorString(e)); return REN_E_CUDA; }
   return REN_OK;
@@ -273,7 +275,9 @@ int ren_launch_composite_bwd(const RenPlan& p, long long n_rays, int K, const fl
   a.graw = graw; a.g_bkgd = g_bkgd;
   long long blocks = (n_rays + 3) / 4;
   if (blocks > 148 * 64) blocks = 148 * 64;
+  ren_prof_begin(REN_K_COMPOSITE_BWD, st);
   ren_composite_bwd<<<(unsigned)blocks, 128, 0, st>>>(a);
+  ren_prof_end(REN_K_COMPOSITE_BWD, st);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { ren_set_error("composite bwd launch: %s", cudaGetErrorString(e)); return REN_E_CUDA; }
   return REN_OK;

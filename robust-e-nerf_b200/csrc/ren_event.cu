@@ -201,7 +201,9 @@ extern "C" int ren_event_rays(int64_t B, const float* position, const int64_t* s
   a.pose_pos = pose_pos; a.pose_quat = pose_quat; a.k_inv = k_inv; a.n_renders = n_renders;
   a.out_ts = out_ts; a.out_o = out_o; a.out_d = out_d; a.out_rot = out_rot;
   a.out_ts_diff = out_ts_diff; a.out_start = out_start;
+  ren_prof_begin(REN_K_EVENT, (cudaStream_t)stream);
   ren_event_rays_kernel<<<(unsigned)((B + 127) / 128), 128, 0, (cudaStream_t)stream>>>(a);
+  ren_prof_end(REN_K_EVENT, (cudaStream_t)stream);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { ren_set_error("ren_event_rays launch: %s", cudaGetErrorString(e)); return REN_E_CUDA; }
   return REN_OK;
@@ -224,8 +226,10 @@ extern "C" int ren_trajectory(int64_t n, const double* ts, int64_t n_poses, cons
                               float* out_rot, void* stream) {
   if (n < 0 || n_poses < 2) { ren_set_error("ren_trajectory: bad sizes"); return REN_E_INVALID; }
   if (n == 0) return REN_OK;
+  ren_prof_begin(REN_K_EVENT, (cudaStream_t)stream);
   ren_trajectory_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
       n, ts, n_poses, (const long long*)pose_ts, pose_pos, pose_quat, out_pos, out_rot);
+  ren_prof_end(REN_K_EVENT, (cudaStream_t)stream);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { ren_set_error("ren_trajectory launch: %s", cudaGetErrorString(e)); return REN_E_CUDA; }
   return REN_OK;
@@ -331,8 +335,12 @@ extern "C" int ren_event_diff_loss(int64_t B, int32_t error_fn, int32_t all_vali
   cudaError_t e = cudaMemsetAsync(scratch, 0, 16, st);
   if (e != cudaSuccess) { ren_set_error("diff loss memset: %s", cudaGetErrorString(e)); return REN_E_CUDA; }
   const unsigned blocks = (unsigned)((B + 255) / 256);
+  ren_prof_begin(REN_K_LOSS, st);
   ren_diff_loss_kernel<<<blocks, 256, 0, st>>>(a);
+  ren_prof_end(REN_K_LOSS, st);
+  ren_prof_begin(REN_K_LOSS, st);
   ren_diff_loss_finish_kernel<<<blocks, 256, 0, st>>>(a);
+  ren_prof_end(REN_K_LOSS, st);
   e = cudaGetLastError();
   if (e != cudaSuccess) { ren_set_error("diff loss launch: %s", cudaGetErrorString(e)); return REN_E_CUDA; }
   return REN_OK;
@@ -362,9 +370,11 @@ extern "C" int ren_adam_step(int64_t n, float* params, const float* grads, float
   if (n <= 0 || step < 1) { ren_set_error("ren_adam_step: bad arguments"); return REN_E_INVALID; }
   const double bc1 = 1.0 - pow((double)beta1, (double)step);
   const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  ren_prof_begin(REN_K_ADAM, (cudaStream_t)stream);
   ren_adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       n, params, grads, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, grad_scale,
       (float)bc1, (float)sqrt(bc2));
+  ren_prof_end(REN_K_ADAM, (cudaStream_t)stream);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { ren_set_error("ren_adam_step launch: %s", cudaGetErrorString(e)); return REN_E_CUDA; }
   return REN_OK;

@@ -548,7 +548,9 @@ int ren_simt_launch_fwd(const RenPlan& p, long long n_rays, int K, const float* 
   const long long n_tiles = (S + TM - 1) / TM;
   long long grid = n_tiles < (long long)sm_count() * 8 ? n_tiles : (long long)sm_count() * 8;
   if (grid < 1) return REN_OK;
+  ren_prof_begin(REN_K_FIELD_FWD, st);
   ren_simt_field_fwd<<<(unsigned)grid, NTHREADS, smem, st>>>(a);
+  ren_prof_end(REN_K_FIELD_FWD, st);
   e = cudaGetLastError();
   if (e != cudaSuccess) { ren_set_error("simt fwd launch: %s", cudaGetErrorString(e)); return REN_E_CUDA; }
   return REN_OK;
@@ -565,7 +567,9 @@ int ren_simt_launch_dgrad(const RenPlan& p, long long S, const float* params, co
   const long long n_tiles = (S + TM - 1) / TM;
   long long grid = n_tiles < (long long)sm_count() * 8 ? n_tiles : (long long)sm_count() * 8;
   if (grid < 1) return REN_OK;
+  ren_prof_begin(REN_K_FIELD_DGRAD, st);
   ren_simt_field_dgrad<<<(unsigned)grid, NTHREADS, smem, st>>>(a);
+  ren_prof_end(REN_K_FIELD_DGRAD, st);
   e = cudaGetLastError();
   if (e != cudaSuccess) { ren_set_error("simt dgrad launch: %s", cudaGetErrorString(e)); return REN_E_CUDA; }
   return REN_OK;
@@ -636,7 +640,9 @@ int ren_simt_launch_wgrad(const RenPlan& p, long long S, const float* stash, con
   if (splits < 1) splits = 1;
   a.splits = splits;
   a.S = S;
+  ren_prof_begin(REN_K_WGRAD, st);
   ren_simt_wgrad<<<(unsigned)(total * splits), NTHREADS, 0, st>>>(a);
+  ren_prof_end(REN_K_WGRAD, st);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { ren_set_error("simt wgrad launch: %s", cudaGetErrorString(e)); return REN_E_CUDA; }
   return REN_OK;

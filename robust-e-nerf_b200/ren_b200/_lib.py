@@ -43,6 +43,9 @@ _P = C.c_void_p
 _SIGNATURES = {
     "ren_version": (C.c_int, []),
     "ren_last_error": (C.c_char_p, []),
+    "ren_launch_count": (C.c_int64, []),
+    "ren_timing_enable": (C.c_int, [C.c_int32]),
+    "ren_timing_collect": (C.c_int, [C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "ren_param_count": (C.c_int, [C.POINTER(RenFieldDesc), C.POINTER(C.c_int64)]),
     "ren_param_layout": (C.c_int, [C.POINTER(RenFieldDesc), C.POINTER(C.c_int32), C.POINTER(C.c_int64),
                                    C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
