@@ -176,7 +176,9 @@ class NeRF(torch.nn.Module):
             self._bkgd_mode = "parameter"
             holder = _Holder()
             holder.render_bkgd = _Holder()
-            holder.render_bkgd.original = torch.nn.Parameter(torch.ones(radiance_dim))
+            # parametrize stores right_inverse(init): softplus(original) == ones (utils/modules.py:46-54)
+            holder.render_bkgd.original = torch.nn.Parameter(
+                torch.log(torch.expm1(torch.ones(radiance_dim))))
             self.parametrizations = holder          # key: parametrizations.render_bkgd.original
         else:
             self._bkgd_mode = "buffer"
