@@ -274,7 +274,7 @@ extern "C" int ren_workspace_bytes(const RenFieldDesc* f, const RenRenderDesc* r
   const long long S = (long long)n_rays * K;
   size_t n;
   if (for_backward) {
-    n = sizeof(float) * (size_t)((p.act_floats + 1 + p.C) * S);
+    n = sizeof(float) * (size_t)ren_delta_floats(p, S);
   } else {
     n = (has_stash ? 0 : sizeof(float) * (size_t)((1 + p.C) * S)) + ren_tc_workspace_bytes(p, S);
   }
@@ -352,10 +352,10 @@ extern "C" int ren_render_backward(const RenFieldDesc* f, const RenRenderDesc* r
   if (stash_bytes < sizeof(float) * (size_t)ren_stash_floats(p, S)) { ren_set_error("stash too small"); return REN_E_WORKSPACE; }
   float* ws = (float*)align256(workspace);
   const size_t ws_left = workspace_bytes - ((char*)ws - (char*)workspace);
-  const size_t need = sizeof(float) * (size_t)((p.act_floats + 1 + p.C) * S);
+  const size_t need = sizeof(float) * (size_t)ren_delta_floats(p, S);
   if (ws_left < need) { ren_set_error("workspace too small for backward (%zu < %zu)", ws_left, need); return REN_E_WORKSPACE; }
   float* delta = ws;
-  float* graw = ws + p.act_floats * S;
+  float* graw = ws + p.act_floats * ren_pad128(S);
   const float* st_f = (const float*)stash;
   const float* raw = st_f + ren_stash_raw(p, S);
   cudaStream_t st = (cudaStream_t)stream;

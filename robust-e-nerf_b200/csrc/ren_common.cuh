@@ -50,20 +50,33 @@ struct RenPlan {
 //   [mat m : S x mat_width[m]] for m in 0..n_mats-1, then encP [S x 64], encD [S x 32],
 //   then raw [S x (1+C)] (sigma_raw or -inf when outside the contracted box, c_raw).
 // The delta workspace used by backward mirrors the mats + graw [S x (1+C)].
+//
+// Activation / delta matrices are stored BLOCKED so that the thread-per-sample-row epilogues
+// write full lines: a [S x N] matrix is tiled into 128-sample x 8-feature blocks of 4 KB,
+//   index(s, n) = ((s / 128) * (N / 8) + n / 8) * 1024 + (s % 128) * 8 + n % 8
+// (the fp32 image of the tcgen05 K-major core-matrix operand layout); S is padded to 128.
+__host__ __device__ inline long long ren_pad128(long long S) { return (S + 127) & ~127LL; }
+__host__ __device__ inline long long ren_blk(long long s, int n, int N) {
+  return (((s >> 7) * (N >> 3) + (n >> 3)) << 10) + ((s & 127) << 3) + (n & 7);
+}
 __host__ __device__ inline long long ren_stash_mat(const RenPlan& p, long long S, int m) {
-  return p.mat_off[m] * S;
+  return p.mat_off[m] * ren_pad128(S);
 }
 __host__ __device__ inline long long ren_stash_encp(const RenPlan& p, long long S) {
-  return p.act_floats * S;
+  return p.act_floats * ren_pad128(S);
 }
 __host__ __device__ inline long long ren_stash_encd(const RenPlan& p, long long S) {
-  return (p.act_floats + REN_PE_MAX) * S;
+  return (p.act_floats + REN_PE_MAX) * ren_pad128(S);
 }
 __host__ __device__ inline long long ren_stash_raw(const RenPlan& p, long long S) {
-  return (p.act_floats + REN_PE_MAX + REN_DE_MAX) * S;
+  return (p.act_floats + REN_PE_MAX + REN_DE_MAX) * ren_pad128(S);
 }
 __host__ __device__ inline long long ren_stash_floats(const RenPlan& p, long long S) {
-  return (p.act_floats + REN_PE_MAX + REN_DE_MAX + 1 + p.C) * S;
+  return (p.act_floats + REN_PE_MAX + REN_DE_MAX + 1 + p.C) * ren_pad128(S);
+}
+// floats of the backward workspace: delta mats (blocked) + graw [S][1+C]
+__host__ __device__ inline long long ren_delta_floats(const RenPlan& p, long long S) {
+  return (p.act_floats + 1 + p.C) * ren_pad128(S);
 }
 
 #ifdef __CUDACC__
@@ -200,6 +213,7 @@ __device__ __forceinline__ void ren_encode(const float* x, int deg, int padded, 
   store(1, x[1]);
   store(2, x[2]);
   float sc = 1.f;
+#pragma unroll
   for (int i = 0; i < deg; ++i) {
 #pragma unroll
     for (int a = 0; a < 3; ++a) {

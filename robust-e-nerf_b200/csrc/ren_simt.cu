@@ -176,7 +176,7 @@ __device__ __forceinline__ void fwd_layer(const RenPlan& p, const RenLayer& L, c
           const int m = ty * 8 + i;
           *reinterpret_cast<float4*>(out + m * WS + n) = v;
           if (stash_mat != nullptr && s0 + m < S)
-            *reinterpret_cast<float4*>(stash_mat + (s0 + m) * L.N + n) = v;
+            *reinterpret_cast<float4*>(stash_mat + ren_blk(s0 + m, n, L.N)) = v;
         }
       }
     }
@@ -243,10 +243,10 @@ extern "C" __global__ void __launch_bounds__(NTHREADS, 1) ren_simt_field_fwd(con
                        __fmul_rn(d[2], 3.141592653589793f)};
         ren_encode(dz, p.f.dir_deg, REN_DE_MAX, [&](int j, float v) { eD[j] = v; });
         if (a.stash) {
-          float* gP = a.stash + ren_stash_encp(p, S) + sidx * REN_PE_MAX;
-          float* gD = a.stash + ren_stash_encd(p, S) + sidx * REN_DE_MAX;
-          for (int j = 0; j < REN_PE_MAX; ++j) gP[j] = eP[j];
-          for (int j = 0; j < REN_DE_MAX; ++j) gD[j] = eD[j];
+          float* gP = a.stash + ren_stash_encp(p, S);
+          float* gD = a.stash + ren_stash_encd(p, S);
+          for (int j = 0; j < REN_PE_MAX; ++j) gP[ren_blk(sidx, j, REN_PE_MAX)] = eP[j];
+          for (int j = 0; j < REN_DE_MAX; ++j) gD[ren_blk(sidx, j, REN_DE_MAX)] = eD[j];
         }
       } else {
         for (int j = 0; j < REN_PE_MAX; ++j) eP[j] = 0.f;
@@ -331,7 +331,7 @@ __device__ __forceinline__ void bwd_layer(const RenPlan& p, const RenLayer& L, c
           }
           if (prev_act) {
             float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (s0 + m < S) y = *reinterpret_cast<const float4*>(aprev_mat + (s0 + m) * Kout + k);
+            if (s0 + m < S) y = *reinterpret_cast<const float4*>(aprev_mat + ren_blk(s0 + m, k, Kout));
             v.x *= ren_hidden_grad_from_out(p.f.hidden_activation, y.x);
             v.y *= ren_hidden_grad_from_out(p.f.hidden_activation, y.y);
             v.z *= ren_hidden_grad_from_out(p.f.hidden_activation, y.z);
@@ -340,7 +340,7 @@ __device__ __forceinline__ void bwd_layer(const RenPlan& p, const RenLayer& L, c
           if (s0 + m >= S) v = make_float4(0.f, 0.f, 0.f, 0.f);
           *reinterpret_cast<float4*>(din + m * WS + k) = v;
           if (delta_mat != nullptr && s0 + m < S)
-            *reinterpret_cast<float4*>(delta_mat + (s0 + m) * Kout + k) = v;
+            *reinterpret_cast<float4*>(delta_mat + ren_blk(s0 + m, k, Kout)) = v;
         }
       }
     }
@@ -381,8 +381,8 @@ extern "C" __global__ void __launch_bounds__(NTHREADS, 1) ren_simt_field_dgrad(c
         float v = 0.f;
         for (int c = 0; c < p.C; ++c) v = fmaf(gc[m * 4 + c], __ldg(a.params + p.rgb_w + c * ldo + k), v);
         if (s0 + m < S) {
-          if (Llast->act) v *= ren_hidden_grad_from_out(p.f.hidden_activation, amat[(s0 + m) * Kin + k]);
-          dmat[(s0 + m) * Kin + k] = v;
+          if (Llast->act) v *= ren_hidden_grad_from_out(p.f.hidden_activation, amat[ren_blk(s0 + m, k, Kin)]);
+          dmat[ren_blk(s0 + m, k, Kin)] = v;
         } else {
           v = 0.f;
         }
@@ -423,8 +423,9 @@ extern "C" __global__ void __launch_bounds__(NTHREADS, 1) ren_simt_field_dgrad(c
 // dW[n][koff + k] += sum_m D[m][n] * H[m][k];  db[n] += sum_m D[m][n] (k-tile 0 only).
 #define WG_MAXP 48
 struct WgradProblem {
-  const float* D; int ldd;   // [S][ldd], N valid columns
-  const float* H; int ldh;   // [S][ldh], Kc valid columns
+  const float* D; int ldd;   // N valid columns; blocked [S x ldd] (ren_blk) or row-major [S][ldd]
+  const float* H; int ldh;   // Kc valid columns; blocked [S x ldh]
+  int d_rowmajor;            // D is the row-major graw matrix
   int N, Kc;
   float* dW; int ldw;        // dW + koff already applied
   float* db;                 // NULL to skip
@@ -469,8 +470,9 @@ extern "C" __global__ void __launch_bounds__(NTHREADS, 2) ren_simt_wgrad(const W
       const int idx = e * NTHREADS + tid;
       const int mm = idx >> 7, cc = idx & 127;
       const long long m = m0 + mm;
-      dreg[e] = (m < m_end && n0 + cc < P.N) ? __ldg(P.D + m * P.ldd + n0 + cc) : 0.f;
-      hreg[e] = (m < m_end && k0 + cc < P.Kc) ? __ldg(P.H + m * P.ldh + k0 + cc) : 0.f;
+      dreg[e] = (m < m_end && n0 + cc < P.N)
+                    ? __ldg(P.D + (P.d_rowmajor ? m * P.ldd + n0 + cc : ren_blk(m, n0 + cc, P.ldd))) : 0.f;
+      hreg[e] = (m < m_end && k0 + cc < P.Kc) ? __ldg(P.H + ren_blk(m, k0 + cc, P.ldh)) : 0.f;
     }
   };
   auto commit = [&](int buf) {
@@ -586,6 +588,7 @@ int ren_simt_launch_wgrad(const RenPlan& p, long long S, const float* stash, con
                  float* db) {
     WgradProblem& P = a.pr[np++];
     P.D = D; P.ldd = ldd; P.N = N; P.H = H; P.ldh = ldh; P.Kc = Kc; P.dW = dW; P.ldw = ldw; P.db = db;
+    P.d_rowmajor = (D == graw || D == graw + 1) ? 1 : 0;
     P.ntn = (N + 127) / 128; P.ntk = (Kc + 127) / 128;
   };
   auto add_layer = [&](const RenLayer& L, const float* in_main, int ld_main) {

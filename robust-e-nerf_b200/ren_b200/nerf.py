@@ -44,14 +44,15 @@ class _Encoder(torch.nn.Module):
 class RenderFunction(torch.autograd.Function):
     """ren_render_forward / ren_render_backward as one differentiable op.
 
-    inputs : owner (NeRF), o (B,3), d (B,3), jitter (B)|None, bkgd (C)|None, *params
+    inputs : owner (NeRF), want_grad (bool: grad mode of the caller), o (B,3), d (B,3),
+             jitter (B)|None, bkgd (C)|None, *params
     outputs: radiance (B,C), opacity (B), depth_raw (B), n_kept (B) int32
     Gradients flow to the MLP parameters and `bkgd` (ray gradients are not provided:
     SURVEY.md App. A9 lists them for the tau-trainable configuration only).
     """
 
     @staticmethod
-    def forward(ctx, owner, o, d, jitter, bkgd, *params):
+    def forward(ctx, owner, want_grad, o, d, jitter, bkgd, *params):
         lib = _lib.load()
         if not o.is_cuda:
             raise RuntimeError("ren_b200 renders on CUDA tensors only (no CPU fallback)")
@@ -59,7 +60,7 @@ class RenderFunction(torch.autograd.Function):
         C_ = owner.radiance_dim
         fdesc, rdesc, K = owner._descs()
         flat = owner.flat_params()
-        need_grad = any(ctx.needs_input_grad[4:])
+        need_grad = bool(want_grad) and any(ctx.needs_input_grad[5:])
         dev = o.device
         o = o.contiguous().float()
         d = d.contiguous().float()
@@ -117,7 +118,7 @@ class RenderFunction(torch.autograd.Function):
             _lib.ptr(stash), stash.numel(), _lib.ptr(g_flat), _lib.ptr(g_bkgd), _lib.ptr(ws),
             ws.numel(), _lib.stream_ptr()), "ren_render_backward")
         grads = owner._split_flat(g_flat)
-        return (None, None, None, None, g_bkgd) + tuple(grads)
+        return (None, None, None, None, None, g_bkgd) + tuple(grads)
 
 
 class NeRF(torch.nn.Module):
@@ -331,7 +332,8 @@ class NeRF(torch.nn.Module):
             jitter = torch.rand((o.shape[0],), device=o.device, dtype=torch.float32)
         if not self.training:
             jitter = None
-        return RenderFunction.apply(self, o, d, jitter, self.background(), *self.mlp_parameters())
+        return RenderFunction.apply(self, torch.is_grad_enabled(), o, d, jitter, self.background(),
+                                    *self.mlp_parameters())
 
     def forward(self, ray_origin, ray_direction, jitter=None):
         """models/nerf.py:230-286.  `jitter` (optional, (N,) in [0,1)) injects the per-ray

@@ -16,7 +16,7 @@ from oracle import synth
 pytestmark = pytest.mark.gpu
 
 REL_BAR = 1e-4
-ENGINES = ["simt_fp32", "auto"]
+ENGINES = ["simt_fp32", "auto"]          # auto = tcgen05 (fp16x3) when the shape is covered
 
 
 def _log_i(rad, imin=1e-3):
