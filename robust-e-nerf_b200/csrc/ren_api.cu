@@ -4,7 +4,7 @@
 #include <stdio.h>
 #include <string.h>
 
-#include "ren_common.cuh"
+#include "ren_tc.cuh"
 
 // engines
 int ren_simt_launch_fwd(const RenPlan& p, long long n_rays, int K, const float* o, const float* d,
@@ -19,13 +19,19 @@ int ren_launch_composite(const RenPlan& p, long long n_rays, int K, const float*
 int ren_launch_composite_bwd(const RenPlan& p, long long n_rays, int K, const float* o, const float* d,
                              const float* jitter, const float* raw, const float* bkgd,
                              const float* g_radiance, const float* g_opacity, const float* g_depth,
-                             float* graw, float* g_bkgd, cudaStream_t st);
+                             float* graw, float* g_bkgd, unsigned int* gmax, cudaStream_t st);
 // tcgen05 engine (ren_tc.cu)
 int ren_tc_supported(const RenPlan& p);
-size_t ren_tc_workspace_bytes(const RenPlan& p, long long S);
+size_t ren_tc_fwd_workspace_bytes(const RenPlan& p);
+size_t ren_tc_bwd_pack_bytes(const RenPlan& p);
 int ren_tc_launch_fwd(const RenPlan& p, long long n_rays, int K, const float* o, const float* d,
-                      const float* jitter, const float* params, float* stash, float* raw, void* ws,
+                      const float* jitter, const float* params, void* stash, float* raw, void* ws,
                       size_t ws_bytes, cudaStream_t st);
+int ren_tc_launch_dgrad(const RenPlan& p, long long S, const float* params, const void* stash,
+                        const float* graw, const unsigned int* gmax, void* delta, void* ws, size_t ws_bytes,
+                        cudaStream_t st);
+int ren_tc_launch_wgrad(const RenPlan& p, long long S, const void* stash, const void* delta,
+                        const float* graw, const unsigned int* gmax, float* g_params, cudaStream_t st);
 
 static thread_local char g_err[512] = "";
 
@@ -244,10 +250,22 @@ extern "C" int ren_samples_per_ray(const RenFieldDesc* f, const RenRenderDesc* r
   return REN_OK;
 }
 
+// AUTO resolves to the tcgen05 engine whenever the network shape is covered.
 static int pick_engine(const RenPlan& p) {
   int e = p.r.engine;
   if (e == REN_ENGINE_AUTO) e = ren_tc_supported(p) ? REN_ENGINE_TC_F16X3 : REN_ENGINE_SIMT_FP32;
   return e;
+}
+static int check_engine(const RenPlan& p, int engine) {
+  if (engine != REN_ENGINE_SIMT_FP32 && !ren_tc_supported(p)) {
+    ren_set_error("tcgen05 engine covers net_width 256 / net_width_condition 128 / 1 condition layer / "
+                  "pos 10 / dir 4 encoders only; use engine simt_fp32 or auto");
+    return REN_E_UNSUPPORTED;
+  }
+  return REN_OK;
+}
+static size_t stash_bytes_for(const RenPlan& p, int engine, long long S) {
+  return engine == REN_ENGINE_SIMT_FP32 ? sizeof(float) * (size_t)ren_stash_floats(p, S) : tcs_bytes(p, S);
 }
 
 extern "C" int ren_stash_bytes(const RenFieldDesc* f, const RenRenderDesc* r, int64_t n_rays, int32_t K,
@@ -255,14 +273,19 @@ extern "C" int ren_stash_bytes(const RenFieldDesc* f, const RenRenderDesc* r, in
   RenPlan p;
   int rc = ren_build_plan(f, r, &p);
   if (rc) return rc;
+  rc = validate_render(r);
+  if (rc) return rc;
   if (n_rays < 0 || K < 1) { ren_set_error("bad n_rays/K"); return REN_E_INVALID; }
-  *bytes = sizeof(float) * (size_t)ren_stash_floats(p, (long long)n_rays * K);
+  const int engine = pick_engine(p);
+  rc = check_engine(p, engine);
+  if (rc) return rc;
+  *bytes = stash_bytes_for(p, engine, (long long)n_rays * K);
   return REN_OK;
 }
 
 // workspace:
-//   forward : raw [S][1+C] when there is no stash to hold it, + tcgen05 scratch
-//   backward: delta mats [S][act_floats] + graw [S][1+C]
+//   forward : raw [S][1+C] when there is no stash to hold it, + packed weights (tcgen05)
+//   backward: delta matrices + graw [S][1+C] (+ packed transposed weights)
 extern "C" int ren_workspace_bytes(const RenFieldDesc* f, const RenRenderDesc* r, int64_t n_rays, int32_t K,
                                    int32_t has_stash, int32_t for_backward, size_t* bytes) {
   RenPlan p;
@@ -272,13 +295,19 @@ extern "C" int ren_workspace_bytes(const RenFieldDesc* f, const RenRenderDesc* r
   if (rc) return rc;
   if (n_rays < 0 || K < 1) { ren_set_error("bad n_rays/K"); return REN_E_INVALID; }
   const long long S = (long long)n_rays * K;
+  const int engine = pick_engine(p);
+  rc = check_engine(p, engine);
+  if (rc) return rc;
   size_t n;
-  if (for_backward) {
-    n = sizeof(float) * (size_t)ren_delta_floats(p, S);
+  if (engine == REN_ENGINE_SIMT_FP32) {
+    n = for_backward ? sizeof(float) * (size_t)ren_delta_floats(p, S)
+                     : (has_stash ? 0 : sizeof(float) * (size_t)((1 + p.C) * ren_pad128(S)));
   } else {
-    n = (has_stash ? 0 : sizeof(float) * (size_t)((1 + p.C) * S)) + ren_tc_workspace_bytes(p, S);
+    n = for_backward ? tcd_bytes(p, S) + ren_tc_bwd_pack_bytes(p)
+                     : (has_stash ? 0 : sizeof(float) * (size_t)((1 + p.C) * ren_pad128(S))) +
+                           ren_tc_fwd_workspace_bytes(p);
   }
-  *bytes = n + 512;
+  *bytes = n + 2048;
   return REN_OK;
 }
 
@@ -303,29 +332,30 @@ extern "C" int ren_render_forward(const RenFieldDesc* f, const RenRenderDesc* r,
     return REN_E_INVALID;
   }
   if (r->stratified && jitter == nullptr) { ren_set_error("stratified marching needs a jitter buffer"); return REN_E_INVALID; }
+  const int engine = pick_engine(p);
+  rc = check_engine(p, engine);
+  if (rc) return rc;
+  p.r.engine = engine;
   const long long S = (long long)n_rays * K;
   cudaStream_t st = (cudaStream_t)stream;
   float* raw;
-  void* ws = align256(workspace);
-  size_t ws_left = workspace ? workspace_bytes - ((char*)ws - (char*)workspace) : 0;
+  char* ws = (char*)align256(workspace);
+  size_t ws_left = workspace ? workspace_bytes - (size_t)(ws - (char*)workspace) : 0;
   if (stash) {
-    if (stash_bytes < sizeof(float) * (size_t)ren_stash_floats(p, S)) { ren_set_error("stash too small"); return REN_E_WORKSPACE; }
-    raw = (float*)stash + ren_stash_raw(p, S);
+    if (stash_bytes < stash_bytes_for(p, engine, S)) { ren_set_error("stash too small"); return REN_E_WORKSPACE; }
+    raw = engine == REN_ENGINE_SIMT_FP32 ? (float*)stash + ren_stash_raw(p, S)
+                                         : (float*)((char*)stash + tcs_raw(p, S));
   } else {
-    const size_t need = sizeof(float) * (size_t)((1 + p.C) * S);
+    const size_t need = sizeof(float) * (size_t)((1 + p.C) * ren_pad128(S));
     if (!workspace || ws_left < need) { ren_set_error("workspace too small for raw samples (%zu < %zu)", ws_left, need); return REN_E_WORKSPACE; }
     raw = (float*)ws;
-    ws = align256((char*)ws + need);
-    ws_left = workspace_bytes - ((char*)ws - (char*)workspace);
+    ws = (char*)align256(ws + need);
+    ws_left = workspace_bytes - (size_t)(ws - (char*)workspace);
   }
-  const int engine = pick_engine(p);
-  if (engine == REN_ENGINE_SIMT_FP32) {
+  if (engine == REN_ENGINE_SIMT_FP32)
     rc = ren_simt_launch_fwd(p, n_rays, K, rays_o, rays_d, jitter, params, (float*)stash, raw, st);
-  } else {
-    if (!ren_tc_supported(p)) { ren_set_error("tcgen05 engine does not cover this network shape"); return REN_E_UNSUPPORTED; }
-    p.r.engine = engine;
-    rc = ren_tc_launch_fwd(p, n_rays, K, rays_o, rays_d, jitter, params, (float*)stash, raw, ws, ws_left, st);
-  }
+  else
+    rc = ren_tc_launch_fwd(p, n_rays, K, rays_o, rays_d, jitter, params, stash, raw, ws, ws_left, st);
   if (rc) return rc;
   return ren_launch_composite(p, n_rays, K, rays_o, rays_d, jitter, raw, bkgd, radiance, opacity, depth,
                               n_kept, st);
@@ -348,21 +378,42 @@ extern "C" int ren_render_backward(const RenFieldDesc* f, const RenRenderDesc* r
     ren_set_error("ren_render_backward: null pointer argument");
     return REN_E_INVALID;
   }
+  const int engine = pick_engine(p);
+  rc = check_engine(p, engine);
+  if (rc) return rc;
+  p.r.engine = engine;
   const long long S = (long long)n_rays * K;
-  if (stash_bytes < sizeof(float) * (size_t)ren_stash_floats(p, S)) { ren_set_error("stash too small"); return REN_E_WORKSPACE; }
-  float* ws = (float*)align256(workspace);
-  const size_t ws_left = workspace_bytes - ((char*)ws - (char*)workspace);
-  const size_t need = sizeof(float) * (size_t)ren_delta_floats(p, S);
-  if (ws_left < need) { ren_set_error("workspace too small for backward (%zu < %zu)", ws_left, need); return REN_E_WORKSPACE; }
-  float* delta = ws;
-  float* graw = ws + p.act_floats * ren_pad128(S);
-  const float* st_f = (const float*)stash;
-  const float* raw = st_f + ren_stash_raw(p, S);
+  if (stash_bytes < stash_bytes_for(p, engine, S)) { ren_set_error("stash too small"); return REN_E_WORKSPACE; }
+  char* ws = (char*)align256(workspace);
+  const size_t ws_left = workspace_bytes - (size_t)(ws - (char*)workspace);
   cudaStream_t st = (cudaStream_t)stream;
+  if (engine == REN_ENGINE_SIMT_FP32) {
+    const size_t need = sizeof(float) * (size_t)ren_delta_floats(p, S);
+    if (ws_left < need) { ren_set_error("workspace too small for backward (%zu < %zu)", ws_left, need); return REN_E_WORKSPACE; }
+    float* delta = (float*)ws;
+    float* graw = delta + p.act_floats * ren_pad128(S);
+    const float* st_f = (const float*)stash;
+    const float* raw = st_f + ren_stash_raw(p, S);
+    rc = ren_launch_composite_bwd(p, n_rays, K, rays_o, rays_d, jitter, raw, bkgd, g_radiance, g_opacity,
+                                  g_depth, graw, g_bkgd, nullptr, st);
+    if (rc) return rc;
+    rc = ren_simt_launch_dgrad(p, S, params, st_f, graw, delta, st);
+    if (rc) return rc;
+    return ren_simt_launch_wgrad(p, S, st_f, delta, graw, g_params, st);
+  }
+  const size_t need = tcd_bytes(p, S);
+  if (ws_left < need + 1024) { ren_set_error("workspace too small for backward (%zu < %zu)", ws_left, need); return REN_E_WORKSPACE; }
+  char* delta = ws;
+  float* graw = (float*)(ws + tcd_graw(p, S));
+  char* pack_ws = (char*)align256(ws + need);
+  const size_t pack_left = workspace_bytes - (size_t)(pack_ws - (char*)workspace);
+  const float* raw = (const float*)((const char*)stash + tcs_raw(p, S));
+  unsigned int* gmax = (unsigned int*)(ws + tcd_gmax(p, S));
+  if (cudaMemsetAsync(gmax, 0, 256, st) != cudaSuccess) { ren_set_error("gmax memset failed"); return REN_E_CUDA; }
   rc = ren_launch_composite_bwd(p, n_rays, K, rays_o, rays_d, jitter, raw, bkgd, g_radiance, g_opacity,
-                                g_depth, graw, g_bkgd, st);
+                                g_depth, graw, g_bkgd, gmax, st);
   if (rc) return rc;
-  rc = ren_simt_launch_dgrad(p, S, params, st_f, graw, delta, st);
+  rc = ren_tc_launch_dgrad(p, S, params, stash, graw, gmax, delta, pack_ws, pack_left, st);
   if (rc) return rc;
-  return ren_simt_launch_wgrad(p, S, st_f, delta, graw, g_params, st);
+  return ren_tc_launch_wgrad(p, S, stash, delta, graw, gmax, g_params, st);
 }

@@ -29,6 +29,7 @@ struct CompArgs {
   const float* g_depth;
   float* graw;           // [S][1+C]
   float* g_bkgd;         // [C] or NULL
+  unsigned int* gmax;    // max |graw| as float bits (tcgen05 backward loss scaling) or NULL
 };
 
 __device__ __forceinline__ float warp_incl_scan(float v, int lane) {
@@ -189,6 +190,7 @@ extern "C" __global__ void __launch_bounds__(128) ren_composite_bwd(const CompAr
   const RenPlan& p = a.p;
   const int C1 = 1 + p.C;
   float gb_acc[3] = {0.f, 0.f, 0.f};
+  float gabs = 0.f;
   for (long long r = warp; r < a.n_rays; r += n_warps) {
     float gC[3] = {0.f, 0.f, 0.f}, bk[3] = {0.f, 0.f, 0.f};
     for (int c = 0; c < p.C; ++c) {
@@ -238,13 +240,23 @@ extern "C" __global__ void __launch_bounds__(128) ren_composite_bwd(const CompAr
           gs = dsdt * __fsub_rn(b.t1, b.t0) * b.dact_s;
         }
         g[0] = gs;
-        for (int c = 0; c < p.C; ++c) g[1 + c] = b.keep ? gC[c] * b.w * b.dact_c[c] : 0.f;
+        gabs = fmaxf(gabs, fabsf(gs));
+        for (int c = 0; c < p.C; ++c) {
+          const float gcv = b.keep ? gC[c] * b.w * b.dact_c[c] : 0.f;
+          g[1 + c] = gcv;
+          gabs = fmaxf(gabs, fabsf(gcv));
+        }
       }
     });
   }
   if (a.g_bkgd && a.bkgd && lane == 0)
     for (int c = 0; c < p.C; ++c)
       if (gb_acc[c] != 0.f) atomicAdd(a.g_bkgd + c, gb_acc[c]);
+  if (a.gmax != nullptr) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) gabs = fmaxf(gabs, __shfl_xor_sync(0xffffffffu, gabs, o));
+    if (lane == 0 && gabs > 0.f && gabs < INFINITY) atomicMax(a.gmax, __float_as_uint(gabs));
+  }
 }
 
 int ren_launch_composite(const RenPlan& p, long long n_rays, int K, const float* o, const float* d,
@@ -267,12 +279,12 @@ int ren_launch_composite(const RenPlan& p, long long n_rays, int K, const float*
 int ren_launch_composite_bwd(const RenPlan& p, long long n_rays, int K, const float* o, const float* d,
                              const float* jitter, const float* raw, const float* bkgd,
                              const float* g_radiance, const float* g_opacity, const float* g_depth,
-                             float* graw, float* g_bkgd, cudaStream_t st) {
+                             float* graw, float* g_bkgd, unsigned int* gmax, cudaStream_t st) {
   if (n_rays <= 0) return REN_OK;
   CompArgs a = {};
   a.p = p; a.n_rays = n_rays; a.K = K; a.rays_o = o; a.rays_d = d; a.jitter = jitter; a.raw = raw;
   a.bkgd = bkgd; a.g_radiance = g_radiance; a.g_opacity = g_opacity; a.g_depth = g_depth;
-  a.graw = graw; a.g_bkgd = g_bkgd;
+  a.graw = graw; a.g_bkgd = g_bkgd; a.gmax = gmax;
   long long blocks = (n_rays + 3) / 4;
   if (blocks > 148 * 64) blocks = 148 * 64;
   ren_prof_begin(REN_K_COMPOSITE_BWD, st);

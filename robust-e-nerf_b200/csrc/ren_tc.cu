@@ -1,58 +1,67 @@
-// ren_tc.cu -- tcgen05 engine of the field MLP (REN_ENGINE_TC_F16X3 / REN_ENGINE_TC_F16).
+// ren_tc.cu -- tcgen05 "chain" kernel of the field MLP: forward and dgrad (REN_ENGINE_TC_*).
 //
-// One persistent CTA per SM.  Warp-specialised roles:
-//   warp 0      weight producer: streams pre-packed fp16 (hi|lo) weight K-chunks from L2 into a
-//               3-stage shared-memory ring with 1-D bulk TMA (cp.async.bulk + mbarrier tx)
-//   warp 1      MMA issuer: one thread issues tcgen05.mma (kind::f16, M=128, N=256/128, K=16),
-//               accumulator in TMEM (256 columns x 128 lanes fp32)
-//   warps 2-9   prologue (march -> position -> contraction -> sin/cos encoding) and epilogue
-//               (tcgen05.ld -> bias + softplus(beta=100) -> fp16 hi/lo split -> next layer's A
-//               operand in shared memory; sigma / radiance heads as per-row dot products)
-// A tile is 128 consecutive samples (= TMEM lanes).  Activations never leave the SM (except the
-// optional fp32 stash the backward pass reads).
+// One persistent CTA per SM, one 128-sample tile in flight.  Warp-specialised roles:
+//   warp 0       weight producer: streams pre-packed fp16 (hi|lo) weight K-chunks from L2 into a
+//                3-stage shared-memory ring with 1-D bulk TMA (cp.async.bulk + mbarrier tx bytes)
+//   warp 1       MMA issuer: one thread issues tcgen05.mma (kind::f16, M=128, N=256/128/16, K=16);
+//                accumulators live in TMEM (512 columns x 128 lanes, fp32)
+//   warps 2-17   prologue + epilogue: tcgen05.ld -> bias/activation (fwd) or activation derivative
+//                (dgrad) -> fp16 hi/lo split -> the next GEMM's A operand in shared memory (+ the
+//                fp16 stash in HBM).  Lane quadrant = warp % 4 (TMEM access rule), 4 warps share
+//                a quadrant and split the columns.
+// The whole network is a chain of GEMM "steps" described by a table, so forward and dgrad are
+// the same kernel: activations / deltas never leave the SM between layers.  The sigma and
+// radiance heads (N = 1..3) are N=16 MMAs, and in dgrad the head gradients re-enter as K=16
+// rank-1 segments -- there is no per-element head arithmetic.
 //
-// fp32-class accuracy from fp16 tensor cores: x = hi + lo with hi = fp16(x), lo = fp16(x - hi);
-// A*W ~= A_hi*W_hi + A_lo*W_hi + A_hi*W_lo accumulated in fp32 (3 MMAs per K step; the dropped
-// lo*lo term is 2^-22 relative).  SURVEY.md section 7.3-1: single-pass fp16/bf16/TF32 misses the 1e-4 bar.
+// fp32-class accuracy from fp16 tensor cores: x = hi + lo, hi = fp16(x), lo = fp16(x - hi);
+// A*W ~= A_hi*W_hi + A_lo*W_hi + A_hi*W_lo in fp32 (3 MMAs per K step; the dropped lo*lo term is
+// 2^-22 relative).  Single-pass fp16/bf16/TF32 misses the 1e-4 bar.
 //
-// Operand layout (both operands K-major, SWIZZLE_NONE): 8x8 fp16 core matrices of 128 contiguous
-// bytes; element (row, k) of a [rows x K] operand at (k/8)*(rows*16) + row*16 + (k%8)*2.  A warp of
-// epilogue threads (32 consecutive rows) therefore writes 512 contiguous bytes per k-core.
-#include <cuda_fp16.h>
+// Operand layout (K-major, SWIZZLE_NONE): 8x8 fp16 core matrices of 128 contiguous bytes;
+// element (row, k) of a [rows x K] operand at (k/8)*(rows*16) + row*16 + (k%8)*2, so a warp of
+// epilogue threads (32 consecutive rows) writes 512 contiguous bytes per 8-feature group.
+#include <string.h>
 
-#include "ren_common.cuh"
+#include "ren_tc.cuh"
 
-#define TC_M 128
-#define TC_THREADS 320
+#define TC_EPI_WARPS 16
+#define TC_THREADS (64 + 32 * TC_EPI_WARPS)   // 576
 #define TC_STAGES 3
 #define TC_MAX_STEPS 24
 
 // shared-memory map (bytes)
-#define SM_A_HI 0
+#define SM_A_HI 0          // main activations  [128 x 256] hi
 #define SM_A_LO 65536
-#define SM_P_HI 131072
+#define SM_P_HI 131072     // region 1: positional encoding [128 x 64] (dgrad: column 0 = d sigma_raw)
 #define SM_P_LO 147456
-#define SM_D_HI 163840
+#define SM_D_HI 163840     // region 2: direction encoding [128 x 32] (dgrad: columns 0..C-1 = d c_raw)
 #define SM_D_LO 172032
 #define SM_RING 180224
 #define SM_STAGE_BYTES 16384
 #define SM_BAR (SM_RING + TC_STAGES * SM_STAGE_BYTES)   // 229376
 #define SM_TMEM_PTR (SM_BAR + 64)
-#define SM_SIG_PART (SM_BAR + 128)                      // [128] f32
-#define SM_RGB_PART (SM_SIG_PART + 512)                 // [3][128] f32
-#define SM_TOTAL (SM_RGB_PART + 1536)                   // 231552
+#define SM_TOTAL (SM_BAR + 128)
+
+#define TMEM_COL_SIGMA 256
+#define TMEM_COL_RGB 272
+
+enum { EPI_F_HIDDEN = 0, EPI_F_LINEAR = 1, EPI_F_HEADS = 2, EPI_D_ACT = 3, EPI_D_LINEAR = 4 };
 
 struct TcStep {
-  int seg_region[2];   // 0 main activations, 1 positional encoding, 2 direction encoding
+  int seg_region[2];   // 0 main, 1 positional-encoding region, 2 direction-encoding region
   int seg_ksteps[2];   // K/16 per segment (0 = unused)
-  int seg_K[2];        // true (unpadded) K per segment
-  int N;               // 256 or 128
-  int w_off, ldw, bias_off;
-  int epi;             // 0 hidden activation, 1 linear (bottleneck), 2 condition layer (+ radiance head)
-  int mat;             // stash matrix index
-  int last_trunk;      // accumulate the sigma head in this epilogue
-  long long pack_off;  // byte offset of this step's packed weights
-  int n_chunks;        // total K steps
+  int N;               // MMA N: 256 / 128 / 16
+  int epi;             // EPI_*
+  int out_mat;         // stash (fwd) / delta (dgrad) matrix written by the epilogue, -1 none
+  int act_mat;         // dgrad: stash matrix of the activation whose derivative multiplies, -1 none
+  int write_a;         // result becomes the next step's main A operand
+  int bias_off;        // float offset of this step's bias vector in the packed bias area, -1 none
+  int tmem_col;        // accumulator base column
+  int n_chunks;        // main weight chunks (one per K step, N*64 bytes each)
+  int head_chunk;      // fwd: one extra 16 KB chunk = the N=16 sigma-head block over K=256
+  long long pack_off;       // byte offset of the main chunks
+  long long head_pack_off;  // byte offset of the head chunk
 };
 
 struct TcArgs {
@@ -66,78 +75,14 @@ struct TcArgs {
   const float* rays_d;
   const float* jitter;
   const float* params;
-  const unsigned char* pack;
-  float* stash;
-  float* raw;
+  const unsigned char* pack;     // packed weights
+  const float* pack_bias;        // packed (16 B aligned) biases
+  unsigned char* stash;          // fp16 stash (tcs_* layout); fwd: written when STASH, dgrad: read
+  unsigned char* delta;          // dgrad: fp16 delta mats (written)
+  float* raw;                    // fwd: [S][1+C] raw sigma / radiance
+  const float* graw;             // dgrad: [S][1+C] d loss / d raw
+  const unsigned int* gmax;      // dgrad: max |graw| (float bits) -> power-of-two delta scale
 };
-
-// ------------------------------------------------------------------ PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred P1;\n"
-      "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-      "@P1 bra DONE;\n"
-      "bra WAIT_LOOP;\n"
-      "DONE:\n"
-      "}\n" ::"r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-               "l"(src), "r"(bytes), "r"(bar)
-               : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                           uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// UMMA shared-memory descriptor, K-major, no swizzle: LBO = byte stride between K cores,
-// SBO = byte stride between 8-row groups (cute/arch/mma_sm100_desc.hpp SmemDescriptor, version 1).
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
-  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) |
-         ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46);
-}
-// instruction descriptor: D=f32, A=B=f16, both K-major, M=128
-__device__ __forceinline__ uint32_t umma_idesc(int N) {
-  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
-}
 
 __device__ __forceinline__ uint32_t region_hi(int region) {
   return region == 0 ? SM_A_HI : (region == 1 ? SM_P_HI : SM_D_HI);
@@ -149,53 +94,44 @@ __device__ __forceinline__ uint32_t region_lo(int region) {
 // softplus(beta=100, threshold=20) on the MUFU pipe (ex2 + lg2); absolute error ~2e-9
 __device__ __forceinline__ float softplus100_fast(float x) {
   const float z = x * 100.f;
-  const float e = __expf(z);
-  const float y = __logf(1.f + e) * 0.01f;
+  const float y = __logf(1.f + __expf(z)) * 0.01f;
   return z > 20.f ? x : y;
 }
+// d softplus / dx from the OUTPUT a: sigmoid(100 x) = 1 - exp(-100 a)
+__device__ __forceinline__ float softplus100_grad_fast(float a) { return 1.f - __expf(-100.f * a); }
 
-// 8 activations -> 16 B of fp16 hi and 16 B of fp16 lo
-__device__ __forceinline__ void split8(const float* y, uint4* hi, uint4* lo) {
-  uint32_t h[4], l[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const __half2 hh = __floats2half2_rn(y[2 * i], y[2 * i + 1]);
-    const float2 hf = __half22float2(hh);
-    const __half2 ll = __floats2half2_rn(y[2 * i] - hf.x, y[2 * i + 1] - hf.y);
-    h[i] = *reinterpret_cast<const uint32_t*>(&hh);
-    l[i] = *reinterpret_cast<const uint32_t*>(&ll);
-  }
-  *hi = make_uint4(h[0], h[1], h[2], h[3]);
-  *lo = make_uint4(l[0], l[1], l[2], l[3]);
+// feature j of SinusoidalEncoder(x) with max degree DEG (external/mlp.py:227-243), j compile-time
+template <int DEG>
+__device__ __forceinline__ float enc_feature(const float* x, int j) {
+  if (j < 3) return x[j];
+  if (j >= 3 + 6 * DEG) return 0.f;
+  const int jj = j - 3;
+  const bool shifted = jj >= 3 * DEG;
+  const int q = shifted ? jj - 3 * DEG : jj;
+  const int i = q / 3, a = q - 3 * i;
+  const float xb = __fmul_rn(x[a], (float)(1 << i));
+  return sinf(shifted ? __fadd_rn(xb, 1.5707963267948966f) : xb);
 }
-
-// Writes an encoding of NF (<= KP) features into the blocked operand region (hi/lo) and the stash.
-template <int DEG, int KP>
-__device__ __forceinline__ void encode_to_operand(const float* x, bool valid, unsigned char* smem, uint32_t hi_off,
-                                                  uint32_t lo_off, int m, float* stash_mat, long long sidx) {
-  float f[KP];
-  if (valid) {
-    ren_encode(x, DEG, KP, [&](int j, float v) { f[j] = v; });
-  } else {
+// encode k-cores [C0, C1) of an encoding into an operand region (+ fp16 stash)
+template <int DEG, int KP, int C0, int C1>
+__device__ __forceinline__ void encode_cores(const float* x, bool valid, unsigned char* smem, uint32_t hi_off,
+                                             uint32_t lo_off, int m, unsigned char* stash_mat, long long sidx) {
 #pragma unroll
-    for (int j = 0; j < KP; ++j) f[j] = 0.f;
-  }
+  for (int c = C0; c < C1; ++c) {
+    float f[8];
 #pragma unroll
-  for (int c = 0; c < KP / 8; ++c) {
+    for (int j = 0; j < 8; ++j) f[j] = valid ? enc_feature<DEG>(x, c * 8 + j) : 0.f;
     uint4 hi, lo;
-    split8(f + c * 8, &hi, &lo);
+    split8(f, &hi, &lo);
     *reinterpret_cast<uint4*>(smem + hi_off + c * (TC_M * 16) + m * 16) = hi;
     *reinterpret_cast<uint4*>(smem + lo_off + c * (TC_M * 16) + m * 16) = lo;
-  }
-  if (stash_mat != nullptr && valid) {
-#pragma unroll
-    for (int j = 0; j < KP; j += 4)
-      *reinterpret_cast<float4*>(stash_mat + ren_blk(sidx, j, KP)) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+    if (stash_mat != nullptr)
+      *reinterpret_cast<uint4*>(stash_mat + 2 * ren_blk(sidx, c * 8, KP)) = hi;
   }
 }
 
-template <bool STASH>
-__global__ void __launch_bounds__(TC_THREADS, 1) ren_tc_field_fwd(const TcArgs a) {
+template <int MODE, bool STASH>   // MODE 0: forward, 1: dgrad
+__global__ void __launch_bounds__(TC_THREADS, 1) ren_tc_chain(const TcArgs a) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const RenPlan& p = a.p;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -207,18 +143,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ren_tc_field_fwd(const TcArgs a
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + SM_TMEM_PTR);
   const long long S = a.n_rays * a.K;
   const long long n_tiles = (S + TC_M - 1) / TC_M;
+  const int C1 = 1 + p.C;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < TC_STAGES; ++s) {
       mbar_init(bar_full + 8 * s, 1);
       mbar_init(bar_empty + 8 * s, 1);
     }
-    mbar_init(bar_aready, 256);
+    mbar_init(bar_aready, 32 * TC_EPI_WARPS);
     mbar_init(bar_accfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(sbase + SM_TMEM_PTR) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(sbase + SM_TMEM_PTR) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
@@ -241,6 +178,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ren_tc_field_fwd(const TcArgs a
             mbar_arrive_expect_tx(bar_full + 8 * s, bytes);
             bulk_g2s(sbase + SM_RING + s * SM_STAGE_BYTES, src + (size_t)c * bytes, bytes, bar_full + 8 * s);
           }
+          if (st.head_chunk) {
+            const uint32_t s = it % TC_STAGES, ph = (it / TC_STAGES) & 1u;
+            mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+            mbar_arrive_expect_tx(bar_full + 8 * s, SM_STAGE_BYTES);
+            bulk_g2s(sbase + SM_RING + s * SM_STAGE_BYTES, a.pack + st.head_pack_off, SM_STAGE_BYTES,
+                     bar_full + 8 * s);
+            ++it;
+          }
         }
       }
     }
@@ -248,13 +193,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ren_tc_field_fwd(const TcArgs a
     // ===================== MMA issuer =====================
     if (lane == 0) {
       uint32_t it = 0, ev = 0;
+      const uint32_t idesc16 = umma_idesc(16, 0, 0);
       for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         for (int g = 0; g < a.n_steps; ++g, ++ev) {
           const TcStep& st = a.steps[g];
           mbar_wait(bar_aready, ev & 1u);
           tc_fence_after();
-          const uint32_t idesc = umma_idesc(st.N);
+          const uint32_t idesc = umma_idesc(st.N, 0, 0);
           const uint32_t b_lbo = (uint32_t)st.N * 16u;
+          const uint32_t d_addr = tmem_base + (uint32_t)st.tmem_col;
           int c = 0;
           for (int seg = 0; seg < 2; ++seg) {
             const uint32_t a_hi = sbase + region_hi(st.seg_region[seg]);
@@ -266,15 +213,35 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ren_tc_field_fwd(const TcArgs a
               const uint32_t wb = sbase + SM_RING + s * SM_STAGE_BYTES;
               const uint64_t da_hi = umma_desc(a_hi + ks * 4096, TC_M * 16, 128);
               const uint64_t db_hi = umma_desc(wb, b_lbo, 128);
-              tc_mma_f16(tmem_base, da_hi, db_hi, idesc, c > 0 ? 1u : 0u);
+              tc_mma_f16(d_addr, da_hi, db_hi, idesc, c > 0 ? 1u : 0u);
               if (a.split3) {
                 const uint64_t da_lo = umma_desc(a_lo + ks * 4096, TC_M * 16, 128);
                 const uint64_t db_lo = umma_desc(wb + st.N * 32, b_lbo, 128);
-                tc_mma_f16(tmem_base, da_lo, db_hi, idesc, 1u);
-                tc_mma_f16(tmem_base, da_hi, db_lo, idesc, 1u);
+                tc_mma_f16(d_addr, da_lo, db_hi, idesc, 1u);
+                tc_mma_f16(d_addr, da_hi, db_lo, idesc, 1u);
               }
               tc_commit(bar_empty + 8 * s);   // frees the ring slot when these MMAs have read it
             }
+          }
+          if (st.head_chunk) {
+            // sigma head: [128 x 256] main operand times the N=16 block (row 0 = w_sigma)
+            const uint32_t s = it % TC_STAGES, ph = (it / TC_STAGES) & 1u;
+            mbar_wait(bar_full + 8 * s, ph);
+            tc_fence_after();
+            const uint32_t wb = sbase + SM_RING + s * SM_STAGE_BYTES;
+            for (int ks = 0; ks < 16; ++ks) {
+              const uint64_t da_hi = umma_desc(sbase + SM_A_HI + ks * 4096, TC_M * 16, 128);
+              const uint64_t db_hi = umma_desc(wb + ks * 1024, 256, 128);
+              tc_mma_f16(tmem_base + TMEM_COL_SIGMA, da_hi, db_hi, idesc16, ks > 0 ? 1u : 0u);
+              if (a.split3) {
+                const uint64_t da_lo = umma_desc(sbase + SM_A_LO + ks * 4096, TC_M * 16, 128);
+                const uint64_t db_lo = umma_desc(wb + ks * 1024 + 512, 256, 128);
+                tc_mma_f16(tmem_base + TMEM_COL_SIGMA, da_lo, db_hi, idesc16, 1u);
+                tc_mma_f16(tmem_base + TMEM_COL_SIGMA, da_hi, db_lo, idesc16, 1u);
+              }
+            }
+            tc_commit(bar_empty + 8 * s);
+            ++it;
           }
           tc_commit(bar_accfull);             // accumulator complete -> epilogue
         }
@@ -282,101 +249,163 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ren_tc_field_fwd(const TcArgs a
     }
   } else {
     // ===================== prologue + epilogue warps =====================
-    const int ew = warp - 2;                 // 0..7
     const int q = warp & 3;                  // TMEM lane quadrant this warp may access
-    const int half = ew >> 2;                // column half
+    const int cg = (warp - 2) >> 2;          // column group 0..3
     const int m = q * 32 + lane;             // row of the tile == TMEM lane
     const uint32_t tmem_lane = tmem_base + ((uint32_t)(q * 32) << 16);
-    float* sig_part = reinterpret_cast<float*>(smem + SM_SIG_PART);
-    float* rgb_part = reinterpret_cast<float*>(smem + SM_RGB_PART);
-    const int C1 = 1 + p.C;
     uint32_t ev = 0;
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const long long sidx = tile * TC_M + m;
       const bool valid = sidx < S;
-      // ---- prologue: half 0 -> positional encoding, half 1 -> direction encoding
       bool selector = false;
-      {
+      if (MODE == 0) {
+        // ---- forward prologue: column groups 0-2 encode the position (k-cores 0-2 / 3-5 / 6-7),
+        //      group 3 encodes the direction
         float o[3] = {0.f, 0.f, 0.f}, d[3] = {0.f, 0.f, 1.f};
-        float t0 = 0.f, t1 = 0.f, t_max = 0.f;
+        long long r = 0;
+        int k = 0;
         if (valid) {
-          const long long r = sidx / a.K;
-          const int k = (int)(sidx - r * a.K);
+          r = sidx / a.K;
+          k = (int)(sidx - r * a.K);
 #pragma unroll
           for (int c = 0; c < 3; ++c) {
             o[c] = a.rays_o[r * 3 + c];
             d[c] = a.rays_d[r * 3 + c];
           }
-          if (half == 0) {
-            float t_min;
-            ren_ray_range(p.f, p.r, o, d, a.jitter ? a.jitter[r] : 0.f, &t_min, &t_max);
-            ren_march_to(p.r, t_min, k, &t0, &t1);
-          }
         }
-        if (half == 0) {
+        if (cg < 3) {
           float z[3] = {0.f, 0.f, 0.f};
           if (valid) {
+            float t_min, t_max, t0, t1;
+            ren_ray_range(p.f, p.r, o, d, a.jitter ? a.jitter[r] : 0.f, &t_min, &t_max);
+            ren_march_to(p.r, t_min, k, &t0, &t1);
             selector = ren_field_input(p.f, o, d, t0, t1, z);
             if (!ren_alive(t0, t1, t_max)) selector = false;
           }
-          encode_to_operand<10, 64>(z, valid, smem, SM_P_HI, SM_P_LO, m,
-                                    STASH ? a.stash + ren_stash_encp(p, S) : nullptr, sidx);
+          unsigned char* sm = STASH ? a.stash + tcs_encp(p, S) : nullptr;
+          if (cg == 0) encode_cores<10, 64, 0, 3>(z, valid, smem, SM_P_HI, SM_P_LO, m, sm, sidx);
+          else if (cg == 1) encode_cores<10, 64, 3, 6>(z, valid, smem, SM_P_HI, SM_P_LO, m, sm, sidx);
+          else encode_cores<10, 64, 6, 8>(z, valid, smem, SM_P_HI, SM_P_LO, m, sm, sidx);
         } else {
-          float dz[3] = {__fmul_rn(d[0], 3.141592653589793f), __fmul_rn(d[1], 3.141592653589793f),
-                         __fmul_rn(d[2], 3.141592653589793f)};
-          encode_to_operand<4, 32>(dz, valid, smem, SM_D_HI, SM_D_LO, m,
-                                   STASH ? a.stash + ren_stash_encd(p, S) : nullptr, sidx);
+          const float dz[3] = {__fmul_rn(d[0], 3.141592653589793f), __fmul_rn(d[1], 3.141592653589793f),
+                               __fmul_rn(d[2], 3.141592653589793f)};
+          encode_cores<4, 32, 0, 4>(dz, valid, smem, SM_D_HI, SM_D_LO, m, STASH ? a.stash + tcs_encd(p, S) : nullptr,
+                                    sidx);
+        }
+      } else {
+        // ---- dgrad prologue: head gradients enter as rank-1 K=16 segments:
+        //      region 1 column 0 = d sigma_raw, region 2 columns 0..C-1 = d c_raw
+        if (cg == 0) {
+          float gs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          float gc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          if (valid) {
+            const float sc = delta_scale(a.gmax);
+            gs[0] = a.graw[sidx * C1] * sc;
+            for (int c = 0; c < p.C; ++c) gc[c] = a.graw[sidx * C1 + 1 + c] * sc;
+          }
+          uint4 hi, lo;
+          split8(gs, &hi, &lo);
+          *reinterpret_cast<uint4*>(smem + SM_P_HI + m * 16) = hi;
+          *reinterpret_cast<uint4*>(smem + SM_P_LO + m * 16) = lo;
+          split8(gc, &hi, &lo);
+          *reinterpret_cast<uint4*>(smem + SM_D_HI + m * 16) = hi;
+          *reinterpret_cast<uint4*>(smem + SM_D_LO + m * 16) = lo;
+        } else if (cg == 1) {
+          const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);   // second K core of both rank-1 segments
+          *reinterpret_cast<uint4*>(smem + SM_P_HI + TC_M * 16 + m * 16) = z4;
+          *reinterpret_cast<uint4*>(smem + SM_P_LO + TC_M * 16 + m * 16) = z4;
+          *reinterpret_cast<uint4*>(smem + SM_D_HI + TC_M * 16 + m * 16) = z4;
+          *reinterpret_cast<uint4*>(smem + SM_D_LO + TC_M * 16 + m * 16) = z4;
         }
       }
       fence_proxy_async();
       mbar_arrive(bar_aready);
-      float sig_acc = 0.f;
-      float rgb_acc[3] = {0.f, 0.f, 0.f};
+
       // ---- one epilogue per GEMM step
       for (int g = 0; g < a.n_steps; ++g, ++ev) {
         const TcStep& st = a.steps[g];
+        const int ncol = st.N >> 2;                  // columns this warp handles (64 / 32 / 4)
+        const int col0 = cg * ncol;
+        // dgrad: prefetch this thread's slice of the activation stash while the MMAs run
+        uint4 act_pref[8];
+        if (MODE == 1 && st.epi == EPI_D_ACT && valid) {
+          const unsigned char* am = a.stash + tcs_mat(p, S, st.act_mat);
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (i * 8 < ncol)
+              act_pref[i] = __ldg(reinterpret_cast<const uint4*>(am + 2 * ren_blk(sidx, col0 + i * 8, st.N)));
+        }
         mbar_wait(bar_accfull, ev & 1u);
         tc_fence_after();
-        const int ncol = st.N >> 1;                  // columns this warp handles
-        const int col0 = half * ncol;
-        float* stash_row = (STASH && valid) ? a.stash + ren_stash_mat(p, S, st.mat) : nullptr;
-        for (int cb = 0; cb < ncol; cb += 32) {
-          uint32_t r[32];
-          tc_ld32(tmem_lane + (uint32_t)(col0 + cb), r);
+        if (st.epi == EPI_F_HEADS) {
+          if (cg == 0) {
+            uint32_t rs[16], rc[16];
+            tc_ld16(tmem_lane + TMEM_COL_SIGMA, rs);
+            tc_ld16(tmem_lane + TMEM_COL_RGB, rc);
+            tc_ld_wait();
+            if (valid) {
+              const float sraw = __uint_as_float(rs[0]) + __ldg(a.params + p.sig_b);
+              a.raw[sidx * C1] = selector ? sraw : -INFINITY;
+              for (int c = 0; c < p.C; ++c)
+                a.raw[sidx * C1 + 1 + c] = __uint_as_float(rc[c]) + __ldg(a.params + p.rgb_b + c);
+            }
+          }
+        } else {
+          unsigned char* out_mat = nullptr;
+          if (MODE == 0) {
+            if (STASH && st.out_mat >= 0) out_mat = a.stash + tcs_mat(p, S, st.out_mat);
+          } else if (st.out_mat >= 0) {      // padded rows are written as zeros (wgrad reads whole tiles)
+            out_mat = a.delta + tcs_mat(p, S, st.out_mat);
+          }
+          const float* bias = (MODE == 0 && st.bias_off >= 0) ? a.pack_bias + st.bias_off : nullptr;
+          const uint32_t tcol = tmem_lane + (uint32_t)(st.tmem_col + col0);
+          uint32_t r[2][16];
+          tc_ld16(tcol, r[0]);
+          tc_ld_wait();
 #pragma unroll
-          for (int j8 = 0; j8 < 4; ++j8) {
-            float y[8];
-            const int n0 = col0 + cb + j8 * 8;
+          for (int cb = 0; cb < 64; cb += 32) {       // fully unrolled: register arrays stay registers
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float x = __uint_as_float(r[j8 * 8 + j]) + __ldg(a.params + st.bias_off + n0 + j);
-              if (st.epi == 1) {
-                y[j] = x;
-              } else {
-                y[j] = (p.f.hidden_activation == REN_HIDDEN_SOFTPLUS100) ? softplus100_fast(x) : fmaxf(x, 0.f);
+            for (int hb = 0; hb < 2; ++hb) {
+              const int cbb = cb + hb * 16;
+              if (cbb < ncol) {
+                if (cbb + 16 < ncol) tc_ld16(tcol + cbb + 16, r[hb ^ 1]);   // prefetch the next block
+#pragma unroll
+                for (int j8 = 0; j8 < 2; ++j8) {
+                  const int n0 = col0 + cbb + j8 * 8;
+                  float y[8];
+                  if (MODE == 0) {
+                    const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + n0));
+                    const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + n0 + 4));
+                    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                      const float x = __uint_as_float(r[hb][j8 * 8 + j]) + bb[j];
+                      if (st.epi == EPI_F_LINEAR) y[j] = x;
+                      else y[j] = (p.f.hidden_activation == REN_HIDDEN_SOFTPLUS100) ? softplus100_fast(x) : fmaxf(x, 0.f);
+                    }
+                  } else {
+                    float av[8];
+                    if (st.epi == EPI_D_ACT) unpack8(act_pref[(cbb >> 3) + j8], av);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                      float v = __uint_as_float(r[hb][j8 * 8 + j]);
+                      if (st.epi == EPI_D_ACT)
+                        v *= (p.f.hidden_activation == REN_HIDDEN_SOFTPLUS100) ? softplus100_grad_fast(av[j])
+                                                                               : (av[j] > 0.f ? 1.f : 0.f);
+                      y[j] = valid ? v : 0.f;
+                    }
+                  }
+                  uint4 hi, lo;
+                  split8(y, &hi, &lo);
+                  if (st.write_a) {
+                    const uint32_t off = (uint32_t)(n0 >> 3) * (TC_M * 16) + (uint32_t)m * 16;
+                    *reinterpret_cast<uint4*>(smem + SM_A_HI + off) = hi;
+                    *reinterpret_cast<uint4*>(smem + SM_A_LO + off) = lo;
+                  }
+                  if (out_mat != nullptr) *reinterpret_cast<uint4*>(out_mat + 2 * ren_blk(sidx, n0, st.N)) = hi;
+                }
+                tc_ld_wait();
               }
-            }
-            if (st.last_trunk) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) sig_acc = fmaf(y[j], __ldg(a.params + p.sig_w + n0 + j), sig_acc);
-            }
-            if (st.epi == 2) {
-              for (int c = 0; c < p.C; ++c) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                  rgb_acc[c] = fmaf(y[j], __ldg(a.params + p.rgb_w + c * p.WC + n0 + j), rgb_acc[c]);
-              }
-            } else {
-              uint4 hi, lo;
-              split8(y, &hi, &lo);
-              const uint32_t off = (uint32_t)(n0 >> 3) * (TC_M * 16) + (uint32_t)m * 16;
-              *reinterpret_cast<uint4*>(smem + SM_A_HI + off) = hi;
-              *reinterpret_cast<uint4*>(smem + SM_A_LO + off) = lo;
-            }
-            if (STASH && stash_row != nullptr) {
-              float* dst = stash_row + ren_blk(sidx, n0, st.N);   // 32 contiguous bytes, lanes contiguous
-              *reinterpret_cast<float4*>(dst) = make_float4(y[0], y[1], y[2], y[3]);
-              *reinterpret_cast<float4*>(dst + 4) = make_float4(y[4], y[5], y[6], y[7]);
             }
           }
         }
@@ -386,152 +415,278 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ren_tc_field_fwd(const TcArgs a
           mbar_arrive(bar_aready);
         }
       }
-      // ---- heads: combine the two column halves, write raw sigma / radiance
-      if (half == 1) {
-        sig_part[m] = sig_acc;
-        for (int c = 0; c < p.C; ++c) rgb_part[c * TC_M + m] = rgb_acc[c];
-      }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (half == 0 && valid) {
-        const float sraw = sig_acc + sig_part[m] + __ldg(a.params + p.sig_b);
-        a.raw[sidx * C1] = selector ? sraw : -INFINITY;
-        for (int c = 0; c < p.C; ++c)
-          a.raw[sidx * C1 + 1 + c] = rgb_acc[c] + rgb_part[c * TC_M + m] + __ldg(a.params + p.rgb_b + c);
-      }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     __syncwarp();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem_base) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
   }
 }
 
 // ------------------------------------------------------------------ weight packing
+// A pack job writes one B operand: chunks of 16 K' values, each chunk = [hi: N x 16][lo: N x 16]
+// in the core-matrix layout.  mode 0: B[n][k'] = W[n*ldw + col(k')] (forward; two input segments);
+// mode 1: B[n][k'] = W[k'*ldw + n] (transposed, dgrad); mode 2: fp32 copy of a bias vector.
+#define TC_MAX_PACK 64
+struct PackJob {
+  long long dst_off;   // bytes (modes 0/1) or floats (mode 2)
+  int mode, N, n_ksteps;
+  int w_off, ldw;
+  int Ntrue;           // valid rows n
+  int ks0, K0, K1;     // mode 0: segment 0 padded K steps / true widths; mode 1: K0 = valid K'
+};
 struct PackArgs {
-  TcStep steps[TC_MAX_STEPS];
-  int n_steps;
+  PackJob jobs[TC_MAX_PACK];
+  int n_jobs;
   const float* params;
   unsigned char* pack;
+  float* pack_bias;
 };
 
-extern "C" __global__ void ren_tc_pack_weights(const PackArgs a) {
+extern "C" __global__ void ren_tc_pack(const PackArgs a) {
   const int g = blockIdx.y;
-  if (g >= a.n_steps) return;
-  const TcStep& st = a.steps[g];
-  const int total = st.n_chunks * 16 * st.N;    // elements (k-major sweep)
+  if (g >= a.n_jobs) return;
+  const PackJob& jb = a.jobs[g];
+  if (jb.mode == 2) {
+    for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < jb.N; n += gridDim.x * blockDim.x)
+      a.pack_bias[jb.dst_off + n] = n < jb.Ntrue ? a.params[jb.w_off + n] : 0.f;
+    return;
+  }
+  const int total = jb.n_ksteps * 16 * jb.N;
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
-    const int n = e % st.N;
-    const int kc = e / st.N;                   // concatenated (padded) k index
+    const int n = e % jb.N;
+    const int kc = e / jb.N;
     const int c = kc >> 4, kk = kc & 15;
-    const int k0pad = st.seg_ksteps[0] * 16;
     float w = 0.f;
-    if (kc < k0pad) {
-      if (kc < st.seg_K[0]) w = a.params[st.w_off + (long long)n * st.ldw + kc];
-    } else {
-      const int k1 = kc - k0pad;
-      if (k1 < st.seg_K[1]) w = a.params[st.w_off + (long long)n * st.ldw + st.seg_K[0] + k1];
+    if (n < jb.Ntrue) {
+      if (jb.mode == 0) {
+        const int k0pad = jb.ks0 * 16;
+        if (kc < k0pad) {
+          if (kc < jb.K0) w = a.params[jb.w_off + (long long)n * jb.ldw + kc];
+        } else if (kc - k0pad < jb.K1) {
+          w = a.params[jb.w_off + (long long)n * jb.ldw + jb.K0 + (kc - k0pad)];
+        }
+      } else if (kc < jb.K0) {
+        w = a.params[jb.w_off + (long long)kc * jb.ldw + n];
+      }
     }
     const __half hi = __float2half_rn(w);
     const __half lo = __float2half_rn(w - __half2float(hi));
-    unsigned char* chunk = a.pack + st.pack_off + (size_t)c * st.N * 64;
-    const size_t off = (size_t)(kk >> 3) * (st.N * 16) + (size_t)n * 16 + (kk & 7) * 2;
+    unsigned char* chunk = a.pack + jb.dst_off + (size_t)c * jb.N * 64;
+    const size_t off = (size_t)(kk >> 3) * (jb.N * 16) + (size_t)n * 16 + (kk & 7) * 2;
     *reinterpret_cast<__half*>(chunk + off) = hi;
-    *reinterpret_cast<__half*>(chunk + (size_t)st.N * 32 + off) = lo;
+    *reinterpret_cast<__half*>(chunk + (size_t)jb.N * 32 + off) = lo;
   }
 }
 
 // ------------------------------------------------------------------ host side
-static int build_steps(const RenPlan& p, TcStep* steps, long long* pack_bytes) {
-  int n = 0;
-  long long off = 0;
-  auto add = [&](const RenLayer& L, int epi, int last_trunk) {
-    TcStep& s = steps[n++];
+struct TcProgram {
+  TcStep steps[TC_MAX_STEPS];
+  int n_steps;
+  PackJob jobs[TC_MAX_PACK];
+  int n_jobs;
+  long long pack_bytes;    // packed weights
+  long long bias_floats;   // packed biases
+};
+
+static void add_pack(TcProgram& P, int mode, long long dst, int N, int n_ksteps, int w_off, int ldw, int Ntrue,
+                     int ks0, int K0, int K1) {
+  PackJob& j = P.jobs[P.n_jobs++];
+  j.dst_off = dst; j.mode = mode; j.N = N; j.n_ksteps = n_ksteps; j.w_off = w_off; j.ldw = ldw; j.Ntrue = Ntrue;
+  j.ks0 = ks0; j.K0 = K0; j.K1 = K1;
+}
+
+static void build_forward(const RenPlan& p, TcProgram& P) {
+  memset(&P, 0, sizeof(P));
+  long long off = 0, boff = 0;
+  auto add_layer = [&](const RenLayer& L, int epi) -> TcStep& {
+    TcStep& s = P.steps[P.n_steps++];
     s.seg_region[0] = L.src0 == 1 ? 1 : 0;
-    s.seg_K[0] = L.K0;
     s.seg_ksteps[0] = (L.K0 + 15) / 16;
-    s.seg_region[1] = L.src1;     // 0 none / 1 encP / 2 encD
-    s.seg_K[1] = L.K1;
+    s.seg_region[1] = L.src1;
     s.seg_ksteps[1] = L.K1 > 0 ? (L.K1 + 15) / 16 : 0;
-    s.N = L.N;
-    s.w_off = L.w_off;
-    s.ldw = L.K0 + L.K1;
-    s.bias_off = L.b_off;
-    s.epi = epi;
-    s.mat = L.mat;
-    s.last_trunk = last_trunk;
+    s.N = L.N; s.epi = epi; s.out_mat = L.mat; s.act_mat = -1; s.write_a = 1; s.tmem_col = 0;
     s.n_chunks = s.seg_ksteps[0] + s.seg_ksteps[1];
     s.pack_off = off;
+    add_pack(P, 0, off, L.N, s.n_chunks, L.w_off, L.K0 + L.K1, L.N, s.seg_ksteps[0], L.K0, L.K1);
     off += (long long)s.n_chunks * s.N * 64;
+    s.bias_off = (int)boff;
+    add_pack(P, 2, boff, 256, 0, L.b_off, 0, L.N, 0, 0, 0);
+    boff += 256;
+    return s;
   };
-  for (int i = 0; i < p.D; ++i) add(p.trunk[i], 0, i == p.D - 1);
-  add(p.bott, 1, 0);
-  add(p.cond[0], 2, 0);
-  *pack_bytes = off;
-  return n;
+  for (int i = 0; i < p.D; ++i) add_layer(p.trunk[i], EPI_F_HIDDEN);
+  {
+    TcStep& s = add_layer(p.bott, EPI_F_LINEAR);
+    // sigma head rides on the bottleneck step (same A operand = last trunk activations)
+    s.head_chunk = 1;
+    s.head_pack_off = off;
+    add_pack(P, 0, off, 16, 16, p.sig_w, p.W, 1, 16, p.W, 0);
+    off += SM_STAGE_BYTES;
+  }
+  add_layer(p.cond[0], EPI_F_HIDDEN);
+  {
+    // radiance head: [128 x WC] condition activations times the N=16 block (rows 0..C-1 = W_o)
+    TcStep& s = P.steps[P.n_steps++];
+    s.seg_region[0] = 0; s.seg_ksteps[0] = p.WC / 16; s.seg_region[1] = 0; s.seg_ksteps[1] = 0;
+    s.N = 16; s.epi = EPI_F_HEADS; s.out_mat = -1; s.act_mat = -1; s.write_a = 0; s.bias_off = -1;
+    s.tmem_col = TMEM_COL_RGB; s.n_chunks = s.seg_ksteps[0]; s.pack_off = off;
+    add_pack(P, 0, off, 16, s.n_chunks, p.rgb_w, p.WC, p.C, s.n_chunks, p.WC, 0);
+    off += (long long)s.n_chunks * 16 * 64;
+  }
+  P.pack_bytes = off;
+  P.bias_floats = boff;
+}
+
+static void build_dgrad(const RenPlan& p, TcProgram& P) {
+  memset(&P, 0, sizeof(P));
+  long long off = 0;
+  auto add = [&](int region0, int ks0, int region1, int ks1, int N, int epi, int out_mat, int act_mat,
+                 int write_a) -> TcStep& {
+    TcStep& s = P.steps[P.n_steps++];
+    s.seg_region[0] = region0; s.seg_ksteps[0] = ks0; s.seg_region[1] = region1; s.seg_ksteps[1] = ks1;
+    s.N = N; s.epi = epi; s.out_mat = out_mat; s.act_mat = act_mat; s.write_a = write_a; s.bias_off = -1;
+    s.tmem_col = 0; s.n_chunks = ks0 + ks1; s.pack_off = off;
+    return s;
+  };
+  // t0: d g = (d c_raw) W_o, times act'(g)            [rank-C segment in region 2]
+  {
+    TcStep& s = add(2, 1, 0, 0, p.WC, EPI_D_ACT, p.cond[0].mat, p.cond[0].mat, 1);
+    add_pack(P, 1, off, p.WC, 1, p.rgb_w, p.WC, p.WC, 0, p.C, 0);
+    off += (long long)s.n_chunks * s.N * 64;
+  }
+  // t1: d bott = d g_pre W_r0[:, :W]                   (bottleneck is linear)
+  {
+    TcStep& s = add(0, p.WC / 16, 0, 0, p.W, EPI_D_LINEAR, p.bott.mat, -1, 1);
+    add_pack(P, 1, off, p.W, s.n_chunks, p.cond[0].w_off, p.cond[0].K0 + p.cond[0].K1, p.W, 0, p.WC, 0);
+    off += (long long)s.n_chunks * s.N * 64;
+  }
+  // t2: d a_{D-1} = d bott W_b + (d sigma_raw) w_sigma, times act'(a_{D-1})
+  {
+    const int last = p.trunk[p.D - 1].mat;
+    TcStep& s = add(0, p.W / 16, 1, 1, p.W, EPI_D_ACT, last, last, p.D > 1 ? 1 : 0);
+    add_pack(P, 1, off, p.W, p.W / 16, p.bott.w_off, p.bott.K0 + p.bott.K1, p.W, 0, p.W, 0);
+    add_pack(P, 1, off + (long long)(p.W / 16) * p.W * 64, p.W, 1, p.sig_w, p.W, p.W, 0, 1, 0);
+    off += (long long)s.n_chunks * s.N * 64;
+  }
+  // trunk layers D-1 .. 1: d a_{i-1} = Delta_i W_i[:, :W], times act'(a_{i-1})
+  for (int i = p.D - 1; i >= 1; --i) {
+    const RenLayer& L = p.trunk[i];
+    TcStep& s = add(0, p.W / 16, 0, 0, p.W, EPI_D_ACT, p.trunk[i - 1].mat, p.trunk[i - 1].mat, i > 1 ? 1 : 0);
+    add_pack(P, 1, off, p.W, s.n_chunks, L.w_off, L.K0 + L.K1, p.W, 0, p.W, 0);
+    off += (long long)s.n_chunks * s.N * 64;
+  }
+  P.pack_bytes = off;
+  P.bias_floats = 0;
 }
 
 int ren_tc_supported(const RenPlan& p) {
   return p.W == 256 && p.WC == 128 && p.CD == 1 && p.hid_K1 == 0 && p.f.pos_deg == 10 && p.f.dir_deg == 4 &&
-         p.D + 2 <= TC_MAX_STEPS && p.C <= 3;
+         p.D >= 1 && p.D + 3 <= TC_MAX_STEPS && p.C <= 3 && p.trunk[0].K1 == 0;
 }
 
-size_t ren_tc_workspace_bytes(const RenPlan& p, long long S) {
-  (void)S;
+static size_t program_bytes(const TcProgram& P) { return (size_t)P.pack_bytes + (size_t)P.bias_floats * 4 + 2048; }
+
+size_t ren_tc_fwd_workspace_bytes(const RenPlan& p) {
   if (!ren_tc_supported(p)) return 0;
-  TcStep steps[TC_MAX_STEPS];
-  long long bytes = 0;
-  build_steps(p, steps, &bytes);
-  return (size_t)bytes + 1024;
+  TcProgram P;
+  build_forward(p, P);
+  return program_bytes(P);
+}
+size_t ren_tc_bwd_pack_bytes(const RenPlan& p) {
+  if (!ren_tc_supported(p)) return 0;
+  TcProgram P;
+  build_dgrad(p, P);
+  return program_bytes(P);
 }
 
-int ren_tc_launch_fwd(const RenPlan& p, long long n_rays, int K, const float* o, const float* d,
-                      const float* jitter, const float* params, float* stash, float* raw, void* ws,
-                      size_t ws_bytes, cudaStream_t st) {
-  TcArgs a;
-  static_assert(sizeof(TcArgs) <= 4000, "kernel parameter block too large");
-  long long pack_bytes = 0;
-  a.p = p;
-  a.n_steps = build_steps(p, a.steps, &pack_bytes);
-  unsigned char* pack = (unsigned char*)(((uintptr_t)ws + 1023) & ~(uintptr_t)1023);
-  if (ws == nullptr || (size_t)(pack - (unsigned char*)ws) + (size_t)pack_bytes > ws_bytes) {
-    ren_set_error("workspace too small for packed weights (%lld B needed)", pack_bytes);
-    return REN_E_WORKSPACE;
-  }
+static int run_pack(const TcProgram& P, const float* params, unsigned char* pack, float* pack_bias,
+                    cudaStream_t st) {
   PackArgs pa;
-  for (int i = 0; i < a.n_steps; ++i) pa.steps[i] = a.steps[i];
-  pa.n_steps = a.n_steps;
-  pa.params = params;
-  pa.pack = pack;
+  for (int i = 0; i < P.n_jobs; ++i) pa.jobs[i] = P.jobs[i];
+  pa.n_jobs = P.n_jobs; pa.params = params; pa.pack = pack; pa.pack_bias = pack_bias;
   ren_prof_begin(REN_K_PACK, st);
-  ren_tc_pack_weights<<<dim3(32, a.n_steps), 256, 0, st>>>(pa);
+  ren_tc_pack<<<dim3(16, P.n_jobs), 256, 0, st>>>(pa);
   ren_prof_end(REN_K_PACK, st);
-  a.split3 = p.r.engine == REN_ENGINE_TC_F16 ? 0 : 1;
-  a.n_rays = n_rays; a.K = K; a.rays_o = o; a.rays_d = d; a.jitter = jitter; a.params = params;
-  a.pack = pack; a.stash = stash; a.raw = raw;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { ren_set_error("tc pack launch: %s", cudaGetErrorString(e)); return REN_E_CUDA; }
+  return REN_OK;
+}
+
+template <int MODE, bool STASH>
+static int launch_chain(const TcArgs& a, long long n_tiles, int kind, cudaStream_t st) {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const long long n_tiles = (n_rays * K + TC_M - 1) / TC_M;
   const int grid = (int)(n_tiles < sms ? n_tiles : sms);
   if (grid < 1) return REN_OK;
-  cudaError_t e;
-  if (stash) {
-    e = cudaFuncSetAttribute(ren_tc_field_fwd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
-    if (e != cudaSuccess) { ren_set_error("tc fwd smem attr: %s", cudaGetErrorString(e)); return REN_E_CUDA; }
-    ren_prof_begin(REN_K_FIELD_FWD, st);
-    ren_tc_field_fwd<true><<<grid, TC_THREADS, SM_TOTAL, st>>>(a);
-    ren_prof_end(REN_K_FIELD_FWD, st);
-  } else {
-    e = cudaFuncSetAttribute(ren_tc_field_fwd<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
-    if (e != cudaSuccess) { ren_set_error("tc fwd smem attr: %s", cudaGetErrorString(e)); return REN_E_CUDA; }
-    ren_prof_begin(REN_K_FIELD_FWD, st);
-    ren_tc_field_fwd<false><<<grid, TC_THREADS, SM_TOTAL, st>>>(a);
-    ren_prof_end(REN_K_FIELD_FWD, st);
-  }
+  cudaError_t e = cudaFuncSetAttribute(ren_tc_chain<MODE, STASH>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
+  if (e != cudaSuccess) { ren_set_error("tc chain smem attr: %s", cudaGetErrorString(e)); return REN_E_CUDA; }
+  ren_prof_begin(kind, st);
+  ren_tc_chain<MODE, STASH><<<grid, TC_THREADS, SM_TOTAL, st>>>(a);
+  ren_prof_end(kind, st);
   e = cudaGetLastError();
-  if (e != cudaSuccess) { ren_set_error("tc fwd launch: %s", cudaGetErrorString(e)); return REN_E_CUDA; }
+  if (e != cudaSuccess) { ren_set_error("tc chain launch: %s", cudaGetErrorString(e)); return REN_E_CUDA; }
   return REN_OK;
+}
+
+static int carve_pack(const TcProgram& P, void* ws, size_t ws_bytes, unsigned char** pack, float** pack_bias) {
+  unsigned char* base = (unsigned char*)(((uintptr_t)ws + 1023) & ~(uintptr_t)1023);
+  const size_t need = (size_t)(base - (unsigned char*)ws) + (size_t)P.pack_bytes + (size_t)P.bias_floats * 4 + 16;
+  if (ws == nullptr || need > ws_bytes) {
+    ren_set_error("workspace too small for packed weights (%zu > %zu)", need, ws_bytes);
+    return REN_E_WORKSPACE;
+  }
+  *pack = base;
+  *pack_bias = (float*)(base + ((P.pack_bytes + 15) & ~15LL));
+  return REN_OK;
+}
+
+int ren_tc_launch_fwd(const RenPlan& p, long long n_rays, int K, const float* o, const float* d,
+                      const float* jitter, const float* params, void* stash, float* raw, void* ws,
+                      size_t ws_bytes, cudaStream_t st) {
+  TcProgram P;
+  build_forward(p, P);
+  unsigned char* pack; float* pack_bias;
+  int rc = carve_pack(P, ws, ws_bytes, &pack, &pack_bias);
+  if (rc) return rc;
+  rc = run_pack(P, params, pack, pack_bias, st);
+  if (rc) return rc;
+  TcArgs a;
+  static_assert(sizeof(TcArgs) <= 4000, "kernel parameter block too large");
+  memset(&a, 0, sizeof(a));
+  a.p = p;
+  for (int i = 0; i < P.n_steps; ++i) a.steps[i] = P.steps[i];
+  a.n_steps = P.n_steps;
+  a.split3 = p.r.engine == REN_ENGINE_TC_F16 ? 0 : 1;
+  a.n_rays = n_rays; a.K = K; a.rays_o = o; a.rays_d = d; a.jitter = jitter; a.params = params;
+  a.pack = pack; a.pack_bias = pack_bias; a.stash = (unsigned char*)stash; a.raw = raw;
+  const long long n_tiles = (n_rays * K + TC_M - 1) / TC_M;
+  return stash ? launch_chain<0, true>(a, n_tiles, REN_K_FIELD_FWD, st)
+               : launch_chain<0, false>(a, n_tiles, REN_K_FIELD_FWD, st);
+}
+
+int ren_tc_launch_dgrad(const RenPlan& p, long long S, const float* params, const void* stash,
+                        const float* graw, const unsigned int* gmax, void* delta, void* ws, size_t ws_bytes,
+                        cudaStream_t st) {
+  TcProgram P;
+  build_dgrad(p, P);
+  unsigned char* pack; float* pack_bias;
+  int rc = carve_pack(P, ws, ws_bytes, &pack, &pack_bias);
+  if (rc) return rc;
+  rc = run_pack(P, params, pack, pack_bias, st);
+  if (rc) return rc;
+  TcArgs a;
+  memset(&a, 0, sizeof(a));
+  a.p = p;
+  for (int i = 0; i < P.n_steps; ++i) a.steps[i] = P.steps[i];
+  a.n_steps = P.n_steps;
+  a.split3 = p.r.engine == REN_ENGINE_TC_F16 ? 0 : 1;
+  a.n_rays = S; a.K = 1;            // dgrad only needs the flat sample count
+  a.params = params; a.pack = pack; a.pack_bias = pack_bias;
+  a.stash = (unsigned char*)stash; a.delta = (unsigned char*)delta; a.graw = graw; a.gmax = gmax;
+  const long long n_tiles = (S + TC_M - 1) / TC_M;
+  return launch_chain<1, false>(a, n_tiles, REN_K_FIELD_DGRAD, st);
 }

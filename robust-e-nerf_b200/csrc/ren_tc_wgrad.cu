@@ -1,0 +1,305 @@
+// ren_tc_wgrad.cu -- weight gradients of the field MLP on tcgen05 (REN_ENGINE_TC_*).
+//
+//   dW[n][k] = sum_s Delta[s][n] * H[s][k],   db[n] = sum_s Delta[s][n]
+//
+// The reduction runs over SAMPLES, so both operands are consumed MN-major straight from the
+// fp16 blocked stash / delta matrices (ren_tc.cuh): a 128-sample tile of a matrix is one
+// contiguous run in HBM and one bulk-TMA copy into shared memory -- no register staging, no
+// transposes.  A job = (layer, 128-row half of n, sample range); its fp32 accumulator
+// [128 x H-width] stays in TMEM for the whole sample range and is atomically added into the flat
+// gradient buffer once at the end.  The bias gradient is the same MMA against a block of ones.
+//   warp 0   producer (2-stage ring of {Delta half tile 32 KB, H tile <= 64 KB})
+//   warp 1   MMA issuer (8 K-steps of 16 samples per tile; + the N=16 ones block)
+//   warps 2-5 final epilogue (tcgen05.ld -> red.global.add.f32)
+// The sigma / radiance head gradients (N = 1..3) are a bandwidth-bound SIMT pass.
+#include <string.h>
+
+#include "ren_tc.cuh"
+
+#define WG_THREADS 192
+#define WG_STAGES 2
+#define WG_MAX_MATS 48
+#define SMW_D_BYTES 32768
+#define SMW_H_BYTES 65536
+#define SMW_STAGE (SMW_D_BYTES + SMW_H_BYTES)   // 98304
+#define SMW_ONES (WG_STAGES * SMW_STAGE)        // 196608
+#define SMW_BAR (SMW_ONES + 4096)
+#define SMW_TMEM_PTR (SMW_BAR + 64)
+#define SMW_TOTAL (SMW_BAR + 128)
+#define WG_TMEM_ONES 256
+
+struct WgMat {
+  long long d_off;   // bytes into the delta buffer: fp16 blocked [Sp x Nd]
+  long long h_off;   // bytes into the stash buffer: fp16 blocked [Sp x Hw]
+  int Nd, n_half, Hw;
+  int w_off, ldw, col0, Ktrue;   // dW[n][col0 + k], k < Ktrue
+  int b_off;                     // bias gradient offset or -1
+};
+struct WgArgs {
+  WgMat mats[WG_MAX_MATS];
+  int n_mats, splits;
+  long long n_tiles;
+  const unsigned char* stash;
+  const unsigned char* delta;
+  const unsigned int* gmax;    // deltas carry the power-of-two scale delta_scale(gmax)
+  float* g_params;
+};
+
+extern "C" __global__ void __launch_bounds__(WG_THREADS, 1) ren_tc_wgrad(const WgArgs a) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bar_full = sbase + SMW_BAR;          // [2]
+  const uint32_t bar_empty = sbase + SMW_BAR + 16;    // [2]
+  const uint32_t bar_accfull = sbase + SMW_BAR + 32;
+  const uint32_t bar_accempty = sbase + SMW_BAR + 40;
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + SMW_TMEM_PTR);
+  const int n_jobs = a.n_mats * a.splits;
+  const long long tiles_per = (a.n_tiles + a.splits - 1) / a.splits;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < WG_STAGES; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    mbar_init(bar_accfull, 1);
+    mbar_init(bar_accempty, 128);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // block of fp16 ones: the bias-gradient operand
+  for (int i = threadIdx.x; i < 4096 / 4; i += WG_THREADS)
+    reinterpret_cast<uint32_t*>(smem + SMW_ONES)[i] = 0x3C003C00u;
+  fence_proxy_async();
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(sbase + SMW_TMEM_PTR) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int job = blockIdx.x; job < n_jobs; job += gridDim.x) {
+        const WgMat& mt = a.mats[job / a.splits];
+        const int split = job % a.splits;
+        const long long t0 = split * tiles_per, t1 = min(a.n_tiles, t0 + tiles_per);
+        const uint32_t hbytes = (uint32_t)mt.Hw * 256u;
+        for (long long t = t0; t < t1; ++t, ++it) {
+          const uint32_t s = it % WG_STAGES, ph = (it / WG_STAGES) & 1u;
+          mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+          mbar_arrive_expect_tx(bar_full + 8 * s, SMW_D_BYTES + hbytes);
+          const unsigned char* dsrc = a.delta + mt.d_off + (size_t)t * mt.Nd * 256 + (size_t)mt.n_half * SMW_D_BYTES;
+          const unsigned char* hsrc = a.stash + mt.h_off + (size_t)t * hbytes;
+          bulk_g2s(sbase + s * SMW_STAGE, dsrc, SMW_D_BYTES, bar_full + 8 * s);
+          bulk_g2s(sbase + s * SMW_STAGE + SMW_D_BYTES, hsrc, hbytes, bar_full + 8 * s);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      uint32_t it = 0, jn = 0;
+      const uint32_t idesc_ones = umma_idesc(16, 1, 1);
+      for (int job = blockIdx.x; job < n_jobs; job += gridDim.x) {
+        const WgMat& mt = a.mats[job / a.splits];
+        const int split = job % a.splits;
+        const long long t0 = split * tiles_per, t1 = min(a.n_tiles, t0 + tiles_per);
+        if (t0 >= t1) continue;
+        mbar_wait(bar_accempty, (jn & 1u) ^ 1u);     // previous job's accumulator has been drained
+        tc_fence_after();
+        const uint32_t idesc = umma_idesc(mt.Hw, 1, 1);
+        uint32_t first = 1;
+        for (long long t = t0; t < t1; ++t, ++it) {
+          const uint32_t s = it % WG_STAGES, ph = (it / WG_STAGES) & 1u;
+          mbar_wait(bar_full + 8 * s, ph);
+          tc_fence_after();
+          const uint32_t db = sbase + s * SMW_STAGE, hb = db + SMW_D_BYTES;
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {
+            // MN-major operands: LBO = 128 B between 8-sample K blocks, SBO = 2 KB between 8-wide groups
+            const uint64_t da = umma_desc(db + ks * 256, 128, 2048);
+            const uint64_t dh = umma_desc(hb + ks * 256, 128, 2048);
+            const uint64_t d1 = umma_desc(sbase + SMW_ONES + ks * 256, 128, 2048);
+            tc_mma_f16(tmem_base, da, dh, idesc, first ? 0u : 1u);
+            tc_mma_f16(tmem_base + WG_TMEM_ONES, da, d1, idesc_ones, first ? 0u : 1u);
+            first = 0;
+          }
+          tc_commit(bar_empty + 8 * s);
+        }
+        tc_commit(bar_accfull);
+        ++jn;
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int nl = q * 32 + lane;                       // accumulator lane == local output row n
+    const uint32_t tmem_lane = tmem_base + ((uint32_t)(q * 32) << 16);
+    uint32_t jn = 0;
+    const float unscale = 1.f / delta_scale(a.gmax);
+    for (int job = blockIdx.x; job < n_jobs; job += gridDim.x) {
+      const WgMat& mt = a.mats[job / a.splits];
+      const int split = job % a.splits;
+      const long long t0 = split * tiles_per, t1 = min(a.n_tiles, t0 + tiles_per);
+      if (t0 >= t1) continue;
+      mbar_wait(bar_accfull, jn & 1u);
+      tc_fence_after();
+      const int n = mt.n_half * 128 + nl;
+      float* row = a.g_params + mt.w_off + (long long)n * mt.ldw + mt.col0;
+      for (int cb = 0; cb < mt.Hw; cb += 16) {
+        uint32_t r[16];
+        tc_ld16(tmem_lane + (uint32_t)cb, r);
+        tc_ld_wait();
+        if (n < mt.Nd) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (cb + j < mt.Ktrue) atomicAdd(row + cb + j, __uint_as_float(r[j]) * unscale);
+        }
+      }
+      if (mt.b_off >= 0) {
+        uint32_t r[16];
+        tc_ld16(tmem_lane + WG_TMEM_ONES, r);
+        tc_ld_wait();
+        if (n < mt.Nd) atomicAdd(a.g_params + mt.b_off + n, __uint_as_float(r[0]) * unscale);
+      }
+      tc_fence_before();
+      mbar_arrive(bar_accempty);
+      ++jn;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------ head gradients (SIMT)
+// which 0: d w_sigma[k] = sum_s g_sigma[s] a_last[s][k] (N = 256), d b_sigma
+// which 1: d W_o[c][j]  = sum_s g_c[s][c] g[s][j]        (N = 128), d b_o[c]
+struct HeadArgs {
+  const unsigned char* h[2];   // fp16 blocked activation matrices
+  int N[2];
+  int w_off[2], b_off[2], n_ch[2], g_col[2];
+  const float* graw;           // [S][C1]
+  int C1;
+  long long S, n_tiles;
+  float* g_params;
+};
+
+extern "C" __global__ void __launch_bounds__(256) ren_tc_head_wgrad(const HeadArgs a) {
+  const int which = blockIdx.y;
+  const int N = a.N[which], groups = N >> 3, nch = a.n_ch[which];
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int fg = (int)(warp % groups);                  // this warp's 8-feature group
+  const long long tstride = n_warps / groups;
+  if (tstride == 0 || warp >= tstride * groups) return;
+  float acc[3][8];
+  float bsum[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[c][j] = 0.f;
+  for (long long t = warp / groups; t < a.n_tiles; t += tstride) {
+    const uint4* blk = reinterpret_cast<const uint4*>(a.h[which]) + ((size_t)t * groups + fg) * 128;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int sl = lane * 4 + i;
+      const long long s = t * 128 + sl;
+      if (s >= a.S) continue;
+      float f[8];
+      unpack8(__ldg(blk + sl), f);
+      for (int c = 0; c < nch; ++c) {
+        const float g = __ldg(a.graw + s * a.C1 + a.g_col[which] + c);
+        bsum[c] += g;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[c][j] = fmaf(g, f[j], acc[c][j]);
+      }
+    }
+  }
+  for (int c = 0; c < nch; ++c) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float v = acc[c][j];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) atomicAdd(a.g_params + a.w_off[which] + c * N + fg * 8 + j, v);
+    }
+    float b = bsum[c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) b += __shfl_xor_sync(0xffffffffu, b, o);
+    if (lane == 0 && fg == 0) atomicAdd(a.g_params + a.b_off[which] + c, b);
+  }
+}
+
+// ------------------------------------------------------------------ host side
+int ren_tc_launch_wgrad(const RenPlan& p, long long S, const void* stash, const void* delta,
+                        const float* graw, const unsigned int* gmax, float* g_params, cudaStream_t st) {
+  WgArgs a;
+  static_assert(sizeof(WgArgs) <= 4000, "kernel parameter block too large");
+  memset(&a, 0, sizeof(a));
+  int n = 0;
+  auto add = [&](int dmat, int Nd, long long h_off, int Hw, int w_off, int ldw, int col0, int Ktrue, int b_off) {
+    for (int h = 0; h < Nd / 128; ++h) {
+      WgMat& m = a.mats[n++];
+      m.d_off = (long long)tcs_mat(p, S, dmat); m.Nd = Nd; m.n_half = h; m.h_off = h_off; m.Hw = Hw;
+      m.w_off = w_off; m.ldw = ldw; m.col0 = col0; m.Ktrue = Ktrue; m.b_off = b_off;
+    }
+  };
+  auto add_layer = [&](const RenLayer& L, int prev_mat, int prev_w) {
+    const int ldw = L.K0 + L.K1;
+    if (L.src0 == 1) add(L.mat, L.N, (long long)tcs_encp(p, S), REN_PE_MAX, L.w_off, ldw, 0, L.K0, L.b_off);
+    else add(L.mat, L.N, (long long)tcs_mat(p, S, prev_mat), prev_w, L.w_off, ldw, 0, L.K0, L.b_off);
+    if (L.K1 > 0) {
+      if (L.src1 == 1) add(L.mat, L.N, (long long)tcs_encp(p, S), REN_PE_MAX, L.w_off, ldw, L.K0, L.K1, -1);
+      else add(L.mat, L.N, (long long)tcs_encd(p, S), REN_DE_MAX, L.w_off, ldw, L.K0, L.K1, -1);
+    }
+  };
+  int prev = -1, prevw = 0;
+  for (int i = 0; i < p.D; ++i) {
+    add_layer(p.trunk[i], prev, prevw);
+    prev = p.trunk[i].mat; prevw = p.trunk[i].N;
+  }
+  const int last_trunk = prev;
+  add_layer(p.bott, prev, prevw);
+  add_layer(p.cond[0], p.bott.mat, p.bott.N);
+  if (n > WG_MAX_MATS) { ren_set_error("too many wgrad matrices"); return REN_E_INVALID; }
+  a.n_mats = n;
+  a.n_tiles = (S + TC_M - 1) / TC_M;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int splits = (2 * sms + n - 1) / n;
+  if (splits > a.n_tiles) splits = (int)a.n_tiles;
+  if (splits < 1) splits = 1;
+  a.splits = splits;
+  a.stash = (const unsigned char*)stash; a.delta = (const unsigned char*)delta; a.g_params = g_params;
+  a.gmax = gmax;
+  const int n_jobs = n * splits;
+  const int grid = n_jobs < sms ? n_jobs : sms;
+  cudaError_t e = cudaFuncSetAttribute(ren_tc_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, SMW_TOTAL);
+  if (e != cudaSuccess) { ren_set_error("tc wgrad smem attr: %s", cudaGetErrorString(e)); return REN_E_CUDA; }
+  ren_prof_begin(REN_K_WGRAD, st);
+  ren_tc_wgrad<<<grid, WG_THREADS, SMW_TOTAL, st>>>(a);
+  ren_prof_end(REN_K_WGRAD, st);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) { ren_set_error("tc wgrad launch: %s", cudaGetErrorString(e)); return REN_E_CUDA; }
+
+  HeadArgs h;
+  memset(&h, 0, sizeof(h));
+  h.h[0] = (const unsigned char*)stash + tcs_mat(p, S, last_trunk); h.N[0] = p.W;
+  h.w_off[0] = p.sig_w; h.b_off[0] = p.sig_b; h.n_ch[0] = 1; h.g_col[0] = 0;
+  h.h[1] = (const unsigned char*)stash + tcs_mat(p, S, p.cond[0].mat); h.N[1] = p.WC;
+  h.w_off[1] = p.rgb_w; h.b_off[1] = p.rgb_b; h.n_ch[1] = p.C; h.g_col[1] = 1;
+  h.graw = graw; h.C1 = 1 + p.C; h.S = S; h.n_tiles = a.n_tiles; h.g_params = g_params;
+  ren_prof_begin(REN_K_WGRAD, st);
+  ren_tc_head_wgrad<<<dim3(sms * 2, 2), 256, 0, st>>>(h);
+  ren_prof_end(REN_K_WGRAD, st);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) { ren_set_error("tc head wgrad launch: %s", cudaGetErrorString(e)); return REN_E_CUDA; }
+  return REN_OK;
+}

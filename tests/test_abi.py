@@ -106,9 +106,20 @@ def test_invalid_arguments_fail_loudly(built_lib):
 def test_sizes(built_lib):
     from ren_b200 import _lib
     f = _lib.make_field_desc()
-    r = _lib.make_render_desc(near_plane=0.5, far_plane=4.5, render_step_size=4 / 128)
     S = 1024 * 128
-    per_sample = 8 * 256 + 256 + 128 + 64 + 32 + 2
-    assert _lib.stash_bytes(f, r, 1024, 128) == 4 * S * per_sample
-    assert _lib.workspace_bytes(f, r, 1024, 128, True, True) >= 4 * S * (8 * 256 + 256 + 128 + 2)
+    acts = 8 * 256 + 256 + 128
+    # fp32 engine: blocked fp32 stash (activations + encodings + raw sigma/radiance)
+    r = _lib.make_render_desc(near_plane=0.5, far_plane=4.5, render_step_size=4 / 128, engine="simt_fp32")
+    assert _lib.stash_bytes(f, r, 1024, 128) == 4 * S * (acts + 64 + 32 + 2)
+    assert _lib.workspace_bytes(f, r, 1024, 128, True, True) >= 4 * S * (acts + 2)
     assert _lib.workspace_bytes(f, r, 1024, 128, False, False) >= 4 * S * 2
+    # tcgen05 engine (auto for the 8x256 network): fp16 stash, fp32 raw
+    r = _lib.make_render_desc(near_plane=0.5, far_plane=4.5, render_step_size=4 / 128, engine="auto")
+    assert _lib.stash_bytes(f, r, 1024, 128) == S * (2 * (acts + 64 + 32) + 4 * 2)
+    assert _lib.workspace_bytes(f, r, 1024, 128, True, True) >= S * (2 * acts + 4 * 2)
+    # a shape the tcgen05 engine does not cover falls back to fp32 under auto and is refused when forced
+    f64 = _lib.make_field_desc(net_depth=4, net_width=64)
+    assert _lib.stash_bytes(f64, r, 8, 128) == 4 * 1024 * (4 * 64 + 64 + 128 + 64 + 32 + 2)
+    forced = _lib.make_render_desc(near_plane=0.5, far_plane=4.5, render_step_size=4 / 128, engine="tc_f16x3")
+    with pytest.raises(RuntimeError, match="tcgen05"):
+        _lib.stash_bytes(f64, forced, 8, 128)

@@ -154,7 +154,10 @@ def test_training_step_matches_oracle_fresh_inputs(B, N, contraction, bk, engine
         g64, g32 = params64[k].grad, params[k].grad.double()
         e_cuda, e_ref = float((got - g64).norm()), float((g32 - g64).norm())
         worst = max(worst, e_cuda / max(float(g64.norm()), 1e-30))
-        assert e_cuda <= max(5 * e_ref, 1e-3 * float(g64.norm())), (k, e_cuda, e_ref, float(g64.norm()))
+        # the tcgen05 backward keeps activations / deltas as single fp16 values for the weight-gradient
+        # GEMMs (2^-11 operand rounding): 5e-3; the fp32 engine: 1e-3
+        bar = 1e-3 if engine == "simt_fp32" else 5e-3
+        assert e_cuda <= max(5 * e_ref, bar * float(g64.norm())), (k, e_cuda, e_ref, float(g64.norm()))
     print(f"[fresh {B}x{N} {contraction}/{engine}] worst gradient normwise rel vs fp64 oracle = {worst:.2e}")
     if bk:
         got = m.nerf.parametrizations.render_bkgd.original.grad
