@@ -91,42 +91,57 @@ __device__ __forceinline__ uint32_t region_lo(int region) {
   return region == 0 ? SM_A_LO : (region == 1 ? SM_P_LO : SM_D_LO);
 }
 
-// softplus(beta=100, threshold=20) on the MUFU pipe (ex2 + lg2); absolute error ~2e-9
+__device__ __forceinline__ float ex2_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float lg2_ftz(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// softplus(beta=100, threshold=20) = ln2/100 * lg2(1 + ex2(100 log2e x)) on the MUFU pipe: 2 MUFU +
+// 5 FP32 ops per element, absolute error ~2e-9 (results below 2^-126 flush to zero)
 __device__ __forceinline__ float softplus100_fast(float x) {
-  const float z = x * 100.f;
-  const float y = __logf(1.f + __expf(z)) * 0.01f;
-  return z > 20.f ? x : y;
+  const float t = x * 144.26950408889634f;                 // 100 * log2(e)
+  const float y = lg2_ftz(1.f + ex2_ftz(t)) * 0.0069314718055994531f;   // ln(2) / 100
+  return t > 28.853900817779268f ? x : y;                  // 100 x > 20
 }
 // d softplus / dx from the OUTPUT a: sigmoid(100 x) = 1 - exp(-100 a)
-__device__ __forceinline__ float softplus100_grad_fast(float a) { return 1.f - __expf(-100.f * a); }
+__device__ __forceinline__ float softplus100_grad_fast(float a) { return 1.f - ex2_ftz(a * -144.26950408889634f); }
 
-// feature j of SinusoidalEncoder(x) with max degree DEG (external/mlp.py:227-243), j compile-time
-template <int DEG>
-__device__ __forceinline__ float enc_feature(const float* x, int j) {
-  if (j < 3) return x[j];
-  if (j >= 3 + 6 * DEG) return 0.f;
+// One out-of-line accurate sine keeps the kernel small (84 inlined sinf bodies were ~100 KB of
+// SASS and stalled the epilogue warps on instruction fetch).
+__device__ __noinline__ float ren_sinf(float x) { return sinf(x); }
+
+// feature j of SinusoidalEncoder(x) with max degree deg (external/mlp.py:227-243)
+__device__ __forceinline__ float enc_feature(const float* x, int deg, int j) {
+  if (j < 3) return j == 0 ? x[0] : (j == 1 ? x[1] : x[2]);
+  if (j >= 3 + 6 * deg) return 0.f;
   const int jj = j - 3;
-  const bool shifted = jj >= 3 * DEG;
-  const int q = shifted ? jj - 3 * DEG : jj;
+  const bool shifted = jj >= 3 * deg;
+  const int q = shifted ? jj - 3 * deg : jj;
   const int i = q / 3, a = q - 3 * i;
-  const float xb = __fmul_rn(x[a], (float)(1 << i));
-  return sinf(shifted ? __fadd_rn(xb, 1.5707963267948966f) : xb);
+  const float xa = a == 0 ? x[0] : (a == 1 ? x[1] : x[2]);
+  const float xb = __fmul_rn(xa, __int_as_float((127 + i) << 23));     // exact 2^i
+  return ren_sinf(shifted ? __fadd_rn(xb, 1.5707963267948966f) : xb);
 }
-// encode k-cores [C0, C1) of an encoding into an operand region (+ fp16 stash)
-template <int DEG, int KP, int C0, int C1>
-__device__ __forceinline__ void encode_cores(const float* x, bool valid, unsigned char* smem, uint32_t hi_off,
-                                             uint32_t lo_off, int m, unsigned char* stash_mat, long long sidx) {
-#pragma unroll
-  for (int c = C0; c < C1; ++c) {
+// encode k-cores [c0, c1) of an encoding into an operand region (+ fp16 stash)
+__device__ __forceinline__ void encode_cores(const float* x, int deg, int kp, int c0, int c1, bool valid,
+                                             unsigned char* smem, uint32_t hi_off, uint32_t lo_off, int m,
+                                             unsigned char* stash_mat, long long sidx) {
+#pragma unroll 1
+  for (int c = c0; c < c1; ++c) {
     float f[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) f[j] = valid ? enc_feature<DEG>(x, c * 8 + j) : 0.f;
+    for (int j = 0; j < 8; ++j) f[j] = valid ? enc_feature(x, deg, c * 8 + j) : 0.f;
     uint4 hi, lo;
     split8(f, &hi, &lo);
     *reinterpret_cast<uint4*>(smem + hi_off + c * (TC_M * 16) + m * 16) = hi;
     *reinterpret_cast<uint4*>(smem + lo_off + c * (TC_M * 16) + m * 16) = lo;
     if (stash_mat != nullptr)
-      *reinterpret_cast<uint4*>(stash_mat + 2 * ren_blk(sidx, c * 8, KP)) = hi;
+      *reinterpret_cast<uint4*>(stash_mat + 2 * ren_blk(sidx, c * 8, kp)) = hi;
   }
 }
 
@@ -283,14 +298,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ren_tc_chain(const TcArgs a) {
             if (!ren_alive(t0, t1, t_max)) selector = false;
           }
           unsigned char* sm = STASH ? a.stash + tcs_encp(p, S) : nullptr;
-          if (cg == 0) encode_cores<10, 64, 0, 3>(z, valid, smem, SM_P_HI, SM_P_LO, m, sm, sidx);
-          else if (cg == 1) encode_cores<10, 64, 3, 6>(z, valid, smem, SM_P_HI, SM_P_LO, m, sm, sidx);
-          else encode_cores<10, 64, 6, 8>(z, valid, smem, SM_P_HI, SM_P_LO, m, sm, sidx);
+          const int c0 = cg == 0 ? 0 : (cg == 1 ? 3 : 6), c1 = cg == 0 ? 3 : (cg == 1 ? 6 : 8);
+          encode_cores(z, 10, 64, c0, c1, valid, smem, SM_P_HI, SM_P_LO, m, sm, sidx);
         } else {
           const float dz[3] = {__fmul_rn(d[0], 3.141592653589793f), __fmul_rn(d[1], 3.141592653589793f),
                                __fmul_rn(d[2], 3.141592653589793f)};
-          encode_cores<4, 32, 0, 4>(dz, valid, smem, SM_D_HI, SM_D_LO, m, STASH ? a.stash + tcs_encd(p, S) : nullptr,
-                                    sidx);
+          encode_cores(dz, 4, 32, 0, 4, valid, smem, SM_D_HI, SM_D_LO, m,
+                       STASH ? a.stash + tcs_encd(p, S) : nullptr, sidx);
         }
       } else {
         // ---- dgrad prologue: head gradients enter as rank-1 K=16 segments:
@@ -327,13 +341,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ren_tc_chain(const TcArgs a) {
         const int ncol = st.N >> 2;                  // columns this warp handles (64 / 32 / 4)
         const int col0 = cg * ncol;
         // dgrad: prefetch this thread's slice of the activation stash while the MMAs run
+        // byte offset of this thread's 8-feature group g8 inside a blocked fp16 matrix of width N:
+        //   (tile * N/8 + g8) * 2048 + m * 16   == the shared-memory operand offset + a per-tile base
+        const size_t tile_off = (size_t)tile * (size_t)(st.N >> 3) * 2048 + (size_t)m * 16;
         uint4 act_pref[8];
         if (MODE == 1 && st.epi == EPI_D_ACT && valid) {
-          const unsigned char* am = a.stash + tcs_mat(p, S, st.act_mat);
+          const unsigned char* am = a.stash + tcs_mat(p, S, st.act_mat) + tile_off + (size_t)(col0 >> 3) * 2048;
 #pragma unroll
           for (int i = 0; i < 8; ++i)
-            if (i * 8 < ncol)
-              act_pref[i] = __ldg(reinterpret_cast<const uint4*>(am + 2 * ren_blk(sidx, col0 + i * 8, st.N)));
+            if (i * 8 < ncol) act_pref[i] = __ldg(reinterpret_cast<const uint4*>(am + i * 2048));
         }
         mbar_wait(bar_accfull, ev & 1u);
         tc_fence_after();
@@ -351,12 +367,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ren_tc_chain(const TcArgs a) {
             }
           }
         } else {
-          unsigned char* out_mat = nullptr;
+          unsigned char* out_mat = nullptr;       // already offset to this thread's row of the tile
           if (MODE == 0) {
-            if (STASH && st.out_mat >= 0) out_mat = a.stash + tcs_mat(p, S, st.out_mat);
+            if (STASH && st.out_mat >= 0) out_mat = a.stash + tcs_mat(p, S, st.out_mat) + tile_off;
           } else if (st.out_mat >= 0) {      // padded rows are written as zeros (wgrad reads whole tiles)
-            out_mat = a.delta + tcs_mat(p, S, st.out_mat);
+            out_mat = a.delta + tcs_mat(p, S, st.out_mat) + tile_off;
           }
+          unsigned char* a_row = smem + (uint32_t)m * 16;
           const float* bias = (MODE == 0 && st.bias_off >= 0) ? a.pack_bias + st.bias_off : nullptr;
           const uint32_t tcol = tmem_lane + (uint32_t)(st.tmem_col + col0);
           uint32_t r[2][16];
@@ -397,12 +414,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ren_tc_chain(const TcArgs a) {
                   }
                   uint4 hi, lo;
                   split8(y, &hi, &lo);
+                  const uint32_t goff = (uint32_t)(n0 >> 3) * (TC_M * 16);
                   if (st.write_a) {
-                    const uint32_t off = (uint32_t)(n0 >> 3) * (TC_M * 16) + (uint32_t)m * 16;
-                    *reinterpret_cast<uint4*>(smem + SM_A_HI + off) = hi;
-                    *reinterpret_cast<uint4*>(smem + SM_A_LO + off) = lo;
+                    *reinterpret_cast<uint4*>(a_row + SM_A_HI + goff) = hi;
+                    *reinterpret_cast<uint4*>(a_row + SM_A_LO + goff) = lo;
                   }
-                  if (out_mat != nullptr) *reinterpret_cast<uint4*>(out_mat + 2 * ren_blk(sidx, n0, st.N)) = hi;
+                  if (out_mat != nullptr) *reinterpret_cast<uint4*>(out_mat + goff) = hi;
                 }
                 tc_ld_wait();
               }
