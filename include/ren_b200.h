@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define REN_ABI_VERSION 1
+#define REN_ABI_VERSION 2
 
 enum {
   REN_OK = 0,
@@ -142,13 +142,48 @@ int ren_render_forward(const RenFieldDesc* f, const RenRenderDesc* r, int64_t n_
 /* Reverse pass of the above (replaces autograd through the same reference files).
  *   g_radiance (n_rays,C), g_opacity (n_rays), g_depth (n_rays): upstream grads (NULL = 0)
  *   g_params   flat fp32, ACCUMULATED into (caller zeroes)
- *   g_bkgd     (C) accumulated, or NULL */
+ *   g_bkgd     (C) accumulated, or NULL
+ *   g_rays     (n_rays,6) f32 = d loss / d [o | d] (written) or NULL -- needed only when the
+ *              timestamps are trainable (refractory period) */
 int ren_render_backward(const RenFieldDesc* f, const RenRenderDesc* r, int64_t n_rays, int32_t K,
                         const float* rays_o, const float* rays_d, const float* jitter,
                         const float* params, const float* bkgd, const float* g_radiance,
                         const float* g_opacity, const float* g_depth, const void* stash,
-                        size_t stash_bytes, float* g_params, float* g_bkgd, void* workspace,
-                        size_t workspace_bytes, void* stream);
+                        size_t stash_bytes, float* g_params, float* g_bkgd, float* g_rays,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* Tangent-mode render: the same render PLUS its derivative along one scalar per ray (the pose
+ * interpolation weight w of the ray's timestamp), replacing
+ * `autograd.gradient(log_intensity, ts, create_graph=True)` (utils/autograd.py:4-34, call site
+ * models/robust_e_nerf.py:394-398) by a forward-mode pass: value and tangent rows go through the
+ * same GEMMs, so d logI / d t = radiance_dot / (radiance + min_modeled_intensity) * dw/dt.
+ *   rays_o_dot, rays_d_dot (n_rays,3) f32: d o / d w, d d / d w (ren_event_rays)
+ *   radiance_dot (n_rays,C), opacity_dot (n_rays): d radiance / d w, d opacity / d w
+ * The march (t0, t1) carries no gradient, as in the reference (nerfacc marches under no_grad).
+ * Stash / workspace sizes come from ren_tangent_stash_bytes / ren_tangent_workspace_bytes. */
+int ren_tangent_stash_bytes(const RenFieldDesc* f, const RenRenderDesc* r, int64_t n_rays, int32_t K,
+                            size_t* bytes);
+int ren_tangent_workspace_bytes(const RenFieldDesc* f, const RenRenderDesc* r, int64_t n_rays, int32_t K,
+                                int32_t has_stash, int32_t for_backward, size_t* bytes);
+int ren_render_tangent_forward(const RenFieldDesc* f, const RenRenderDesc* r, int64_t n_rays, int32_t K,
+                               const float* rays_o, const float* rays_d, const float* rays_o_dot,
+                               const float* rays_d_dot, const float* jitter, const float* params,
+                               const float* bkgd, float* radiance, float* opacity, float* depth,
+                               float* radiance_dot, float* opacity_dot, int32_t* n_kept, void* stash,
+                               size_t stash_bytes, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Reverse pass of the tangent-mode render (the reference's double-backward through
+ * external/mlp.py, external/vol_rendering.py): upstream grads of the five per-ray outputs ->
+ * g_params / g_bkgd (accumulated) and, when g_rays != NULL, (n_rays,12) f32 =
+ * d loss / d [o | d | o_dot | d_dot] (written), which chain to the timestamp / refractory period. */
+int ren_render_tangent_backward(const RenFieldDesc* f, const RenRenderDesc* r, int64_t n_rays, int32_t K,
+                                const float* rays_o, const float* rays_d, const float* rays_o_dot,
+                                const float* rays_d_dot, const float* jitter, const float* params,
+                                const float* bkgd, const float* g_radiance, const float* g_opacity,
+                                const float* g_depth, const float* g_radiance_dot,
+                                const float* g_opacity_dot, const void* stash, size_t stash_bytes,
+                                float* g_params, float* g_bkgd, float* g_rays, void* workspace,
+                                size_t workspace_bytes, void* stream);
 
 /* Replaces `RefractoryPeriod.forward` (models/event_generation_params.py:196-203), the
  * supervision-timestamp derivation (models/robust_e_nerf.py:322-357),
@@ -160,13 +195,18 @@ int ren_render_backward(const RenFieldDesc* f, const RenRenderDesc* r, int64_t n
  *   pose_ts (P) i64, pose_pos (P,3) f32, pose_quat (P,4) f32 XYZW; k_inv (9) f32
  *   n_renders = 2: rays for [diff_start | diff_end]; 3: [grad | diff_start | diff_end]
  *   out_ts (n_renders,B) f64; out_o,out_d (n_renders,B,3) f32; out_rot (n_renders,B,9) f32 or NULL
- *   out_ts_diff (B) f64 (the diff interval length), out_start (B) f64 = start_ts + tau */
+ *   out_ts_diff (B) f64 (the diff interval length), out_start (B) f64 = start_ts + tau
+ *   out_o_dot, out_d_dot, out_d_ddot (n_renders,B,3) f32 and out_dw_dt (n_renders,B) f64, all NULL
+ *   or all set: first / second derivative of the ray wrt the pose-interpolation weight w and
+ *   dw/dt = 1 / (pose bin width) -- what autograd propagates through
+ *   models/trajectories.py:63-91 for the log-intensity-gradient loss and a trainable tau */
 int ren_event_rays(int64_t B, const float* position, const int64_t* start_ts,
                    const int64_t* end_ts, const double* nz_ts_diff, const double* nz_diff_start,
                    const double* nz_grad_ts, const double* tau, int64_t n_poses,
                    const int64_t* pose_ts, const float* pose_pos, const float* pose_quat,
                    const float* k_inv, int32_t n_renders, double* out_ts, float* out_o,
                    float* out_d, float* out_rot, double* out_ts_diff, double* out_start,
+                   float* out_o_dot, float* out_d_dot, float* out_d_ddot, double* out_dw_dt,
                    void* stream);
 
 /* Replaces `LinearTrajectory.forward` (models/trajectories.py:30-91) alone: pose at n

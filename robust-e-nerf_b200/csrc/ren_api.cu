@@ -8,11 +8,24 @@
 
 // engines
 int ren_simt_launch_fwd(const RenPlan& p, long long n_rays, int K, const float* o, const float* d,
-                        const float* jitter, const float* params, float* stash, float* raw, cudaStream_t st);
+                        const float* o_dot, const float* d_dot, const float* jitter, const float* params,
+                        float* stash, float* raw, cudaStream_t st);
 int ren_simt_launch_dgrad(const RenPlan& p, long long S, const float* params, const float* stash,
-                          const float* graw, float* delta, cudaStream_t st);
+                          const float* graw, float* delta, int tangent, cudaStream_t st);
 int ren_simt_launch_wgrad(const RenPlan& p, long long S, const float* stash, const float* delta,
-                          const float* graw, float* g_params, cudaStream_t st);
+                          const float* graw, float* g_params, int tangent, cudaStream_t st);
+int ren_launch_composite_tan(const RenPlan& p, long long n_rays, int K, const float* o, const float* d,
+                             const float* jitter, const float* raw, const float* bkgd, float* radiance,
+                             float* opacity, float* depth, float* radiance_dot, float* opacity_dot,
+                             int* n_kept, cudaStream_t st);
+int ren_launch_composite_tan_bwd(const RenPlan& p, long long n_rays, int K, const float* o, const float* d,
+                                 const float* jitter, const float* raw, const float* bkgd,
+                                 const float* g_radiance, const float* g_opacity, const float* g_depth,
+                                 const float* g_radiance_dot, const float* g_opacity_dot, float* graw,
+                                 float* g_bkgd, cudaStream_t st);
+int ren_launch_raygrad(const RenPlan& p, long long n_rays, int K, const float* o, const float* d,
+                       const float* o_dot, const float* d_dot, const float* jitter, const float* params,
+                       const float* delta, float* g_rays, cudaStream_t st);
 int ren_launch_composite(const RenPlan& p, long long n_rays, int K, const float* o, const float* d,
                          const float* jitter, const float* raw, const float* bkgd, float* radiance,
                          float* opacity, float* depth, int* n_kept, cudaStream_t st);
@@ -353,7 +366,7 @@ extern "C" int ren_render_forward(const RenFieldDesc* f, const RenRenderDesc* r,
     ws_left = workspace_bytes - (size_t)(ws - (char*)workspace);
   }
   if (engine == REN_ENGINE_SIMT_FP32)
-    rc = ren_simt_launch_fwd(p, n_rays, K, rays_o, rays_d, jitter, params, (float*)stash, raw, st);
+    rc = ren_simt_launch_fwd(p, n_rays, K, rays_o, rays_d, nullptr, nullptr, jitter, params, (float*)stash, raw, st);
   else
     rc = ren_tc_launch_fwd(p, n_rays, K, rays_o, rays_d, jitter, params, stash, raw, ws, ws_left, st);
   if (rc) return rc;
@@ -365,8 +378,8 @@ extern "C" int ren_render_backward(const RenFieldDesc* f, const RenRenderDesc* r
                                    const float* rays_o, const float* rays_d, const float* jitter,
                                    const float* params, const float* bkgd, const float* g_radiance,
                                    const float* g_opacity, const float* g_depth, const void* stash,
-                                   size_t stash_bytes, float* g_params, float* g_bkgd, void* workspace,
-                                   size_t workspace_bytes, void* stream) {
+                                   size_t stash_bytes, float* g_params, float* g_bkgd, float* g_rays,
+                                   void* workspace, size_t workspace_bytes, void* stream) {
   RenPlan p;
   int rc = ren_build_plan(f, r, &p);
   if (rc) return rc;
@@ -397,9 +410,17 @@ extern "C" int ren_render_backward(const RenFieldDesc* f, const RenRenderDesc* r
     rc = ren_launch_composite_bwd(p, n_rays, K, rays_o, rays_d, jitter, raw, bkgd, g_radiance, g_opacity,
                                   g_depth, graw, g_bkgd, nullptr, st);
     if (rc) return rc;
-    rc = ren_simt_launch_dgrad(p, S, params, st_f, graw, delta, st);
+    rc = ren_simt_launch_dgrad(p, S, params, st_f, graw, delta, 0, st);
     if (rc) return rc;
-    return ren_simt_launch_wgrad(p, S, st_f, delta, graw, g_params, st);
+    if (g_rays) {
+      rc = ren_launch_raygrad(p, n_rays, K, rays_o, rays_d, nullptr, nullptr, jitter, params, delta, g_rays, st);
+      if (rc) return rc;
+    }
+    return ren_simt_launch_wgrad(p, S, st_f, delta, graw, g_params, 0, st);
+  }
+  if (g_rays) {
+    ren_set_error("ray gradients (trainable refractory period) are provided by the simt_fp32 engine only");
+    return REN_E_UNSUPPORTED;
   }
   const size_t need = tcd_bytes(p, S);
   if (ws_left < need + 1024) { ren_set_error("workspace too small for backward (%zu < %zu)", ws_left, need); return REN_E_WORKSPACE; }
@@ -416,4 +437,111 @@ extern "C" int ren_render_backward(const RenFieldDesc* f, const RenRenderDesc* r
   rc = ren_tc_launch_dgrad(p, S, params, stash, graw, gmax, delta, pack_ws, pack_left, st);
   if (rc) return rc;
   return ren_tc_launch_wgrad(p, S, stash, delta, graw, gmax, g_params, st);
+}
+
+// ------------------------------------------------------------------ tangent mode (fp32 FFMA engine)
+static int tangent_plan(const RenFieldDesc* f, const RenRenderDesc* r, int64_t n_rays, int32_t K, RenPlan* p) {
+  int rc = ren_build_plan(f, r, p);
+  if (rc) return rc;
+  rc = validate_render(r);
+  if (rc) return rc;
+  if (n_rays < 0 || K < 1) { ren_set_error("bad n_rays/K"); return REN_E_INVALID; }
+  p->r.engine = REN_ENGINE_SIMT_FP32;
+  return REN_OK;
+}
+
+extern "C" int ren_tangent_stash_bytes(const RenFieldDesc* f, const RenRenderDesc* r, int64_t n_rays, int32_t K,
+                                       size_t* bytes) {
+  RenPlan p;
+  int rc = tangent_plan(f, r, n_rays, K, &p);
+  if (rc) return rc;
+  *bytes = sizeof(float) * (size_t)ren_stash_floats(p, 2 * (long long)n_rays * K);
+  return REN_OK;
+}
+
+extern "C" int ren_tangent_workspace_bytes(const RenFieldDesc* f, const RenRenderDesc* r, int64_t n_rays,
+                                           int32_t K, int32_t has_stash, int32_t for_backward, size_t* bytes) {
+  RenPlan p;
+  int rc = tangent_plan(f, r, n_rays, K, &p);
+  if (rc) return rc;
+  const long long S2 = 2 * (long long)n_rays * K;
+  const size_t n = for_backward ? sizeof(float) * (size_t)ren_delta_floats(p, S2)
+                                : (has_stash ? 0 : sizeof(float) * (size_t)((1 + p.C) * ren_pad128(S2)));
+  *bytes = n + 2048;
+  return REN_OK;
+}
+
+extern "C" int ren_render_tangent_forward(const RenFieldDesc* f, const RenRenderDesc* r, int64_t n_rays, int32_t K,
+                                          const float* rays_o, const float* rays_d, const float* rays_o_dot,
+                                          const float* rays_d_dot, const float* jitter, const float* params,
+                                          const float* bkgd, float* radiance, float* opacity, float* depth,
+                                          float* radiance_dot, float* opacity_dot, int32_t* n_kept, void* stash,
+                                          size_t stash_bytes, void* workspace, size_t workspace_bytes,
+                                          void* stream) {
+  RenPlan p;
+  int rc = tangent_plan(f, r, n_rays, K, &p);
+  if (rc) return rc;
+  if (n_rays == 0) return REN_OK;
+  if (!rays_o || !rays_d || !rays_o_dot || !rays_d_dot || !params || !radiance || !opacity || !depth ||
+      !radiance_dot || !opacity_dot || !n_kept) {
+    ren_set_error("ren_render_tangent_forward: null pointer argument");
+    return REN_E_INVALID;
+  }
+  if (r->stratified && jitter == nullptr) { ren_set_error("stratified marching needs a jitter buffer"); return REN_E_INVALID; }
+  const long long S2 = 2 * (long long)n_rays * K;
+  cudaStream_t st = (cudaStream_t)stream;
+  float* raw;
+  if (stash) {
+    if (stash_bytes < sizeof(float) * (size_t)ren_stash_floats(p, S2)) { ren_set_error("stash too small"); return REN_E_WORKSPACE; }
+    raw = (float*)stash + ren_stash_raw(p, S2);
+  } else {
+    char* ws = (char*)align256(workspace);
+    const size_t ws_left = workspace ? workspace_bytes - (size_t)(ws - (char*)workspace) : 0;
+    const size_t need = sizeof(float) * (size_t)((1 + p.C) * ren_pad128(S2));
+    if (!workspace || ws_left < need) { ren_set_error("workspace too small for raw samples (%zu < %zu)", ws_left, need); return REN_E_WORKSPACE; }
+    raw = (float*)ws;
+  }
+  rc = ren_simt_launch_fwd(p, n_rays, K, rays_o, rays_d, rays_o_dot, rays_d_dot, jitter, params, (float*)stash, raw, st);
+  if (rc) return rc;
+  return ren_launch_composite_tan(p, n_rays, K, rays_o, rays_d, jitter, raw, bkgd, radiance, opacity, depth,
+                                  radiance_dot, opacity_dot, n_kept, st);
+}
+
+extern "C" int ren_render_tangent_backward(const RenFieldDesc* f, const RenRenderDesc* r, int64_t n_rays, int32_t K,
+                                           const float* rays_o, const float* rays_d, const float* rays_o_dot,
+                                           const float* rays_d_dot, const float* jitter, const float* params,
+                                           const float* bkgd, const float* g_radiance, const float* g_opacity,
+                                           const float* g_depth, const float* g_radiance_dot,
+                                           const float* g_opacity_dot, const void* stash, size_t stash_bytes,
+                                           float* g_params, float* g_bkgd, float* g_rays, void* workspace,
+                                           size_t workspace_bytes, void* stream) {
+  RenPlan p;
+  int rc = tangent_plan(f, r, n_rays, K, &p);
+  if (rc) return rc;
+  if (n_rays == 0) return REN_OK;
+  if (!rays_o || !rays_d || !rays_o_dot || !rays_d_dot || !params || !stash || !g_params || !workspace) {
+    ren_set_error("ren_render_tangent_backward: null pointer argument");
+    return REN_E_INVALID;
+  }
+  const long long S2 = 2 * (long long)n_rays * K;
+  if (stash_bytes < sizeof(float) * (size_t)ren_stash_floats(p, S2)) { ren_set_error("stash too small"); return REN_E_WORKSPACE; }
+  char* ws = (char*)align256(workspace);
+  const size_t ws_left = workspace_bytes - (size_t)(ws - (char*)workspace);
+  const size_t need = sizeof(float) * (size_t)ren_delta_floats(p, S2);
+  if (ws_left < need) { ren_set_error("workspace too small for backward (%zu < %zu)", ws_left, need); return REN_E_WORKSPACE; }
+  cudaStream_t st = (cudaStream_t)stream;
+  float* delta = (float*)ws;
+  float* graw = delta + p.act_floats * ren_pad128(S2);
+  const float* st_f = (const float*)stash;
+  const float* raw = st_f + ren_stash_raw(p, S2);
+  rc = ren_launch_composite_tan_bwd(p, n_rays, K, rays_o, rays_d, jitter, raw, bkgd, g_radiance, g_opacity, g_depth,
+                                    g_radiance_dot, g_opacity_dot, graw, g_bkgd, st);
+  if (rc) return rc;
+  rc = ren_simt_launch_dgrad(p, S2, params, st_f, graw, delta, 1, st);
+  if (rc) return rc;
+  if (g_rays) {
+    rc = ren_launch_raygrad(p, n_rays, K, rays_o, rays_d, rays_o_dot, rays_d_dot, jitter, params, delta, g_rays, st);
+    if (rc) return rc;
+  }
+  return ren_simt_launch_wgrad(p, S2, st_f, delta, graw, g_params, 1, st);
 }

@@ -98,6 +98,41 @@ __device__ __forceinline__ float ren_hidden_grad_from_out(int kind, float y) {
   return kind == REN_HIDDEN_SOFTPLUS100 ? ren_softplus_grad_from_out(y, 100.f)
                                         : (y > 0.f ? 1.f : 0.f);
 }
+// tangent mode (d/dt of the hidden activations): act'(x) from the PRE-activation x
+// (torch softplus backward: z/(z+1) with z = exp(beta x), 1 above the threshold)
+__device__ __forceinline__ float ren_hidden_grad_from_pre(int kind, float x) {
+  if (kind != REN_HIDDEN_SOFTPLUS100) return x > 0.f ? 1.f : 0.f;
+  const float z = x * 100.f;
+  return (z > 20.f) ? 1.f : 1.f / (1.f + expf(-z));
+}
+// act''(x) * xdot expressed through the stashed outputs: y = act(x), ydot = act'(x) xdot.
+// softplus(beta): act'' = beta s (1 - s) with s = act'  =>  act'' xdot = beta (1 - s) ydot
+__device__ __forceinline__ float ren_hidden_curv_from_out(int kind, float y, float ydot) {
+  if (kind != REN_HIDDEN_SOFTPLUS100) return 0.f;
+  return 100.f * expf(-100.f * y) * ydot;
+}
+// second derivatives of the output activations wrt their raw value (reverse pass of the tangent
+// render; the reference obtains them by double-backward).  _TruncExp.backward multiplies by
+// exp(clamp(x, max=15)) (external/ngp.py:54-58), whose own derivative vanishes above the clamp.
+__device__ __forceinline__ float ren_density_act2(int kind, float raw) {
+  if (kind == REN_DENSITY_SHIFTED_TRUNC_EXP) {
+    const float x = raw - 1.f;
+    return x < 15.f ? expf(x) : 0.f;
+  }
+  const float x = (kind == REN_DENSITY_SHIFTED_SOFTPLUS) ? raw - 1.f : raw;
+  if (x > 20.f) return 0.f;
+  const float s = 1.f / (1.f + expf(-x));
+  return s * (1.f - s);
+}
+__device__ __forceinline__ float ren_radiance_act2(int kind, float raw) {
+  if (kind == REN_RADIANCE_SOFTPLUS) {
+    if (raw > 20.f) return 0.f;
+    const float s = 1.f / (1.f + expf(-raw));
+    return s * (1.f - s);
+  }
+  const float s = 1.f / (1.f + expf(-raw));
+  return s * (1.f - s) * (1.f - 2.f * s);
+}
 // density activation and its derivative wrt the raw value (external/ngp.py:45-65,
 // models/nerf.py:8-25).  raw == -inf encodes "outside the box" (selector false).
 __device__ __forceinline__ float ren_density_act(int kind, float raw, float* dact) {
@@ -220,6 +255,27 @@ __device__ __forceinline__ void ren_encode(const float* x, int deg, int padded, 
       float xb = __fmul_rn(x[a], sc);
       store(3 + i * 3 + a, sinf(xb));
       store(3 + deg * 3 + i * 3 + a, sinf(__fadd_rn(xb, 1.5707963267948966f)));
+    }
+    sc *= 2.f;
+  }
+  for (int j = 3 + 6 * deg; j < padded; ++j) store(j, 0.f);
+}
+
+// d/dt of SinusoidalEncoder(x) given xdot: [xdot | 2^i cos(2^i x) xdot | 2^i cos(2^i x + pi/2) xdot]
+template <typename Store>
+__device__ __forceinline__ void ren_encode_tangent(const float* x, const float* xdot, int deg, int padded,
+                                                   Store store) {
+  store(0, xdot[0]);
+  store(1, xdot[1]);
+  store(2, xdot[2]);
+  float sc = 1.f;
+#pragma unroll
+  for (int i = 0; i < deg; ++i) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      float xb = __fmul_rn(x[a], sc);
+      store(3 + i * 3 + a, cosf(xb) * sc * xdot[a]);
+      store(3 + deg * 3 + i * 3 + a, cosf(__fadd_rn(xb, 1.5707963267948966f)) * sc * xdot[a]);
     }
     sc *= 2.f;
   }

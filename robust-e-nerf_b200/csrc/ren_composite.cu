@@ -30,6 +30,12 @@ struct CompArgs {
   float* graw;           // [S][1+C]
   float* g_bkgd;         // [C] or NULL
   unsigned int* gmax;    // max |graw| as float bits (tcgen05 backward loss scaling) or NULL
+  // tangent mode: raw / graw have 2 rows per sample (value, d/dw)
+  int tangent;
+  float* radiance_dot;   // [n_rays][C]
+  float* opacity_dot;    // [n_rays]
+  const float* g_radiance_dot;
+  const float* g_opacity_dot;
 };
 
 __device__ __forceinline__ float warp_incl_scan(float v, int lane) {
@@ -86,7 +92,7 @@ __device__ __forceinline__ void walk_ray(const CompArgs& a, long long r, int lan
     b.c[0] = b.c[1] = b.c[2] = 0.f;
     b.dact_c[0] = b.dact_c[1] = b.dact_c[2] = 0.f;
     if (b.alive) {
-      const float* rw = a.raw + (r * a.K + k) * C1;
+      const float* rw = a.raw + (r * a.K + k) * (a.tangent ? 2 : 1) * C1;
       sraw = rw[0];
       for (int c = 0; c < p.C; ++c) b.c[c] = ren_radiance_act(p.f.radiance_activation, rw[1 + c], &b.dact_c[c]);
     }
@@ -257,6 +263,229 @@ extern "C" __global__ void __launch_bounds__(128) ren_composite_bwd(const CompAr
     for (int o = 16; o > 0; o >>= 1) gabs = fmaxf(gabs, __shfl_xor_sync(0xffffffffu, gabs, o));
     if (lane == 0 && gabs > 0.f && gabs < INFINITY) atomicMax(a.gmax, __float_as_uint(gabs));
   }
+}
+
+// ------------------------------------------------------------------ tangent mode
+// With a_i = sigma_i dt_i, E_i = sum_{j<i} a_j, T_i = e^{-E_i}, beta_i = e^{-a_i}, w_i = T_i (1 - beta_i):
+//   wdot_i = -Edot_i w_i + T_i beta_i adot_i,   Cdot = sum wdot c + w cdot - bkgd Odot,   Odot = sum wdot
+// (the d/dw image of external/vol_rendering.py:82-126; the visibility cull is piecewise constant).
+struct TanBlk {
+  float adot, cdot[3], sdot_raw, cdot_raw[3], wdot, Edot;
+};
+// per-block tangent quantities; `carry` = sum of kept adot before this block (updated)
+__device__ __forceinline__ TanBlk tan_block(const CompArgs& a, long long r, int k, int lane, const SampleBlk& b,
+                                            float& carry) {
+  const RenPlan& p = a.p;
+  const int C1 = 1 + p.C;
+  TanBlk t;
+  t.sdot_raw = 0.f;
+  t.cdot_raw[0] = t.cdot_raw[1] = t.cdot_raw[2] = 0.f;
+  if (b.keep) {
+    const float* rw = a.raw + ((r * a.K + k) * 2 + 1) * C1;
+    t.sdot_raw = rw[0];
+    for (int c = 0; c < p.C; ++c) t.cdot_raw[c] = rw[1 + c];
+  }
+  t.adot = b.keep ? b.dact_s * t.sdot_raw * __fsub_rn(b.t1, b.t0) : 0.f;
+  for (int c = 0; c < 3; ++c) t.cdot[c] = b.dact_c[c] * t.cdot_raw[c];
+  const float incl = warp_incl_scan(t.adot, lane);
+  t.Edot = carry + (incl - t.adot);
+  carry += __shfl_sync(0xffffffffu, incl, 31);
+  t.wdot = b.keep ? fmaf(-t.Edot, b.w, b.Texcl * expf(-b.sdt) * t.adot) : 0.f;
+  return t;
+}
+
+extern "C" __global__ void __launch_bounds__(128) ren_composite_tan_fwd(const CompArgs a) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const RenPlan& p = a.p;
+  for (long long r = warp; r < a.n_rays; r += n_warps) {
+    float accC[3] = {0.f, 0.f, 0.f}, accO = 0.f, accD = 0.f, accCd[3] = {0.f, 0.f, 0.f}, accOd = 0.f;
+    int kept = 0;
+    float carry = 0.f;
+    walk_ray(a, r, lane, [&](int k, const SampleBlk& b) {
+      const TanBlk t = tan_block(a, r, k, lane, b, carry);
+      if (b.keep) {
+        for (int c = 0; c < p.C; ++c) {
+          accC[c] = fmaf(b.w, b.c[c], accC[c]);
+          accCd[c] = fmaf(t.wdot, b.c[c], fmaf(b.w, t.cdot[c], accCd[c]));
+        }
+        accO += b.w;
+        accOd += t.wdot;
+        accD = fmaf(b.w, __fmul_rn(__fadd_rn(b.t0, b.t1), 0.5f), accD);
+        kept += 1;
+      }
+    });
+    accO = warp_sum(accO);
+    accD = warp_sum(accD);
+    accOd = warp_sum(accOd);
+    for (int c = 0; c < p.C; ++c) { accC[c] = warp_sum(accC[c]); accCd[c] = warp_sum(accCd[c]); }
+    kept = __reduce_add_sync(0xffffffffu, kept);
+    if (lane == 0) {
+      for (int c = 0; c < p.C; ++c) {
+        float v = accC[c], vd = accCd[c];
+        if (a.bkgd) {
+          v = __fadd_rn(v, __fmul_rn(a.bkgd[c], __fsub_rn(1.f, accO)));
+          vd = fmaf(-a.bkgd[c], accOd, vd);
+        }
+        a.radiance[r * p.C + c] = v;
+        a.radiance_dot[r * p.C + c] = vd;
+      }
+      a.opacity[r] = accO;
+      a.opacity_dot[r] = accOd;
+      a.depth[r] = accD;
+      a.n_kept[r] = kept;
+    }
+  }
+}
+
+// Reverse of the tangent compositing.  Per kept sample, with
+//   Wv_i = sum_c gC_c (c_i - b_c) + gO + gD tm_i + sum_c gCd_c cdot_i,   Wt_i = sum_c gCd_c (c_i - b_c) + gOd:
+//   dL/dcdot_i = gCd w_i,   dL/dc_i = gC w_i + gCd wdot_i
+//   dL/dadot_i = Wt_i T_i beta_i - sum_{k>i} Wt_k w_k
+//   dL/da_i    = Wv_i T_i beta_i - Wt_i T_i beta_i (Edot_i + adot_i) - sum_{k>i} (Wv_k w_k + Wt_k wdot_k)
+// then through sigma = f(raw), sigmadot = f'(raw) rawdot and c = r(raw), cdot = r'(raw) rawdot.
+extern "C" __global__ void __launch_bounds__(128) ren_composite_tan_bwd(const CompArgs a) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const RenPlan& p = a.p;
+  const int C1 = 1 + p.C;
+  float gb_acc[3] = {0.f, 0.f, 0.f};
+  for (long long r = warp; r < a.n_rays; r += n_warps) {
+    float gC[3] = {0.f, 0.f, 0.f}, gCd[3] = {0.f, 0.f, 0.f}, bk[3] = {0.f, 0.f, 0.f};
+    for (int c = 0; c < p.C; ++c) {
+      gC[c] = a.g_radiance ? a.g_radiance[r * p.C + c] : 0.f;
+      gCd[c] = a.g_radiance_dot ? a.g_radiance_dot[r * p.C + c] : 0.f;
+      bk[c] = a.bkgd ? a.bkgd[c] : 0.f;
+    }
+    const float gO = a.g_opacity ? a.g_opacity[r] : 0.f;
+    const float gOd = a.g_opacity_dot ? a.g_opacity_dot[r] : 0.f;
+    const float gD = a.g_depth ? a.g_depth[r] : 0.f;
+    auto weights = [&](const SampleBlk& b, const TanBlk& t, float& Wv, float& Wt) {
+      Wv = gO + gD * __fmul_rn(__fadd_rn(b.t0, b.t1), 0.5f);
+      Wt = gOd;
+      for (int c = 0; c < p.C; ++c) {
+        Wv = fmaf(gC[c], b.c[c] - bk[c], fmaf(gCd[c], t.cdot[c], Wv));
+        Wt = fmaf(gCd[c], b.c[c] - bk[c], Wt);
+      }
+    };
+    // pass 1: totals
+    double totA = 0.0, totB = 0.0;     // sum (Wv w + Wt wdot), sum Wt w
+    float accO = 0.f, accOd = 0.f, carry = 0.f;
+    walk_ray(a, r, lane, [&](int k, const SampleBlk& b) {
+      const TanBlk t = tan_block(a, r, k, lane, b, carry);
+      if (b.keep) {
+        float Wv, Wt;
+        weights(b, t, Wv, Wt);
+        totA += (double)Wv * (double)b.w + (double)Wt * (double)t.wdot;
+        totB += (double)Wt * (double)b.w;
+        accO += b.w;
+        accOd += t.wdot;
+      }
+    });
+    totA = warp_sum_d(totA);
+    totB = warp_sum_d(totB);
+    accO = warp_sum(accO);
+    accOd = warp_sum(accOd);
+    if (a.g_bkgd && a.bkgd)
+      for (int c = 0; c < p.C; ++c) gb_acc[c] += gC[c] * (1.f - accO) - gCd[c] * accOd;
+    // pass 2
+    double prefA = 0.0, prefB = 0.0;
+    carry = 0.f;
+    walk_ray(a, r, lane, [&](int k, const SampleBlk& b) {
+      const TanBlk t = tan_block(a, r, k, lane, b, carry);
+      float Wv = 0.f, Wt = 0.f;
+      double ga = 0.0, gbv = 0.0;
+      if (b.keep) {
+        weights(b, t, Wv, Wt);
+        ga = (double)Wv * (double)b.w + (double)Wt * (double)t.wdot;
+        gbv = (double)Wt * (double)b.w;
+      }
+      double inclA = ga, inclB = gbv;
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        double ta = __shfl_up_sync(0xffffffffu, inclA, off);
+        double tb = __shfl_up_sync(0xffffffffu, inclB, off);
+        if (lane >= off) { inclA += ta; inclB += tb; }
+      }
+      const double sufA = totA - (prefA + inclA);
+      const double sufB = totB - (prefB + inclB);
+      prefA += __shfl_sync(0xffffffffu, inclA, 31);
+      prefB += __shfl_sync(0xffffffffu, inclB, 31);
+      if (k < a.K) {
+        float* gv = a.graw + ((r * a.K + k) * 2) * C1;
+        float* gt = gv + C1;
+        float gs = 0.f, gsd = 0.f;
+        if (b.keep) {
+          const float dt = __fsub_rn(b.t1, b.t0);
+          const float Tb = b.Texcl * expf(-b.sdt);
+          const float dadot = Wt * Tb - (float)sufB;
+          const float da = Wv * Tb - Wt * Tb * (t.Edot + t.adot) - (float)sufA;
+          const float sraw = a.raw[((r * a.K + k) * 2) * C1];
+          gsd = dadot * dt * b.dact_s;
+          gs = da * dt * b.dact_s + dadot * dt * ren_density_act2(p.f.density_activation, sraw) * t.sdot_raw;
+        }
+        gv[0] = gs;
+        gt[0] = gsd;
+        for (int c = 0; c < p.C; ++c) {
+          float gcv = 0.f, gcd = 0.f;
+          if (b.keep) {
+            const float craw = a.raw[((r * a.K + k) * 2) * C1 + 1 + c];
+            const float dc = gC[c] * b.w + gCd[c] * t.wdot;
+            const float dcd = gCd[c] * b.w;
+            gcd = dcd * b.dact_c[c];
+            gcv = dc * b.dact_c[c] + dcd * ren_radiance_act2(p.f.radiance_activation, craw) * t.cdot_raw[c];
+          }
+          gv[1 + c] = gcv;
+          gt[1 + c] = gcd;
+        }
+      }
+    });
+  }
+  if (a.g_bkgd && a.bkgd && lane == 0)
+    for (int c = 0; c < p.C; ++c)
+      if (gb_acc[c] != 0.f) atomicAdd(a.g_bkgd + c, gb_acc[c]);
+}
+
+int ren_launch_composite_tan(const RenPlan& p, long long n_rays, int K, const float* o, const float* d,
+                             const float* jitter, const float* raw, const float* bkgd, float* radiance,
+                             float* opacity, float* depth, float* radiance_dot, float* opacity_dot,
+                             int* n_kept, cudaStream_t st) {
+  if (n_rays <= 0) return REN_OK;
+  CompArgs a = {};
+  a.p = p; a.n_rays = n_rays; a.K = K; a.rays_o = o; a.rays_d = d; a.jitter = jitter; a.raw = raw;
+  a.bkgd = bkgd; a.radiance = radiance; a.opacity = opacity; a.depth = depth; a.n_kept = n_kept;
+  a.tangent = 1; a.radiance_dot = radiance_dot; a.opacity_dot = opacity_dot;
+  long long blocks = (n_rays + 3) / 4;
+  if (blocks > 148 * 64) blocks = 148 * 64;
+  ren_prof_begin(REN_K_COMPOSITE_FWD, st);
+  ren_composite_tan_fwd<<<(unsigned)blocks, 128, 0, st>>>(a);
+  ren_prof_end(REN_K_COMPOSITE_FWD, st);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { ren_set_error("composite tangent fwd launch: %s", cudaGetErrorString(e)); return REN_E_CUDA; }
+  return REN_OK;
+}
+
+int ren_launch_composite_tan_bwd(const RenPlan& p, long long n_rays, int K, const float* o, const float* d,
+                                 const float* jitter, const float* raw, const float* bkgd,
+                                 const float* g_radiance, const float* g_opacity, const float* g_depth,
+                                 const float* g_radiance_dot, const float* g_opacity_dot, float* graw,
+                                 float* g_bkgd, cudaStream_t st) {
+  if (n_rays <= 0) return REN_OK;
+  CompArgs a = {};
+  a.p = p; a.n_rays = n_rays; a.K = K; a.rays_o = o; a.rays_d = d; a.jitter = jitter; a.raw = raw;
+  a.bkgd = bkgd; a.g_radiance = g_radiance; a.g_opacity = g_opacity; a.g_depth = g_depth;
+  a.g_radiance_dot = g_radiance_dot; a.g_opacity_dot = g_opacity_dot;
+  a.graw = graw; a.g_bkgd = g_bkgd; a.tangent = 1;
+  long long blocks = (n_rays + 3) / 4;
+  if (blocks > 148 * 64) blocks = 148 * 64;
+  ren_prof_begin(REN_K_COMPOSITE_BWD, st);
+  ren_composite_tan_bwd<<<(unsigned)blocks, 128, 0, st>>>(a);
+  ren_prof_end(REN_K_COMPOSITE_BWD, st);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { ren_set_error("composite tangent bwd launch: %s", cudaGetErrorString(e)); return REN_E_CUDA; }
+  return REN_OK;
 }
 
 int ren_launch_composite(const RenPlan& p, long long n_rays, int K, const float* o, const float* d,

@@ -10,6 +10,7 @@
 //                            utils/modules.py:77-102)
 //   ren_adam_kernel         torch.optim.Adam step on a flat buffer
 #include "ren_common.cuh"
+#include "ren_dual.cuh"
 
 // torch.lerp: |w| < 0.5 ? a + w (b-a) : b - (b-a)(1-w), both as single FMAs
 __device__ __forceinline__ double lerp_d(double a, double b, double w) {
@@ -37,10 +38,75 @@ __device__ __forceinline__ float norm3(const float* v) {
   return __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(v[0], v[0]), __fmul_rn(v[1], v[1])), __fmul_rn(v[2], v[2])));
 }
 
+// First and second derivative of the ray (o, d) of a pixel wrt the pose-interpolation weight w
+// (models/trajectories.py:63-91 -> utils/tensor_ops.py:157-179 -> roma rotvec_to_unitquat /
+// unitquat_to_rotmat -> models/nerf.py:206-228), by second-order jets through the same operation
+// sequence the reference differentiates with autograd.  The relative rotation vector does not
+// depend on w.  o = lerp(P_l, P_r, w): d o / d w = P_r - P_l, second derivative 0.
+__device__ __forceinline__ void quat_mul_j(const J2* p, const J2* q, J2* out) {
+  out[0] = p[3] * q[0] + q[3] * p[0] + (p[1] * q[2] - p[2] * q[1]);
+  out[1] = p[3] * q[1] + q[3] * p[1] + (p[2] * q[0] - p[0] * q[2]);
+  out[2] = p[3] * q[2] + q[3] * p[2] + (p[0] * q[1] - p[1] * q[0]);
+  out[3] = p[3] * q[3] - (p[0] * q[0] + p[1] * q[1] + p[2] * q[2]);
+}
+__device__ __forceinline__ void ray_dir_jet(float w, const float* q0, const float* q1in, const float* vpix,
+                                            float* d_dot, float* d_ddot) {
+  float q1[4];
+  float dot = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(q0[0], q1in[0]), __fmul_rn(q0[1], q1in[1])),
+                                  __fmul_rn(q0[2], q1in[2])), __fmul_rn(q0[3], q1in[3]));
+  for (int c = 0; c < 4; ++c) q1[c] = dot < 0.f ? -q1in[c] : q1in[c];
+  const float conj[4] = {-q0[0], -q0[1], -q0[2], q0[3]};
+  float rel[4];
+  rel[0] = conj[3] * q1[0] + q1[3] * conj[0] + (conj[1] * q1[2] - conj[2] * q1[1]);
+  rel[1] = conj[3] * q1[1] + q1[3] * conj[1] + (conj[2] * q1[0] - conj[0] * q1[2]);
+  rel[2] = conj[3] * q1[2] + q1[3] * conj[2] + (conj[0] * q1[1] - conj[1] * q1[0]);
+  rel[3] = conj[3] * q1[3] - (conj[0] * q1[0] + conj[1] * q1[1] + conj[2] * q1[2]);
+  const float ang = 2.f * atan2f(sqrtf(rel[0] * rel[0] + rel[1] * rel[1] + rel[2] * rel[2]), rel[3]);
+  float scale;
+  if (fabsf(ang) <= 1e-3f) {
+    const float a2 = ang * ang;
+    scale = 2.f + a2 / 12.f + 7.f * a2 * a2 / 2880.f;
+  } else {
+    scale = ang / sinf(0.5f * ang);
+  }
+  const J2 wj(w, 1.f, 0.f);
+  J2 rv[3];
+  for (int c = 0; c < 3; ++c) rv[c] = wj * J2(scale * rel[c]);
+  const J2 n = j2_sqrt(rv[0] * rv[0] + rv[1] * rv[1] + rv[2] * rv[2]);
+  J2 s;
+  if (n.v <= 1e-3f) {
+    const J2 n2 = n * n;
+    s = J2(0.5f) - n2 * J2(1.f / 48.f) + n2 * n2 * J2(1.f / 3840.f);
+  } else {
+    s = j2_sin(n * J2(0.5f)) / n;
+  }
+  const J2 rot[4] = {s * rv[0], s * rv[1], s * rv[2], j2_cos(n * J2(0.5f))};
+  const J2 q0j[4] = {J2(q0[0]), J2(q0[1]), J2(q0[2]), J2(q0[3])};
+  J2 q[4];
+  quat_mul_j(q0j, rot, q);
+  const J2 x = q[0], y = q[1], z = q[2], ww = q[3];
+  const J2 x2 = x * x, y2 = y * y, z2 = z * z, w2 = ww * ww;
+  const J2 xy = x * y, zw = z * ww, xz = x * z, yw = y * ww, yz = y * z, xw = x * ww;
+  const J2 two(2.f);
+  const J2 R[9] = {x2 - y2 - z2 + w2, two * (xy - zw), two * (xz + yw),
+                   two * (xy + zw), y2 - x2 - z2 + w2, two * (yz - xw),
+                   two * (xz - yw), two * (yz + xw), z2 - x2 - y2 + w2};
+  J2 dv[3];
+  for (int r = 0; r < 3; ++r) dv[r] = R[r * 3] * J2(vpix[0]) + R[r * 3 + 1] * J2(vpix[1]) + R[r * 3 + 2] * J2(vpix[2]);
+  const J2 nrm = j2_sqrt(dv[0] * dv[0] + dv[1] * dv[1] + dv[2] * dv[2]);
+  for (int c = 0; c < 3; ++c) {
+    const J2 d = dv[c] / nrm;
+    d_dot[c] = d.d;
+    d_ddot[c] = d.dd;
+  }
+}
+
+struct PoseBin { long long left, right; double width; float w; };
+
 // LinearTrajectory.forward for one timestamp -> position p[3], rotation R[9] (row-major)
 __device__ __forceinline__ void pose_at(double ts, long long n_poses, const long long* __restrict__ T,
                                         const float* __restrict__ P, const float* __restrict__ Q,
-                                        float* p, float* R) {
+                                        float* p, float* R, PoseBin* bin = nullptr) {
   // searchsorted (left): first i with T[i] >= ts
   long long lo = 0, hi = n_poses;
   while (lo < hi) {
@@ -54,6 +120,7 @@ __device__ __forceinline__ void pose_at(double ts, long long n_poses, const long
   long long wl = left < n_poses - 1 ? left : n_poses - 2;
   const double width = (double)(T[wl + 1] - T[wl]);
   const float w = (float)((ts - (double)T[left]) / width);
+  if (bin) { bin->left = left; bin->right = right; bin->width = width; bin->w = w; }
 #pragma unroll
   for (int c = 0; c < 3; ++c) p[c] = lerp_f(P[left * 3 + c], P[right * 3 + c], w);
   // slerp (utils/tensor_ops.py:114-180, shortest path)
@@ -132,6 +199,10 @@ struct EventRaysArgs {
   float* out_rot;
   double* out_ts_diff;
   double* out_start;
+  float* out_o_dot;     // (n_renders,B,3) d o / d w          (all four NULL or all set)
+  float* out_d_dot;     // (n_renders,B,3) d d / d w
+  float* out_d_ddot;    // (n_renders,B,3) d^2 d / d w^2
+  double* out_dw_dt;    // (n_renders,B)   d w / d t = 1 / bin width (ns^-1)
 };
 
 extern "C" __global__ void ren_event_rays_kernel(const EventRaysArgs a) {
@@ -159,7 +230,8 @@ extern "C" __global__ void ren_event_rays_kernel(const EventRaysArgs a) {
     v[r] = fmaf(a.k_inv[r * 3 + 2], 1.f, fmaf(a.k_inv[r * 3 + 1], py, __fmul_rn(a.k_inv[r * 3], px)));
   for (int j = 0; j < nr; ++j) {
     float p[3], R[9];
-    pose_at(ts[j], a.n_poses, a.pose_ts, a.pose_pos, a.pose_quat, p, R);
+    PoseBin bin;
+    pose_at(ts[j], a.n_poses, a.pose_ts, a.pose_pos, a.pose_quat, p, R, &bin);
     float dv[3];
 #pragma unroll
     for (int r = 0; r < 3; ++r)
@@ -174,6 +246,17 @@ extern "C" __global__ void ren_event_rays_kernel(const EventRaysArgs a) {
     }
     if (a.out_rot)
       for (int c = 0; c < 9; ++c) a.out_rot[o * 9 + c] = R[c];
+    if (a.out_o_dot) {
+      float dd[3], ddd[3];
+      ray_dir_jet(bin.w, a.pose_quat + bin.left * 4, a.pose_quat + bin.right * 4, v, dd, ddd);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        a.out_o_dot[o * 3 + c] = a.pose_pos[bin.right * 3 + c] - a.pose_pos[bin.left * 3 + c];
+        a.out_d_dot[o * 3 + c] = dd[c];
+        a.out_d_ddot[o * 3 + c] = ddd[c];
+      }
+      a.out_dw_dt[o] = 1.0 / bin.width;
+    }
   }
 }
 
@@ -183,7 +266,8 @@ extern "C" int ren_event_rays(int64_t B, const float* position, const int64_t* s
                               const double* tau, int64_t n_poses, const int64_t* pose_ts,
                               const float* pose_pos, const float* pose_quat, const float* k_inv,
                               int32_t n_renders, double* out_ts, float* out_o, float* out_d,
-                              float* out_rot, double* out_ts_diff, double* out_start, void* stream) {
+                              float* out_rot, double* out_ts_diff, double* out_start, float* out_o_dot,
+                              float* out_d_dot, float* out_d_ddot, double* out_dw_dt, void* stream) {
   if (B < 0 || n_poses < 2 || (n_renders != 2 && n_renders != 3)) {
     ren_set_error("ren_event_rays: bad sizes (B=%lld, n_poses=%lld, n_renders=%d)", (long long)B,
                   (long long)n_poses, n_renders);
@@ -193,8 +277,14 @@ extern "C" int ren_event_rays(int64_t B, const float* position, const int64_t* s
     ren_set_error("ren_event_rays: n_renders=3 needs nz_grad_ts");
     return REN_E_INVALID;
   }
+  const int n_jet = (out_o_dot != nullptr) + (out_d_dot != nullptr) + (out_d_ddot != nullptr) + (out_dw_dt != nullptr);
+  if (n_jet != 0 && n_jet != 4) {
+    ren_set_error("ren_event_rays: the four ray-derivative outputs must be all NULL or all set");
+    return REN_E_INVALID;
+  }
   if (B == 0) return REN_OK;
   EventRaysArgs a;
+  a.out_o_dot = out_o_dot; a.out_d_dot = out_d_dot; a.out_d_ddot = out_d_ddot; a.out_dw_dt = out_dw_dt;
   a.B = B; a.position = position; a.start_ts = (const long long*)start_ts;
   a.end_ts = (const long long*)end_ts; a.nz_ts_diff = nz_ts_diff; a.nz_diff_start = nz_diff_start;
   a.nz_grad_ts = nz_grad_ts; a.tau = tau; a.n_poses = n_poses; a.pose_ts = (const long long*)pose_ts;

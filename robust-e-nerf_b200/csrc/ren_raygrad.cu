@@ -1,0 +1,208 @@
+// ren_raygrad.cu -- gradient of the loss with respect to the rays.
+//
+// Needed only when the supervision timestamps are trainable (refractory period,
+// models/event_generation_params.py:170-203): the reference's autograd continues from the MLP
+// input through SinusoidalEncoder (external/mlp.py:227-243), contract_input_space
+// (external/mlp.py:321-335), the sample position o + d (t0+t1)/2 (external/utils.py:87) and the
+// direction scaling d*pi (external/mlp.py:353-355) to (o, d), then through LinearTrajectory to t.
+//
+// Input: the pre-activation gradients Delta of every layer that consumes an encoding (fp32 blocked
+// delta workspace of the SIMT engine).  Per row: dEnc = Delta W[:, encoding columns]; value mode
+// reduces it to d loss / d (o, d); tangent mode (rows = (value, d/dw) pairs) also needs the second
+// derivative of the contraction, taken with hyper-dual numbers, and returns
+// d loss / d (o, d, o_dot, d_dot).
+#include "ren_common.cuh"
+#include "ren_dual.cuh"
+
+#define RG_ROWS 4
+#define RG_THREADS (64 * RG_ROWS)
+#define RG_MAX_SRC 8
+
+struct RgSource {
+  const float* D;   // Delta matrix (blocked [rows x N]) or graw (row-major [rows][ldd])
+  int N;            // rows of W feeding (== width of D)
+  int ldd;          // blocked: N; row-major: 1 + C
+  int rowmajor;
+  const float* W;   // params + w_off + column offset of the encoding segment
+  int ldw;
+  int enc;          // 1 positional, 2 direction
+};
+struct RgArgs {
+  RenPlan p;
+  RgSource src[RG_MAX_SRC];
+  int n_src;
+  long long n_rays;
+  int K;
+  int tangent;
+  const float* rays_o;
+  const float* rays_d;
+  const float* rays_o_dot;
+  const float* rays_d_dot;
+  const float* jitter;
+  float* g_rays;    // [n_rays][6] (value) or [n_rays][12] (tangent)
+};
+
+// d loss / d x and d loss / d xdot of one encoder from d loss / d enc (gv) and d loss / d enc_dot (gt)
+__device__ __forceinline__ void enc_backward(const float* x, const float* xdot, int deg, const float* gv,
+                                             const float* gt, bool tangent, float* gx, float* gxd) {
+  for (int a = 0; a < 3; ++a) {
+    gx[a] = gv[a];
+    gxd[a] = tangent ? gt[a] : 0.f;
+  }
+  float sc = 1.f;
+  for (int i = 0; i < deg; ++i) {
+    for (int a = 0; a < 3; ++a) {
+      const float xb = __fmul_rn(x[a], sc);
+      const float xs = __fadd_rn(xb, 1.5707963267948966f);
+      const int js = 3 + i * 3 + a, jc = 3 + deg * 3 + i * 3 + a;
+      const float c0 = cosf(xb) * sc, c1 = cosf(xs) * sc;
+      gx[a] = fmaf(gv[js], c0, fmaf(gv[jc], c1, gx[a]));
+      if (tangent) {
+        const float s0 = sinf(xb) * sc * sc, s1 = sinf(xs) * sc * sc;
+        gx[a] -= (gt[js] * s0 + gt[jc] * s1) * xdot[a];
+        gxd[a] = fmaf(gt[js], c0, fmaf(gt[jc], c1, gxd[a]));
+      }
+    }
+    sc *= 2.f;
+  }
+}
+
+extern "C" __global__ void __launch_bounds__(RG_THREADS) ren_raygrad_kernel(const RgArgs a) {
+  __shared__ float gP[RG_ROWS][REN_PE_MAX];
+  __shared__ float gD[RG_ROWS][REN_DE_MAX];
+  const RenPlan& p = a.p;
+  const long long S = a.n_rays * a.K * (a.tangent ? 2 : 1);     // rows
+  const int j = threadIdx.x & 63, lr = threadIdx.x >> 6;
+  for (long long row0 = (long long)blockIdx.x * RG_ROWS; row0 < S; row0 += (long long)gridDim.x * RG_ROWS) {
+    const long long row = row0 + lr;
+    float accP = 0.f, accD = 0.f;
+    if (row < S) {
+      for (int si = 0; si < a.n_src; ++si) {
+        const RgSource& sc = a.src[si];
+        const int width = sc.enc == 1 ? p.PE : p.DE;
+        if (j >= width) continue;
+        float acc = 0.f;
+        for (int n = 0; n < sc.N; ++n) {
+          const float dv = sc.rowmajor ? sc.D[row * sc.ldd + n] : sc.D[ren_blk(row, n, sc.ldd)];
+          acc = fmaf(dv, __ldg(sc.W + (long long)n * sc.ldw + j), acc);
+        }
+        if (sc.enc == 1) accP += acc; else accD += acc;
+      }
+    }
+    gP[lr][j] = accP;
+    if (j < REN_DE_MAX) gD[lr][j] = accD;
+    __syncthreads();
+    const int per = a.tangent ? 2 : 1;
+    if (threadIdx.x < RG_ROWS / per) {
+      const long long r0 = row0 + threadIdx.x * per;
+      if (r0 < S) {
+        const long long smp = r0 / per;
+        const long long r = smp / a.K;
+        const int k = (int)(smp - r * a.K);
+        float o[3], d[3], od[3] = {0.f, 0.f, 0.f}, dd[3] = {0.f, 0.f, 0.f};
+        for (int c = 0; c < 3; ++c) {
+          o[c] = a.rays_o[r * 3 + c];
+          d[c] = a.rays_d[r * 3 + c];
+          if (a.tangent) { od[c] = a.rays_o_dot[r * 3 + c]; dd[c] = a.rays_d_dot[r * 3 + c]; }
+        }
+        float t_min, t_max, t0, t1, z[3];
+        ren_ray_range(p.f, p.r, o, d, a.jitter ? a.jitter[r] : 0.f, &t_min, &t_max);
+        ren_march_to(p.r, t_min, k, &t0, &t1);
+        ren_field_input(p.f, o, d, t0, t1, z);
+        const float tm = __fmul_rn(__fadd_rn(t0, t1), 0.5f);
+        float pos[3], xdot[3];
+        for (int c = 0; c < 3; ++c) {
+          pos[c] = __fadd_rn(o[c], __fmul_rn(__fmul_rn(d[c], __fadd_rn(t0, t1)), 0.5f));
+          xdot[c] = fmaf(dd[c], tm, od[c]);
+        }
+        const float* gvP = gP[threadIdx.x * per];
+        const float* gtP = gP[threadIdx.x * per + (per - 1)];
+        const float* gvD = gD[threadIdx.x * per];
+        const float* gtD = gD[threadIdx.x * per + (per - 1)];
+        float gz[3], gzd[3], gdz[3], gdzd[3];
+        float zdot[3] = {0.f, 0.f, 0.f};
+        if (a.tangent) {
+          Dual pd[3], zd[3];
+          for (int c = 0; c < 3; ++c) pd[c] = Dual(pos[c], xdot[c]);
+          ren_contract_t<Dual>(p.f, pd, zd);
+          for (int c = 0; c < 3; ++c) zdot[c] = zd[c].d;
+        }
+        enc_backward(z, zdot, p.f.pos_deg, gvP, gtP, a.tangent != 0, gz, gzd);
+        const float dz[3] = {__fmul_rn(d[0], 3.141592653589793f), __fmul_rn(d[1], 3.141592653589793f),
+                             __fmul_rn(d[2], 3.141592653589793f)};
+        const float dzd[3] = {dd[0] * 3.141592653589793f, dd[1] * 3.141592653589793f, dd[2] * 3.141592653589793f};
+        enc_backward(dz, dzd, p.f.dir_deg, gvD, gtD, a.tangent != 0, gdz, gdzd);
+        // through the contraction: gx_k = gz . J e_k + gzd . H[e_k, xdot];  gxd_k = gzd . J e_k
+        float gx[3], gxd[3];
+        for (int kk = 0; kk < 3; ++kk) {
+          HDual ph[3], zh[3];
+          for (int c = 0; c < 3; ++c) ph[c] = HDual(pos[c], c == kk ? 1.f : 0.f, xdot[c], 0.f);
+          ren_contract_t<HDual>(p.f, ph, zh);
+          float sx = 0.f, sxd = 0.f;
+          for (int c = 0; c < 3; ++c) {
+            sx = fmaf(gz[c], zh[c].d1, fmaf(gzd[c], zh[c].d12, sx));
+            sxd = fmaf(gzd[c], zh[c].d1, sxd);
+          }
+          gx[kk] = sx;
+          gxd[kk] = sxd;
+        }
+        const int stride = a.tangent ? 12 : 6;
+        float* g = a.g_rays + r * stride;
+        for (int c = 0; c < 3; ++c) {
+          atomicAdd(g + c, gx[c]);
+          atomicAdd(g + 3 + c, fmaf(tm, gx[c], 3.141592653589793f * gdz[c]));
+          if (a.tangent) {
+            atomicAdd(g + 6 + c, gxd[c]);
+            atomicAdd(g + 9 + c, fmaf(tm, gxd[c], 3.141592653589793f * gdzd[c]));
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// delta: fp32 blocked delta workspace (mats mirror of the stash) followed by graw [rows][1+C]
+int ren_launch_raygrad(const RenPlan& p, long long n_rays, int K, const float* o, const float* d,
+                       const float* o_dot, const float* d_dot, const float* jitter, const float* params,
+                       const float* delta, float* g_rays, cudaStream_t st) {
+  if (n_rays <= 0) return REN_OK;
+  RgArgs a;
+  a.p = p; a.n_rays = n_rays; a.K = K; a.tangent = o_dot != nullptr ? 1 : 0;
+  a.rays_o = o; a.rays_d = d; a.rays_o_dot = o_dot; a.rays_d_dot = d_dot; a.jitter = jitter; a.g_rays = g_rays;
+  const long long S = n_rays * K * (a.tangent ? 2 : 1);
+  const float* graw = delta + p.act_floats * ren_pad128(S);
+  int n = 0;
+  auto add = [&](const float* D, int N, int ldd, int rowmajor, const float* W, int ldw, int enc) {
+    if (n < RG_MAX_SRC) {
+      RgSource& s = a.src[n];
+      s.D = D; s.N = N; s.ldd = ldd; s.rowmajor = rowmajor; s.W = W; s.ldw = ldw; s.enc = enc;
+    }
+    ++n;
+  };
+  auto add_layer = [&](const RenLayer& L) {
+    const float* D = delta + ren_stash_mat(p, S, L.mat);
+    const int ldw = L.K0 + L.K1;
+    if (L.src0 == 1) add(D, L.N, L.N, 0, params + L.w_off, ldw, 1);
+    if (L.K1 > 0) add(D, L.N, L.N, 0, params + L.w_off + L.K0, ldw, L.src1 == 1 ? 1 : 2);
+  };
+  for (int i = 0; i < p.D; ++i) add_layer(p.trunk[i]);
+  add_layer(p.bott);
+  for (int jj = 0; jj < p.CD; ++jj) add_layer(p.cond[jj]);
+  const int C1 = 1 + p.C;
+  if (p.D == 0) add(graw, 1, C1, 1, params + p.sig_w, p.hid_K0 + p.hid_K1, 1);
+  else if (p.hid_K1 > 0) add(graw, 1, C1, 1, params + p.sig_w + p.hid_K0, p.hid_K0 + p.hid_K1, 1);
+  if (p.CD == 0) add(graw + 1, p.C, C1, 1, params + p.rgb_w + p.W, p.W + p.DE, 2);
+  if (n > RG_MAX_SRC) { ren_set_error("ray gradient: too many encoding consumers (%d)", n); return REN_E_UNSUPPORTED; }
+  a.n_src = n;
+  cudaError_t e = cudaMemsetAsync(g_rays, 0, sizeof(float) * (size_t)n_rays * (a.tangent ? 12 : 6), st);
+  if (e != cudaSuccess) { ren_set_error("ray gradient memset: %s", cudaGetErrorString(e)); return REN_E_CUDA; }
+  long long blocks = (S + RG_ROWS - 1) / RG_ROWS;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  ren_prof_begin(REN_K_FIELD_DGRAD, st);
+  ren_raygrad_kernel<<<(unsigned)blocks, RG_THREADS, 0, st>>>(a);
+  ren_prof_end(REN_K_FIELD_DGRAD, st);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) { ren_set_error("ray gradient launch: %s", cudaGetErrorString(e)); return REN_E_CUDA; }
+  return REN_OK;
+}

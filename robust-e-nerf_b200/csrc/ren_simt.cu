@@ -8,9 +8,15 @@
 //                        (external/utils.py:83-96, external/mlp.py:99-113,193-205,350-358)
 //   ren_simt_field_dgrad reverse pass through the same layers (activation stash in HBM)
 //   ren_simt_wgrad       dW = Delta^T H split over samples, db = colsum(Delta)
+//
+// Tangent mode (TAN): the tile holds 32 samples x {value row, d/dw row} (row = 2*sample + kind), so the
+// same GEMMs push the activations AND their derivative along the ray's pose-interpolation weight
+// through the network (the reference gets d logI / d t by autograd with create_graph=True,
+// models/robust_e_nerf.py:394-398); stash / delta matrices simply have 2S rows.
 #include "ren_common.cuh"
+#include "ren_dual.cuh"
 
-#define TM 64          // samples per tile
+#define TM 64          // rows per tile
 #define KC 16          // K chunk
 #define NTHREADS 256
 
@@ -23,7 +29,9 @@ struct FwdArgs {
   const float* jitter;
   const float* params;
   float* stash;     // full stash (training) or NULL
-  float* raw;       // [S][1+C] (inside stash when training, else workspace)
+  float* raw;       // [S][1+C] (inside stash when training, else workspace); tangent: [2S][1+C]
+  const float* rays_o_dot;   // tangent mode: d o / d w, d d / d w per ray
+  const float* rays_d_dot;
 };
 
 struct DgradArgs {
@@ -31,7 +39,7 @@ struct DgradArgs {
   long long S;
   const float* params;
   const float* stash;
-  const float* graw;  // [S][1+C]
+  const float* graw;  // [S][1+C]   (S = rows: 2 per sample in tangent mode)
   float* delta;       // mats mirror of stash: Delta (pre-activation grads)
 };
 
@@ -138,6 +146,8 @@ static inline size_t simt_smem_bytes(int WS) {
 }
 
 // One dense layer on the resident tile: Out = act(W [In0 | In1] + b); optional HBM stash.
+// TAN: odd rows carry the tangent: out = act'(pre of the even row) * (W in), no bias.
+template <bool TAN>
 __device__ __forceinline__ void fwd_layer(const RenPlan& p, const RenLayer& L, const float* params,
                                           const Smem& s, const float* in_main, float* out, int WS,
                                           float* stash_mat, long long s0, long long S) {
@@ -163,15 +173,28 @@ __device__ __forceinline__ void fwd_layer(const RenPlan& p, const RenLayer& L, c
       if (n < L.N) {  // N is a multiple of 4
         const float* bp = params + L.b_off + n;   // flat-buffer offsets are not 16 B aligned
         const float4 b = make_float4(__ldg(bp), __ldg(bp + 1), __ldg(bp + 2), __ldg(bp + 3));
+        float4 dact = make_float4(1.f, 1.f, 1.f, 1.f);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          float4 v = make_float4(acc[i][h * 4 + 0] + b.x, acc[i][h * 4 + 1] + b.y,
-                                 acc[i][h * 4 + 2] + b.z, acc[i][h * 4 + 3] + b.w);
-          if (L.act) {
-            v.x = ren_hidden_act(p.f.hidden_activation, v.x);
-            v.y = ren_hidden_act(p.f.hidden_activation, v.y);
-            v.z = ren_hidden_act(p.f.hidden_activation, v.z);
-            v.w = ren_hidden_act(p.f.hidden_activation, v.w);
+          float4 v;
+          if (TAN && (i & 1)) {
+            v = make_float4(acc[i][h * 4 + 0] * dact.x, acc[i][h * 4 + 1] * dact.y,
+                            acc[i][h * 4 + 2] * dact.z, acc[i][h * 4 + 3] * dact.w);
+          } else {
+            v = make_float4(acc[i][h * 4 + 0] + b.x, acc[i][h * 4 + 1] + b.y,
+                            acc[i][h * 4 + 2] + b.z, acc[i][h * 4 + 3] + b.w);
+            if (L.act) {
+              if (TAN) {
+                dact.x = ren_hidden_grad_from_pre(p.f.hidden_activation, v.x);
+                dact.y = ren_hidden_grad_from_pre(p.f.hidden_activation, v.y);
+                dact.z = ren_hidden_grad_from_pre(p.f.hidden_activation, v.z);
+                dact.w = ren_hidden_grad_from_pre(p.f.hidden_activation, v.w);
+              }
+              v.x = ren_hidden_act(p.f.hidden_activation, v.x);
+              v.y = ren_hidden_act(p.f.hidden_activation, v.y);
+              v.z = ren_hidden_act(p.f.hidden_activation, v.z);
+              v.w = ren_hidden_act(p.f.hidden_activation, v.w);
+            }
           }
           const int m = ty * 8 + i;
           *reinterpret_cast<float4*>(out + m * WS + n) = v;
@@ -207,26 +230,29 @@ __device__ __forceinline__ float row_dot(const float* in0, int st0, int K0, cons
   return acc;
 }
 
-extern "C" __global__ void __launch_bounds__(NTHREADS, 1) ren_simt_field_fwd(const FwdArgs a) {
+template <bool TAN>
+__global__ void __launch_bounds__(NTHREADS, 1) ren_simt_field_fwd(const FwdArgs a) {
   extern __shared__ __align__(16) float smem_f[];
   const RenPlan& p = a.p;
   const int WS = max(p.W, p.WC);
   Smem s = carve(smem_f, WS);
-  const long long S = a.n_rays * a.K;
+  const long long S = a.n_rays * a.K * (TAN ? 2 : 1);     // rows
   const long long n_tiles = (S + TM - 1) / TM;
   const int tid = threadIdx.x;
   float* sel = s.misc;  // [TM]
   for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const long long s0 = tile * TM;
-    // ---- prologue: one thread per sample row
+    // ---- prologue: one thread per row
     if (tid < TM) {
-      const long long sidx = s0 + tid;
+      const long long sidx = s0 + tid;     // row
       float* eP = s.encP + tid * REN_PE_MAX;
       float* eD = s.encD + tid * REN_DE_MAX;
       bool selector = false;
       if (sidx < S) {
-        const long long r = sidx / a.K;
-        const int k = (int)(sidx - r * a.K);
+        const long long smp = TAN ? (sidx >> 1) : sidx;
+        const bool tan_row = TAN && (sidx & 1);
+        const long long r = smp / a.K;
+        const int k = (int)(smp - r * a.K);
         float o[3], d[3];
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
@@ -238,10 +264,29 @@ extern "C" __global__ void __launch_bounds__(NTHREADS, 1) ren_simt_field_fwd(con
         ren_march_to(p.r, t_min, k, &t0, &t1);
         selector = ren_field_input(p.f, o, d, t0, t1, z);
         if (!ren_alive(t0, t1, t_max)) selector = false;  // dead tail sample: masked anyway
-        ren_encode(z, p.f.pos_deg, REN_PE_MAX, [&](int j, float v) { eP[j] = v; });
         float dz[3] = {__fmul_rn(d[0], 3.141592653589793f), __fmul_rn(d[1], 3.141592653589793f),
                        __fmul_rn(d[2], 3.141592653589793f)};
-        ren_encode(dz, p.f.dir_deg, REN_DE_MAX, [&](int j, float v) { eD[j] = v; });
+        if (!tan_row) {
+          ren_encode(z, p.f.pos_deg, REN_PE_MAX, [&](int j, float v) { eP[j] = v; });
+          ren_encode(dz, p.f.dir_deg, REN_DE_MAX, [&](int j, float v) { eD[j] = v; });
+        } else {
+          // x = o + d tm, xdot = odot + ddot tm (t0, t1 carry no gradient: nerfacc marches under
+          // no_grad); zdot = J_contract(x) xdot by dual numbers
+          const float tm = __fmul_rn(__fadd_rn(t0, t1), 0.5f);
+          Dual pd[3], zd[3];
+          float zdot[3], ddz[3];
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const float od = a.rays_o_dot[r * 3 + c], dd = a.rays_d_dot[r * 3 + c];
+            pd[c] = Dual(__fadd_rn(o[c], __fmul_rn(__fmul_rn(d[c], __fadd_rn(t0, t1)), 0.5f)), fmaf(dd, tm, od));
+            ddz[c] = dd * 3.141592653589793f;
+          }
+          ren_contract_t<Dual>(p.f, pd, zd);
+#pragma unroll
+          for (int c = 0; c < 3; ++c) zdot[c] = zd[c].d;
+          ren_encode_tangent(z, zdot, p.f.pos_deg, REN_PE_MAX, [&](int j, float v) { eP[j] = v; });
+          ren_encode_tangent(dz, ddz, p.f.dir_deg, REN_DE_MAX, [&](int j, float v) { eD[j] = v; });
+        }
         if (a.stash) {
           float* gP = a.stash + ren_stash_encp(p, S);
           float* gD = a.stash + ren_stash_encd(p, S);
@@ -260,8 +305,8 @@ extern "C" __global__ void __launch_bounds__(NTHREADS, 1) ren_simt_field_fwd(con
     float* nxt = s.bufB;
     for (int i = 0; i < p.D; ++i) {
       const RenLayer& L = p.trunk[i];
-      fwd_layer(p, L, a.params, s, cur, nxt, WS,
-                a.stash ? a.stash + ren_stash_mat(p, S, L.mat) : nullptr, s0, S);
+      fwd_layer<TAN>(p, L, a.params, s, cur, nxt, WS,
+                     a.stash ? a.stash + ren_stash_mat(p, S, L.mat) : nullptr, s0, S);
       float* t = cur; cur = nxt; nxt = t;
     }
     // ---- sigma head (per-row dot product on the hidden features)
@@ -271,18 +316,22 @@ extern "C" __global__ void __launch_bounds__(NTHREADS, 1) ren_simt_field_fwd(con
                         REN_PE_MAX, p.hid_K1, w);
       const int m = tid >> 2;
       if ((tid & 3) == 0 && s0 + m < S) {
-        v += a.params[p.sig_b];
-        a.raw[(s0 + m) * (1 + p.C)] = sel[m] != 0.f ? v : -INFINITY;
+        if (TAN && (m & 1)) {
+          a.raw[(s0 + m) * (1 + p.C)] = v;                 // d sigma_raw / d w (no bias)
+        } else {
+          v += a.params[p.sig_b];
+          a.raw[(s0 + m) * (1 + p.C)] = sel[m] != 0.f ? v : -INFINITY;
+        }
       }
     }
     // ---- bottleneck (linear) + view-conditioned hidden layers
-    fwd_layer(p, p.bott, a.params, s, cur, nxt, WS,
-              a.stash ? a.stash + ren_stash_mat(p, S, p.bott.mat) : nullptr, s0, S);
+    fwd_layer<TAN>(p, p.bott, a.params, s, cur, nxt, WS,
+                   a.stash ? a.stash + ren_stash_mat(p, S, p.bott.mat) : nullptr, s0, S);
     { float* t = cur; cur = nxt; nxt = t; }
     for (int j = 0; j < p.CD; ++j) {
       const RenLayer& L = p.cond[j];
-      fwd_layer(p, L, a.params, s, cur, nxt, WS,
-                a.stash ? a.stash + ren_stash_mat(p, S, L.mat) : nullptr, s0, S);
+      fwd_layer<TAN>(p, L, a.params, s, cur, nxt, WS,
+                     a.stash ? a.stash + ren_stash_mat(p, S, L.mat) : nullptr, s0, S);
       float* t = cur; cur = nxt; nxt = t;
     }
     // ---- radiance head
@@ -291,7 +340,8 @@ extern "C" __global__ void __launch_bounds__(NTHREADS, 1) ren_simt_field_fwd(con
       const float* w = a.params + p.rgb_w + c * (p.CD > 0 ? Kin : Kin + p.DE);
       float v = row_dot(cur, WS, Kin, s.encD, REN_DE_MAX, p.CD > 0 ? 0 : p.DE, w);
       const int m = tid >> 2;
-      if ((tid & 3) == 0 && s0 + m < S) a.raw[(s0 + m) * (1 + p.C) + 1 + c] = v + a.params[p.rgb_b + c];
+      if ((tid & 3) == 0 && s0 + m < S)
+        a.raw[(s0 + m) * (1 + p.C) + 1 + c] = (TAN && (m & 1)) ? v : v + a.params[p.rgb_b + c];
     }
     __syncthreads();
   }
@@ -300,6 +350,9 @@ extern "C" __global__ void __launch_bounds__(NTHREADS, 1) ren_simt_field_fwd(con
 // ------------------------------------------------------------------ dgrad
 // One reverse GEMM: dIn[m][k] = sum_n Dout[m][n] W[n][k] for k < Kout (first input segment),
 // optionally += gs[m] * wsig[k]; then *= act'(a_prev[m][k]) (a_prev from the stash) -> out + HBM.
+// TAN: rows come in (value, tangent) pairs with adjoints (abar, abar_dot); through y = act(x),
+// ydot = act'(x) xdot:  d/dx = abar act'(x) + abar_dot act''(x) xdot,  d/dxdot = abar_dot act'(x).
+template <bool TAN>
 __device__ __forceinline__ void bwd_layer(const RenPlan& p, const RenLayer& L, const float* params,
                                           const Smem& s, const float* dout, float* din, int WS,
                                           const float* gs, const float* wsig,
@@ -319,8 +372,9 @@ __device__ __forceinline__ void bwd_layer(const RenPlan& p, const RenLayer& L, c
       if (k < Kout) {
         float4 ws4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (wsig) ws4 = make_float4(__ldg(wsig + k), __ldg(wsig + k + 1), __ldg(wsig + k + 2), __ldg(wsig + k + 3));
+        float4 vprev = make_float4(0.f, 0.f, 0.f, 0.f), sprev = vprev, yprev = vprev;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 7; i >= 0; --i) {       // descending: the tangent row (odd) of a pair comes first
           const int m = ty * 8 + i;
           float4 v = make_float4(acc[i][h * 4 + 0], acc[i][h * 4 + 1], acc[i][h * 4 + 2],
                                  acc[i][h * 4 + 3]);
@@ -332,10 +386,31 @@ __device__ __forceinline__ void bwd_layer(const RenPlan& p, const RenLayer& L, c
           if (prev_act) {
             float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
             if (s0 + m < S) y = *reinterpret_cast<const float4*>(aprev_mat + ren_blk(s0 + m, k, Kout));
-            v.x *= ren_hidden_grad_from_out(p.f.hidden_activation, y.x);
-            v.y *= ren_hidden_grad_from_out(p.f.hidden_activation, y.y);
-            v.z *= ren_hidden_grad_from_out(p.f.hidden_activation, y.z);
-            v.w *= ren_hidden_grad_from_out(p.f.hidden_activation, y.w);
+            if (TAN && (i & 1)) {
+              // tangent row: y = ydot; the derivative factor comes from the value row below it
+              float4 yv = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (s0 + m - 1 < S) yv = *reinterpret_cast<const float4*>(aprev_mat + ren_blk(s0 + m - 1, k, Kout));
+              sprev = make_float4(ren_hidden_grad_from_out(p.f.hidden_activation, yv.x),
+                                  ren_hidden_grad_from_out(p.f.hidden_activation, yv.y),
+                                  ren_hidden_grad_from_out(p.f.hidden_activation, yv.z),
+                                  ren_hidden_grad_from_out(p.f.hidden_activation, yv.w));
+              vprev = v;                     // abar_dot
+              yprev = make_float4(ren_hidden_curv_from_out(p.f.hidden_activation, yv.x, y.x),
+                                  ren_hidden_curv_from_out(p.f.hidden_activation, yv.y, y.y),
+                                  ren_hidden_curv_from_out(p.f.hidden_activation, yv.z, y.z),
+                                  ren_hidden_curv_from_out(p.f.hidden_activation, yv.w, y.w));
+              v.x *= sprev.x; v.y *= sprev.y; v.z *= sprev.z; v.w *= sprev.w;
+            } else if (TAN) {
+              v.x = fmaf(vprev.x, yprev.x, v.x * sprev.x);
+              v.y = fmaf(vprev.y, yprev.y, v.y * sprev.y);
+              v.z = fmaf(vprev.z, yprev.z, v.z * sprev.z);
+              v.w = fmaf(vprev.w, yprev.w, v.w * sprev.w);
+            } else {
+              v.x *= ren_hidden_grad_from_out(p.f.hidden_activation, y.x);
+              v.y *= ren_hidden_grad_from_out(p.f.hidden_activation, y.y);
+              v.z *= ren_hidden_grad_from_out(p.f.hidden_activation, y.z);
+              v.w *= ren_hidden_grad_from_out(p.f.hidden_activation, y.w);
+            }
           }
           if (s0 + m >= S) v = make_float4(0.f, 0.f, 0.f, 0.f);
           *reinterpret_cast<float4*>(din + m * WS + k) = v;
@@ -348,7 +423,8 @@ __device__ __forceinline__ void bwd_layer(const RenPlan& p, const RenLayer& L, c
   __syncthreads();
 }
 
-extern "C" __global__ void __launch_bounds__(NTHREADS, 1) ren_simt_field_dgrad(const DgradArgs a) {
+template <bool TAN>
+__global__ void __launch_bounds__(NTHREADS, 1) ren_simt_field_dgrad(const DgradArgs a) {
   extern __shared__ __align__(16) float smem_f[];
   const RenPlan& p = a.p;
   const int WS = max(p.W, p.WC);
@@ -376,17 +452,43 @@ extern "C" __global__ void __launch_bounds__(NTHREADS, 1) ren_simt_field_dgrad(c
       const RenLayer* Llast = p.CD > 0 ? &p.cond[p.CD - 1] : &p.bott;
       const float* amat = a.stash + ren_stash_mat(p, S, Llast->mat);
       float* dmat = a.delta + ren_stash_mat(p, S, Llast->mat);
-      for (int e = tid; e < TM * Kin; e += NTHREADS) {
-        const int m = e / Kin, k = e - m * Kin;
-        float v = 0.f;
-        for (int c = 0; c < p.C; ++c) v = fmaf(gc[m * 4 + c], __ldg(a.params + p.rgb_w + c * ldo + k), v);
-        if (s0 + m < S) {
-          if (Llast->act) v *= ren_hidden_grad_from_out(p.f.hidden_activation, amat[ren_blk(s0 + m, k, Kin)]);
-          dmat[ren_blk(s0 + m, k, Kin)] = v;
-        } else {
-          v = 0.f;
+      if (!TAN) {
+        for (int e = tid; e < TM * Kin; e += NTHREADS) {
+          const int m = e / Kin, k = e - m * Kin;
+          float v = 0.f;
+          for (int c = 0; c < p.C; ++c) v = fmaf(gc[m * 4 + c], __ldg(a.params + p.rgb_w + c * ldo + k), v);
+          if (s0 + m < S) {
+            if (Llast->act) v *= ren_hidden_grad_from_out(p.f.hidden_activation, amat[ren_blk(s0 + m, k, Kin)]);
+            dmat[ren_blk(s0 + m, k, Kin)] = v;
+          } else {
+            v = 0.f;
+          }
+          cur[m * WS + k] = v;
         }
-        cur[m * WS + k] = v;
+      } else {
+        for (int e = tid; e < (TM / 2) * Kin; e += NTHREADS) {
+          const int m = 2 * (e / Kin), k = e % Kin;      // value row m, tangent row m + 1
+          float v = 0.f, vt = 0.f;
+          for (int c = 0; c < p.C; ++c) {
+            const float w = __ldg(a.params + p.rgb_w + c * ldo + k);
+            v = fmaf(gc[m * 4 + c], w, v);
+            vt = fmaf(gc[(m + 1) * 4 + c], w, vt);
+          }
+          if (s0 + m + 1 < S) {
+            if (Llast->act) {
+              const float y = amat[ren_blk(s0 + m, k, Kin)], yd = amat[ren_blk(s0 + m + 1, k, Kin)];
+              const float sg = ren_hidden_grad_from_out(p.f.hidden_activation, y);
+              v = fmaf(vt, ren_hidden_curv_from_out(p.f.hidden_activation, y, yd), v * sg);
+              vt *= sg;
+            }
+            dmat[ren_blk(s0 + m, k, Kin)] = v;
+            dmat[ren_blk(s0 + m + 1, k, Kin)] = vt;
+          } else {
+            v = 0.f; vt = 0.f;
+          }
+          cur[m * WS + k] = v;
+          cur[(m + 1) * WS + k] = vt;
+        }
       }
       __syncthreads();
     }
@@ -394,24 +496,24 @@ extern "C" __global__ void __launch_bounds__(NTHREADS, 1) ren_simt_field_dgrad(c
     for (int j = p.CD - 1; j >= 0; --j) {
       const RenLayer& L = p.cond[j];
       const RenLayer& Lp = j > 0 ? p.cond[j - 1] : p.bott;
-      bwd_layer(p, L, a.params, s, cur, nxt, WS, nullptr, nullptr,
-                a.stash + ren_stash_mat(p, S, Lp.mat), Lp.act,
-                a.delta + ren_stash_mat(p, S, Lp.mat), L.K0, s0, S);
+      bwd_layer<TAN>(p, L, a.params, s, cur, nxt, WS, nullptr, nullptr,
+                     a.stash + ren_stash_mat(p, S, Lp.mat), Lp.act,
+                     a.delta + ren_stash_mat(p, S, Lp.mat), L.K0, s0, S);
       float* t = cur; cur = nxt; nxt = t;
     }
     // ---- bottleneck reverse + sigma head, into the last trunk layer's pre-activation grad
     if (p.D > 0) {
       const RenLayer& Lp = p.trunk[p.D - 1];
-      bwd_layer(p, p.bott, a.params, s, cur, nxt, WS, gsig, a.params + p.sig_w,
-                a.stash + ren_stash_mat(p, S, Lp.mat), Lp.act,
-                a.delta + ren_stash_mat(p, S, Lp.mat), p.hid_K0, s0, S);
+      bwd_layer<TAN>(p, p.bott, a.params, s, cur, nxt, WS, gsig, a.params + p.sig_w,
+                     a.stash + ren_stash_mat(p, S, Lp.mat), Lp.act,
+                     a.delta + ren_stash_mat(p, S, Lp.mat), p.hid_K0, s0, S);
       float* t = cur; cur = nxt; nxt = t;
       for (int i = p.D - 1; i >= 1; --i) {
         const RenLayer& L = p.trunk[i];
         const RenLayer& Lq = p.trunk[i - 1];
-        bwd_layer(p, L, a.params, s, cur, nxt, WS, nullptr, nullptr,
-                  a.stash + ren_stash_mat(p, S, Lq.mat), Lq.act,
-                  a.delta + ren_stash_mat(p, S, Lq.mat), L.K0, s0, S);
+        bwd_layer<TAN>(p, L, a.params, s, cur, nxt, WS, nullptr, nullptr,
+                       a.stash + ren_stash_mat(p, S, Lq.mat), Lq.act,
+                       a.delta + ren_stash_mat(p, S, Lq.mat), L.K0, s0, S);
         float* t2 = cur; cur = nxt; nxt = t2;
       }
     }
@@ -437,6 +539,7 @@ struct WgradArgs {
   int n_problems;
   int splits;
   long long S;
+  int tangent;               // rows alternate (value, tangent): only value rows feed the bias gradient
 };
 #define WG_MC 16
 
@@ -453,7 +556,7 @@ extern "C" __global__ void __launch_bounds__(NTHREADS, 2) ren_simt_wgrad(const W
   const int local = tile_id - a.tile_prefix[pi];
   const int tn = local / P.ntk, tk = local - tn * P.ntk;
   const int n0 = tn * 128, k0 = tk * 128;
-  const long long per = (a.S + a.splits - 1) / a.splits;
+  const long long per = ((a.S + a.splits - 1) / a.splits + 15) & ~15LL;
   const long long m_begin = (long long)split * per;
   const long long m_end = min(a.S, m_begin + per);
   const int ty = tid >> 4, tx = tid & 15;  // ty: 16 groups of 8 n; tx: 16 groups of (4 + 4) k
@@ -500,9 +603,10 @@ extern "C" __global__ void __launch_bounds__(NTHREADS, 2) ren_simt_wgrad(const W
       float4 h1 = *reinterpret_cast<const float4*>(&Hs[buf][mm][64 + tx * 4]);
       const float dv[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
       const float hv[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+      const bool brow = !(a.tangent && (mm & 1));    // m0 is a multiple of 16: row parity == mm parity
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        bsum[i] += dv[i];
+        if (brow) bsum[i] += dv[i];
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(dv[i], hv[j], acc[i][j]);
       }
@@ -537,21 +641,24 @@ static int sm_count() {
 }
 
 int ren_simt_launch_fwd(const RenPlan& p, long long n_rays, int K, const float* o, const float* d,
-                        const float* jitter, const float* params, float* stash, float* raw,
-                        cudaStream_t st) {
+                        const float* o_dot, const float* d_dot, const float* jitter, const float* params,
+                        float* stash, float* raw, cudaStream_t st) {
   FwdArgs a;
   a.p = p; a.n_rays = n_rays; a.K = K; a.rays_o = o; a.rays_d = d; a.jitter = jitter;
-  a.params = params; a.stash = stash; a.raw = raw;
+  a.params = params; a.stash = stash; a.raw = raw; a.rays_o_dot = o_dot; a.rays_d_dot = d_dot;
+  const bool tan = o_dot != nullptr;
   const int WS = p.W > p.WC ? p.W : p.WC;
   const size_t smem = simt_smem_bytes(WS);
-  cudaError_t e = cudaFuncSetAttribute(ren_simt_field_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = tan ? cudaFuncSetAttribute(ren_simt_field_fwd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                      : cudaFuncSetAttribute(ren_simt_field_fwd<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { ren_set_error("simt fwd smem attr (%zu B): %s", smem, cudaGetErrorString(e)); return REN_E_CUDA; }
-  const long long S = n_rays * K;
+  const long long S = n_rays * K * (tan ? 2 : 1);
   const long long n_tiles = (S + TM - 1) / TM;
   long long grid = n_tiles < (long long)sm_count() * 8 ? n_tiles : (long long)sm_count() * 8;
   if (grid < 1) return REN_OK;
   ren_prof_begin(REN_K_FIELD_FWD, st);
-  ren_simt_field_fwd<<<(unsigned)grid, NTHREADS, smem, st>>>(a);
+  if (tan) ren_simt_field_fwd<true><<<(unsigned)grid, NTHREADS, smem, st>>>(a);
+  else ren_simt_field_fwd<false><<<(unsigned)grid, NTHREADS, smem, st>>>(a);
   ren_prof_end(REN_K_FIELD_FWD, st);
   e = cudaGetLastError();
   if (e != cudaSuccess) { ren_set_error("simt fwd launch: %s", cudaGetErrorString(e)); return REN_E_CUDA; }
@@ -559,18 +666,20 @@ int ren_simt_launch_fwd(const RenPlan& p, long long n_rays, int K, const float* 
 }
 
 int ren_simt_launch_dgrad(const RenPlan& p, long long S, const float* params, const float* stash,
-                          const float* graw, float* delta, cudaStream_t st) {
+                          const float* graw, float* delta, int tangent, cudaStream_t st) {
   DgradArgs a;
   a.p = p; a.S = S; a.params = params; a.stash = stash; a.graw = graw; a.delta = delta;
   const int WS = p.W > p.WC ? p.W : p.WC;
   const size_t smem = simt_smem_bytes(WS);
-  cudaError_t e = cudaFuncSetAttribute(ren_simt_field_dgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = tangent ? cudaFuncSetAttribute(ren_simt_field_dgrad<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                          : cudaFuncSetAttribute(ren_simt_field_dgrad<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { ren_set_error("simt dgrad smem attr: %s", cudaGetErrorString(e)); return REN_E_CUDA; }
   const long long n_tiles = (S + TM - 1) / TM;
   long long grid = n_tiles < (long long)sm_count() * 8 ? n_tiles : (long long)sm_count() * 8;
   if (grid < 1) return REN_OK;
   ren_prof_begin(REN_K_FIELD_DGRAD, st);
-  ren_simt_field_dgrad<<<(unsigned)grid, NTHREADS, smem, st>>>(a);
+  if (tangent) ren_simt_field_dgrad<true><<<(unsigned)grid, NTHREADS, smem, st>>>(a);
+  else ren_simt_field_dgrad<false><<<(unsigned)grid, NTHREADS, smem, st>>>(a);
   ren_prof_end(REN_K_FIELD_DGRAD, st);
   e = cudaGetLastError();
   if (e != cudaSuccess) { ren_set_error("simt dgrad launch: %s", cudaGetErrorString(e)); return REN_E_CUDA; }
@@ -579,8 +688,9 @@ int ren_simt_launch_dgrad(const RenPlan& p, long long S, const float* params, co
 
 // dW/db for every layer from (stash activations, delta workspace, graw).
 int ren_simt_launch_wgrad(const RenPlan& p, long long S, const float* stash, const float* delta,
-                          const float* graw, float* g_params, cudaStream_t st) {
+                          const float* graw, float* g_params, int tangent, cudaStream_t st) {
   WgradArgs a;
+  a.tangent = tangent;
   int np = 0;
   const float* encP = stash + ren_stash_encp(p, S);
   const float* encD = stash + ren_stash_encd(p, S);

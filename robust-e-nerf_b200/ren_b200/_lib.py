@@ -17,6 +17,7 @@ DENSITY_ACT = {"shifted_trunc_exp": 0, "softplus": 1, "shifted_softplus": 2}
 RADIANCE_ACT = {"softplus": 0, "sigmoid": 1}
 CONTRACTION = {"aabb": 0, "sphere": 1, "tanh": 2}
 ERROR_FN = {"l1": 0, "mse": 1, "mape": 2}
+ABI_VERSION = 2
 
 
 class RenFieldDesc(C.Structure):
@@ -60,9 +61,21 @@ _SIGNATURES = {
                                      _P, C.c_size_t, _P]),
     "ren_render_backward": (C.c_int, [C.POINTER(RenFieldDesc), C.POINTER(RenRenderDesc), C.c_int64,
                                       C.c_int32, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P,
-                                      _P, _P, C.c_size_t, _P]),
+                                      _P, _P, _P, C.c_size_t, _P]),
+    "ren_tangent_stash_bytes": (C.c_int, [C.POINTER(RenFieldDesc), C.POINTER(RenRenderDesc), C.c_int64,
+                                          C.c_int32, C.POINTER(C.c_size_t)]),
+    "ren_tangent_workspace_bytes": (C.c_int, [C.POINTER(RenFieldDesc), C.POINTER(RenRenderDesc),
+                                              C.c_int64, C.c_int32, C.c_int32, C.c_int32,
+                                              C.POINTER(C.c_size_t)]),
+    "ren_render_tangent_forward": (C.c_int, [C.POINTER(RenFieldDesc), C.POINTER(RenRenderDesc), C.c_int64,
+                                             C.c_int32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
+                                             _P, _P, C.c_size_t, _P, C.c_size_t, _P]),
+    "ren_render_tangent_backward": (C.c_int, [C.POINTER(RenFieldDesc), C.POINTER(RenRenderDesc),
+                                              C.c_int64, C.c_int32, _P, _P, _P, _P, _P, _P, _P, _P, _P,
+                                              _P, _P, _P, _P, C.c_size_t, _P, _P, _P, _P, C.c_size_t,
+                                              _P]),
     "ren_event_rays": (C.c_int, [C.c_int64, _P, _P, _P, _P, _P, _P, _P, C.c_int64, _P, _P, _P, _P,
-                                 C.c_int32, _P, _P, _P, _P, _P, _P, _P]),
+                                 C.c_int32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "ren_trajectory": (C.c_int, [C.c_int64, _P, C.c_int64, _P, _P, _P, _P, _P, _P]),
     "ren_event_diff_loss": (C.c_int, [C.c_int64, C.c_int32, C.c_int32, C.c_float, _P, _P, _P, _P, _P,
                                       _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
@@ -92,8 +105,8 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.ren_version() != 1:
-        raise RuntimeError(f"libren_b200 ABI version {lib.ren_version()} != 1")
+    if lib.ren_version() != ABI_VERSION:
+        raise RuntimeError(f"libren_b200 ABI version {lib.ren_version()} != {ABI_VERSION}")
     _lib = lib
     return lib
 
@@ -186,4 +199,18 @@ def workspace_bytes(fdesc, rdesc, n_rays, K, has_stash, for_backward):
     n = C.c_size_t(0)
     check(load().ren_workspace_bytes(C.byref(fdesc), C.byref(rdesc), n_rays, K, int(has_stash),
                                      int(for_backward), C.byref(n)), "ren_workspace_bytes")
+    return int(n.value)
+
+
+def tangent_stash_bytes(fdesc, rdesc, n_rays, K):
+    n = C.c_size_t(0)
+    check(load().ren_tangent_stash_bytes(C.byref(fdesc), C.byref(rdesc), n_rays, K, C.byref(n)),
+          "ren_tangent_stash_bytes")
+    return int(n.value)
+
+
+def tangent_workspace_bytes(fdesc, rdesc, n_rays, K, has_stash, for_backward):
+    n = C.c_size_t(0)
+    check(load().ren_tangent_workspace_bytes(C.byref(fdesc), C.byref(rdesc), n_rays, K, int(has_stash),
+                                             int(for_backward), C.byref(n)), "ren_tangent_workspace_bytes")
     return int(n.value)

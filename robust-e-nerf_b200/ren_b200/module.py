@@ -204,6 +204,32 @@ class DiffLossFunction(torch.autograd.Function):
         return (g_c0 * g_loss, g_c1 * g_loss, None, None, g_ev, None, None, None, None, None, None)
 
 
+class RayChainFunction(torch.autograd.Function):
+    """Ties the rays `ren_event_rays` produced to the (differentiable, f64) supervision
+    timestamp they were generated at, so that d loss / d ts -- and from there the refractory
+    period -- follows the reference's autograd path through `LinearTrajectory.forward` and
+    `pixel_params_to_ray` (robust_e_nerf/models/trajectories.py:63-91, models/nerf.py:206-228):
+        d loss/d ts = (g_o . o' + g_d . d' + g_ddot . d'') * dw/dt      (o'' = 0 for a lerp)
+    with ' = d/dw taken by second-order jets inside the kernel."""
+
+    @staticmethod
+    def forward(ctx, ts, o, d, o_dot, d_dot, d_ddot, dw_dt):
+        ctx.save_for_backward(o_dot, d_dot, d_ddot, dw_dt)
+        return o.clone(), d.clone(), o_dot.clone(), d_dot.clone()
+
+    @staticmethod
+    def backward(ctx, g_o, g_d, g_odot, g_ddot):
+        o_dot, d_dot, d_ddot, dw_dt = ctx.saved_tensors
+        g_w = torch.zeros_like(dw_dt)
+        if g_o is not None:
+            g_w = g_w + (g_o * o_dot).sum(-1).double()
+        if g_d is not None:
+            g_w = g_w + (g_d * d_dot).sum(-1).double()
+        if g_ddot is not None:
+            g_w = g_w + (g_ddot * d_ddot).sum(-1).double()
+        return g_w * dw_dt, None, None, None, None, None, None
+
+
 # ------------------------------------------------------------------ task module
 class RobustENeRF(LightningModule):
     INTRINSICS_KEY = "intrinsics"
@@ -293,8 +319,9 @@ class RobustENeRF(LightningModule):
     def _loss_cfg(self, group, name):
         return _get(_get(self.hparams["loss"], group), name)
 
-    def event_rays(self, event, normalized, n_renders=2):
-        """Steps b-d of SURVEY.md section 3.2 + `pixel_params_to_ray` in one launch."""
+    def event_rays(self, event, normalized, n_renders=2, jets=False):
+        """Steps b-d of SURVEY.md section 3.2 + `pixel_params_to_ray` in one launch.  `jets`: also
+        return d/dw and d^2/dw^2 of the rays and dw/dt (tangent render, trainable tau)."""
         B = event["start_ts"].numel()
         dev = event["start_ts"].device
         tau = self.refractory_period.refractory_period.detach().reshape(1).contiguous()
@@ -304,6 +331,12 @@ class RobustENeRF(LightningModule):
         out_rot = torch.empty((n_renders, B, 3, 3), device=dev, dtype=torch.float32)
         ts_diff = torch.empty((B,), device=dev, dtype=torch.float64)
         start = torch.empty((B,), device=dev, dtype=torch.float64)
+        o_dot = d_dot = d_ddot = dw_dt = None
+        if jets:
+            o_dot = torch.empty((n_renders, B, 3), device=dev, dtype=torch.float32)
+            d_dot = torch.empty((n_renders, B, 3), device=dev, dtype=torch.float32)
+            d_ddot = torch.empty((n_renders, B, 3), device=dev, dtype=torch.float32)
+            dw_dt = torch.empty((n_renders, B), device=dev, dtype=torch.float64)
         tr = self.trajectory
         c = lambda t: t.contiguous()
         _lib.check(_lib.load().ren_event_rays(
@@ -314,8 +347,24 @@ class RobustENeRF(LightningModule):
             tr.T_wc_timestamp.numel(), _lib.ptr(tr.T_wc_timestamp), _lib.ptr(tr.T_wc_position),
             _lib.ptr(tr.T_wc_orientation), _lib.ptr(c(self.train_intrinsics_inv)), n_renders,
             _lib.ptr(out_ts), _lib.ptr(out_o), _lib.ptr(out_d), _lib.ptr(out_rot), _lib.ptr(ts_diff),
-            _lib.ptr(start), _lib.stream_ptr()), "ren_event_rays")
-        return dict(ts=out_ts, o=out_o, d=out_d, rot=out_rot, ts_diff=ts_diff, start=start)
+            _lib.ptr(start), _lib.ptr(o_dot), _lib.ptr(d_dot), _lib.ptr(d_ddot), _lib.ptr(dw_dt),
+            _lib.stream_ptr()), "ren_event_rays")
+        return dict(ts=out_ts, o=out_o, d=out_d, rot=out_rot, ts_diff=ts_diff, start=start,
+                    o_dot=o_dot, d_dot=d_dot, d_ddot=d_ddot, dw_dt=dw_dt)
+
+    def _supervision_timestamps(self, event, normalized, with_grad_ts):
+        """robust_e_nerf.py:322-357 in differentiable f64 torch ((B,) ops): used only when the
+        refractory period is trainable, to chain d loss / d ts to tau."""
+        tau = self.refractory_period.refractory_period
+        start = event["start_ts"] + tau
+        end = event["end_ts"]
+        ts_diff = (end - start) * normalized["ts_diff"]
+        d_start = torch.lerp(start, torch.max(end - ts_diff, start), normalized["diff_start_ts"])
+        d_end = torch.min(d_start + ts_diff, end)
+        ts = [d_start, d_end]
+        if with_grad_ts:
+            ts = [torch.lerp(d_start, d_end, normalized["grad_ts"])] + ts
+        return start, ts
 
     def render_pixels(self, intrinsics_inverse, pixel_position, T_wc_position, T_wc_orientation,
                       jitter=None):
@@ -334,8 +383,8 @@ class RobustENeRF(LightningModule):
         return intensity, opacity, depth, spp, is_valid
 
     def training_step(self, batch, batch_index, jitter=None):
-        """robust_e_nerf.py:301-517.  `jitter` (optional dict with (B,) tensors `diff_start`,
-        `diff_end`) injects the per-ray stratified offsets (tests / parity runs)."""
+        """robust_e_nerf.py:301-517.  `jitter` (optional dict with (B,) tensors `grad`,
+        `diff_start`, `diff_end`) injects the per-ray stratified offsets (tests / parity runs)."""
         event = {k: v.squeeze(dim=0) for k, v in batch["event"].items()}
         normalized = {k: v.squeeze(dim=0) for k, v in batch["normalized"].items()}
         B = event["start_ts"].numel()
@@ -343,27 +392,62 @@ class RobustENeRF(LightningModule):
             assert v.shape[0] == B
         w_grad = self._loss_cfg("weight", "log_intensity_grad")
         w_diff = self._loss_cfg("weight", "log_intensity_diff")
-        if w_grad > 0:
-            raise NotImplementedError(
-                "log_intensity_grad loss (tangent-mode render, SURVEY.md section 7.1-5) is not built yet")
-        if not _get(self.hparams["refractory_period"], "freeze"):
-            raise NotImplementedError(
-                "a trainable refractory period needs ray gradients (SURVEY.md App. A9): not built yet")
-        assert w_diff > 0
+        if w_diff <= 0:
+            raise NotImplementedError("ren_b200 trains with the log-intensity-difference loss on "
+                                      "(every shipped config: configs/train/*.yaml:103-104)")
+        tau_train = any(p.requires_grad for p in self.refractory_period.parameters()) and torch.is_grad_enabled()
         dev = event["start_ts"].device
+        imin = self.hparams["min_modeled_intensity"]
+        all_valid = self.render_bkgd is not None
         # a: contrast threshold (tiny torch ops on (B,))
         ev_diff = self.contrast_threshold(event["num_pos"], event["num_neg"])
-        # b-d + raygen
-        rays = self.event_rays(event, normalized, 2)
+        # b-d + raygen: [grad |] diff_start | diff_end
+        nr = 3 if w_grad > 0 else 2
+        rays = self.event_rays(event, normalized, nr, jets=(w_grad > 0 or tau_train))
         if self.global_step is not None:
             self.nerf.update_occ_grid(self.global_step, self.trajectory.T_wc_position)   # :375-379
-        # f: both renders in one launch (start rays | end rays)
+        ro = [rays["o"][j] for j in range(nr)]
+        rd = [rays["d"][j] for j in range(nr)]
+        rod = [rays["o_dot"][j] if rays["o_dot"] is not None else None for j in range(nr)]
+        rdd = [rays["d_dot"][j] if rays["d_dot"] is not None else None for j in range(nr)]
+        start = rays["start"]
+        if tau_train:
+            # differentiable timestamps -> rays (d loss / d ts chains to tau)
+            start, ts = self._supervision_timestamps(event, normalized, w_grad > 0)
+            for j in range(nr):
+                ro[j], rd[j], rod[j], rdd[j] = RayChainFunction.apply(
+                    ts[j], rays["o"][j], rays["d"][j], rays["o_dot"][j], rays["d_dot"][j],
+                    rays["d_ddot"][j], rays["dw_dt"][j])
+        n_kept_all, opac_all = [], []
+        losses = {}
+        # f: gradient render (tangent mode) + log-intensity-gradient loss (f64, (B,) torch ops)
+        if w_grad > 0:
+            u = jitter["grad"].to(dev, torch.float32) if jitter is not None else None
+            rad, opac_g, _d, rad_dot, _od, n_kept = self.nerf.render_tangent_raw(ro[0], rd[0], rod[0], rdd[0], u)
+            if self.has_bayer_filter:
+                ch = event["channel_idx"].to(torch.int64).unsqueeze(-1)                 # :887-890
+                cg, cg_dot = rad.gather(1, ch).squeeze(-1), rad_dot.gather(1, ch).squeeze(-1)
+            else:
+                cg, cg_dot = rad[:, 0], rad_dot[:, 0]
+            # d logI / d ts = (dC/dw) / (C + I_min) [f32] * dw/dt [f64]   (trajectories.py:63-65 cast)
+            log_i_grad = (cg_dot / (cg + imin)).double() * rays["dw_dt"][0]
+            rate = ev_diff / (event["end_ts"] - start)                                  # loss.py:38-41
+            err = self._error(self._loss_cfg("error_fn", "log_intensity_grad"), log_i_grad, rate)
+            valid_g = torch.ones_like(opac_g, dtype=torch.bool) if all_valid else opac_g > 0
+            losses["log_intensity_grad"] = err[valid_g].mean()
+            n_kept_all.append(n_kept)
+            opac_all.append(opac_g)
+            self.last_grad = dict(log_intensity_grad=log_i_grad, valid=valid_g, target=rate,
+                                  log_intensity=torch.log(cg + imin))
+        # f: both difference renders in one launch (start rays | end rays)
         if jitter is None:
             u = torch.rand((2 * B,), device=dev, dtype=torch.float32)
         else:
             u = torch.cat((jitter["diff_start"], jitter["diff_end"])).to(dev, torch.float32)
-        rad, opac, _depth, n_kept = self.nerf.render_raw(rays["o"].reshape(2 * B, 3),
-                                                         rays["d"].reshape(2 * B, 3), u)
+        rad, opac, _depth, n_kept = self.nerf.render_raw(torch.cat((ro[nr - 2], ro[nr - 1])),
+                                                         torch.cat((rd[nr - 2], rd[nr - 1])), u)
+        n_kept_all += [n_kept[:B], n_kept[B:]]
+        opac_all += [opac[:B], opac[B:]]
         if self.has_bayer_filter:
             ch = event["channel_idx"].to(torch.int64).repeat(2).unsqueeze(-1)             # :887-890
             c = rad.gather(1, ch).squeeze(-1)
@@ -374,32 +458,47 @@ class RobustENeRF(LightningModule):
         # h-j: loss
         loss_raw, log_i0, log_i1, n_valid = DiffLossFunction.apply(
             c0, c1, o0, o1, ev_diff, rays["ts_diff"], rays["start"], event["end_ts"].contiguous(),
-            self._loss_cfg("error_fn", "log_intensity_diff"), self.render_bkgd is not None,
-            self.hparams["min_modeled_intensity"])
+            self._loss_cfg("error_fn", "log_intensity_diff"), all_valid, imin)
+        losses["log_intensity_diff"] = loss_raw
         mcr = 1 / self.contrast_threshold.mean_contrast_threshold
-        pw = {None: 1.0, "mean_contrast_reciprocal": mcr, "mean_contrast_reciprocal_sq": mcr ** 2}[
-            self._loss_cfg("param_weight", "log_intensity_diff")]
-        mean_loss = pw * loss_raw
-        train_loss = mean_loss * w_diff
+        pw = {None: 1.0, "mean_contrast_reciprocal": mcr, "mean_contrast_reciprocal_sq": mcr ** 2}
+        train_loss = 0
+        for name in list(losses):
+            losses[name] = pw[self._loss_cfg("param_weight", name)] * losses[name]
+            train_loss = train_loss + losses[name] * self._loss_cfg("weight", name)
         # i: dynamic batch size (host sync, as in the reference; only with a trainer attached)
-        mean_spp = n_kept.sum() / (2 * B)
+        mean_spp = sum(nk.sum() / B for nk in n_kept_all) / len(n_kept_all)
         if self.trainer is not None:
             mean_spp = self.update_train_batch_size(mean_spp, batch_index)
         # k: logging
         self.log("train/loss", train_loss, prog_bar=True)
-        self.log("train/log_intensity_diff", mean_loss)
+        for name, val in losses.items():
+            self.log(f"train/{name}", val)
         if not _get(self.hparams["contrast_threshold"], "freeze"):
             self.log("train/p2n_contrast_threshold_ratio", self.contrast_threshold.p2n_contrast_threshold_ratio)
+        if not _get(self.hparams["refractory_period"], "freeze"):
+            self.log("train/refractory_period", self.refractory_period.refractory_period)
         self.log("train/batch_size", B)
         self.log("train/mean_num_samples_per_ray", mean_spp)
-        self.log("train/mean_ray_occ_rate", (n_kept > 0).float().mean())
+        self.log("train/mean_ray_occ_rate", sum((op > 0).float().mean() for op in opac_all) / len(opac_all))
         if self.render_bkgd is None:
-            self.log("train/mean_valid_rate", (opac > 0).float().mean())
+            self.log("train/mean_valid_rate", sum((op > 0).float().mean() for op in opac_all) / len(opac_all))
         else:
             self.log("train/mean_valid_rate", torch.ones((), device=dev))
         self.last = dict(start_log_intensity=log_i0, end_log_intensity=log_i1, n_valid=n_valid,
                          rays=rays, opacity=opac)
         return train_loss
+
+    @staticmethod
+    def _error(kind, inp, tgt):
+        """loss_metric/loss.py:16-30, utils/modules.py:77-102 (MAPE eps = float64 machine eps)."""
+        if kind == "l1":
+            return (inp - tgt).abs()
+        if kind == "mse":
+            return (inp - tgt) ** 2
+        if kind == "mape":
+            return (inp - tgt).abs() / tgt.abs().clamp(min=2.220446049250313e-16)
+        raise NotImplementedError(kind)
 
     def update_train_batch_size(self, mean_num_samples_per_ray, batch_index):
         """robust_e_nerf.py:907-950."""

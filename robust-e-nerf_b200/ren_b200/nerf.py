@@ -47,8 +47,9 @@ class RenderFunction(torch.autograd.Function):
     inputs : owner (NeRF), want_grad (bool: grad mode of the caller), o (B,3), d (B,3),
              jitter (B)|None, bkgd (C)|None, *params
     outputs: radiance (B,C), opacity (B), depth_raw (B), n_kept (B) int32
-    Gradients flow to the MLP parameters and `bkgd` (ray gradients are not provided:
-    SURVEY.md App. A9 lists them for the tau-trainable configuration only).
+    Gradients flow to the MLP parameters and `bkgd`; when `o` / `d` require grad (trainable
+    refractory period) the reverse pass also returns d loss / d (o, d) -- the
+    fp32 FFMA engine computes them, so such a call is routed to `simt_fp32`.
     """
 
     @staticmethod
@@ -58,9 +59,10 @@ class RenderFunction(torch.autograd.Function):
             raise RuntimeError("ren_b200 renders on CUDA tensors only (no CPU fallback)")
         B = o.shape[0]
         C_ = owner.radiance_dim
-        fdesc, rdesc, K = owner._descs()
+        ray_grad = bool(want_grad) and (ctx.needs_input_grad[2] or ctx.needs_input_grad[3])
+        fdesc, rdesc, K = owner._descs("simt_fp32" if ray_grad else None)
         flat = owner.flat_params()
-        need_grad = bool(want_grad) and any(ctx.needs_input_grad[5:])
+        need_grad = bool(want_grad) and (ray_grad or any(ctx.needs_input_grad[5:]))
         dev = o.device
         o = o.contiguous().float()
         d = d.contiguous().float()
@@ -93,6 +95,7 @@ class RenderFunction(torch.autograd.Function):
             ctx.has_jitter = jitter is not None
             ctx.has_bkgd = bkgd is not None
             ctx.n_params = len(params)
+            ctx.ray_grad = ray_grad
         ctx.mark_non_differentiable(n_kept)
         return radiance, opacity, depth, n_kept
 
@@ -112,13 +115,101 @@ class RenderFunction(torch.autograd.Function):
         ws = torch.empty((ws_n,), device=dev, dtype=torch.uint8)
         cg = lambda t: None if t is None else t.contiguous().float()
         g_rad, g_op, g_depth = cg(g_rad), cg(g_op), cg(g_depth)
+        g_rays = torch.empty((B, 6), device=dev, dtype=torch.float32) if ctx.ray_grad else None
         _lib.check(lib.ren_render_backward(
             C.byref(fdesc), C.byref(rdesc), B, K, _lib.ptr(o), _lib.ptr(d), _lib.ptr(jitter),
             _lib.ptr(flat), _lib.ptr(bkgd), _lib.ptr(g_rad), _lib.ptr(g_op), _lib.ptr(g_depth),
-            _lib.ptr(stash), stash.numel(), _lib.ptr(g_flat), _lib.ptr(g_bkgd), _lib.ptr(ws),
-            ws.numel(), _lib.stream_ptr()), "ren_render_backward")
+            _lib.ptr(stash), stash.numel(), _lib.ptr(g_flat), _lib.ptr(g_bkgd), _lib.ptr(g_rays),
+            _lib.ptr(ws), ws.numel(), _lib.stream_ptr()), "ren_render_backward")
         grads = owner._split_flat(g_flat)
-        return (None, None, None, None, None, g_bkgd) + tuple(grads)
+        g_o = g_rays[:, 0:3] if ctx.ray_grad else None
+        g_d = g_rays[:, 3:6] if ctx.ray_grad else None
+        return (None, None, g_o, g_d, None, g_bkgd) + tuple(grads)
+
+
+class RenderTangentFunction(torch.autograd.Function):
+    """ren_render_tangent_forward / _backward: the render and its derivative along the ray's pose
+    interpolation weight w (forward mode), differentiable once more in reverse mode -- what the
+    reference obtains with `autograd.gradient(..., create_graph=True)` followed by `backward()`
+    (robust_e_nerf/utils/autograd.py:4-34, robust_e_nerf/models/robust_e_nerf.py:394-398).
+
+    inputs : owner, want_grad, o, d, o_dot, d_dot (B,3), jitter (B)|None, bkgd (C)|None, *params
+    outputs: radiance (B,C), opacity (B), depth_raw (B), radiance_dot (B,C), opacity_dot (B), n_kept
+    """
+
+    @staticmethod
+    def forward(ctx, owner, want_grad, o, d, o_dot, d_dot, jitter, bkgd, *params):
+        lib = _lib.load()
+        if not o.is_cuda:
+            raise RuntimeError("ren_b200 renders on CUDA tensors only (no CPU fallback)")
+        B = o.shape[0]
+        C_ = owner.radiance_dim
+        fdesc, rdesc, K = owner._descs("simt_fp32")
+        flat = owner.flat_params()
+        ray_grad = bool(want_grad) and any(ctx.needs_input_grad[2:6])
+        need_grad = bool(want_grad) and (ray_grad or any(ctx.needs_input_grad[7:]))
+        dev = o.device
+        o, d, o_dot, d_dot = (t.contiguous().float() for t in (o, d, o_dot, d_dot))
+        if jitter is not None:
+            jitter = jitter.contiguous().float()
+        if bkgd is not None:
+            bkgd = bkgd.contiguous().float()
+        radiance = torch.empty((B, C_), device=dev, dtype=torch.float32)
+        radiance_dot = torch.empty((B, C_), device=dev, dtype=torch.float32)
+        opacity = torch.empty((B,), device=dev, dtype=torch.float32)
+        opacity_dot = torch.empty((B,), device=dev, dtype=torch.float32)
+        depth = torch.empty((B,), device=dev, dtype=torch.float32)
+        n_kept = torch.empty((B,), device=dev, dtype=torch.int32)
+        stash, stash_n = None, 0
+        if need_grad:
+            stash_n = _lib.tangent_stash_bytes(fdesc, rdesc, B, K)
+            stash = torch.empty((stash_n,), device=dev, dtype=torch.uint8)
+        ws = torch.empty((_lib.tangent_workspace_bytes(fdesc, rdesc, B, K, need_grad, False),),
+                         device=dev, dtype=torch.uint8)
+        _lib.check(lib.ren_render_tangent_forward(
+            C.byref(fdesc), C.byref(rdesc), B, K, _lib.ptr(o), _lib.ptr(d), _lib.ptr(o_dot),
+            _lib.ptr(d_dot), _lib.ptr(jitter), _lib.ptr(flat), _lib.ptr(bkgd), _lib.ptr(radiance),
+            _lib.ptr(opacity), _lib.ptr(depth), _lib.ptr(radiance_dot), _lib.ptr(opacity_dot),
+            _lib.ptr(n_kept), _lib.ptr(stash), stash_n, _lib.ptr(ws), ws.numel(), _lib.stream_ptr()),
+            "ren_render_tangent_forward")
+        if need_grad:
+            ctx.owner = owner
+            ctx.descs = (fdesc, rdesc, K)
+            empty = torch.empty(0, device=dev)
+            ctx.save_for_backward(o, d, o_dot, d_dot, jitter if jitter is not None else empty,
+                                  bkgd if bkgd is not None else empty, stash, flat)
+            ctx.has_jitter = jitter is not None
+            ctx.has_bkgd = bkgd is not None
+            ctx.ray_grad = ray_grad
+        ctx.mark_non_differentiable(n_kept)
+        return radiance, opacity, depth, radiance_dot, opacity_dot, n_kept
+
+    @staticmethod
+    def backward(ctx, g_rad, g_op, g_depth, g_rad_dot, g_op_dot, _g_kept):
+        lib = _lib.load()
+        o, d, o_dot, d_dot, jitter, bkgd, stash, flat = ctx.saved_tensors
+        fdesc, rdesc, K = ctx.descs
+        owner = ctx.owner
+        B = o.shape[0]
+        dev = o.device
+        jitter = jitter if ctx.has_jitter else None
+        bkgd = bkgd if ctx.has_bkgd else None
+        g_flat = torch.zeros_like(flat)
+        g_bkgd = torch.zeros_like(bkgd) if bkgd is not None else None
+        ws = torch.empty((_lib.tangent_workspace_bytes(fdesc, rdesc, B, K, True, True),), device=dev,
+                         dtype=torch.uint8)
+        cg = lambda t: None if t is None else t.contiguous().float()
+        g_rad, g_op, g_depth, g_rad_dot, g_op_dot = (cg(t) for t in (g_rad, g_op, g_depth, g_rad_dot, g_op_dot))
+        g_rays = torch.empty((B, 12), device=dev, dtype=torch.float32) if ctx.ray_grad else None
+        _lib.check(lib.ren_render_tangent_backward(
+            C.byref(fdesc), C.byref(rdesc), B, K, _lib.ptr(o), _lib.ptr(d), _lib.ptr(o_dot),
+            _lib.ptr(d_dot), _lib.ptr(jitter), _lib.ptr(flat), _lib.ptr(bkgd), _lib.ptr(g_rad),
+            _lib.ptr(g_op), _lib.ptr(g_depth), _lib.ptr(g_rad_dot), _lib.ptr(g_op_dot), _lib.ptr(stash),
+            stash.numel(), _lib.ptr(g_flat), _lib.ptr(g_bkgd), _lib.ptr(g_rays), _lib.ptr(ws),
+            ws.numel(), _lib.stream_ptr()), "ren_render_tangent_backward")
+        grads = owner._split_flat(g_flat)
+        gr = [g_rays[:, 3 * i:3 * i + 3] if ctx.ray_grad else None for i in range(4)]
+        return (None, None, gr[0], gr[1], gr[2], gr[3], None, g_bkgd) + tuple(grads)
 
 
 class NeRF(torch.nn.Module):
@@ -297,8 +388,9 @@ class NeRF(torch.nn.Module):
         return None
 
     # ------------------------------------------------------------------ rendering
-    def _descs(self):
-        key = (self.training, self.engine)
+    def _descs(self, engine=None):
+        engine = self.engine if engine is None else engine
+        key = (self.training, engine)
         hit = self._desc_cache.get(key)
         if hit is None:
             rdesc = _lib.make_render_desc(
@@ -306,7 +398,7 @@ class NeRF(torch.nn.Module):
                 render_step_size=float(self.render_step_size), cone_angle=self.cone_angle,
                 early_stop_eps=self.early_stop_eps, alpha_thre=self.alpha_thre,
                 stratified=self.training,                    # external/utils.py:115
-                engine=self.engine)
+                engine=engine)
             K = _lib.samples_per_ray(self._fdesc, rdesc)
             hit = (self._fdesc, rdesc, K)
             self._desc_cache[key] = hit
@@ -334,6 +426,16 @@ class NeRF(torch.nn.Module):
             jitter = None
         return RenderFunction.apply(self, torch.is_grad_enabled(), o, d, jitter, self.background(),
                                     *self.mlp_parameters())
+
+    def render_tangent_raw(self, o, d, o_dot, d_dot, jitter=None):
+        """Render + derivative along the pose interpolation weight: (radiance (B,C), opacity (B),
+        un-normalised depth (B), radiance_dot (B,C), opacity_dot (B), n_kept (B) i32)."""
+        if self.training and jitter is None:
+            jitter = torch.rand((o.shape[0],), device=o.device, dtype=torch.float32)
+        if not self.training:
+            jitter = None
+        return RenderTangentFunction.apply(self, torch.is_grad_enabled(), o, d, o_dot, d_dot, jitter,
+                                           self.background(), *self.mlp_parameters())
 
     def forward(self, ray_origin, ray_direction, jitter=None):
         """models/nerf.py:230-286.  `jitter` (optional, (N,) in [0,1)) injects the per-ray
