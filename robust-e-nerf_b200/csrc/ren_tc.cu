@@ -1,67 +1,78 @@
 // ren_tc.cu -- tcgen05 "chain" kernel of the field MLP: forward and dgrad (REN_ENGINE_TC_*).
 //
-// One persistent CTA per SM, one 128-sample tile in flight.  Warp-specialised roles:
-//   warp 0       weight producer: streams pre-packed fp16 (hi|lo) weight K-chunks from L2 into a
-//                3-stage shared-memory ring with 1-D bulk TMA (cp.async.bulk + mbarrier tx bytes)
-//   warp 1       MMA issuer: one thread issues tcgen05.mma (kind::f16, M=128, N=256/128/16, K=16);
-//                accumulators live in TMEM (512 columns x 128 lanes, fp32)
-//   warps 2-17   prologue + epilogue: tcgen05.ld -> bias/activation (fwd) or activation derivative
-//                (dgrad) -> fp16 hi/lo split -> the next GEMM's A operand in shared memory (+ the
-//                fp16 stash in HBM).  Lane quadrant = warp % 4 (TMEM access rule), 4 warps share
-//                a quadrant and split the columns.
-// The whole network is a chain of GEMM "steps" described by a table, so forward and dgrad are
-// the same kernel: activations / deltas never leave the SM between layers.  The sigma and
-// radiance heads (N = 1..3) are N=16 MMAs, and in dgrad the head gradients re-enter as K=16
-// rank-1 segments -- there is no per-element head arithmetic.
+// One persistent CTA per SM, one 128-sample tile in flight, ALL activations resident in tensor
+// memory: the 512 TMEM columns are four 128-column regions used in ping-pong pairs.  A layer
+// reads its A operand (fp16 hi/lo, packed two features per 32-bit column) from one pair and
+// accumulates fp32 into the other; the epilogue converts each accumulator region IN PLACE into the
+// next layer's A operand (tcgen05.ld -> bias/activation -> hi/lo split -> tcgen05.st), so no
+// activation ever touches shared memory and the two 128-column halves of a layer pipeline against
+// the tensor pipe: while the epilogue warps convert N-half 0, the MMAs of N-half 1 run, and the
+// next layer's K-half-0 MMAs start as soon as half 0 is converted.
+//   warp 0       weight producer: pre-packed fp16 (hi|lo) [128 x 16] weight chunks, L2 -> 16-stage
+//                shared-memory ring with 1-D bulk TMA (cp.async.bulk + mbarrier tx bytes)
+//   warp 1       MMA issuer: one thread issues tcgen05.mma kind::f16, M=128, N=128, K=16; A from
+//                TMEM (activations) or shared memory (positional / direction encodings)
+//   warps 2-17   prologue (march, contraction, 84 sines -> encodings in shared memory) + epilogues.
+//                Lane quadrant = warp % 4 (TMEM access rule); the 4 warps of a quadrant split the 128
+//                columns of a half 32 each and write their 32 packed columns back over their own.
+// fp32-class accuracy from fp16 tensor cores: x = hi + lo; A*W ~= A_hi*W_hi + A_lo*W_hi + A_hi*W_lo
+// (3 MMAs per K step).  Single-pass fp16/bf16/TF32 misses the 1e-4 bar.
 //
-// fp32-class accuracy from fp16 tensor cores: x = hi + lo, hi = fp16(x), lo = fp16(x - hi);
-// A*W ~= A_hi*W_hi + A_lo*W_hi + A_hi*W_lo in fp32 (3 MMAs per K step; the dropped lo*lo term is
-// 2^-22 relative).  Single-pass fp16/bf16/TF32 misses the 1e-4 bar.
+// Hidden softplus(beta=100) runs in the log2 domain: the packed weights carry the factor
+// 100*log2(e), the accumulator is u = 100 log2e (W h + b), the stored activation is
+// g = max(u,0) + lg2(1 + 2^-|u|) = 100 log2e * softplus_100(pre), and the next layer's weights absorb
+// the inverse factor -- 4 FP32 + 2 MUFU instructions per element.  The fp16 stash keeps g for the
+// hidden layers (the weight-gradient kernels unscale).
 //
-// Operand layout (K-major, SWIZZLE_NONE): 8x8 fp16 core matrices of 128 contiguous bytes;
-// element (row, k) of a [rows x K] operand at (k/8)*(rows*16) + row*16 + (k%8)*2, so a warp of
-// epilogue threads (32 consecutive rows) writes 512 contiguous bytes per 8-feature group.
+// The sigma / radiance heads (N = 1..3) are per-thread dot products in the epilogue of the layer that
+// feeds them; in dgrad the head gradients re-enter as rank-1 updates in the epilogue.
 #include <string.h>
 
 #include "ren_tc.cuh"
 
 #define TC_EPI_WARPS 16
 #define TC_THREADS (64 + 32 * TC_EPI_WARPS)   // 576
-#define TC_STAGES 3
-#define TC_MAX_STEPS 24
+#define TC_STAGES 16
+#define TC_MAX_STEPS 20
 
 // shared-memory map (bytes)
-#define SM_A_HI 0          // main activations  [128 x 256] hi
-#define SM_A_LO 65536
-#define SM_P_HI 131072     // region 1: positional encoding [128 x 64] (dgrad: column 0 = d sigma_raw)
-#define SM_P_LO 147456
-#define SM_D_HI 163840     // region 2: direction encoding [128 x 32] (dgrad: columns 0..C-1 = d c_raw)
-#define SM_D_LO 172032
-#define SM_RING 180224
-#define SM_STAGE_BYTES 16384
-#define SM_BAR (SM_RING + TC_STAGES * SM_STAGE_BYTES)   // 229376
-#define SM_TMEM_PTR (SM_BAR + 64)
-#define SM_TOTAL (SM_BAR + 128)
+#define SM_P_HI 0          // positional encoding [128 x 64] hi (K-major core matrices)
+#define SM_P_LO 16384
+#define SM_D_HI 32768      // direction encoding [128 x 32]
+#define SM_D_LO 40960
+#define SM_RING 49152
+#define SM_STAGE_BYTES 8192
+#define SM_VEC (SM_RING + TC_STAGES * SM_STAGE_BYTES)   // 180224: float vectors (biases, head weights)
+#define VEC_BIAS 0                                      // [TC_MAX_STEPS][256] -> only n_steps used
+#define VEC_WSIG (12 * 256)
+#define VEC_WO (VEC_WSIG + 256)                         // [3][128]
+#define VEC_HB (VEC_WO + 384)                           // sigma bias, rgb biases
+#define VEC_FLOATS (VEC_HB + 4)                         // 3716
+#define SM_PART (SM_VEC + 16384)                        // head partial sums: float4 [4][128]
+#define SM_BAR (SM_PART + 8192)
+#define SM_TMEM_PTR (SM_BAR + 320)
+#define SM_TOTAL (SM_BAR + 512)
 
-#define TMEM_COL_SIGMA 256
-#define TMEM_COL_RGB 272
+#define LOG2E_100 144.26950408889634f      // 100 * log2(e)
+#define LN2_OVER_100 0.0069314718055994531f
 
-enum { EPI_F_HIDDEN = 0, EPI_F_LINEAR = 1, EPI_F_HEADS = 2, EPI_D_ACT = 3, EPI_D_LINEAR = 4 };
+enum { EPI_F_HIDDEN = 0, EPI_F_LINEAR = 1, EPI_F_LAST = 2, EPI_D_ACT = 3, EPI_D_LINEAR = 4 };
 
 struct TcStep {
-  int seg_region[2];   // 0 main, 1 positional-encoding region, 2 direction-encoding region
-  int seg_ksteps[2];   // K/16 per segment (0 = unused)
-  int N;               // MMA N: 256 / 128 / 16
-  int epi;             // EPI_*
-  int out_mat;         // stash (fwd) / delta (dgrad) matrix written by the epilogue, -1 none
-  int act_mat;         // dgrad: stash matrix of the activation whose derivative multiplies, -1 none
-  int write_a;         // result becomes the next step's main A operand
-  int bias_off;        // float offset of this step's bias vector in the packed bias area, -1 none
-  int tmem_col;        // accumulator base column
-  int n_chunks;        // main weight chunks (one per K step, N*64 bytes each)
-  int head_chunk;      // fwd: one extra 16 KB chunk = the N=16 sigma-head block over K=256
-  long long pack_off;       // byte offset of the main chunks
-  long long head_pack_off;  // byte offset of the head chunk
+  int N;          // 256 (two halves) or 128 (one)
+  int acc_col;    // accumulator base column (0 or 256)
+  int a_col;      // TMEM A base column
+  int a_k;        // K taken from TMEM: 0, 128 or 256
+  int seg;        // shared-memory K segment: 0 none, 1 positional encoding (4 K steps), 2 direction (2)
+  int epi;        // EPI_*
+  int out_mat;    // stash (fwd) / delta (dgrad) matrix written by the epilogue, -1 none
+  int act_mat;    // dgrad: stash matrix of the activation whose derivative multiplies, -1 none
+  int write_a;    // result becomes the next step's A operand
+  int bias_idx;   // row of the shared bias table, -1 none
+  int rank1;      // dgrad: += g_sigma * w_sigma[n] before the activation derivative
+  int sig_head;   // fwd: this epilogue also accumulates the sigma head
+  float acc_scale;   // EPI_F_LINEAR: out = acc_scale * acc + bias (keeps the packed weights out of fp16 subnormals)
+  long long pack_off;   // byte offset of this step's weight chunks (in MMA issue order)
 };
 
 struct TcArgs {
@@ -69,27 +80,20 @@ struct TcArgs {
   TcStep steps[TC_MAX_STEPS];
   int n_steps;
   int split3;
+  int softplus;                  // hidden activation is softplus(beta=100) (log2-domain epilogue)
   long long n_rays;
   int K;
   const float* rays_o;
   const float* rays_d;
   const float* jitter;
-  const float* params;
   const unsigned char* pack;     // packed weights
-  const float* pack_bias;        // packed (16 B aligned) biases
+  const float* vec;              // packed float vectors (VEC_* layout)
   unsigned char* stash;          // fp16 stash (tcs_* layout); fwd: written when STASH, dgrad: read
   unsigned char* delta;          // dgrad: fp16 delta mats (written)
   float* raw;                    // fwd: [S][1+C] raw sigma / radiance
   const float* graw;             // dgrad: [S][1+C] d loss / d raw
   const unsigned int* gmax;      // dgrad: max |graw| (float bits) -> power-of-two delta scale
 };
-
-__device__ __forceinline__ uint32_t region_hi(int region) {
-  return region == 0 ? SM_A_HI : (region == 1 ? SM_P_HI : SM_D_HI);
-}
-__device__ __forceinline__ uint32_t region_lo(int region) {
-  return region == 0 ? SM_A_LO : (region == 1 ? SM_P_LO : SM_D_LO);
-}
 
 __device__ __forceinline__ float ex2_ftz(float x) {
   float y;
@@ -101,15 +105,30 @@ __device__ __forceinline__ float lg2_ftz(float x) {
   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// softplus(beta=100, threshold=20) = ln2/100 * lg2(1 + ex2(100 log2e x)) on the MUFU pipe: 2 MUFU +
-// 5 FP32 ops per element, absolute error ~2e-9 (results below 2^-126 flush to zero)
-__device__ __forceinline__ float softplus100_fast(float x) {
-  const float t = x * 144.26950408889634f;                 // 100 * log2(e)
-  const float y = lg2_ftz(1.f + ex2_ftz(t)) * 0.0069314718055994531f;   // ln(2) / 100
-  return t > 28.853900817779268f ? x : y;                  // 100 x > 20
+// log2-domain softplus: u = 100 log2e x  ->  100 log2e * softplus_100(x)
+__device__ __forceinline__ float softplus_log2(float u) { return fmaxf(u, 0.f) + lg2_ftz(1.f + ex2_ftz(-fabsf(u))); }
+// d softplus / dx from g = 100 log2e * softplus_100(x): sigmoid(100 x) = 1 - 2^-g
+__device__ __forceinline__ float softplus_grad_log2(float g) { return 1.f - ex2_ftz(-g); }
+
+__device__ __forceinline__ void tc_mma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
 }
-// d softplus / dx from the OUTPUT a: sigmoid(100 x) = 1 - exp(-100 a)
-__device__ __forceinline__ float softplus100_grad_fast(float a) { return 1.f - ex2_ftz(a * -144.26950408889634f); }
+__device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tc_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // One out-of-line accurate sine keeps the kernel small (84 inlined sinf bodies were ~100 KB of
 // SASS and stalled the epilogue warps on instruction fetch).
@@ -145,17 +164,26 @@ __device__ __forceinline__ void encode_cores(const float* x, int deg, int kp, in
   }
 }
 
+// K sources of a step in MMA issue order: 0 = shared-memory segment, 1 = TMEM K-half 0, 2 = TMEM K-half 1
+__host__ __device__ inline int step_src_ksteps(const TcStep& st, int src) {
+  if (src == 0) return st.seg == 1 ? 4 : (st.seg == 2 ? 2 : 0);
+  if (src == 1) return st.a_k >= 128 ? 8 : 0;
+  return st.a_k >= 256 ? 8 : 0;
+}
+
 template <int MODE, bool STASH>   // MODE 0: forward, 1: dgrad
 __global__ void __launch_bounds__(TC_THREADS, 1) ren_tc_chain(const TcArgs a) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const RenPlan& p = a.p;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t sbase = smem_u32(smem);
-  const uint32_t bar_full = sbase + SM_BAR;            // [3]
-  const uint32_t bar_empty = sbase + SM_BAR + 24;      // [3]
-  const uint32_t bar_aready = sbase + SM_BAR + 48;
-  const uint32_t bar_accfull = sbase + SM_BAR + 56;
+  const uint32_t bar_full = sbase + SM_BAR;                 // [16]
+  const uint32_t bar_empty = sbase + SM_BAR + 128;          // [16]
+  const uint32_t bar_p = sbase + SM_BAR + 256;              // encodings of the tile are in shared memory
+  const uint32_t bar_a = sbase + SM_BAR + 264;              // [2] A K-half h of the next step is in TMEM
+  const uint32_t bar_acc = sbase + SM_BAR + 280;            // [2] accumulator N-half h is complete
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + SM_TMEM_PTR);
+  float* vec = reinterpret_cast<float*>(smem + SM_VEC);
   const long long S = a.n_rays * a.K;
   const long long n_tiles = (S + TC_M - 1) / TC_M;
   const int C1 = 1 + p.C;
@@ -165,10 +193,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ren_tc_chain(const TcArgs a) {
       mbar_init(bar_full + 8 * s, 1);
       mbar_init(bar_empty + 8 * s, 1);
     }
-    mbar_init(bar_aready, 32 * TC_EPI_WARPS);
-    mbar_init(bar_accfull, 1);
+    mbar_init(bar_p, 32 * TC_EPI_WARPS);
+    for (int h = 0; h < 2; ++h) {
+      mbar_init(bar_a + 8 * h, 32 * TC_EPI_WARPS);
+      mbar_init(bar_acc + 8 * h, 1);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  for (int i = threadIdx.x; i < VEC_FLOATS; i += TC_THREADS) vec[i] = a.vec[i];
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(sbase + SM_TMEM_PTR) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -185,21 +217,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ren_tc_chain(const TcArgs a) {
       for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         for (int g = 0; g < a.n_steps; ++g) {
           const TcStep& st = a.steps[g];
-          const uint32_t bytes = (uint32_t)st.N * 64u;
+          const int nh = st.N >> 7;
+          const int n_chunks = nh * (step_src_ksteps(st, 0) + step_src_ksteps(st, 1) + step_src_ksteps(st, 2));
           const unsigned char* src = a.pack + st.pack_off;
-          for (int c = 0; c < st.n_chunks; ++c, ++it) {
-            const uint32_t s = it % TC_STAGES, ph = (it / TC_STAGES) & 1u;
-            mbar_wait(bar_empty + 8 * s, ph ^ 1u);
-            mbar_arrive_expect_tx(bar_full + 8 * s, bytes);
-            bulk_g2s(sbase + SM_RING + s * SM_STAGE_BYTES, src + (size_t)c * bytes, bytes, bar_full + 8 * s);
-          }
-          if (st.head_chunk) {
+          for (int c = 0; c < n_chunks; ++c, ++it) {
             const uint32_t s = it % TC_STAGES, ph = (it / TC_STAGES) & 1u;
             mbar_wait(bar_empty + 8 * s, ph ^ 1u);
             mbar_arrive_expect_tx(bar_full + 8 * s, SM_STAGE_BYTES);
-            bulk_g2s(sbase + SM_RING + s * SM_STAGE_BYTES, a.pack + st.head_pack_off, SM_STAGE_BYTES,
+            bulk_g2s(sbase + SM_RING + s * SM_STAGE_BYTES, src + (size_t)c * SM_STAGE_BYTES, SM_STAGE_BYTES,
                      bar_full + 8 * s);
-            ++it;
           }
         }
       }
@@ -207,72 +233,80 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ren_tc_chain(const TcArgs a) {
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      uint32_t it = 0, ev = 0;
-      const uint32_t idesc16 = umma_idesc(16, 0, 0);
+      uint32_t it = 0, n_p = 0, n_a[2] = {0u, 0u};
+      const uint32_t idesc = umma_idesc(128, 0, 0);
       for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        for (int g = 0; g < a.n_steps; ++g, ++ev) {
-          const TcStep& st = a.steps[g];
-          mbar_wait(bar_aready, ev & 1u);
+        if (MODE == 0) {
+          mbar_wait(bar_p, n_p & 1u);
+          ++n_p;
           tc_fence_after();
-          const uint32_t idesc = umma_idesc(st.N, 0, 0);
-          const uint32_t b_lbo = (uint32_t)st.N * 16u;
-          const uint32_t d_addr = tmem_base + (uint32_t)st.tmem_col;
-          int c = 0;
-          for (int seg = 0; seg < 2; ++seg) {
-            const uint32_t a_hi = sbase + region_hi(st.seg_region[seg]);
-            const uint32_t a_lo = sbase + region_lo(st.seg_region[seg]);
-            for (int ks = 0; ks < st.seg_ksteps[seg]; ++ks, ++c, ++it) {
-              const uint32_t s = it % TC_STAGES, ph = (it / TC_STAGES) & 1u;
-              mbar_wait(bar_full + 8 * s, ph);
+        }
+        for (int g = 0; g < a.n_steps; ++g) {
+          const TcStep& st = a.steps[g];
+          const int nh = st.N >> 7;
+          int last_src = 0;
+          for (int src = 0; src < 3; ++src)
+            if (step_src_ksteps(st, src) > 0) last_src = src;
+          uint32_t started[2] = {0u, 0u};
+          for (int src = 0; src < 3; ++src) {
+            const int nks = step_src_ksteps(st, src);
+            if (nks == 0) continue;
+            if (src > 0) {
+              mbar_wait(bar_a + 8 * (src - 1), n_a[src - 1] & 1u);
+              ++n_a[src - 1];
               tc_fence_after();
-              const uint32_t wb = sbase + SM_RING + s * SM_STAGE_BYTES;
-              const uint64_t da_hi = umma_desc(a_hi + ks * 4096, TC_M * 16, 128);
-              const uint64_t db_hi = umma_desc(wb, b_lbo, 128);
-              tc_mma_f16(d_addr, da_hi, db_hi, idesc, c > 0 ? 1u : 0u);
-              if (a.split3) {
-                const uint64_t da_lo = umma_desc(a_lo + ks * 4096, TC_M * 16, 128);
-                const uint64_t db_lo = umma_desc(wb + st.N * 32, b_lbo, 128);
-                tc_mma_f16(d_addr, da_lo, db_hi, idesc, 1u);
-                tc_mma_f16(d_addr, da_hi, db_lo, idesc, 1u);
+            }
+            const uint32_t seg_hi = sbase + (st.seg == 1 ? SM_P_HI : SM_D_HI);
+            const uint32_t seg_lo = sbase + (st.seg == 1 ? SM_P_LO : SM_D_LO);
+            for (int h = 0; h < nh; ++h) {
+              const uint32_t d_addr = tmem_base + (uint32_t)(st.acc_col + 128 * h);
+              for (int ks = 0; ks < nks; ++ks, ++it) {
+                const uint32_t s = it % TC_STAGES, ph = (it / TC_STAGES) & 1u;
+                mbar_wait(bar_full + 8 * s, ph);
+                tc_fence_after();
+                const uint32_t wb = sbase + SM_RING + s * SM_STAGE_BYTES;
+                const uint64_t db_hi = umma_desc(wb, 2048, 128);
+                const uint64_t db_lo = umma_desc(wb + 4096, 2048, 128);
+                if (src == 0) {
+                  const uint64_t da_hi = umma_desc(seg_hi + ks * 4096, TC_M * 16, 128);
+                  tc_mma_f16(d_addr, da_hi, db_hi, idesc, started[h]);
+                  if (a.split3) {
+                    const uint64_t da_lo = umma_desc(seg_lo + ks * 4096, TC_M * 16, 128);
+                    tc_mma_f16(d_addr, da_lo, db_hi, idesc, 1u);
+                    tc_mma_f16(d_addr, da_hi, db_lo, idesc, 1u);
+                  }
+                } else {
+                  // features [16 ks, 16 ks + 16) of K-half (src-1): hi at +32 (ks/2) + 8 (ks%2), lo 16 further
+                  const uint32_t a_hi = tmem_base + (uint32_t)(st.a_col + 128 * (src - 1) + 32 * (ks >> 1) + 8 * (ks & 1));
+                  tc_mma_f16_ts(d_addr, a_hi, db_hi, idesc, started[h]);
+                  if (a.split3) {
+                    tc_mma_f16_ts(d_addr, a_hi + 16, db_hi, idesc, 1u);
+                    tc_mma_f16_ts(d_addr, a_hi, db_lo, idesc, 1u);
+                  }
+                }
+                started[h] = 1u;
+                tc_commit(bar_empty + 8 * s);   // frees the ring slot when these MMAs have read it
               }
-              tc_commit(bar_empty + 8 * s);   // frees the ring slot when these MMAs have read it
+              if (src == last_src) tc_commit(bar_acc + 8 * h);   // accumulator half complete -> epilogue
             }
           }
-          if (st.head_chunk) {
-            // sigma head: [128 x 256] main operand times the N=16 block (row 0 = w_sigma)
-            const uint32_t s = it % TC_STAGES, ph = (it / TC_STAGES) & 1u;
-            mbar_wait(bar_full + 8 * s, ph);
-            tc_fence_after();
-            const uint32_t wb = sbase + SM_RING + s * SM_STAGE_BYTES;
-            for (int ks = 0; ks < 16; ++ks) {
-              const uint64_t da_hi = umma_desc(sbase + SM_A_HI + ks * 4096, TC_M * 16, 128);
-              const uint64_t db_hi = umma_desc(wb + ks * 1024, 256, 128);
-              tc_mma_f16(tmem_base + TMEM_COL_SIGMA, da_hi, db_hi, idesc16, ks > 0 ? 1u : 0u);
-              if (a.split3) {
-                const uint64_t da_lo = umma_desc(sbase + SM_A_LO + ks * 4096, TC_M * 16, 128);
-                const uint64_t db_lo = umma_desc(wb + ks * 1024 + 512, 256, 128);
-                tc_mma_f16(tmem_base + TMEM_COL_SIGMA, da_lo, db_hi, idesc16, 1u);
-                tc_mma_f16(tmem_base + TMEM_COL_SIGMA, da_hi, db_lo, idesc16, 1u);
-              }
-            }
-            tc_commit(bar_empty + 8 * s);
-            ++it;
-          }
-          tc_commit(bar_accfull);             // accumulator complete -> epilogue
         }
       }
     }
   } else {
     // ===================== prologue + epilogue warps =====================
     const int q = warp & 3;                  // TMEM lane quadrant this warp may access
-    const int cg = (warp - 2) >> 2;          // column group 0..3
+    const int cg = (warp - 2) >> 2;          // column group 0..3: 32 of the 128 columns of a half
     const int m = q * 32 + lane;             // row of the tile == TMEM lane
     const uint32_t tmem_lane = tmem_base + ((uint32_t)(q * 32) << 16);
-    uint32_t ev = 0;
+    float4* part = reinterpret_cast<float4*>(smem + SM_PART);   // [4][128]
+    uint32_t n_acc[2] = {0u, 0u};
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const long long sidx = tile * TC_M + m;
       const bool valid = sidx < S;
       bool selector = false;
+      float gs = 0.f;                        // dgrad: scaled d loss / d sigma_raw of this row
+      float head_acc[4] = {0.f, 0.f, 0.f, 0.f};
       if (MODE == 0) {
         // ---- forward prologue: column groups 0-2 encode the position (k-cores 0-2 / 3-5 / 6-7),
         //      group 3 encodes the direction
@@ -306,131 +340,156 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ren_tc_chain(const TcArgs a) {
           encode_cores(dz, 4, 32, 0, 4, valid, smem, SM_D_HI, SM_D_LO, m,
                        STASH ? a.stash + tcs_encd(p, S) : nullptr, sidx);
         }
+        fence_proxy_async();
+        mbar_arrive(bar_p);
       } else {
-        // ---- dgrad prologue: head gradients enter as rank-1 K=16 segments:
-        //      region 1 column 0 = d sigma_raw, region 2 columns 0..C-1 = d c_raw
-        if (cg == 0) {
-          float gs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-          float gc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-          if (valid) {
-            const float sc = delta_scale(a.gmax);
-            gs[0] = a.graw[sidx * C1] * sc;
-            for (int c = 0; c < p.C; ++c) gc[c] = a.graw[sidx * C1 + 1 + c] * sc;
+        // ---- dgrad prologue: Delta of the view-conditioned layer, elementwise:
+        //      d g[n] = act'(g[n]) * sum_c (d c_raw[c]) W_o[c][n]  -> A K-half 0 of the first step
+        const TcStep& st0 = a.steps[0];
+        const int mat = p.cond[0].mat;
+        const size_t tile_off = (size_t)tile * (size_t)(p.WC >> 3) * 2048 + (size_t)m * 16 + (size_t)(cg * 4) * 2048;
+        uint4 act[4];
+        if (valid) {
+          const unsigned char* am = a.stash + tcs_mat(p, S, mat) + tile_off;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) act[i] = __ldg(reinterpret_cast<const uint4*>(am + i * 2048));
+        }
+        float gc[3] = {0.f, 0.f, 0.f};
+        if (valid) {
+          const float sc = delta_scale(a.gmax);
+          gs = a.graw[sidx * C1] * sc;
+          for (int c = 0; c < p.C; ++c) gc[c] = a.graw[sidx * C1 + 1 + c] * sc;
+        }
+        uint32_t hi16[16], lo16[16];
+        unsigned char* dm = a.delta + tcs_mat(p, S, mat) + tile_off;
+#pragma unroll
+        for (int j8 = 0; j8 < 4; ++j8) {
+          float av[8], y[8];
+          unpack8(act[j8], av);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int n = cg * 32 + j8 * 8 + j;
+            float v = gc[0] * vec[VEC_WO + n];
+            if (p.C > 1) v = fmaf(gc[1], vec[VEC_WO + 128 + n], v);
+            if (p.C > 2) v = fmaf(gc[2], vec[VEC_WO + 256 + n], v);
+            v *= a.softplus ? softplus_grad_log2(av[j]) : (av[j] > 0.f ? 1.f : 0.f);
+            y[j] = valid ? v : 0.f;
           }
           uint4 hi, lo;
-          split8(gs, &hi, &lo);
-          *reinterpret_cast<uint4*>(smem + SM_P_HI + m * 16) = hi;
-          *reinterpret_cast<uint4*>(smem + SM_P_LO + m * 16) = lo;
-          split8(gc, &hi, &lo);
-          *reinterpret_cast<uint4*>(smem + SM_D_HI + m * 16) = hi;
-          *reinterpret_cast<uint4*>(smem + SM_D_LO + m * 16) = lo;
-        } else if (cg == 1) {
-          const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);   // second K core of both rank-1 segments
-          *reinterpret_cast<uint4*>(smem + SM_P_HI + TC_M * 16 + m * 16) = z4;
-          *reinterpret_cast<uint4*>(smem + SM_P_LO + TC_M * 16 + m * 16) = z4;
-          *reinterpret_cast<uint4*>(smem + SM_D_HI + TC_M * 16 + m * 16) = z4;
-          *reinterpret_cast<uint4*>(smem + SM_D_LO + TC_M * 16 + m * 16) = z4;
+          split8(y, &hi, &lo);
+          hi16[j8 * 4 + 0] = hi.x; hi16[j8 * 4 + 1] = hi.y; hi16[j8 * 4 + 2] = hi.z; hi16[j8 * 4 + 3] = hi.w;
+          lo16[j8 * 4 + 0] = lo.x; lo16[j8 * 4 + 1] = lo.y; lo16[j8 * 4 + 2] = lo.z; lo16[j8 * 4 + 3] = lo.w;
+          *reinterpret_cast<uint4*>(dm + j8 * 2048) = hi;
         }
+        const uint32_t tcol = tmem_lane + (uint32_t)(st0.a_col + 32 * cg);
+        tc_st16(tcol, hi16);
+        tc_st16(tcol + 16, lo16);
+        tc_st_wait();
+        tc_fence_before();
+        mbar_arrive(bar_a);
       }
-      fence_proxy_async();
-      mbar_arrive(bar_aready);
 
-      // ---- one epilogue per GEMM step
-      for (int g = 0; g < a.n_steps; ++g, ++ev) {
+      // ---- one epilogue per GEMM step and N-half
+      for (int g = 0; g < a.n_steps; ++g) {
         const TcStep& st = a.steps[g];
-        const int ncol = st.N >> 2;                  // columns this warp handles (64 / 32 / 4)
-        const int col0 = cg * ncol;
-        // dgrad: prefetch this thread's slice of the activation stash while the MMAs run
-        // byte offset of this thread's 8-feature group g8 inside a blocked fp16 matrix of width N:
-        //   (tile * N/8 + g8) * 2048 + m * 16   == the shared-memory operand offset + a per-tile base
-        const size_t tile_off = (size_t)tile * (size_t)(st.N >> 3) * 2048 + (size_t)m * 16;
-        uint4 act_pref[8];
-        if (MODE == 1 && st.epi == EPI_D_ACT && valid) {
-          const unsigned char* am = a.stash + tcs_mat(p, S, st.act_mat) + tile_off + (size_t)(col0 >> 3) * 2048;
+        const int nh = st.N >> 7;
+        for (int h = 0; h < nh; ++h) {
+          const int n0 = 128 * h + 32 * cg;            // first of this thread's 32 features
+          // byte offset of this thread's first 8-feature group inside a blocked fp16 matrix of width N
+          const size_t tile_off = (size_t)tile * (size_t)(st.N >> 3) * 2048 + (size_t)m * 16 + (size_t)(n0 >> 3) * 2048;
+          uint4 act[4];
+          if (MODE == 1 && st.epi == EPI_D_ACT && valid) {
+            // prefetch this thread's slice of the activation stash while the MMAs run
+            const unsigned char* am = a.stash + tcs_mat(p, S, st.act_mat) + tile_off;
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
-            if (i * 8 < ncol) act_pref[i] = __ldg(reinterpret_cast<const uint4*>(am + i * 2048));
-        }
-        mbar_wait(bar_accfull, ev & 1u);
-        tc_fence_after();
-        if (st.epi == EPI_F_HEADS) {
-          if (cg == 0) {
-            uint32_t rs[16], rc[16];
-            tc_ld16(tmem_lane + TMEM_COL_SIGMA, rs);
-            tc_ld16(tmem_lane + TMEM_COL_RGB, rc);
-            tc_ld_wait();
-            if (valid) {
-              const float sraw = __uint_as_float(rs[0]) + __ldg(a.params + p.sig_b);
-              a.raw[sidx * C1] = selector ? sraw : -INFINITY;
-              for (int c = 0; c < p.C; ++c)
-                a.raw[sidx * C1 + 1 + c] = __uint_as_float(rc[c]) + __ldg(a.params + p.rgb_b + c);
-            }
+            for (int i = 0; i < 4; ++i) act[i] = __ldg(reinterpret_cast<const uint4*>(am + i * 2048));
           }
-        } else {
-          unsigned char* out_mat = nullptr;       // already offset to this thread's row of the tile
+          mbar_wait(bar_acc + 8 * h, n_acc[h] & 1u);
+          ++n_acc[h];
+          tc_fence_after();
+          const uint32_t tcol = tmem_lane + (uint32_t)(st.acc_col + n0);
+          uint32_t r[32];
+          tc_ld16(tcol, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
+          tc_ld16(tcol + 16, *reinterpret_cast<uint32_t(*)[16]>(&r[16]));
+          tc_ld_wait();
+          unsigned char* out_mat = nullptr;        // already offset to this thread's row / first group
           if (MODE == 0) {
             if (STASH && st.out_mat >= 0) out_mat = a.stash + tcs_mat(p, S, st.out_mat) + tile_off;
-          } else if (st.out_mat >= 0) {      // padded rows are written as zeros (wgrad reads whole tiles)
+          } else if (st.out_mat >= 0) {            // padded rows are written as zeros (wgrad reads whole tiles)
             out_mat = a.delta + tcs_mat(p, S, st.out_mat) + tile_off;
           }
-          unsigned char* a_row = smem + (uint32_t)m * 16;
-          const float* bias = (MODE == 0 && st.bias_off >= 0) ? a.pack_bias + st.bias_off : nullptr;
-          const uint32_t tcol = tmem_lane + (uint32_t)(st.tmem_col + col0);
-          uint32_t r[2][16];
-          tc_ld16(tcol, r[0]);
-          tc_ld_wait();
+          const float* bias = (MODE == 0 && st.bias_idx >= 0) ? vec + VEC_BIAS + st.bias_idx * 256 + n0 : nullptr;
+          uint32_t hi16[16], lo16[16];
 #pragma unroll
-          for (int cb = 0; cb < 64; cb += 32) {       // fully unrolled: register arrays stay registers
+          for (int j8 = 0; j8 < 4; ++j8) {
+            float y[8];
+            if (MODE == 0) {
+              const float4 b0 = *reinterpret_cast<const float4*>(bias + j8 * 8);
+              const float4 b1 = *reinterpret_cast<const float4*>(bias + j8 * 8 + 4);
+              const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-            for (int hb = 0; hb < 2; ++hb) {
-              const int cbb = cb + hb * 16;
-              if (cbb < ncol) {
-                if (cbb + 16 < ncol) tc_ld16(tcol + cbb + 16, r[hb ^ 1]);   // prefetch the next block
-#pragma unroll
-                for (int j8 = 0; j8 < 2; ++j8) {
-                  const int n0 = col0 + cbb + j8 * 8;
-                  float y[8];
-                  if (MODE == 0) {
-                    const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + n0));
-                    const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + n0 + 4));
-                    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                      const float x = __uint_as_float(r[hb][j8 * 8 + j]) + bb[j];
-                      if (st.epi == EPI_F_LINEAR) y[j] = x;
-                      else y[j] = (p.f.hidden_activation == REN_HIDDEN_SOFTPLUS100) ? softplus100_fast(x) : fmaxf(x, 0.f);
-                    }
-                  } else {
-                    float av[8];
-                    if (st.epi == EPI_D_ACT) unpack8(act_pref[(cbb >> 3) + j8], av);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                      float v = __uint_as_float(r[hb][j8 * 8 + j]);
-                      if (st.epi == EPI_D_ACT)
-                        v *= (p.f.hidden_activation == REN_HIDDEN_SOFTPLUS100) ? softplus100_grad_fast(av[j])
-                                                                               : (av[j] > 0.f ? 1.f : 0.f);
-                      y[j] = valid ? v : 0.f;
-                    }
-                  }
-                  uint4 hi, lo;
-                  split8(y, &hi, &lo);
-                  const uint32_t goff = (uint32_t)(n0 >> 3) * (TC_M * 16);
-                  if (st.write_a) {
-                    *reinterpret_cast<uint4*>(a_row + SM_A_HI + goff) = hi;
-                    *reinterpret_cast<uint4*>(a_row + SM_A_LO + goff) = lo;
-                  }
-                  if (out_mat != nullptr) *reinterpret_cast<uint4*>(out_mat + goff) = hi;
+              for (int j = 0; j < 8; ++j) {
+                if (st.epi == EPI_F_LINEAR) {
+                  y[j] = fmaf(__uint_as_float(r[j8 * 8 + j]), st.acc_scale, bb[j]);
+                } else {
+                  const float x = __uint_as_float(r[j8 * 8 + j]) + bb[j];
+                  y[j] = a.softplus ? softplus_log2(x) : fmaxf(x, 0.f);
                 }
-                tc_ld_wait();
+              }
+              if (st.sig_head) {
+                const float4 w0 = *reinterpret_cast<const float4*>(vec + VEC_WSIG + n0 + j8 * 8);
+                const float4 w1 = *reinterpret_cast<const float4*>(vec + VEC_WSIG + n0 + j8 * 8 + 4);
+                const float ww[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+                for (int j = 0; j < 8; ++j) head_acc[0] = fmaf(y[j], ww[j], head_acc[0]);
+              }
+              if (st.epi == EPI_F_LAST) {
+                for (int c = 0; c < p.C; ++c) {
+                  const float* wo = vec + VEC_WO + c * 128 + n0 + j8 * 8;
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) head_acc[1 + c] = fmaf(y[j], wo[j], head_acc[1 + c]);
+                }
+              }
+            } else {
+              float av[8];
+              if (st.epi == EPI_D_ACT) unpack8(act[j8], av);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                float v = __uint_as_float(r[j8 * 8 + j]);
+                if (st.rank1) v = fmaf(gs, vec[VEC_WSIG + n0 + j8 * 8 + j], v);
+                if (st.epi == EPI_D_ACT)
+                  v *= a.softplus ? softplus_grad_log2(av[j]) : (av[j] > 0.f ? 1.f : 0.f);
+                y[j] = valid ? v : 0.f;
               }
             }
+            uint4 hi, lo;
+            split8(y, &hi, &lo);
+            hi16[j8 * 4 + 0] = hi.x; hi16[j8 * 4 + 1] = hi.y; hi16[j8 * 4 + 2] = hi.z; hi16[j8 * 4 + 3] = hi.w;
+            lo16[j8 * 4 + 0] = lo.x; lo16[j8 * 4 + 1] = lo.y; lo16[j8 * 4 + 2] = lo.z; lo16[j8 * 4 + 3] = lo.w;
+            if (out_mat != nullptr) *reinterpret_cast<uint4*>(out_mat + j8 * 2048) = hi;
+          }
+          if (st.write_a) {
+            tc_st16(tcol, hi16);
+            tc_st16(tcol + 16, lo16);
+            tc_st_wait();
+            tc_fence_before();
+            mbar_arrive(bar_a + 8 * h);
           }
         }
-        tc_fence_before();
-        if (g + 1 < a.n_steps) {
-          fence_proxy_async();
-          mbar_arrive(bar_aready);
+      }
+      if (MODE == 0) {
+        // ---- heads: combine the four column groups of each row
+        part[cg * 128 + m] = make_float4(head_acc[0], head_acc[1], head_acc[2], head_acc[3]);
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");
+        if (cg == 0 && valid) {
+          const float4 p0 = part[m], p1 = part[128 + m], p2 = part[256 + m], p3 = part[384 + m];
+          const float sraw = (p0.x + p1.x) + (p2.x + p3.x) + vec[VEC_HB];
+          a.raw[sidx * C1] = selector ? sraw : -INFINITY;
+          a.raw[sidx * C1 + 1] = (p0.y + p1.y) + (p2.y + p3.y) + vec[VEC_HB + 1];
+          if (p.C > 1) a.raw[sidx * C1 + 2] = (p0.z + p1.z) + (p2.z + p3.z) + vec[VEC_HB + 2];
+          if (p.C > 2) a.raw[sidx * C1 + 3] = (p0.w + p1.w) + (p2.w + p3.w) + vec[VEC_HB + 3];
         }
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");
       }
     }
   }
@@ -443,23 +502,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ren_tc_chain(const TcArgs a) {
 }
 
 // ------------------------------------------------------------------ weight packing
-// A pack job writes one B operand: chunks of 16 K' values, each chunk = [hi: N x 16][lo: N x 16]
-// in the core-matrix layout.  mode 0: B[n][k'] = W[n*ldw + col(k')] (forward; two input segments);
-// mode 1: B[n][k'] = W[k'*ldw + n] (transposed, dgrad); mode 2: fp32 copy of a bias vector.
-#define TC_MAX_PACK 64
+// A pack job writes consecutive [128 x 16] B chunks: chunk = [hi: 2 K-cores x 128 rows x 16 B][lo: same].
+//   mode 0: B[n][k] = scale * W[(n0+n)*ldw + col0 + k]   (forward;  k < Ktrue, n0+n < Ntrue)
+//   mode 1: B[n][k] = W[(col0+k)*ldw + n0 + n]           (dgrad: transposed)
+//   mode 2: vec[dst + i] = scale * params[w_off + i], i < Ntrue (zero up to n_ksteps entries)
+#define TC_MAX_PACK 72
 struct PackJob {
   long long dst_off;   // bytes (modes 0/1) or floats (mode 2)
-  int mode, N, n_ksteps;
-  int w_off, ldw;
-  int Ntrue;           // valid rows n
-  int ks0, K0, K1;     // mode 0: segment 0 padded K steps / true widths; mode 1: K0 = valid K'
+  int mode, n0, Ntrue, n_ksteps, k0, Ktrue;
+  int w_off, ldw, col0;
+  float scale;
 };
 struct PackArgs {
   PackJob jobs[TC_MAX_PACK];
   int n_jobs;
   const float* params;
   unsigned char* pack;
-  float* pack_bias;
+  float* vec;
 };
 
 extern "C" __global__ void ren_tc_pack(const PackArgs a) {
@@ -467,34 +526,28 @@ extern "C" __global__ void ren_tc_pack(const PackArgs a) {
   if (g >= a.n_jobs) return;
   const PackJob& jb = a.jobs[g];
   if (jb.mode == 2) {
-    for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < jb.N; n += gridDim.x * blockDim.x)
-      a.pack_bias[jb.dst_off + n] = n < jb.Ntrue ? a.params[jb.w_off + n] : 0.f;
+    for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < jb.n_ksteps; n += gridDim.x * blockDim.x)
+      a.vec[jb.dst_off + n] = n < jb.Ntrue ? a.params[jb.w_off + n] * jb.scale : 0.f;
     return;
   }
-  const int total = jb.n_ksteps * 16 * jb.N;
+  const int total = jb.n_ksteps * 16 * 128;
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
-    const int n = e % jb.N;
-    const int kc = e / jb.N;
+    int n, kc;
+    if (jb.mode == 0) { kc = e % (jb.n_ksteps * 16); n = e / (jb.n_ksteps * 16); }   // reads run along k
+    else { n = e % 128; kc = e / 128; }                                              // reads run along n
     const int c = kc >> 4, kk = kc & 15;
+    const int k = jb.k0 + kc;
     float w = 0.f;
-    if (n < jb.Ntrue) {
-      if (jb.mode == 0) {
-        const int k0pad = jb.ks0 * 16;
-        if (kc < k0pad) {
-          if (kc < jb.K0) w = a.params[jb.w_off + (long long)n * jb.ldw + kc];
-        } else if (kc - k0pad < jb.K1) {
-          w = a.params[jb.w_off + (long long)n * jb.ldw + jb.K0 + (kc - k0pad)];
-        }
-      } else if (kc < jb.K0) {
-        w = a.params[jb.w_off + (long long)kc * jb.ldw + n];
-      }
+    if (jb.n0 + n < jb.Ntrue && k < jb.Ktrue) {
+      if (jb.mode == 0) w = a.params[jb.w_off + (long long)(jb.n0 + n) * jb.ldw + jb.col0 + k] * jb.scale;
+      else w = a.params[jb.w_off + (long long)(jb.col0 + k) * jb.ldw + jb.n0 + n];
     }
     const __half hi = __float2half_rn(w);
     const __half lo = __float2half_rn(w - __half2float(hi));
-    unsigned char* chunk = a.pack + jb.dst_off + (size_t)c * jb.N * 64;
-    const size_t off = (size_t)(kk >> 3) * (jb.N * 16) + (size_t)n * 16 + (kk & 7) * 2;
+    unsigned char* chunk = a.pack + jb.dst_off + (size_t)c * SM_STAGE_BYTES;
+    const size_t off = (size_t)(kk >> 3) * 2048 + (size_t)n * 16 + (kk & 7) * 2;
     *reinterpret_cast<__half*>(chunk + off) = hi;
-    *reinterpret_cast<__half*>(chunk + (size_t)jb.N * 32 + off) = lo;
+    *reinterpret_cast<__half*>(chunk + 4096 + off) = lo;
   }
 }
 
@@ -505,106 +558,109 @@ struct TcProgram {
   PackJob jobs[TC_MAX_PACK];
   int n_jobs;
   long long pack_bytes;    // packed weights
-  long long bias_floats;   // packed biases
 };
 
-static void add_pack(TcProgram& P, int mode, long long dst, int N, int n_ksteps, int w_off, int ldw, int Ntrue,
-                     int ks0, int K0, int K1) {
+static void add_vec(TcProgram& P, int dst, int count, int n_valid, int w_off, float scale) {
   PackJob& j = P.jobs[P.n_jobs++];
-  j.dst_off = dst; j.mode = mode; j.N = N; j.n_ksteps = n_ksteps; j.w_off = w_off; j.ldw = ldw; j.Ntrue = Ntrue;
-  j.ks0 = ks0; j.K0 = K0; j.K1 = K1;
+  memset(&j, 0, sizeof(j));
+  j.dst_off = dst; j.mode = 2; j.n_ksteps = count; j.Ntrue = n_valid; j.w_off = w_off; j.scale = scale;
+}
+
+// chunks of one step in MMA issue order: source (segment, K-half 0, K-half 1) -> N-half -> K step
+static void add_step_pack(TcProgram& P, TcStep& s, long long& off, int mode, int w_off, int ldw, int Ntrue,
+                          int main_col0, int main_K, float main_scale, int seg_col0, int seg_K, float seg_scale) {
+  s.pack_off = off;
+  const int nh = s.N >> 7;
+  for (int src = 0; src < 3; ++src) {
+    const int nks = step_src_ksteps(s, src);
+    if (nks == 0) continue;
+    for (int h = 0; h < nh; ++h) {
+      PackJob& j = P.jobs[P.n_jobs++];
+      memset(&j, 0, sizeof(j));
+      j.dst_off = off; j.mode = mode; j.n0 = 128 * h; j.Ntrue = Ntrue; j.n_ksteps = nks;
+      j.w_off = w_off; j.ldw = ldw;
+      if (src == 0) { j.k0 = 0; j.Ktrue = seg_K; j.col0 = seg_col0; j.scale = seg_scale; }
+      else { j.k0 = 128 * (src - 1); j.Ktrue = main_K; j.col0 = main_col0; j.scale = main_scale; }
+      off += (long long)nks * SM_STAGE_BYTES;
+    }
+  }
 }
 
 static void build_forward(const RenPlan& p, TcProgram& P) {
   memset(&P, 0, sizeof(P));
-  long long off = 0, boff = 0;
-  auto add_layer = [&](const RenLayer& L, int epi) -> TcStep& {
-    TcStep& s = P.steps[P.n_steps++];
-    s.seg_region[0] = L.src0 == 1 ? 1 : 0;
-    s.seg_ksteps[0] = (L.K0 + 15) / 16;
-    s.seg_region[1] = L.src1;
-    s.seg_ksteps[1] = L.K1 > 0 ? (L.K1 + 15) / 16 : 0;
-    s.N = L.N; s.epi = epi; s.out_mat = L.mat; s.act_mat = -1; s.write_a = 1; s.tmem_col = 0;
-    s.n_chunks = s.seg_ksteps[0] + s.seg_ksteps[1];
-    s.pack_off = off;
-    add_pack(P, 0, off, L.N, s.n_chunks, L.w_off, L.K0 + L.K1, L.N, s.seg_ksteps[0], L.K0, L.K1);
-    off += (long long)s.n_chunks * s.N * 64;
-    s.bias_off = (int)boff;
-    add_pack(P, 2, boff, 256, 0, L.b_off, 0, L.N, 0, 0, 0);
-    boff += 256;
+  const bool sp = p.f.hidden_activation == REN_HIDDEN_SOFTPLUS100;
+  const float cs = sp ? LOG2E_100 : 1.f, kap = sp ? LN2_OVER_100 : 1.f;
+  long long off = 0;
+  int acc = 0, prev_acc = 0;
+  auto add_layer = [&](const RenLayer& L, int epi, int N, float out_scale, float main_in_scale) -> TcStep& {
+    TcStep& s = P.steps[P.n_steps];
+    memset(&s, 0, sizeof(s));
+    s.N = N; s.acc_col = acc; s.a_col = prev_acc; s.epi = epi; s.out_mat = L.mat; s.act_mat = -1;
+    s.write_a = epi != EPI_F_LAST; s.bias_idx = P.n_steps;
+    int seg_col0 = 0, seg_K = 0, main_K = 0;
+    if (L.src0 == 1) { s.a_k = 0; s.seg = 1; seg_col0 = 0; seg_K = L.K0; }          // first layer: encoding only
+    else {
+      s.a_k = L.K0; main_K = L.K0;
+      if (L.K1 > 0) { s.seg = L.src1; seg_col0 = L.K0; seg_K = L.K1; }
+    }
+    const float main_scale = (out_scale * main_in_scale > 0.999f && out_scale * main_in_scale < 1.001f)
+                                 ? 1.f : out_scale * main_in_scale;     // 100 log2e * ln2/100 == 1 exactly
+    add_step_pack(P, s, off, 0, L.w_off, L.K0 + L.K1, L.N, 0, main_K, main_scale, seg_col0, seg_K, out_scale);
+    add_vec(P, VEC_BIAS + P.n_steps * 256, 256, L.N, L.b_off, out_scale);
+    ++P.n_steps;
+    prev_acc = acc;
+    acc = 256 - acc;
     return s;
   };
-  for (int i = 0; i < p.D; ++i) add_layer(p.trunk[i], EPI_F_HIDDEN);
-  {
-    TcStep& s = add_layer(p.bott, EPI_F_LINEAR);
-    // sigma head rides on the bottleneck step (same A operand = last trunk activations)
-    s.head_chunk = 1;
-    s.head_pack_off = off;
-    add_pack(P, 0, off, 16, 16, p.sig_w, p.W, 1, 16, p.W, 0);
-    off += SM_STAGE_BYTES;
+  for (int i = 0; i < p.D; ++i) {
+    TcStep& s = add_layer(p.trunk[i], EPI_F_HIDDEN, 256, cs, 1.f / cs);
+    if (i == p.D - 1) s.sig_head = 1;
   }
-  add_layer(p.cond[0], EPI_F_HIDDEN);
-  {
-    // radiance head: [128 x WC] condition activations times the N=16 block (rows 0..C-1 = W_o)
-    TcStep& s = P.steps[P.n_steps++];
-    s.seg_region[0] = 0; s.seg_ksteps[0] = p.WC / 16; s.seg_region[1] = 0; s.seg_ksteps[1] = 0;
-    s.N = 16; s.epi = EPI_F_HEADS; s.out_mat = -1; s.act_mat = -1; s.write_a = 0; s.bias_off = -1;
-    s.tmem_col = TMEM_COL_RGB; s.n_chunks = s.seg_ksteps[0]; s.pack_off = off;
-    add_pack(P, 0, off, 16, s.n_chunks, p.rgb_w, p.WC, p.C, s.n_chunks, p.WC, 0);
-    off += (long long)s.n_chunks * 16 * 64;
-  }
+  add_layer(p.bott, EPI_F_LINEAR, 256, 1.f, 1.f).acc_scale = kap;   // bott = kap * (W_b g) + b_b
+  add_layer(p.cond[0], EPI_F_LAST, 128, cs, 1.f);
+  add_vec(P, VEC_WSIG, 256, p.W, p.sig_w, kap);
+  for (int c = 0; c < 3; ++c) add_vec(P, VEC_WO + 128 * c, 128, c < p.C ? p.WC : 0, p.rgb_w + (c < p.C ? c : 0) * p.WC, kap);
+  add_vec(P, VEC_HB, 1, 1, p.sig_b, 1.f);
+  add_vec(P, VEC_HB + 1, 3, p.C, p.rgb_b, 1.f);
   P.pack_bytes = off;
-  P.bias_floats = boff;
 }
 
 static void build_dgrad(const RenPlan& p, TcProgram& P) {
   memset(&P, 0, sizeof(P));
   long long off = 0;
-  auto add = [&](int region0, int ks0, int region1, int ks1, int N, int epi, int out_mat, int act_mat,
-                 int write_a) -> TcStep& {
+  int acc = 256, prev_acc = 0;     // the prologue writes the first A operand (Delta of the condition layer) at column 0
+  auto add = [&](int a_k, int epi, int out_mat, int act_mat, int write_a, int rank1, int w_off, int ldw) {
     TcStep& s = P.steps[P.n_steps++];
-    s.seg_region[0] = region0; s.seg_ksteps[0] = ks0; s.seg_region[1] = region1; s.seg_ksteps[1] = ks1;
-    s.N = N; s.epi = epi; s.out_mat = out_mat; s.act_mat = act_mat; s.write_a = write_a; s.bias_off = -1;
-    s.tmem_col = 0; s.n_chunks = ks0 + ks1; s.pack_off = off;
-    return s;
+    memset(&s, 0, sizeof(s));
+    s.N = 256; s.acc_col = acc; s.a_col = prev_acc; s.a_k = a_k; s.seg = 0; s.epi = epi; s.out_mat = out_mat;
+    s.act_mat = act_mat; s.write_a = write_a; s.bias_idx = -1; s.rank1 = rank1;
+    add_step_pack(P, s, off, 1, w_off, ldw, p.W, 0, a_k, 1.f, 0, 0, 1.f);
+    prev_acc = acc;
+    acc = 256 - acc;
   };
-  // t0: d g = (d c_raw) W_o, times act'(g)            [rank-C segment in region 2]
-  {
-    TcStep& s = add(2, 1, 0, 0, p.WC, EPI_D_ACT, p.cond[0].mat, p.cond[0].mat, 1);
-    add_pack(P, 1, off, p.WC, 1, p.rgb_w, p.WC, p.WC, 0, p.C, 0);
-    off += (long long)s.n_chunks * s.N * 64;
-  }
-  // t1: d bott = d g_pre W_r0[:, :W]                   (bottleneck is linear)
-  {
-    TcStep& s = add(0, p.WC / 16, 0, 0, p.W, EPI_D_LINEAR, p.bott.mat, -1, 1);
-    add_pack(P, 1, off, p.W, s.n_chunks, p.cond[0].w_off, p.cond[0].K0 + p.cond[0].K1, p.W, 0, p.WC, 0);
-    off += (long long)s.n_chunks * s.N * 64;
-  }
+  // t1: d bott = d g_pre W_r0[:, :W]                    (bottleneck is linear)
+  add(p.WC, EPI_D_LINEAR, p.bott.mat, -1, 1, 0, p.cond[0].w_off, p.cond[0].K0 + p.cond[0].K1);
   // t2: d a_{D-1} = d bott W_b + (d sigma_raw) w_sigma, times act'(a_{D-1})
   {
     const int last = p.trunk[p.D - 1].mat;
-    TcStep& s = add(0, p.W / 16, 1, 1, p.W, EPI_D_ACT, last, last, p.D > 1 ? 1 : 0);
-    add_pack(P, 1, off, p.W, p.W / 16, p.bott.w_off, p.bott.K0 + p.bott.K1, p.W, 0, p.W, 0);
-    add_pack(P, 1, off + (long long)(p.W / 16) * p.W * 64, p.W, 1, p.sig_w, p.W, p.W, 0, 1, 0);
-    off += (long long)s.n_chunks * s.N * 64;
+    add(p.W, EPI_D_ACT, last, last, p.D > 1 ? 1 : 0, 1, p.bott.w_off, p.bott.K0 + p.bott.K1);
   }
   // trunk layers D-1 .. 1: d a_{i-1} = Delta_i W_i[:, :W], times act'(a_{i-1})
   for (int i = p.D - 1; i >= 1; --i) {
     const RenLayer& L = p.trunk[i];
-    TcStep& s = add(0, p.W / 16, 0, 0, p.W, EPI_D_ACT, p.trunk[i - 1].mat, p.trunk[i - 1].mat, i > 1 ? 1 : 0);
-    add_pack(P, 1, off, p.W, s.n_chunks, L.w_off, L.K0 + L.K1, p.W, 0, p.W, 0);
-    off += (long long)s.n_chunks * s.N * 64;
+    add(p.W, EPI_D_ACT, p.trunk[i - 1].mat, p.trunk[i - 1].mat, i > 1 ? 1 : 0, 0, L.w_off, L.K0 + L.K1);
   }
+  add_vec(P, VEC_WSIG, 256, p.W, p.sig_w, 1.f);
+  for (int c = 0; c < 3; ++c) add_vec(P, VEC_WO + 128 * c, 128, c < p.C ? p.WC : 0, p.rgb_w + (c < p.C ? c : 0) * p.WC, 1.f);
   P.pack_bytes = off;
-  P.bias_floats = 0;
 }
 
 int ren_tc_supported(const RenPlan& p) {
   return p.W == 256 && p.WC == 128 && p.CD == 1 && p.hid_K1 == 0 && p.f.pos_deg == 10 && p.f.dir_deg == 4 &&
-         p.D >= 1 && p.D + 3 <= TC_MAX_STEPS && p.C <= 3 && p.trunk[0].K1 == 0;
+         p.D >= 1 && p.D + 2 <= 12 && p.C <= 3 && p.trunk[0].K1 == 0;
 }
 
-static size_t program_bytes(const TcProgram& P) { return (size_t)P.pack_bytes + (size_t)P.bias_floats * 4 + 2048; }
+static size_t program_bytes(const TcProgram& P) { return (size_t)P.pack_bytes + (size_t)VEC_FLOATS * 4 + 2048; }
 
 size_t ren_tc_fwd_workspace_bytes(const RenPlan& p) {
   if (!ren_tc_supported(p)) return 0;
@@ -619,13 +675,14 @@ size_t ren_tc_bwd_pack_bytes(const RenPlan& p) {
   return program_bytes(P);
 }
 
-static int run_pack(const TcProgram& P, const float* params, unsigned char* pack, float* pack_bias,
-                    cudaStream_t st) {
+static int run_pack(const TcProgram& P, const float* params, unsigned char* pack, float* vec, cudaStream_t st) {
   PackArgs pa;
+  static_assert(sizeof(PackArgs) <= 4000, "pack parameter block too large");
+  if (P.n_jobs > TC_MAX_PACK) { ren_set_error("tc pack: too many jobs (%d)", P.n_jobs); return REN_E_INVALID; }
   for (int i = 0; i < P.n_jobs; ++i) pa.jobs[i] = P.jobs[i];
-  pa.n_jobs = P.n_jobs; pa.params = params; pa.pack = pack; pa.pack_bias = pack_bias;
+  pa.n_jobs = P.n_jobs; pa.params = params; pa.pack = pack; pa.vec = vec;
   ren_prof_begin(REN_K_PACK, st);
-  ren_tc_pack<<<dim3(16, P.n_jobs), 256, 0, st>>>(pa);
+  ren_tc_pack<<<dim3(8, P.n_jobs), 256, 0, st>>>(pa);
   ren_prof_end(REN_K_PACK, st);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { ren_set_error("tc pack launch: %s", cudaGetErrorString(e)); return REN_E_CUDA; }
@@ -649,16 +706,26 @@ static int launch_chain(const TcArgs& a, long long n_tiles, int kind, cudaStream
   return REN_OK;
 }
 
-static int carve_pack(const TcProgram& P, void* ws, size_t ws_bytes, unsigned char** pack, float** pack_bias) {
+static int carve_pack(const TcProgram& P, void* ws, size_t ws_bytes, unsigned char** pack, float** vec) {
   unsigned char* base = (unsigned char*)(((uintptr_t)ws + 1023) & ~(uintptr_t)1023);
-  const size_t need = (size_t)(base - (unsigned char*)ws) + (size_t)P.pack_bytes + (size_t)P.bias_floats * 4 + 16;
+  const size_t need = (size_t)(base - (unsigned char*)ws) + (size_t)P.pack_bytes + (size_t)VEC_FLOATS * 4 + 16;
   if (ws == nullptr || need > ws_bytes) {
     ren_set_error("workspace too small for packed weights (%zu > %zu)", need, ws_bytes);
     return REN_E_WORKSPACE;
   }
   *pack = base;
-  *pack_bias = (float*)(base + ((P.pack_bytes + 15) & ~15LL));
+  *vec = (float*)(base + ((P.pack_bytes + 15) & ~15LL));
   return REN_OK;
+}
+
+static void fill_args(TcArgs& a, const RenPlan& p, const TcProgram& P) {
+  static_assert(sizeof(TcArgs) <= 4000, "kernel parameter block too large");
+  memset(&a, 0, sizeof(a));
+  a.p = p;
+  for (int i = 0; i < P.n_steps; ++i) a.steps[i] = P.steps[i];
+  a.n_steps = P.n_steps;
+  a.split3 = p.r.engine == REN_ENGINE_TC_F16 ? 0 : 1;
+  a.softplus = p.f.hidden_activation == REN_HIDDEN_SOFTPLUS100 ? 1 : 0;
 }
 
 int ren_tc_launch_fwd(const RenPlan& p, long long n_rays, int K, const float* o, const float* d,
@@ -666,20 +733,15 @@ int ren_tc_launch_fwd(const RenPlan& p, long long n_rays, int K, const float* o,
                       size_t ws_bytes, cudaStream_t st) {
   TcProgram P;
   build_forward(p, P);
-  unsigned char* pack; float* pack_bias;
-  int rc = carve_pack(P, ws, ws_bytes, &pack, &pack_bias);
+  unsigned char* pack; float* vec;
+  int rc = carve_pack(P, ws, ws_bytes, &pack, &vec);
   if (rc) return rc;
-  rc = run_pack(P, params, pack, pack_bias, st);
+  rc = run_pack(P, params, pack, vec, st);
   if (rc) return rc;
   TcArgs a;
-  static_assert(sizeof(TcArgs) <= 4000, "kernel parameter block too large");
-  memset(&a, 0, sizeof(a));
-  a.p = p;
-  for (int i = 0; i < P.n_steps; ++i) a.steps[i] = P.steps[i];
-  a.n_steps = P.n_steps;
-  a.split3 = p.r.engine == REN_ENGINE_TC_F16 ? 0 : 1;
-  a.n_rays = n_rays; a.K = K; a.rays_o = o; a.rays_d = d; a.jitter = jitter; a.params = params;
-  a.pack = pack; a.pack_bias = pack_bias; a.stash = (unsigned char*)stash; a.raw = raw;
+  fill_args(a, p, P);
+  a.n_rays = n_rays; a.K = K; a.rays_o = o; a.rays_d = d; a.jitter = jitter;
+  a.pack = pack; a.vec = vec; a.stash = (unsigned char*)stash; a.raw = raw;
   const long long n_tiles = (n_rays * K + TC_M - 1) / TC_M;
   return stash ? launch_chain<0, true>(a, n_tiles, REN_K_FIELD_FWD, st)
                : launch_chain<0, false>(a, n_tiles, REN_K_FIELD_FWD, st);
@@ -690,19 +752,15 @@ int ren_tc_launch_dgrad(const RenPlan& p, long long S, const float* params, cons
                         cudaStream_t st) {
   TcProgram P;
   build_dgrad(p, P);
-  unsigned char* pack; float* pack_bias;
-  int rc = carve_pack(P, ws, ws_bytes, &pack, &pack_bias);
+  unsigned char* pack; float* vec;
+  int rc = carve_pack(P, ws, ws_bytes, &pack, &vec);
   if (rc) return rc;
-  rc = run_pack(P, params, pack, pack_bias, st);
+  rc = run_pack(P, params, pack, vec, st);
   if (rc) return rc;
   TcArgs a;
-  memset(&a, 0, sizeof(a));
-  a.p = p;
-  for (int i = 0; i < P.n_steps; ++i) a.steps[i] = P.steps[i];
-  a.n_steps = P.n_steps;
-  a.split3 = p.r.engine == REN_ENGINE_TC_F16 ? 0 : 1;
+  fill_args(a, p, P);
   a.n_rays = S; a.K = 1;            // dgrad only needs the flat sample count
-  a.params = params; a.pack = pack; a.pack_bias = pack_bias;
+  a.pack = pack; a.vec = vec;
   a.stash = (unsigned char*)stash; a.delta = (unsigned char*)delta; a.graw = graw; a.gmax = gmax;
   const long long n_tiles = (S + TC_M - 1) / TC_M;
   return launch_chain<1, false>(a, n_tiles, REN_K_FIELD_DGRAD, st);

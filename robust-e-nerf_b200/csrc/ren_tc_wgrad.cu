@@ -34,6 +34,7 @@ struct WgMat {
   int Nd, n_half, Hw;
   int w_off, ldw, col0, Ktrue;   // dW[n][col0 + k], k < Ktrue
   int b_off;                     // bias gradient offset or -1
+  float h_scale;                 // the stash keeps hidden activations in the log2 domain (ren_tc.cu): ln2/100, else 1
 };
 struct WgArgs {
   WgMat mats[WG_MAX_MATS];
@@ -154,7 +155,7 @@ extern "C" __global__ void __launch_bounds__(WG_THREADS, 1) ren_tc_wgrad(const W
         if (n < mt.Nd) {
 #pragma unroll
           for (int j = 0; j < 16; ++j)
-            if (cb + j < mt.Ktrue) atomicAdd(row + cb + j, __uint_as_float(r[j]) * unscale);
+            if (cb + j < mt.Ktrue) atomicAdd(row + cb + j, __uint_as_float(r[j]) * (unscale * mt.h_scale));
         }
       }
       if (mt.b_off >= 0) {
@@ -187,6 +188,7 @@ struct HeadArgs {
   int C1;
   long long S, n_tiles;
   float* g_params;
+  float h_scale;               // log2-domain stash -> true activations
 };
 
 extern "C" __global__ void __launch_bounds__(256) ren_tc_head_wgrad(const HeadArgs a) {
@@ -227,7 +229,7 @@ extern "C" __global__ void __launch_bounds__(256) ren_tc_head_wgrad(const HeadAr
       float v = acc[c][j];
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if (lane == 0) atomicAdd(a.g_params + a.w_off[which] + c * N + fg * 8 + j, v);
+      if (lane == 0) atomicAdd(a.g_params + a.w_off[which] + c * N + fg * 8 + j, v * a.h_scale);
     }
     float b = bsum[c];
 #pragma unroll
@@ -243,30 +245,33 @@ int ren_tc_launch_wgrad(const RenPlan& p, long long S, const void* stash, const 
   static_assert(sizeof(WgArgs) <= 4000, "kernel parameter block too large");
   memset(&a, 0, sizeof(a));
   int n = 0;
-  auto add = [&](int dmat, int Nd, long long h_off, int Hw, int w_off, int ldw, int col0, int Ktrue, int b_off) {
+  const float kap = p.f.hidden_activation == REN_HIDDEN_SOFTPLUS100 ? 0.0069314718055994531f : 1.f;
+  auto add = [&](int dmat, int Nd, long long h_off, int Hw, int w_off, int ldw, int col0, int Ktrue, int b_off,
+                 float h_scale) {
     for (int h = 0; h < Nd / 128; ++h) {
       WgMat& m = a.mats[n++];
       m.d_off = (long long)tcs_mat(p, S, dmat); m.Nd = Nd; m.n_half = h; m.h_off = h_off; m.Hw = Hw;
-      m.w_off = w_off; m.ldw = ldw; m.col0 = col0; m.Ktrue = Ktrue; m.b_off = b_off;
+      m.w_off = w_off; m.ldw = ldw; m.col0 = col0; m.Ktrue = Ktrue; m.b_off = b_off; m.h_scale = h_scale;
     }
   };
-  auto add_layer = [&](const RenLayer& L, int prev_mat, int prev_w) {
+  // prev_scale: scale of the stashed main input (hidden activations are kept in the log2 domain)
+  auto add_layer = [&](const RenLayer& L, int prev_mat, int prev_w, float prev_scale) {
     const int ldw = L.K0 + L.K1;
-    if (L.src0 == 1) add(L.mat, L.N, (long long)tcs_encp(p, S), REN_PE_MAX, L.w_off, ldw, 0, L.K0, L.b_off);
-    else add(L.mat, L.N, (long long)tcs_mat(p, S, prev_mat), prev_w, L.w_off, ldw, 0, L.K0, L.b_off);
+    if (L.src0 == 1) add(L.mat, L.N, (long long)tcs_encp(p, S), REN_PE_MAX, L.w_off, ldw, 0, L.K0, L.b_off, 1.f);
+    else add(L.mat, L.N, (long long)tcs_mat(p, S, prev_mat), prev_w, L.w_off, ldw, 0, L.K0, L.b_off, prev_scale);
     if (L.K1 > 0) {
-      if (L.src1 == 1) add(L.mat, L.N, (long long)tcs_encp(p, S), REN_PE_MAX, L.w_off, ldw, L.K0, L.K1, -1);
-      else add(L.mat, L.N, (long long)tcs_encd(p, S), REN_DE_MAX, L.w_off, ldw, L.K0, L.K1, -1);
+      if (L.src1 == 1) add(L.mat, L.N, (long long)tcs_encp(p, S), REN_PE_MAX, L.w_off, ldw, L.K0, L.K1, -1, 1.f);
+      else add(L.mat, L.N, (long long)tcs_encd(p, S), REN_DE_MAX, L.w_off, ldw, L.K0, L.K1, -1, 1.f);
     }
   };
   int prev = -1, prevw = 0;
   for (int i = 0; i < p.D; ++i) {
-    add_layer(p.trunk[i], prev, prevw);
+    add_layer(p.trunk[i], prev, prevw, kap);
     prev = p.trunk[i].mat; prevw = p.trunk[i].N;
   }
   const int last_trunk = prev;
-  add_layer(p.bott, prev, prevw);
-  add_layer(p.cond[0], p.bott.mat, p.bott.N);
+  add_layer(p.bott, prev, prevw, kap);
+  add_layer(p.cond[0], p.bott.mat, p.bott.N, 1.f);
   if (n > WG_MAX_MATS) { ren_set_error("too many wgrad matrices"); return REN_E_INVALID; }
   a.n_mats = n;
   a.n_tiles = (S + TC_M - 1) / TC_M;
@@ -295,7 +300,7 @@ int ren_tc_launch_wgrad(const RenPlan& p, long long S, const void* stash, const 
   h.w_off[0] = p.sig_w; h.b_off[0] = p.sig_b; h.n_ch[0] = 1; h.g_col[0] = 0;
   h.h[1] = (const unsigned char*)stash + tcs_mat(p, S, p.cond[0].mat); h.N[1] = p.WC;
   h.w_off[1] = p.rgb_w; h.b_off[1] = p.rgb_b; h.n_ch[1] = p.C; h.g_col[1] = 1;
-  h.graw = graw; h.C1 = 1 + p.C; h.S = S; h.n_tiles = a.n_tiles; h.g_params = g_params;
+  h.graw = graw; h.C1 = 1 + p.C; h.S = S; h.n_tiles = a.n_tiles; h.g_params = g_params; h.h_scale = kap;
   ren_prof_begin(REN_K_WGRAD, st);
   ren_tc_head_wgrad<<<dim3(sms * 2, 2), 256, 0, st>>>(h);
   ren_prof_end(REN_K_WGRAD, st);
