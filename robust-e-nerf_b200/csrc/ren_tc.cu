@@ -8,10 +8,12 @@
 // activation ever touches shared memory and the two 128-column halves of a layer pipeline against
 // the tensor pipe: while the epilogue warps convert N-half 0, the MMAs of N-half 1 run, and the
 // next layer's K-half-0 MMAs start as soon as half 0 is converted.
-//   warp 0       weight producer: pre-packed fp16 (hi|lo) [128 x 16] weight chunks, L2 -> 16-stage
-//                shared-memory ring with 1-D bulk TMA (cp.async.bulk + mbarrier tx bytes)
-//   warp 1       MMA issuer: one thread issues tcgen05.mma kind::f16, M=128, N=128, K=16; A from
-//                TMEM (activations) or shared memory (positional / direction encodings)
+//   warp 0       weight producer: pre-packed fp16 (hi|lo) weight chunks, L2 -> 4 x 32 KB shared-memory
+//                ring with 1-D bulk TMA (cp.async.bulk + mbarrier tx bytes)
+//   warp 1       MMA issuer: one thread issues tcgen05.mma kind::f16, M=128, K=16; A from TMEM
+//                (activations) or shared memory (positional / direction encodings).  The first K-half
+//                of a layer uses N=256 MMAs, the last K-half runs per N-half (N=128) so that
+//                accumulator half 0 completes -- and its epilogue starts -- a quarter layer early
 //   warps 2-17   prologue (march, contraction, 84 sines -> encodings in shared memory) + epilogues.
 //                Lane quadrant = warp % 4 (TMEM access rule); the 4 warps of a quadrant split the 128
 //                columns of a half 32 each and write their 32 packed columns back over their own.
@@ -26,13 +28,15 @@
 //
 // The sigma / radiance heads (N = 1..3) are per-thread dot products in the epilogue of the layer that
 // feeds them; in dgrad the head gradients re-enter as rank-1 updates in the epilogue.
+#include <stdlib.h>
 #include <string.h>
 
 #include "ren_tc.cuh"
 
 #define TC_EPI_WARPS 16
 #define TC_THREADS (64 + 32 * TC_EPI_WARPS)   // 576
-#define TC_STAGES 16
+#define TC_STAGES 4            // ring stages of up to TC_STAGE_KS K steps (32 KB)
+#define TC_STAGE_KS 4
 #define TC_MAX_STEPS 20
 
 // shared-memory map (bytes)
@@ -41,7 +45,8 @@
 #define SM_D_HI 32768      // direction encoding [128 x 32]
 #define SM_D_LO 40960
 #define SM_RING 49152
-#define SM_STAGE_BYTES 8192
+#define SM_CHUNK_BYTES 8192          // one [128 x 16] hi|lo weight chunk (one K step of one N-half)
+#define SM_STAGE_BYTES (TC_STAGE_KS * SM_CHUNK_BYTES)
 #define SM_VEC (SM_RING + TC_STAGES * SM_STAGE_BYTES)   // 180224: float vectors (biases, head weights)
 #define VEC_BIAS 0                                      // [TC_MAX_STEPS][256] -> only n_steps used
 #define VEC_WSIG (12 * 256)
@@ -81,6 +86,7 @@ struct TcArgs {
   int n_steps;
   int split3;
   int softplus;                  // hidden activation is softplus(beta=100) (log2-domain epilogue)
+  int dbg;                       // timing experiments only (env REN_TC_DBG): 1 no epilogue math, 2 no MMAs, 4 no sines
   long long n_rays;
   int K;
   const float* rays_o;
@@ -171,14 +177,24 @@ __host__ __device__ inline int step_src_ksteps(const TcStep& st, int src) {
   return st.a_k >= 256 ? 8 : 0;
 }
 
+__host__ __device__ inline int step_last_src(const TcStep& st) {
+  return st.a_k >= 256 ? 2 : (st.a_k >= 128 ? 1 : 0);
+}
+// 64-bit shared-memory matrix descriptor from its low word (address/16 | LBO/16 << 16); SBO = 128 B, version 1
+__device__ __forceinline__ uint64_t mk_desc(uint32_t lo32) {
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo32), "r"(0x4008u));
+  return d;
+}
+
 template <int MODE, bool STASH>   // MODE 0: forward, 1: dgrad
 __global__ void __launch_bounds__(TC_THREADS, 1) ren_tc_chain(const TcArgs a) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const RenPlan& p = a.p;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t sbase = smem_u32(smem);
-  const uint32_t bar_full = sbase + SM_BAR;                 // [16]
-  const uint32_t bar_empty = sbase + SM_BAR + 128;          // [16]
+  const uint32_t bar_full = sbase + SM_BAR;                 // [TC_STAGES <= 16]
+  const uint32_t bar_empty = sbase + SM_BAR + 128;          // [TC_STAGES <= 16]
   const uint32_t bar_p = sbase + SM_BAR + 256;              // encodings of the tile are in shared memory
   const uint32_t bar_a = sbase + SM_BAR + 264;              // [2] A K-half h of the next step is in TMEM
   const uint32_t bar_acc = sbase + SM_BAR + 280;            // [2] accumulator N-half h is complete
@@ -193,9 +209,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ren_tc_chain(const TcArgs a) {
       mbar_init(bar_full + 8 * s, 1);
       mbar_init(bar_empty + 8 * s, 1);
     }
-    mbar_init(bar_p, 32 * TC_EPI_WARPS);
+    mbar_init(bar_p, TC_EPI_WARPS);          // one elected lane per epilogue warp arrives
     for (int h = 0; h < 2; ++h) {
-      mbar_init(bar_a + 8 * h, 32 * TC_EPI_WARPS);
+      mbar_init(bar_a + 8 * h, TC_EPI_WARPS);
       mbar_init(bar_acc + 8 * h, 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -212,20 +228,35 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ren_tc_chain(const TcArgs a) {
 
   if (warp == 0) {
     // ===================== weight producer =====================
+    // stage = 32 KB = 2 K steps of a wide [256 x 16] operand or 4 K steps of a [128 x 16] half operand
     if (lane == 0) {
       uint32_t it = 0;
       for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         for (int g = 0; g < a.n_steps; ++g) {
           const TcStep& st = a.steps[g];
           const int nh = st.N >> 7;
-          const int n_chunks = nh * (step_src_ksteps(st, 0) + step_src_ksteps(st, 1) + step_src_ksteps(st, 2));
+          const int last_src = step_last_src(st);
           const unsigned char* src = a.pack + st.pack_off;
-          for (int c = 0; c < n_chunks; ++c, ++it) {
-            const uint32_t s = it % TC_STAGES, ph = (it / TC_STAGES) & 1u;
-            mbar_wait(bar_empty + 8 * s, ph ^ 1u);
-            mbar_arrive_expect_tx(bar_full + 8 * s, SM_STAGE_BYTES);
-            bulk_g2s(sbase + SM_RING + s * SM_STAGE_BYTES, src + (size_t)c * SM_STAGE_BYTES, SM_STAGE_BYTES,
-                     bar_full + 8 * s);
+          for (int sr = 0; sr < 3; ++sr) {
+            const int nks = step_src_ksteps(st, sr);
+            if (nks == 0) continue;
+            const bool wide = sr != last_src && nh == 2;
+            const int per = wide ? 2 : 4, reps = wide ? 1 : nh;
+            const uint32_t chunk = wide ? 2 * SM_CHUNK_BYTES : SM_CHUNK_BYTES;
+            for (int h = 0; h < reps; ++h) {
+              for (int ks0 = 0; ks0 < nks; ks0 += per, ++it) {
+                const uint32_t bytes = (uint32_t)min(per, nks - ks0) * chunk;
+                const uint32_t s = it % TC_STAGES, ph = (it / TC_STAGES) & 1u;
+                mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+                if (a.dbg & 8) {
+                  mbar_arrive(bar_full + 8 * s);
+                } else {
+                  mbar_arrive_expect_tx(bar_full + 8 * s, bytes);
+                  bulk_g2s(sbase + SM_RING + s * SM_STAGE_BYTES, src, bytes, bar_full + 8 * s);
+                }
+                src += bytes;
+              }
+            }
           }
         }
       }
@@ -233,8 +264,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ren_tc_chain(const TcArgs a) {
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      uint32_t it = 0, n_p = 0, n_a[2] = {0u, 0u};
-      const uint32_t idesc = umma_idesc(128, 0, 0);
+      uint32_t it = 0, n_p = 0, n_a0 = 0, n_a1 = 0;
+      const uint32_t idesc128 = umma_idesc(128, 0, 0), idesc256 = umma_idesc(256, 0, 0);
+      const uint32_t split3 = a.split3, nomma = a.dbg & 2;
+      // low words of the shared-memory descriptors are linear in the address (all < 256 KB)
+      const uint32_t ring_lo = ((sbase + SM_RING) >> 4) & 0x3FFFu;
       for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         if (MODE == 0) {
           mbar_wait(bar_p, n_p & 1u);
@@ -244,51 +278,61 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ren_tc_chain(const TcArgs a) {
         for (int g = 0; g < a.n_steps; ++g) {
           const TcStep& st = a.steps[g];
           const int nh = st.N >> 7;
-          int last_src = 0;
-          for (int src = 0; src < 3; ++src)
-            if (step_src_ksteps(st, src) > 0) last_src = src;
-          uint32_t started[2] = {0u, 0u};
+          const int last_src = step_last_src(st);
+          uint32_t fresh = 1u;             // no MMA has touched this step's accumulators yet
           for (int src = 0; src < 3; ++src) {
             const int nks = step_src_ksteps(st, src);
             if (nks == 0) continue;
-            if (src > 0) {
-              mbar_wait(bar_a + 8 * (src - 1), n_a[src - 1] & 1u);
-              ++n_a[src - 1];
-              tc_fence_after();
-            }
-            const uint32_t seg_hi = sbase + (st.seg == 1 ? SM_P_HI : SM_D_HI);
-            const uint32_t seg_lo = sbase + (st.seg == 1 ? SM_P_LO : SM_D_LO);
-            for (int h = 0; h < nh; ++h) {
+            if (src == 1) { mbar_wait(bar_a, n_a0 & 1u); ++n_a0; tc_fence_after(); }
+            if (src == 2) { mbar_wait(bar_a + 8, n_a1 & 1u); ++n_a1; tc_fence_after(); }
+            const bool wide = src != last_src && nh == 2;
+            const int per = wide ? 2 : 4, reps = wide ? 1 : nh;
+            const uint32_t idesc = wide ? idesc256 : idesc128;
+            const uint32_t lbo_bits = (wide ? 256u : 128u) << 16;      // K-core stride / 16
+            const uint32_t chunk16 = wide ? 1024u : 512u;              // chunk bytes / 16
+            const uint32_t seg_lo32 = (((sbase + (st.seg == 1 ? SM_P_HI : SM_D_HI)) >> 4) & 0x3FFFu) | (128u << 16);
+            const uint32_t seg_lo_off = (st.seg == 1 ? (SM_P_LO - SM_P_HI) : (SM_D_LO - SM_D_HI)) >> 4;
+            const uint32_t a_tm = tmem_base + (uint32_t)(st.a_col + 128 * (src - 1));
+            for (int h = 0; h < reps; ++h) {
               const uint32_t d_addr = tmem_base + (uint32_t)(st.acc_col + 128 * h);
-              for (int ks = 0; ks < nks; ++ks, ++it) {
-                const uint32_t s = it % TC_STAGES, ph = (it / TC_STAGES) & 1u;
-                mbar_wait(bar_full + 8 * s, ph);
+              uint32_t acc = fresh ? 0u : 1u;
+              for (int ks0 = 0; ks0 < nks; ks0 += per, ++it) {
+                const uint32_t s = it % TC_STAGES;
+                mbar_wait(bar_full + 8 * s, (it / TC_STAGES) & 1u);
                 tc_fence_after();
-                const uint32_t wb = sbase + SM_RING + s * SM_STAGE_BYTES;
-                const uint64_t db_hi = umma_desc(wb, 2048, 128);
-                const uint64_t db_lo = umma_desc(wb + 4096, 2048, 128);
-                if (src == 0) {
-                  const uint64_t da_hi = umma_desc(seg_hi + ks * 4096, TC_M * 16, 128);
-                  tc_mma_f16(d_addr, da_hi, db_hi, idesc, started[h]);
-                  if (a.split3) {
-                    const uint64_t da_lo = umma_desc(seg_lo + ks * 4096, TC_M * 16, 128);
-                    tc_mma_f16(d_addr, da_lo, db_hi, idesc, 1u);
-                    tc_mma_f16(d_addr, da_hi, db_lo, idesc, 1u);
-                  }
-                } else {
-                  // features [16 ks, 16 ks + 16) of K-half (src-1): hi at +32 (ks/2) + 8 (ks%2), lo 16 further
-                  const uint32_t a_hi = tmem_base + (uint32_t)(st.a_col + 128 * (src - 1) + 32 * (ks >> 1) + 8 * (ks & 1));
-                  tc_mma_f16_ts(d_addr, a_hi, db_hi, idesc, started[h]);
-                  if (a.split3) {
-                    tc_mma_f16_ts(d_addr, a_hi + 16, db_hi, idesc, 1u);
-                    tc_mma_f16_ts(d_addr, a_hi, db_lo, idesc, 1u);
+                const uint32_t b_lo32 = (ring_lo + s * (SM_STAGE_BYTES >> 4)) | lbo_bits;
+                const int cnt = min(per, nks - ks0);
+#pragma unroll
+                for (int kl = 0; kl < 4; ++kl) {
+                  if (kl < cnt && !nomma) {
+                    const int ks = ks0 + kl;
+                    const uint64_t db_hi = mk_desc(b_lo32 + kl * chunk16);
+                    const uint64_t db_lo = mk_desc(b_lo32 + kl * chunk16 + (chunk16 >> 1));
+                    if (src == 0) {
+                      const uint64_t da_hi = mk_desc(seg_lo32 + ks * 256);
+                      const uint64_t da_lo = mk_desc(seg_lo32 + ks * 256 + seg_lo_off);
+                      tc_mma_f16(d_addr, da_hi, db_hi, idesc, acc);
+                      if (split3) {
+                        tc_mma_f16(d_addr, da_lo, db_hi, idesc, 1u);
+                        tc_mma_f16(d_addr, da_hi, db_lo, idesc, 1u);
+                      }
+                    } else {
+                      // features [16 ks, 16 ks + 16) of this K-half: hi at +32 (ks/2) + 8 (ks%2), lo 16 further
+                      const uint32_t a_hi = a_tm + (uint32_t)(32 * (ks >> 1) + 8 * (ks & 1));
+                      tc_mma_f16_ts(d_addr, a_hi, db_hi, idesc, acc);
+                      if (split3) {
+                        tc_mma_f16_ts(d_addr, a_hi + 16, db_hi, idesc, 1u);
+                        tc_mma_f16_ts(d_addr, a_hi, db_lo, idesc, 1u);
+                      }
+                    }
+                    acc = 1u;
                   }
                 }
-                started[h] = 1u;
                 tc_commit(bar_empty + 8 * s);   // frees the ring slot when these MMAs have read it
               }
               if (src == last_src) tc_commit(bar_acc + 8 * h);   // accumulator half complete -> epilogue
             }
+            fresh = 0u;
           }
         }
       }
@@ -303,7 +347,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ren_tc_chain(const TcArgs a) {
     uint32_t n_acc[2] = {0u, 0u};
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const long long sidx = tile * TC_M + m;
-      const bool valid = sidx < S;
+      const bool valid = sidx < S && !(MODE == 0 && (a.dbg & 4));
       bool selector = false;
       float gs = 0.f;                        // dgrad: scaled d loss / d sigma_raw of this row
       float head_acc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -341,7 +385,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ren_tc_chain(const TcArgs a) {
                        STASH ? a.stash + tcs_encd(p, S) : nullptr, sidx);
         }
         fence_proxy_async();
-        mbar_arrive(bar_p);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_p);
       } else {
         // ---- dgrad prologue: Delta of the view-conditioned layer, elementwise:
         //      d g[n] = act'(g[n]) * sum_c (d c_raw[c]) W_o[c][n]  -> A K-half 0 of the first step
@@ -386,7 +431,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ren_tc_chain(const TcArgs a) {
         tc_st16(tcol + 16, lo16);
         tc_st_wait();
         tc_fence_before();
-        mbar_arrive(bar_a);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_a);
       }
 
       // ---- one epilogue per GEMM step and N-half
@@ -409,6 +455,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ren_tc_chain(const TcArgs a) {
           tc_fence_after();
           const uint32_t tcol = tmem_lane + (uint32_t)(st.acc_col + n0);
           uint32_t r[32];
+          if (a.dbg & 16) {
+            if (st.write_a) { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(bar_a + 8 * h); }
+            continue;
+          }
           tc_ld16(tcol, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
           tc_ld16(tcol + 16, *reinterpret_cast<uint32_t(*)[16]>(&r[16]));
           tc_ld_wait();
@@ -433,7 +483,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ren_tc_chain(const TcArgs a) {
                   y[j] = fmaf(__uint_as_float(r[j8 * 8 + j]), st.acc_scale, bb[j]);
                 } else {
                   const float x = __uint_as_float(r[j8 * 8 + j]) + bb[j];
-                  y[j] = a.softplus ? softplus_log2(x) : fmaxf(x, 0.f);
+                  y[j] = (a.dbg & 1) ? x : (a.softplus ? softplus_log2(x) : fmaxf(x, 0.f));
                 }
               }
               if (st.sig_head) {
@@ -473,7 +523,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ren_tc_chain(const TcArgs a) {
             tc_st16(tcol + 16, lo16);
             tc_st_wait();
             tc_fence_before();
-            mbar_arrive(bar_a + 8 * h);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_a + 8 * h);
           }
         }
       }
@@ -502,14 +553,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ren_tc_chain(const TcArgs a) {
 }
 
 // ------------------------------------------------------------------ weight packing
-// A pack job writes consecutive [128 x 16] B chunks: chunk = [hi: 2 K-cores x 128 rows x 16 B][lo: same].
+// A pack job writes consecutive [rows x 16] B chunks (rows = 128 or 256):
+// chunk = [hi: 2 K-cores x rows x 16 B][lo: same].
 //   mode 0: B[n][k] = scale * W[(n0+n)*ldw + col0 + k]   (forward;  k < Ktrue, n0+n < Ntrue)
 //   mode 1: B[n][k] = W[(col0+k)*ldw + n0 + n]           (dgrad: transposed)
 //   mode 2: vec[dst + i] = scale * params[w_off + i], i < Ntrue (zero up to n_ksteps entries)
-#define TC_MAX_PACK 72
+#define TC_MAX_PACK 64
 struct PackJob {
   long long dst_off;   // bytes (modes 0/1) or floats (mode 2)
-  int mode, n0, Ntrue, n_ksteps, k0, Ktrue;
+  int mode, n0, Ntrue, n_ksteps, k0, Ktrue, rows;
   int w_off, ldw, col0;
   float scale;
 };
@@ -530,11 +582,11 @@ extern "C" __global__ void ren_tc_pack(const PackArgs a) {
       a.vec[jb.dst_off + n] = n < jb.Ntrue ? a.params[jb.w_off + n] * jb.scale : 0.f;
     return;
   }
-  const int total = jb.n_ksteps * 16 * 128;
+  const int total = jb.n_ksteps * 16 * jb.rows;
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
     int n, kc;
     if (jb.mode == 0) { kc = e % (jb.n_ksteps * 16); n = e / (jb.n_ksteps * 16); }   // reads run along k
-    else { n = e % 128; kc = e / 128; }                                              // reads run along n
+    else { n = e % jb.rows; kc = e / jb.rows; }                                      // reads run along n
     const int c = kc >> 4, kk = kc & 15;
     const int k = jb.k0 + kc;
     float w = 0.f;
@@ -544,10 +596,10 @@ extern "C" __global__ void ren_tc_pack(const PackArgs a) {
     }
     const __half hi = __float2half_rn(w);
     const __half lo = __float2half_rn(w - __half2float(hi));
-    unsigned char* chunk = a.pack + jb.dst_off + (size_t)c * SM_STAGE_BYTES;
-    const size_t off = (size_t)(kk >> 3) * 2048 + (size_t)n * 16 + (kk & 7) * 2;
+    unsigned char* chunk = a.pack + jb.dst_off + (size_t)c * jb.rows * 64;
+    const size_t off = (size_t)(kk >> 3) * (jb.rows * 16) + (size_t)n * 16 + (kk & 7) * 2;
     *reinterpret_cast<__half*>(chunk + off) = hi;
-    *reinterpret_cast<__half*>(chunk + 4096 + off) = lo;
+    *reinterpret_cast<__half*>(chunk + (size_t)jb.rows * 32 + off) = lo;
   }
 }
 
@@ -571,17 +623,19 @@ static void add_step_pack(TcProgram& P, TcStep& s, long long& off, int mode, int
                           int main_col0, int main_K, float main_scale, int seg_col0, int seg_K, float seg_scale) {
   s.pack_off = off;
   const int nh = s.N >> 7;
+  const int last_src = step_last_src(s);
   for (int src = 0; src < 3; ++src) {
     const int nks = step_src_ksteps(s, src);
     if (nks == 0) continue;
-    for (int h = 0; h < nh; ++h) {
+    const bool wide = src != last_src && nh == 2;     // one [256 x 16] operand instead of two halves
+    for (int h = 0; h < (wide ? 1 : nh); ++h) {
       PackJob& j = P.jobs[P.n_jobs++];
       memset(&j, 0, sizeof(j));
-      j.dst_off = off; j.mode = mode; j.n0 = 128 * h; j.Ntrue = Ntrue; j.n_ksteps = nks;
+      j.dst_off = off; j.mode = mode; j.n0 = 128 * h; j.Ntrue = Ntrue; j.n_ksteps = nks; j.rows = wide ? 256 : 128;
       j.w_off = w_off; j.ldw = ldw;
       if (src == 0) { j.k0 = 0; j.Ktrue = seg_K; j.col0 = seg_col0; j.scale = seg_scale; }
       else { j.k0 = 128 * (src - 1); j.Ktrue = main_K; j.col0 = main_col0; j.scale = main_scale; }
-      off += (long long)nks * SM_STAGE_BYTES;
+      off += (long long)nks * j.rows * 64;
     }
   }
 }
@@ -682,7 +736,7 @@ static int run_pack(const TcProgram& P, const float* params, unsigned char* pack
   for (int i = 0; i < P.n_jobs; ++i) pa.jobs[i] = P.jobs[i];
   pa.n_jobs = P.n_jobs; pa.params = params; pa.pack = pack; pa.vec = vec;
   ren_prof_begin(REN_K_PACK, st);
-  ren_tc_pack<<<dim3(8, P.n_jobs), 256, 0, st>>>(pa);
+  ren_tc_pack<<<dim3(16, P.n_jobs), 256, 0, st>>>(pa);
   ren_prof_end(REN_K_PACK, st);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { ren_set_error("tc pack launch: %s", cudaGetErrorString(e)); return REN_E_CUDA; }
@@ -726,6 +780,8 @@ static void fill_args(TcArgs& a, const RenPlan& p, const TcProgram& P) {
   a.n_steps = P.n_steps;
   a.split3 = p.r.engine == REN_ENGINE_TC_F16 ? 0 : 1;
   a.softplus = p.f.hidden_activation == REN_HIDDEN_SOFTPLUS100 ? 1 : 0;
+  const char* dbg = getenv("REN_TC_DBG");
+  a.dbg = dbg ? atoi(dbg) : 0;
 }
 
 int ren_tc_launch_fwd(const RenPlan& p, long long n_rays, int K, const float* o, const float* d,
