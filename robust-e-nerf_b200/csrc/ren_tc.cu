@@ -34,8 +34,9 @@
 #include "ren_tc.cuh"
 
 #define TC_EPI_WARPS 16
-#define TC_THREADS (64 + 32 * TC_EPI_WARPS)   // 576
-#define TC_STAGES 4            // ring stages of up to TC_STAGE_KS K steps (32 KB)
+#define TC_PRO_WARPS 4                         // forward prologue warps: one thread per sample row
+#define TC_THREADS (64 + 32 * TC_EPI_WARPS + 32 * TC_PRO_WARPS)   // 704
+#define TC_STAGES 3            // ring stages of up to TC_STAGE_KS K steps (32 KB)
 #define TC_STAGE_KS 4
 #define TC_MAX_STEPS 20
 
@@ -44,7 +45,8 @@
 #define SM_P_LO 16384
 #define SM_D_HI 32768      // direction encoding [128 x 32]
 #define SM_D_LO 40960
-#define SM_RING 49152
+#define SM_ENC_BYTES 49152 // one encoding buffer; two of them (the prologue warps run one tile ahead)
+#define SM_RING (2 * SM_ENC_BYTES)
 #define SM_CHUNK_BYTES 8192          // one [128 x 16] hi|lo weight chunk (one K step of one N-half)
 #define SM_STAGE_BYTES (TC_STAGE_KS * SM_CHUNK_BYTES)
 #define SM_VEC (SM_RING + TC_STAGES * SM_STAGE_BYTES)   // 180224: float vectors (biases, head weights)
@@ -54,7 +56,10 @@
 #define VEC_HB (VEC_WO + 384)                           // sigma bias, rgb biases
 #define VEC_FLOATS (VEC_HB + 4)                         // 3716
 #define SM_PART (SM_VEC + 16384)                        // head partial sums: float4 [4][128]
-#define SM_BAR (SM_PART + 8192)
+#define SM_PROG (SM_PART + 8192)                        // stage program: TC_MAX_OPS x 32 B
+#define TC_MAX_OPS 128
+#define SM_SEL (SM_PROG + TC_MAX_OPS * 32)              // selector flags of the two buffered tiles: float [2][128]
+#define SM_BAR (SM_SEL + 1024)
 #define SM_TMEM_PTR (SM_BAR + 320)
 #define SM_TOTAL (SM_BAR + 512)
 
@@ -80,6 +85,19 @@ struct TcStep {
   long long pack_off;   // byte offset of this step's weight chunks (in MMA issue order)
 };
 
+// One ring stage of the tile program (host-built, identical for every tile): what the producer
+// copies and what the MMA issuer does with it.  32 bytes, read as two 128-bit shared-memory loads.
+struct StageOp {
+  uint32_t pack_off;    // byte offset of the stage's weight chunks in the pack buffer
+  uint32_t bytes;       // stage bytes
+  uint32_t d_col;       // accumulator TMEM column
+  uint32_t a_addr;      // A of the first K step: TMEM column (a_smem = 0) or descriptor low word minus base (a_smem = 1)
+  uint32_t a_lo_delta;  // from the hi to the lo part of A (TMEM columns / descriptor units)
+  uint32_t flags;       // [0:2] K steps, [3] wide (N=256), [4] a_smem, [5] first MMA overwrites, [6:7] wait: 1 A-half 0,
+                        // 2 A-half 1, 3 encodings; [8:9] commit accumulator half (1, 2) after the stage
+  uint32_t pad0, pad1;
+};
+
 struct TcArgs {
   RenPlan p;
   TcStep steps[TC_MAX_STEPS];
@@ -94,6 +112,8 @@ struct TcArgs {
   const float* jitter;
   const unsigned char* pack;     // packed weights
   const float* vec;              // packed float vectors (VEC_* layout)
+  const StageOp* prog;           // stage program (global copy)
+  int n_ops;
   unsigned char* stash;          // fp16 stash (tcs_* layout); fwd: written when STASH, dgrad: read
   unsigned char* delta;          // dgrad: fp16 delta mats (written)
   float* raw;                    // fwd: [S][1+C] raw sigma / radiance
@@ -195,9 +215,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ren_tc_chain(const TcArgs a) {
   const uint32_t sbase = smem_u32(smem);
   const uint32_t bar_full = sbase + SM_BAR;                 // [TC_STAGES <= 16]
   const uint32_t bar_empty = sbase + SM_BAR + 128;          // [TC_STAGES <= 16]
-  const uint32_t bar_p = sbase + SM_BAR + 256;              // encodings of the tile are in shared memory
-  const uint32_t bar_a = sbase + SM_BAR + 264;              // [2] A K-half h of the next step is in TMEM
-  const uint32_t bar_acc = sbase + SM_BAR + 280;            // [2] accumulator N-half h is complete
+  const uint32_t bar_p = sbase + SM_BAR + 256;              // [2] encodings of a tile are in shared-memory buffer b
+  const uint32_t bar_pfree = sbase + SM_BAR + 304;          // [2] the MMAs that read buffer b have completed
+  const uint32_t bar_a = sbase + SM_BAR + 272;              // [2] A K-half h of the next step is in TMEM
+  const uint32_t bar_acc = sbase + SM_BAR + 288;            // [2] accumulator N-half h is complete
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + SM_TMEM_PTR);
   float* vec = reinterpret_cast<float*>(smem + SM_VEC);
   const long long S = a.n_rays * a.K;
@@ -209,7 +230,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ren_tc_chain(const TcArgs a) {
       mbar_init(bar_full + 8 * s, 1);
       mbar_init(bar_empty + 8 * s, 1);
     }
-    mbar_init(bar_p, TC_EPI_WARPS);          // one elected lane per epilogue warp arrives
+    for (int h = 0; h < 2; ++h) {
+      mbar_init(bar_p + 8 * h, TC_PRO_WARPS);  // one elected lane per prologue warp arrives
+      mbar_init(bar_pfree + 8 * h, 1);
+    }
     for (int h = 0; h < 2; ++h) {
       mbar_init(bar_a + 8 * h, TC_EPI_WARPS);
       mbar_init(bar_acc + 8 * h, 1);
@@ -217,6 +241,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ren_tc_chain(const TcArgs a) {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int i = threadIdx.x; i < VEC_FLOATS; i += TC_THREADS) vec[i] = a.vec[i];
+  for (int i = threadIdx.x; i < a.n_ops * 8; i += TC_THREADS)
+    reinterpret_cast<uint32_t*>(smem + SM_PROG)[i] = reinterpret_cast<const uint32_t*>(a.prog)[i];
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(sbase + SM_TMEM_PTR) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -228,35 +254,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ren_tc_chain(const TcArgs a) {
 
   if (warp == 0) {
     // ===================== weight producer =====================
-    // stage = 32 KB = 2 K steps of a wide [256 x 16] operand or 4 K steps of a [128 x 16] half operand
     if (lane == 0) {
+      const uint4* prog = reinterpret_cast<const uint4*>(smem + SM_PROG);
       uint32_t it = 0;
       for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        for (int g = 0; g < a.n_steps; ++g) {
-          const TcStep& st = a.steps[g];
-          const int nh = st.N >> 7;
-          const int last_src = step_last_src(st);
-          const unsigned char* src = a.pack + st.pack_off;
-          for (int sr = 0; sr < 3; ++sr) {
-            const int nks = step_src_ksteps(st, sr);
-            if (nks == 0) continue;
-            const bool wide = sr != last_src && nh == 2;
-            const int per = wide ? 2 : 4, reps = wide ? 1 : nh;
-            const uint32_t chunk = wide ? 2 * SM_CHUNK_BYTES : SM_CHUNK_BYTES;
-            for (int h = 0; h < reps; ++h) {
-              for (int ks0 = 0; ks0 < nks; ks0 += per, ++it) {
-                const uint32_t bytes = (uint32_t)min(per, nks - ks0) * chunk;
-                const uint32_t s = it % TC_STAGES, ph = (it / TC_STAGES) & 1u;
-                mbar_wait(bar_empty + 8 * s, ph ^ 1u);
-                if (a.dbg & 8) {
-                  mbar_arrive(bar_full + 8 * s);
-                } else {
-                  mbar_arrive_expect_tx(bar_full + 8 * s, bytes);
-                  bulk_g2s(sbase + SM_RING + s * SM_STAGE_BYTES, src, bytes, bar_full + 8 * s);
-                }
-                src += bytes;
-              }
-            }
+        for (int i = 0; i < a.n_ops; ++i, ++it) {
+          const uint4 o0 = prog[2 * i];
+          const uint32_t s = it % TC_STAGES, ph = (it / TC_STAGES) & 1u;
+          mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+          if (a.dbg & 8) {
+            mbar_arrive(bar_full + 8 * s);
+          } else {
+            mbar_arrive_expect_tx(bar_full + 8 * s, o0.y);
+            bulk_g2s(sbase + SM_RING + s * SM_STAGE_BYTES, a.pack + o0.x, o0.y, bar_full + 8 * s);
           }
         }
       }
@@ -264,129 +274,134 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ren_tc_chain(const TcArgs a) {
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
+      const uint4* prog = reinterpret_cast<const uint4*>(smem + SM_PROG);
       uint32_t it = 0, n_p = 0, n_a0 = 0, n_a1 = 0;
       const uint32_t idesc128 = umma_idesc(128, 0, 0), idesc256 = umma_idesc(256, 0, 0);
       const uint32_t split3 = a.split3, nomma = a.dbg & 2;
       // low words of the shared-memory descriptors are linear in the address (all < 256 KB)
       const uint32_t ring_lo = ((sbase + SM_RING) >> 4) & 0x3FFFu;
-      for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        if (MODE == 0) {
-          mbar_wait(bar_p, n_p & 1u);
-          ++n_p;
+      const uint32_t smem_lo = ((sbase >> 4) & 0x3FFFu) | (128u << 16);      // encodings: K-core stride 2048 B
+      for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n_p) {
+        const uint32_t eb = n_p & 1u;                                   // encoding buffer of this tile
+        const uint32_t enc_lo = smem_lo + eb * (SM_ENC_BYTES >> 4);
+        uint4 o0 = prog[0], o1 = prog[1];
+        for (int i = 0; i < a.n_ops; ++i, ++it) {
+          const uint32_t flags = o1.y, d_addr = tmem_base + o0.z, a0 = o0.w, a_ld = o1.x;
+          // prefetch the next op while this one runs
+          const int nx = (i + 1 < a.n_ops) ? i + 1 : 0;
+          const uint4 p0 = prog[2 * nx], p1 = prog[2 * nx + 1];
+          const uint32_t wt = (flags >> 6) & 3u;
+          if (wt == 1u) { mbar_wait(bar_a, n_a0 & 1u); ++n_a0; tc_fence_after(); }
+          else if (wt == 2u) { mbar_wait(bar_a + 8, n_a1 & 1u); ++n_a1; tc_fence_after(); }
+          else if (wt == 3u) { mbar_wait(bar_p + 8 * eb, (n_p >> 1) & 1u); tc_fence_after(); }
+          const uint32_t s = it % TC_STAGES;
+          mbar_wait(bar_full + 8 * s, (it / TC_STAGES) & 1u);
           tc_fence_after();
-        }
-        for (int g = 0; g < a.n_steps; ++g) {
-          const TcStep& st = a.steps[g];
-          const int nh = st.N >> 7;
-          const int last_src = step_last_src(st);
-          uint32_t fresh = 1u;             // no MMA has touched this step's accumulators yet
-          for (int src = 0; src < 3; ++src) {
-            const int nks = step_src_ksteps(st, src);
-            if (nks == 0) continue;
-            if (src == 1) { mbar_wait(bar_a, n_a0 & 1u); ++n_a0; tc_fence_after(); }
-            if (src == 2) { mbar_wait(bar_a + 8, n_a1 & 1u); ++n_a1; tc_fence_after(); }
-            const bool wide = src != last_src && nh == 2;
-            const int per = wide ? 2 : 4, reps = wide ? 1 : nh;
-            const uint32_t idesc = wide ? idesc256 : idesc128;
-            const uint32_t lbo_bits = (wide ? 256u : 128u) << 16;      // K-core stride / 16
-            const uint32_t chunk16 = wide ? 1024u : 512u;              // chunk bytes / 16
-            const uint32_t seg_lo32 = (((sbase + (st.seg == 1 ? SM_P_HI : SM_D_HI)) >> 4) & 0x3FFFu) | (128u << 16);
-            const uint32_t seg_lo_off = (st.seg == 1 ? (SM_P_LO - SM_P_HI) : (SM_D_LO - SM_D_HI)) >> 4;
-            const uint32_t a_tm = tmem_base + (uint32_t)(st.a_col + 128 * (src - 1));
-            for (int h = 0; h < reps; ++h) {
-              const uint32_t d_addr = tmem_base + (uint32_t)(st.acc_col + 128 * h);
-              uint32_t acc = fresh ? 0u : 1u;
-              for (int ks0 = 0; ks0 < nks; ks0 += per, ++it) {
-                const uint32_t s = it % TC_STAGES;
-                mbar_wait(bar_full + 8 * s, (it / TC_STAGES) & 1u);
-                tc_fence_after();
-                const uint32_t b_lo32 = (ring_lo + s * (SM_STAGE_BYTES >> 4)) | lbo_bits;
-                const int cnt = min(per, nks - ks0);
+          const bool wide = (flags & 8u) != 0u;
+          const uint32_t idesc = wide ? idesc256 : idesc128;
+          const uint32_t chunk16 = wide ? 1024u : 512u;               // chunk bytes / 16
+          const uint32_t b_lo32 = (ring_lo + s * (SM_STAGE_BYTES >> 4)) | ((wide ? 256u : 128u) << 16);
+          const int cnt = (int)(flags & 7u);
+          uint32_t acc = (flags & 32u) ? 0u : 1u;
+          if (!nomma) {
+            if (flags & 16u) {
+              const uint32_t a_lo32 = enc_lo + a0;
 #pragma unroll
-                for (int kl = 0; kl < 4; ++kl) {
-                  if (kl < cnt && !nomma) {
-                    const int ks = ks0 + kl;
-                    const uint64_t db_hi = mk_desc(b_lo32 + kl * chunk16);
-                    const uint64_t db_lo = mk_desc(b_lo32 + kl * chunk16 + (chunk16 >> 1));
-                    if (src == 0) {
-                      const uint64_t da_hi = mk_desc(seg_lo32 + ks * 256);
-                      const uint64_t da_lo = mk_desc(seg_lo32 + ks * 256 + seg_lo_off);
-                      tc_mma_f16(d_addr, da_hi, db_hi, idesc, acc);
-                      if (split3) {
-                        tc_mma_f16(d_addr, da_lo, db_hi, idesc, 1u);
-                        tc_mma_f16(d_addr, da_hi, db_lo, idesc, 1u);
-                      }
-                    } else {
-                      // features [16 ks, 16 ks + 16) of this K-half: hi at +32 (ks/2) + 8 (ks%2), lo 16 further
-                      const uint32_t a_hi = a_tm + (uint32_t)(32 * (ks >> 1) + 8 * (ks & 1));
-                      tc_mma_f16_ts(d_addr, a_hi, db_hi, idesc, acc);
-                      if (split3) {
-                        tc_mma_f16_ts(d_addr, a_hi + 16, db_hi, idesc, 1u);
-                        tc_mma_f16_ts(d_addr, a_hi, db_lo, idesc, 1u);
-                      }
-                    }
-                    acc = 1u;
+              for (int kl = 0; kl < TC_STAGE_KS; ++kl) {
+                if (kl < cnt) {
+                  const uint64_t db_hi = mk_desc(b_lo32 + kl * chunk16);
+                  const uint64_t da_hi = mk_desc(a_lo32 + kl * 256);
+                  tc_mma_f16(d_addr, da_hi, db_hi, idesc, acc);
+                  if (split3) {
+                    tc_mma_f16(d_addr, mk_desc(a_lo32 + kl * 256 + a_ld), db_hi, idesc, 1u);
+                    tc_mma_f16(d_addr, da_hi, mk_desc(b_lo32 + kl * chunk16 + (chunk16 >> 1)), idesc, 1u);
                   }
+                  acc = 1u;
                 }
-                tc_commit(bar_empty + 8 * s);   // frees the ring slot when these MMAs have read it
               }
-              if (src == last_src) tc_commit(bar_acc + 8 * h);   // accumulator half complete -> epilogue
+            } else {
+              const uint32_t a_tm = tmem_base + a0;
+#pragma unroll
+              for (int kl = 0; kl < TC_STAGE_KS; ++kl) {
+                if (kl < cnt) {
+                  // K step ks0 + kl (ks0 even): hi columns at +32 (kl/2) + 8 (kl%2), lo 16 further
+                  const uint32_t a_hi = a_tm + (uint32_t)(32 * (kl >> 1) + 8 * (kl & 1));
+                  const uint64_t db_hi = mk_desc(b_lo32 + kl * chunk16);
+                  tc_mma_f16_ts(d_addr, a_hi, db_hi, idesc, acc);
+                  if (split3) {
+                    tc_mma_f16_ts(d_addr, a_hi + a_ld, db_hi, idesc, 1u);
+                    tc_mma_f16_ts(d_addr, a_hi, mk_desc(b_lo32 + kl * chunk16 + (chunk16 >> 1)), idesc, 1u);
+                  }
+                  acc = 1u;
+                }
+              }
             }
-            fresh = 0u;
           }
+          tc_commit(bar_empty + 8 * s);          // frees the ring slot when these MMAs have read it
+          const uint32_t ca = (flags >> 8) & 3u;
+          if (ca) tc_commit(bar_acc + 8 * (ca - 1u));   // accumulator half complete -> epilogue
+          o0 = p0; o1 = p1;
         }
+        if (MODE == 0) tc_commit(bar_pfree + 8 * eb);   // every MMA reading this tile's encodings is done
+      }
+    }
+  } else if (warp >= 2 + TC_EPI_WARPS) {
+    // ===================== forward prologue warps (one tile ahead of the MMAs) =====================
+    // march -> sample position -> contraction -> sin/cos encodings of one sample row per thread, written
+    // as fp16 hi/lo K-major operands into the free encoding buffer (+ the fp16 stash when training)
+    if (MODE == 0) {
+      const int m = (warp - 2 - TC_EPI_WARPS) * 32 + lane;
+      float* sel = reinterpret_cast<float*>(smem + SM_SEL);
+      uint32_t n_t = 0;
+      for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n_t) {
+        const uint32_t eb = n_t & 1u;
+        const long long sidx = tile * TC_M + m;
+        const bool valid = sidx < S && !(a.dbg & 4);
+        float o[3] = {0.f, 0.f, 0.f}, d[3] = {0.f, 0.f, 1.f}, z[3] = {0.f, 0.f, 0.f};
+        bool selector = false;
+        if (valid) {
+          const long long r = sidx / a.K;
+          const int k = (int)(sidx - r * a.K);
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            o[c] = a.rays_o[r * 3 + c];
+            d[c] = a.rays_d[r * 3 + c];
+          }
+          float t_min, t_max, t0, t1;
+          ren_ray_range(p.f, p.r, o, d, a.jitter ? a.jitter[r] : 0.f, &t_min, &t_max);
+          ren_march_to(p.r, t_min, k, &t0, &t1);
+          selector = ren_field_input(p.f, o, d, t0, t1, z);
+          if (!ren_alive(t0, t1, t_max)) selector = false;
+        }
+        const float dz[3] = {__fmul_rn(d[0], 3.141592653589793f), __fmul_rn(d[1], 3.141592653589793f),
+                             __fmul_rn(d[2], 3.141592653589793f)};
+        mbar_wait(bar_pfree + 8 * eb, ((n_t >> 1) & 1u) ^ 1u);       // the MMAs of tile n_t - 2 are done with it
+        unsigned char* buf = smem + eb * SM_ENC_BYTES;
+        encode_cores(z, 10, 64, 0, 8, valid, buf, SM_P_HI, SM_P_LO, m, STASH ? a.stash + tcs_encp(p, S) : nullptr, sidx);
+        encode_cores(dz, 4, 32, 0, 4, valid, buf, SM_D_HI, SM_D_LO, m, STASH ? a.stash + tcs_encd(p, S) : nullptr, sidx);
+        sel[eb * 128 + m] = selector ? 1.f : 0.f;
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_p + 8 * eb);
       }
     }
   } else {
-    // ===================== prologue + epilogue warps =====================
+    // ===================== epilogue warps =====================
     const int q = warp & 3;                  // TMEM lane quadrant this warp may access
     const int cg = (warp - 2) >> 2;          // column group 0..3: 32 of the 128 columns of a half
     const int m = q * 32 + lane;             // row of the tile == TMEM lane
     const uint32_t tmem_lane = tmem_base + ((uint32_t)(q * 32) << 16);
     float4* part = reinterpret_cast<float4*>(smem + SM_PART);   // [4][128]
     uint32_t n_acc[2] = {0u, 0u};
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    uint32_t n_t = 0;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n_t) {
       const long long sidx = tile * TC_M + m;
       const bool valid = sidx < S && !(MODE == 0 && (a.dbg & 4));
       bool selector = false;
       float gs = 0.f;                        // dgrad: scaled d loss / d sigma_raw of this row
       float head_acc[4] = {0.f, 0.f, 0.f, 0.f};
       if (MODE == 0) {
-        // ---- forward prologue: column groups 0-2 encode the position (k-cores 0-2 / 3-5 / 6-7),
-        //      group 3 encodes the direction
-        float o[3] = {0.f, 0.f, 0.f}, d[3] = {0.f, 0.f, 1.f};
-        long long r = 0;
-        int k = 0;
-        if (valid) {
-          r = sidx / a.K;
-          k = (int)(sidx - r * a.K);
-#pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            o[c] = a.rays_o[r * 3 + c];
-            d[c] = a.rays_d[r * 3 + c];
-          }
-        }
-        if (cg < 3) {
-          float z[3] = {0.f, 0.f, 0.f};
-          if (valid) {
-            float t_min, t_max, t0, t1;
-            ren_ray_range(p.f, p.r, o, d, a.jitter ? a.jitter[r] : 0.f, &t_min, &t_max);
-            ren_march_to(p.r, t_min, k, &t0, &t1);
-            selector = ren_field_input(p.f, o, d, t0, t1, z);
-            if (!ren_alive(t0, t1, t_max)) selector = false;
-          }
-          unsigned char* sm = STASH ? a.stash + tcs_encp(p, S) : nullptr;
-          const int c0 = cg == 0 ? 0 : (cg == 1 ? 3 : 6), c1 = cg == 0 ? 3 : (cg == 1 ? 6 : 8);
-          encode_cores(z, 10, 64, c0, c1, valid, smem, SM_P_HI, SM_P_LO, m, sm, sidx);
-        } else {
-          const float dz[3] = {__fmul_rn(d[0], 3.141592653589793f), __fmul_rn(d[1], 3.141592653589793f),
-                               __fmul_rn(d[2], 3.141592653589793f)};
-          encode_cores(dz, 4, 32, 0, 4, valid, smem, SM_D_HI, SM_D_LO, m,
-                       STASH ? a.stash + tcs_encd(p, S) : nullptr, sidx);
-        }
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_p);
+        // the encodings of this tile come from the prologue warps (one tile ahead)
       } else {
         // ---- dgrad prologue: Delta of the view-conditioned layer, elementwise:
         //      d g[n] = act'(g[n]) * sum_c (d c_raw[c]) W_o[c][n]  -> A K-half 0 of the first step
@@ -453,6 +468,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ren_tc_chain(const TcArgs a) {
           mbar_wait(bar_acc + 8 * h, n_acc[h] & 1u);
           ++n_acc[h];
           tc_fence_after();
+          // the prologue warps published the selector before bar_p of this tile, which the first MMA waited
+          // for; read it now -- the buffer may be recycled as soon as the tile's last MMA completes
+          if (MODE == 0 && g == 0 && h == 0)
+            selector = reinterpret_cast<const volatile float*>(smem + SM_SEL)[(n_t & 1u) * 128 + m] != 0.f;
           const uint32_t tcol = tmem_lane + (uint32_t)(st.acc_col + n0);
           uint32_t r[32];
           if (a.dbg & 16) {
@@ -532,7 +551,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ren_tc_chain(const TcArgs a) {
         // ---- heads: combine the four column groups of each row
         part[cg * 128 + m] = make_float4(head_acc[0], head_acc[1], head_acc[2], head_acc[3]);
         asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");
-        if (cg == 0 && valid) {
+        if (cg == 0 && sidx < S) {
           const float4 p0 = part[m], p1 = part[128 + m], p2 = part[256 + m], p3 = part[384 + m];
           const float sraw = (p0.x + p1.x) + (p2.x + p3.x) + vec[VEC_HB];
           a.raw[sidx * C1] = selector ? sraw : -INFINITY;
@@ -607,6 +626,8 @@ extern "C" __global__ void ren_tc_pack(const PackArgs a) {
 struct TcProgram {
   TcStep steps[TC_MAX_STEPS];
   int n_steps;
+  StageOp ops[TC_MAX_OPS];
+  int n_ops;
   PackJob jobs[TC_MAX_PACK];
   int n_jobs;
   long long pack_bytes;    // packed weights
@@ -709,12 +730,77 @@ static void build_dgrad(const RenPlan& p, TcProgram& P) {
   P.pack_bytes = off;
 }
 
+// Flatten the steps into ring stages, in exactly the order the weights were packed:
+// step -> K source (segment, TMEM K-half 0, TMEM K-half 1) -> N-half (unless wide) -> stage.
+__host__ __device__ inline int build_ops_impl(const TcStep* steps, int n_steps, int mode, StageOp* ops) {
+  int n_ops = 0;
+  for (int g = 0; g < n_steps; ++g) {
+    const TcStep& st = steps[g];
+    const int nh = st.N >> 7;
+    const int last_src = step_last_src(st);
+    long long off = st.pack_off;
+    bool fresh = true;
+    for (int src = 0; src < 3; ++src) {
+      const int nks = step_src_ksteps(st, src);
+      if (nks == 0) continue;
+      const bool wide = src != last_src && nh == 2;
+      const int per = wide ? 2 : 4, reps = wide ? 1 : nh;
+      const long long chunk = wide ? 2 * SM_CHUNK_BYTES : SM_CHUNK_BYTES;
+      for (int h = 0; h < reps; ++h) {
+        for (int ks0 = 0; ks0 < nks; ks0 += per) {
+          if (n_ops >= TC_MAX_OPS) return -1;
+          StageOp& o = ops[n_ops++];
+          o.pad0 = 0; o.pad1 = 0;
+          const int cnt = nks - ks0 < per ? nks - ks0 : per;
+          o.pack_off = (uint32_t)off; o.bytes = (uint32_t)(cnt * chunk);
+          off += cnt * chunk;
+          o.d_col = (uint32_t)(st.acc_col + 128 * h);
+          uint32_t flags = (uint32_t)cnt | (wide ? 8u : 0u);
+          if (src == 0) {
+            flags |= 16u;
+            const int base = st.seg == 1 ? SM_P_HI : SM_D_HI;
+            o.a_addr = (uint32_t)((base + ks0 * 4096) >> 4);
+            o.a_lo_delta = (uint32_t)((st.seg == 1 ? (SM_P_LO - SM_P_HI) : (SM_D_LO - SM_D_HI)) >> 4);
+          } else {
+            o.a_addr = (uint32_t)(st.a_col + 128 * (src - 1) + 32 * (ks0 >> 1));
+            o.a_lo_delta = 16u;
+          }
+          if (fresh && ks0 == 0) flags |= 32u;
+          if (ks0 == 0 && h == 0) {
+            if (src > 0) flags |= (uint32_t)src << 6;
+            else if (mode == 0 && g == 0) flags |= 3u << 6;          // first stage of the tile: encodings ready
+          }
+          if (src == last_src && ks0 + per >= nks) flags |= (uint32_t)(h + 1) << 8;
+          o.flags = flags;
+        }
+      }
+      fresh = false;
+    }
+  }
+  return n_ops;
+}
+struct ProgArgs {
+  TcStep steps[TC_MAX_STEPS];
+  int n_steps, mode;
+  StageOp* prog;
+};
+// the device writes its own copy of the stage program (no host->device copy on the launch path)
+extern "C" __global__ void ren_tc_prog(const ProgArgs a) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) build_ops_impl(a.steps, a.n_steps, a.mode, a.prog);
+}
+static int build_ops(TcProgram& P, int mode) {
+  P.n_ops = build_ops_impl(P.steps, P.n_steps, mode, P.ops);
+  return P.n_ops < 0 ? -1 : 0;
+}
+
 int ren_tc_supported(const RenPlan& p) {
   return p.W == 256 && p.WC == 128 && p.CD == 1 && p.hid_K1 == 0 && p.f.pos_deg == 10 && p.f.dir_deg == 4 &&
          p.D >= 1 && p.D + 2 <= 12 && p.C <= 3 && p.trunk[0].K1 == 0;
 }
 
-static size_t program_bytes(const TcProgram& P) { return (size_t)P.pack_bytes + (size_t)VEC_FLOATS * 4 + 2048; }
+static size_t program_bytes(const TcProgram& P) {
+  return (size_t)P.pack_bytes + (size_t)VEC_FLOATS * 4 + sizeof(StageOp) * TC_MAX_OPS + 2048;
+}
 
 size_t ren_tc_fwd_workspace_bytes(const RenPlan& p) {
   if (!ren_tc_supported(p)) return 0;
@@ -729,7 +815,16 @@ size_t ren_tc_bwd_pack_bytes(const RenPlan& p) {
   return program_bytes(P);
 }
 
-static int run_pack(const TcProgram& P, const float* params, unsigned char* pack, float* vec, cudaStream_t st) {
+static int run_pack(const TcProgram& P, int mode, const float* params, unsigned char* pack, float* vec,
+                    StageOp* prog, cudaStream_t st) {
+  {
+    ProgArgs ga;
+    for (int i = 0; i < P.n_steps; ++i) ga.steps[i] = P.steps[i];
+    ga.n_steps = P.n_steps; ga.mode = mode; ga.prog = prog;
+    ren_prof_begin(REN_K_PACK, st);
+    ren_tc_prog<<<1, 32, 0, st>>>(ga);
+    ren_prof_end(REN_K_PACK, st);
+  }
   PackArgs pa;
   static_assert(sizeof(PackArgs) <= 4000, "pack parameter block too large");
   if (P.n_jobs > TC_MAX_PACK) { ren_set_error("tc pack: too many jobs (%d)", P.n_jobs); return REN_E_INVALID; }
@@ -760,15 +855,18 @@ static int launch_chain(const TcArgs& a, long long n_tiles, int kind, cudaStream
   return REN_OK;
 }
 
-static int carve_pack(const TcProgram& P, void* ws, size_t ws_bytes, unsigned char** pack, float** vec) {
+static int carve_pack(const TcProgram& P, void* ws, size_t ws_bytes, unsigned char** pack, float** vec,
+                      StageOp** prog) {
   unsigned char* base = (unsigned char*)(((uintptr_t)ws + 1023) & ~(uintptr_t)1023);
-  const size_t need = (size_t)(base - (unsigned char*)ws) + (size_t)P.pack_bytes + (size_t)VEC_FLOATS * 4 + 16;
+  const size_t need = (size_t)(base - (unsigned char*)ws) + (size_t)P.pack_bytes + (size_t)VEC_FLOATS * 4 +
+                      sizeof(StageOp) * TC_MAX_OPS + 64;
   if (ws == nullptr || need > ws_bytes) {
     ren_set_error("workspace too small for packed weights (%zu > %zu)", need, ws_bytes);
     return REN_E_WORKSPACE;
   }
   *pack = base;
   *vec = (float*)(base + ((P.pack_bytes + 15) & ~15LL));
+  *prog = (StageOp*)((unsigned char*)*vec + (((size_t)VEC_FLOATS * 4 + 15) & ~(size_t)15));
   return REN_OK;
 }
 
@@ -789,15 +887,16 @@ int ren_tc_launch_fwd(const RenPlan& p, long long n_rays, int K, const float* o,
                       size_t ws_bytes, cudaStream_t st) {
   TcProgram P;
   build_forward(p, P);
-  unsigned char* pack; float* vec;
-  int rc = carve_pack(P, ws, ws_bytes, &pack, &vec);
+  unsigned char* pack; float* vec; StageOp* prog;
+  if (build_ops(P, 0)) { ren_set_error("tc forward: stage program too long"); return REN_E_UNSUPPORTED; }
+  int rc = carve_pack(P, ws, ws_bytes, &pack, &vec, &prog);
   if (rc) return rc;
-  rc = run_pack(P, params, pack, vec, st);
+  rc = run_pack(P, 0, params, pack, vec, prog, st);
   if (rc) return rc;
   TcArgs a;
   fill_args(a, p, P);
   a.n_rays = n_rays; a.K = K; a.rays_o = o; a.rays_d = d; a.jitter = jitter;
-  a.pack = pack; a.vec = vec; a.stash = (unsigned char*)stash; a.raw = raw;
+  a.pack = pack; a.vec = vec; a.prog = prog; a.n_ops = P.n_ops; a.stash = (unsigned char*)stash; a.raw = raw;
   const long long n_tiles = (n_rays * K + TC_M - 1) / TC_M;
   return stash ? launch_chain<0, true>(a, n_tiles, REN_K_FIELD_FWD, st)
                : launch_chain<0, false>(a, n_tiles, REN_K_FIELD_FWD, st);
@@ -808,15 +907,16 @@ int ren_tc_launch_dgrad(const RenPlan& p, long long S, const float* params, cons
                         cudaStream_t st) {
   TcProgram P;
   build_dgrad(p, P);
-  unsigned char* pack; float* vec;
-  int rc = carve_pack(P, ws, ws_bytes, &pack, &vec);
+  unsigned char* pack; float* vec; StageOp* prog;
+  if (build_ops(P, 1)) { ren_set_error("tc dgrad: stage program too long"); return REN_E_UNSUPPORTED; }
+  int rc = carve_pack(P, ws, ws_bytes, &pack, &vec, &prog);
   if (rc) return rc;
-  rc = run_pack(P, params, pack, vec, st);
+  rc = run_pack(P, 1, params, pack, vec, prog, st);
   if (rc) return rc;
   TcArgs a;
   fill_args(a, p, P);
   a.n_rays = S; a.K = 1;            // dgrad only needs the flat sample count
-  a.pack = pack; a.vec = vec;
+  a.pack = pack; a.vec = vec; a.prog = prog; a.n_ops = P.n_ops;
   a.stash = (unsigned char*)stash; a.delta = (unsigned char*)delta; a.graw = graw; a.gmax = gmax;
   const long long n_tiles = (S + TC_M - 1) / TC_M;
   return launch_chain<1, false>(a, n_tiles, REN_K_FIELD_DGRAD, st);
