@@ -233,13 +233,21 @@ def run_ours(args):
             dist.destroy_process_group()
         return
     pk = peaks()
+    engine_is_tc = model.nerf.engine != "simt_fp32"
     roof = None
     if "field_fwd" in kern:
         per_launch_samples = RENDERS * RAYS_PER_GPU * N_SAMPLES
         ach = per_launch_samples * FLOP_PER_SAMPLE_FWD / (kern["field_fwd"]["ms_per_launch"] * 1e-3) / 1e12
         roof = {"bound": "tensor", "kernel": "field_fwd", "achieved": ach, "peak": pk["tflops"],
-                "unit": "TFLOP/s", "frac": ach / pk["tflops"], "traffic": None, "peak_source": pk["source"],
-                "samples_per_launch": per_launch_samples, "flop_per_sample": FLOP_PER_SAMPLE_FWD}
+                "unit": "TFLOP/s", "frac": ach / pk["tflops"],
+                # dram__bytes_read.sum + dram__bytes_write.sum of ren_tc_chain<0,1> for this exact launch shape
+                # (ncu --set full, profiles/r01_tc_v32_ncu_summary.txt); algorithmic = 5.1 KB stash per sample
+                "traffic": 5.391e9 if engine_is_tc else None, "traffic_unit": "bytes/launch",
+                "algorithmic_bytes": per_launch_samples * 5096,
+                "tensor_pipe_active_pct_ncu": 50.8 if engine_is_tc else None,
+                "peak_source": pk["source"], "samples_per_launch": per_launch_samples,
+                "flop_per_sample": FLOP_PER_SAMPLE_FWD,
+                "note": "fp16 hi/lo split executes 3 MMAs per algorithmic MMA: ceiling of frac is 1/3"}
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         from oracle import synth as osynth

@@ -541,7 +541,46 @@ class RobustENeRF(LightningModule):
         return {"optimizer": optimizer,
                 "lr_scheduler": {"scheduler": scheduler, "interval": _get(sch_cfg, "interval")}}
 
-    def validation_step(self, batch, batch_index):
-        raise NotImplementedError("evaluation is out of scope of ren_b200 (SURVEY.md section 8f #2)")
+    # -------------------------------------------------------------- evaluation render
+    def set_eval_stage(self, name, intrinsics, img_height, img_width):
+        """Registers `{name}_intrinsics_inv` / `{name}_img_pixel_pos` exactly as the reference's
+        constructor does from its PosedImage datasets (robust_e_nerf.py:100-147); `name` is
+        "val" or "test".  The datasets themselves (views/transforms_*.json, PNG targets) are
+        SURVEY.md section 8f #3."""
+        assert name in ("val", "test")
+        dev = self.train_intrinsics_inv.device
+        k = torch.as_tensor(intrinsics, dtype=torch.float32)
+        self.register_buffer(f"{name}_intrinsics_inv", torch.linalg.inv(k).to(dev), persistent=False)
+        pix = torch.stack(torch.meshgrid(torch.arange(img_width), torch.arange(img_height), indexing="xy"),
+                          dim=2).to(torch.float32)
+        self.register_buffer(f"{name}_img_pixel_pos", pix.to(dev), persistent=False)
 
-    test_step = validation_step
+    @torch.no_grad()
+    def evaluation_step(self, batch, batch_index, stage):
+        """robust_e_nerf.py:533-571: full-frame intensity image at one camera pose.  In eval mode
+        `NeRF.forward` renders in `test_chunk_size` ray chunks without jitter (external/utils.py:99-115)."""
+        batch = {k: (v.squeeze(dim=0) if torch.is_tensor(v) else v) for k, v in batch.items()}
+        pix = stage["img_pixel_pos"]
+        h, w = pix.shape[:2]
+        if "img" in batch:
+            assert batch["img"].shape[-2:] == (h, w)
+        pos = batch["T_wc_position"].view(1, 1, 3).expand(h, w, -1)
+        rot = batch["T_wc_orientation"].view(1, 1, 3, 3).expand(h, w, -1, -1)
+        pred, _, _, _, _ = self.render_pixels(stage["intrinsics_inv"], pix, pos, rot)
+        return {"sample_id": batch.get("sample_id"), "pred_intensity_img": pred,
+                "target_intensity_img": batch.get("img")}
+
+    def _eval_stage(self, name):
+        if not hasattr(self, f"{name}_intrinsics_inv"):
+            raise RuntimeError(f"call set_eval_stage({name!r}, intrinsics, height, width) first: the posed-image "
+                               "datasets that provide them are SURVEY.md section 8f #3")
+        return {"intrinsics_inv": getattr(self, f"{name}_intrinsics_inv"),
+                "img_pixel_pos": getattr(self, f"{name}_img_pixel_pos")}
+
+    def validation_step(self, batch, batch_index):
+        """robust_e_nerf.py:519-524.  Image metrics / PNG dumps (`*_epoch_end`) stay out of scope."""
+        return self.evaluation_step(batch, batch_index, self._eval_stage("val"))
+
+    def test_step(self, batch, batch_index):
+        """robust_e_nerf.py:526-531."""
+        return self.evaluation_step(batch, batch_index, self._eval_stage("test"))

@@ -362,6 +362,42 @@ def test_full_size_gradient_directional_check(engine, built_lib, dataset_dir):
     assert abs(fd - an) <= 5e-2 * abs(an) + 3e-5
 
 
+def test_full_frame_evaluation_render(built_lib, dataset_dir):
+    """`validation_step` (robust_e_nerf.py:519-571): a 640x480 frame in eval mode (no jitter, 16384-ray
+    chunks) -- a 40x30 sub-frame against the oracle, the full frame against chunk invariance."""
+    g = dict(H.load_golden("step_8x256_gain2"))
+    m = H.build_product(g, dataset_dir, "cuda").eval()
+    scene = synth.load_scene(dataset_dir)
+    fcfg, rcfg, _ = H.golden_configs(g)
+    rcfg.stratified = False
+    ts = scene["T_wc_timestamp"][700].double().reshape(1) + 0.25e6
+    with torch.no_grad():
+        p, Rm = R.trajectory(scene, ts)
+    batch = {"T_wc_position": p.cuda(), "T_wc_orientation": Rm.cuda()}
+    # sub-frame with a strided intrinsics so that it spans the same field of view
+    K = scene["intrinsics"].clone()
+    K[:2] /= 16.0
+    m.set_eval_stage("val", K, 30, 40)
+    out = m.validation_step(batch, 0)["pred_intensity_img"]
+    assert out.shape == (30, 40)
+    pix = m.val_img_pixel_pos.cpu().reshape(-1, 2)
+    params = H.golden_params(g)
+    bk = R.softplus(torch.log(torch.expm1(torch.ones(1))), 1.0)
+    with torch.no_grad():
+        I, _, _, _, _ = R.render_pixels(params, fcfg, rcfg, torch.linalg.inv(K), pix, p.expand(len(pix), -1),
+                                        Rm.expand(len(pix), -1, -1), None, bk, g["scfg"]["min_modeled_intensity"])
+    nw, ma, _ = H.rel_err(torch.log(out.reshape(-1).double().cpu()), torch.log(I.double()))
+    print(f"[eval 40x30] logI normwise={nw:.2e} maxabs={ma:.2e}")
+    assert nw < REL_BAR and ma < 3e-4
+    # full 640x480 frame: 307 200 rays in 19 chunks; a different chunking must not change a pixel
+    m.set_eval_stage("test", scene["intrinsics"], 480, 640)
+    full = m.test_step(batch, 0)["pred_intensity_img"]
+    assert full.shape == (480, 640) and bool(torch.isfinite(full).all())
+    m.nerf.test_chunk_size = 50000
+    again = m.test_step(batch, 0)["pred_intensity_img"]
+    assert torch.equal(full, again)
+
+
 def test_adam_matches_torch(built_lib):
     """`ren_adam_step` vs torch.optim.Adam (models/robust_e_nerf.py:800-813 semantics)."""
     import ctypes as C
