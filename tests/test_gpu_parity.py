@@ -206,6 +206,69 @@ def test_grad_loss_matches_oracle_fresh_inputs(contraction, tau_train, built_lib
         assert abs(float(got_t) - float(th_t64.grad)) <= max(5 * e_ref, 2e-2 * abs(float(th_t64.grad)))
 
 
+@pytest.mark.parametrize("aabb,near,far", [([0.5, -2.1, 0.6, 2.0, -0.6, 1.6], 0.05, 3.0),      # mocap-desk2.yaml:38-48
+                                           ([-2.3, -3.2, 0.0, 1.7, 2.8, 3.0], 0.01, 4.0)])     # office-maze.yaml:38-48
+def test_real_sequence_like_configs(aabb, near, far, built_lib, dataset_dir):
+    """BASELINE configs 4/5 rendering options (non-cubic aabb + sphere contraction, `render_step_size:
+    auto`, cone_angle 0.004, early_stop_eps 1e-4, l_diff + l_grad, ~700-1000 marching steps per ray) on a
+    small fresh batch vs the oracle: loss, per-ray log I and d logI/dt, sample counts."""
+    import math
+    B = 20
+    g = dict(H.load_golden("step_8x256"))
+    g["fcfg"] = dict(g["fcfg"], aabb=aabb, contraction="sphere")
+    step = math.sqrt(3) * max(aabb[3 + i] - aabb[i] for i in range(3)) / 1024          # robust_e_nerf.py:220-226
+    g["rcfg"] = dict(g["rcfg"], near_plane=near, far_plane=far, render_step_size=step, cone_angle=0.004,
+                     early_stop_eps=1e-4, alpha_thre=0.0)
+    g["scfg"] = dict(g["scfg"], w_grad=1e-3, w_diff=1.0)
+    g["learn_bkgd"] = True
+    g["weight_gain"] = 2.0
+    g["weight_checksums"] = {}
+    scene = synth.load_scene(dataset_dir)
+    batch, jitter = synth.make_batch(B, scene["T_wc_timestamp"], rank=5, seed=77)
+    m = H.build_product(g, dataset_dir, "cuda")
+    loss = m.training_step({k: {kk: vv.cuda() for kk, vv in v.items()} for k, v in batch.items()}, 0,
+                           {k: v.cuda() for k, v in jitter.items()})
+    fcfg, rcfg, scfg = H.golden_configs(g)
+    tau_max = scene["max_refractory_period"]
+    torch.set_num_threads(8)
+    params = H.golden_params(g)
+    th_r = torch.log(torch.expm1(torch.tensor(1.0)))
+    th_t = tau_max * torch.logit(scene["refractory_period"].double() / tau_max)
+    th_b = torch.log(torch.expm1(torch.ones(1)))
+    out = R.training_step(params, fcfg, rcfg, scfg, scene, batch, jitter, th_r, th_t, th_b)
+    rel = abs(float(loss) - float(out["loss"])) / abs(float(out["loss"]))
+    nw0, ma0, _ = H.rel_err(m.last["start_log_intensity"], out["start_log_intensity"])
+    nw1, ma1, _ = H.rel_err(m.last["end_log_intensity"], out["end_log_intensity"])
+    nwg, _, _ = H.rel_err(m.last_grad["log_intensity_grad"], out["log_intensity_grad"], floor=1e-12)
+    spp, spp_ref = float(m.logged["train/mean_num_samples_per_ray"]), float(out["mean_num_samples_per_ray"])
+    print(f"[real-like near={near} far={far}] loss rel={rel:.2e} logI normwise={max(nw0, nw1):.2e} "
+          f"maxabs={max(ma0, ma1):.2e} dlogI/dt normwise={nwg:.2e} spp={spp:.2f}/{spp_ref:.2f}")
+    assert rel < REL_BAR and max(nw0, nw1) < REL_BAR and max(ma0, ma1) < 3e-4
+    assert nwg < 1e-3
+    assert abs(spp - spp_ref) <= 1e-3 * spp_ref + 0.5
+
+
+def test_edge_cases(built_lib, dataset_dir):
+    """Empty and ragged inputs: zero rays, a single ray, a ray count whose samples do not fill a tile."""
+    g = dict(H.load_golden("step_8x256"))
+    for engine in ENGINES:
+        m = H.build_product(g, dataset_dir, "cuda", engine)
+        with torch.no_grad():
+            rad, opac, depth, n_kept = m.nerf.render_raw(torch.zeros(0, 3).cuda(), torch.zeros(0, 3).cuda(),
+                                                         torch.zeros(0).cuda())
+            assert rad.shape == (0, 1) and opac.shape == (0,) and n_kept.shape == (0,)
+            o = torch.tensor([[3.0, 0.0, 0.1]]).cuda()
+            d = torch.nn.functional.normalize(-o, dim=-1)
+            one = m.nerf.render_raw(o, d, torch.tensor([0.5]).cuda())
+            o7 = o.repeat(7, 1)
+            seven = m.nerf.render_raw(o7, d.repeat(7, 1), torch.full((7,), 0.5).cuda())
+            assert bool(torch.isfinite(one[0]).all()) and int(one[3]) == 128
+            assert torch.equal(seven[0], one[0].expand(7, -1)) and torch.equal(seven[1], one[1].expand(7))
+        # a ray pointing away from the scene content still renders (all samples far out in the contracted shell)
+        away = m.nerf.render_raw(o, -d, torch.tensor([0.5]).cuda())
+        assert bool(torch.isfinite(away[0]).all())
+
+
 def test_tangent_render_matches_finite_difference(built_lib, dataset_dir):
     """Forward-mode check independent of the oracle, 512 rays x 128 samples, 8x256: the tangent
     output dC/dw equals the central difference of the value render moved along (o_dot, d_dot)."""
