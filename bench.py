@@ -71,7 +71,7 @@ class ClockSampler(threading.Thread):
                     self.rows.append([c.strip() for c in line.split(",")])
             except Exception:
                 pass
-            self.stop_flag.wait(0.2)
+            self.stop_flag.wait(0.02)
 
     def summary(self):
         sm = sorted(int(float(r[1])) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit())

@@ -35,7 +35,8 @@
 
 #define TC_EPI_WARPS 16
 #define TC_PRO_WARPS 4                         // forward prologue warps: one thread per sample row
-#define TC_THREADS (64 + 32 * TC_EPI_WARPS + 32 * TC_PRO_WARPS)   // 704
+#define TC_THREADS_FWD (64 + 32 * TC_EPI_WARPS + 32 * TC_PRO_WARPS)   // 704
+#define TC_THREADS_BWD (64 + 32 * TC_EPI_WARPS)                       // 576: dgrad has no prologue warps
 #define TC_STAGES 3            // ring stages of up to TC_STAGE_KS K steps (32 KB)
 #define TC_STAGE_KS 4
 #define TC_MAX_STEPS 20
@@ -208,7 +209,7 @@ __device__ __forceinline__ uint64_t mk_desc(uint32_t lo32) {
 }
 
 template <int MODE, bool STASH>   // MODE 0: forward, 1: dgrad
-__global__ void __launch_bounds__(TC_THREADS, 1) ren_tc_chain(const TcArgs a) {
+__global__ void __launch_bounds__(MODE == 0 ? TC_THREADS_FWD : TC_THREADS_BWD, 1) ren_tc_chain(const TcArgs a) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const RenPlan& p = a.p;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -240,8 +241,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ren_tc_chain(const TcArgs a) {
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int i = threadIdx.x; i < VEC_FLOATS; i += TC_THREADS) vec[i] = a.vec[i];
-  for (int i = threadIdx.x; i < a.n_ops * 8; i += TC_THREADS)
+  for (int i = threadIdx.x; i < VEC_FLOATS; i += blockDim.x) vec[i] = a.vec[i];
+  for (int i = threadIdx.x; i < a.n_ops * 8; i += blockDim.x)
     reinterpret_cast<uint32_t*>(smem + SM_PROG)[i] = reinterpret_cast<const uint32_t*>(a.prog)[i];
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(sbase + SM_TMEM_PTR) : "memory");
@@ -848,7 +849,7 @@ static int launch_chain(const TcArgs& a, long long n_tiles, int kind, cudaStream
   cudaError_t e = cudaFuncSetAttribute(ren_tc_chain<MODE, STASH>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
   if (e != cudaSuccess) { ren_set_error("tc chain smem attr: %s", cudaGetErrorString(e)); return REN_E_CUDA; }
   ren_prof_begin(kind, st);
-  ren_tc_chain<MODE, STASH><<<grid, TC_THREADS, SM_TOTAL, st>>>(a);
+  ren_tc_chain<MODE, STASH><<<grid, MODE == 0 ? TC_THREADS_FWD : TC_THREADS_BWD, SM_TOTAL, st>>>(a);
   ren_prof_end(kind, st);
   e = cudaGetLastError();
   if (e != cudaSuccess) { ren_set_error("tc chain launch: %s", cudaGetErrorString(e)); return REN_E_CUDA; }
