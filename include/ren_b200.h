@@ -228,6 +228,22 @@ int ren_event_diff_loss(int64_t B, int32_t error_fn, int32_t all_valid, float mi
                         const int64_t* end_ts, float* log_i0, float* log_i1, float* loss,
                         int32_t* n_valid, float* g_c0, float* g_c1, void* scratch, void* stream);
 
+/* Raw event stream -> per-pixel event intervals: replaces the per-event Python loops
+ * `Event.queue_raw_events` (data/datasets.py:189-284) and `Event.extract_max_refractory_period`
+ * (data/datasets.py:132-187) of the reference's dataset preparation (`raw_events.npz` ->
+ * `events.pt`, `max_refractory_period.pt`).  The stream must be time-ordered, as the reference assumes.
+ *   position (n,2) u16 (x,y); timestamp (n) i64 ns; polarity (n) u8 {0,1}
+ *   out_* sized for n events; the first *out_n_valid entries are written, in stream order:
+ *   out_position (n,2) i64, out_start_ts / out_end_ts / out_num_pos / out_num_neg (n) i64
+ *   out_n_valid (1) i64 device scalar; out_min_interval (1) i64 device scalar = the maximum
+ *   refractory period (smallest positive same-pixel interval), INT64_MAX when there is none. */
+int ren_event_queue_workspace_bytes(int64_t n_events, int32_t img_width, int32_t img_height, size_t* bytes);
+int ren_event_queue(int64_t n_events, int32_t img_width, int32_t img_height, const uint16_t* position,
+                    const int64_t* timestamp, const uint8_t* polarity, int64_t* out_position,
+                    int64_t* out_start_ts, int64_t* out_end_ts, int64_t* out_num_pos, int64_t* out_num_neg,
+                    int64_t* out_n_valid, int64_t* out_min_interval, void* workspace, size_t workspace_bytes,
+                    void* stream);
+
 /* Fused Adam step on a flat fp32 buffer (torch.optim.Adam semantics incl. L2
  * weight_decay added to the gradient; models/robust_e_nerf.py:800-813).
  * `step` is the 1-based step count; grad_scale multiplies the gradient first

@@ -79,6 +79,9 @@ _SIGNATURES = {
     "ren_trajectory": (C.c_int, [C.c_int64, _P, C.c_int64, _P, _P, _P, _P, _P, _P]),
     "ren_event_diff_loss": (C.c_int, [C.c_int64, C.c_int32, C.c_int32, C.c_float, _P, _P, _P, _P, _P,
                                       _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "ren_event_queue_workspace_bytes": (C.c_int, [C.c_int64, C.c_int32, C.c_int32, C.POINTER(C.c_size_t)]),
+    "ren_event_queue": (C.c_int, [C.c_int64, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
+                                  C.c_size_t, _P]),
     "ren_adam_step": (C.c_int, [C.c_int64, _P, _P, _P, _P, C.c_float, C.c_float, C.c_float,
                                 C.c_float, C.c_float, C.c_float, C.c_int64, _P]),
 }

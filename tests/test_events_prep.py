@@ -1,0 +1,69 @@
+"""Raw-event conversion: the numpy oracle against the golden vectors minted by the
+UNMODIFIED reference (`Event.queue_raw_events`, `Event.extract_max_refractory_period`,
+`Event.colorize_events`, robust_e_nerf/data/datasets.py:132-328), and -- on the GPU -- `ren_event_queue`
+through the C ABI against both.  Integer work: the bar is bit-exact."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import events_prep as EP
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "events_prep.npz")
+TAGS = ["a", "b", "c"]
+
+
+def _case(g, tag):
+    raw = {k: g[f"{tag}_raw_{k}"] for k in ("position", "timestamp", "polarity")}
+    w, h = (int(v) for v in g[f"{tag}_calib"])
+    calib = {"img_width": w, "img_height": h, "bayer_pattern": str(g[f"{tag}_bayer"])}
+    ref = {k[len(tag) + 3:]: g[k] for k in g.files if k.startswith(f"{tag}_q_")}
+    return raw, calib, ref, g[f"{tag}_max_refractory_period"]
+
+
+@pytest.mark.parametrize("tag", TAGS)
+def test_oracle_matches_reference_golden(tag):
+    g = np.load(GOLDEN)
+    raw, calib, ref, mrp = _case(g, tag)
+    q = EP.queue_raw_events(raw, calib)
+    for k in ("position", "start_ts", "end_ts", "num_pos", "num_neg"):
+        assert q[k].dtype == np.int64 and np.array_equal(q[k], ref[k]), k
+    m = EP.extract_max_refractory_period(raw, calib)
+    assert np.array_equal(np.asarray(m), mrp) and np.asarray(m).dtype == mrp.dtype
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag", TAGS)
+def test_event_queue_matches_reference_golden(tag, built_lib, tmp_path):
+    from ren_b200 import events as E
+    g = np.load(GOLDEN)
+    raw, calib, ref, mrp = _case(g, tag)
+    np.savez(tmp_path / E.RAW_EVENTS_FILENAME, **raw)
+    q = E.colorize_events(E.queue_raw_events(str(tmp_path), calib), calib)
+    for k, v in ref.items():
+        got = q[k].cpu().numpy()
+        assert got.dtype == v.dtype and np.array_equal(got, v), k
+    m = E.extract_max_refractory_period(raw, calib)
+    assert np.array_equal(m.numpy(), mrp) and m.numpy().dtype == mrp.dtype
+
+
+@pytest.mark.gpu
+def test_event_queue_full_size_vs_oracle(built_lib):
+    """4 M events on a 640x480 sensor (the size class of a real sequence) vs the numpy oracle, plus the
+    size-independent invariants: stream order kept, every interval positive, num_pos + num_neg == 1."""
+    from ren_b200 import events as E
+    raw = EP.synth_raw_events(4_000_000, 640, 480, seed=11)
+    calib = {"img_width": 640, "img_height": 480, "bayer_pattern": ""}
+    q, m = E._run(raw, calib, "cuda")
+    ref = EP.queue_raw_events(raw, calib)
+    for k, v in ref.items():
+        assert np.array_equal(q[k].cpu().numpy(), v), k
+    assert m == int(EP.extract_max_refractory_period(raw, calib))
+    assert bool((q["end_ts"] > q["start_ts"]).all()) and bool((q["num_pos"] + q["num_neg"] == 1).all())
+    assert bool((q["end_ts"][1:] >= q["end_ts"][:-1]).all())
+    # empty stream
+    empty = {"position": np.zeros((0, 2), np.uint16), "timestamp": np.zeros((0,), np.int64),
+             "polarity": np.zeros((0,), bool)}
+    q0, m0 = E._run(empty, calib, "cuda")
+    assert q0["end_ts"].numel() == 0 and m0 == np.iinfo(np.int64).max
