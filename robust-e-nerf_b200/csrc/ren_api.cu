@@ -15,14 +15,14 @@ int ren_simt_launch_dgrad(const RenPlan& p, long long S, const float* params, co
 int ren_simt_launch_wgrad(const RenPlan& p, long long S, const float* stash, const float* delta,
                           const float* graw, float* g_params, int tangent, cudaStream_t st);
 int ren_launch_composite_tan(const RenPlan& p, long long n_rays, int K, const float* o, const float* d,
-                             const float* jitter, const float* raw, const float* bkgd, float* radiance,
-                             float* opacity, float* depth, float* radiance_dot, float* opacity_dot,
+                             const float* jitter, const float* raw, const float* raw_dot, const float* bkgd,
+                             float* radiance, float* opacity, float* depth, float* radiance_dot, float* opacity_dot,
                              int* n_kept, cudaStream_t st);
 int ren_launch_composite_tan_bwd(const RenPlan& p, long long n_rays, int K, const float* o, const float* d,
-                                 const float* jitter, const float* raw, const float* bkgd,
+                                 const float* jitter, const float* raw, const float* raw_dot, const float* bkgd,
                                  const float* g_radiance, const float* g_opacity, const float* g_depth,
                                  const float* g_radiance_dot, const float* g_opacity_dot, float* graw,
-                                 float* g_bkgd, cudaStream_t st);
+                                 float* graw_dot, float* g_bkgd, unsigned int* gmax, cudaStream_t st);
 int ren_launch_raygrad(const RenPlan& p, long long n_rays, int K, const float* o, const float* d,
                        const float* o_dot, const float* d_dot, const float* jitter, const float* params,
                        const float* delta, float* g_rays, cudaStream_t st);
@@ -38,13 +38,15 @@ int ren_tc_supported(const RenPlan& p);
 size_t ren_tc_fwd_workspace_bytes(const RenPlan& p);
 size_t ren_tc_bwd_pack_bytes(const RenPlan& p);
 int ren_tc_launch_fwd(const RenPlan& p, long long n_rays, int K, const float* o, const float* d,
+                      const float* o_dot, const float* d_dot, const void* stash_val,
                       const float* jitter, const float* params, void* stash, float* raw, void* ws,
                       size_t ws_bytes, cudaStream_t st);
 int ren_tc_launch_dgrad(const RenPlan& p, long long S, const float* params, const void* stash,
-                        const float* graw, const unsigned int* gmax, void* delta, void* ws, size_t ws_bytes,
-                        cudaStream_t st);
+                        const float* graw, const unsigned int* gmax, void* delta, int pass, const void* stash_dot,
+                        void* extra, void* ws, size_t ws_bytes, cudaStream_t st);
 int ren_tc_launch_wgrad(const RenPlan& p, long long S, const void* stash, const void* delta,
-                        const float* graw, const unsigned int* gmax, float* g_params, cudaStream_t st);
+                        const float* graw, const unsigned int* gmax, float* g_params, int with_bias,
+                        cudaStream_t st);
 
 static thread_local char g_err[512] = "";
 
@@ -368,7 +370,8 @@ extern "C" int ren_render_forward(const RenFieldDesc* f, const RenRenderDesc* r,
   if (engine == REN_ENGINE_SIMT_FP32)
     rc = ren_simt_launch_fwd(p, n_rays, K, rays_o, rays_d, nullptr, nullptr, jitter, params, (float*)stash, raw, st);
   else
-    rc = ren_tc_launch_fwd(p, n_rays, K, rays_o, rays_d, jitter, params, stash, raw, ws, ws_left, st);
+    rc = ren_tc_launch_fwd(p, n_rays, K, rays_o, rays_d, nullptr, nullptr, nullptr, jitter, params, stash, raw, ws,
+                           ws_left, st);
   if (rc) return rc;
   return ren_launch_composite(p, n_rays, K, rays_o, rays_d, jitter, raw, bkgd, radiance, opacity, depth,
                               n_kept, st);
@@ -434,20 +437,34 @@ extern "C" int ren_render_backward(const RenFieldDesc* f, const RenRenderDesc* r
   rc = ren_launch_composite_bwd(p, n_rays, K, rays_o, rays_d, jitter, raw, bkgd, g_radiance, g_opacity,
                                 g_depth, graw, g_bkgd, gmax, st);
   if (rc) return rc;
-  rc = ren_tc_launch_dgrad(p, S, params, stash, graw, gmax, delta, pack_ws, pack_left, st);
+  rc = ren_tc_launch_dgrad(p, S, params, stash, graw, gmax, delta, 0, nullptr, nullptr, pack_ws, pack_left, st);
   if (rc) return rc;
-  return ren_tc_launch_wgrad(p, S, stash, delta, graw, gmax, g_params, st);
+  return ren_tc_launch_wgrad(p, S, stash, delta, graw, gmax, g_params, 1, st);
 }
 
-// ------------------------------------------------------------------ tangent mode (fp32 FFMA engine)
+// ------------------------------------------------------------------ tangent mode
+// fp32 FFMA engine: (value, d/dw) row pairs through one pass.  tcgen05 engine: the value pass, then a
+// tangent pass of the same chain kernel whose epilogue multiplies by act'(pre) from the value stash; the
+// reverse is two dgrad passes (tangent adjoint, which also emits E = abar_dot act'' pre_dot, then value
+// adjoint, which adds E) and two weight-gradient passes.  Ray gradients come from the fp32 engine only.
 static int tangent_plan(const RenFieldDesc* f, const RenRenderDesc* r, int64_t n_rays, int32_t K, RenPlan* p) {
   int rc = ren_build_plan(f, r, p);
   if (rc) return rc;
   rc = validate_render(r);
   if (rc) return rc;
   if (n_rays < 0 || K < 1) { ren_set_error("bad n_rays/K"); return REN_E_INVALID; }
-  p->r.engine = REN_ENGINE_SIMT_FP32;
+  const int engine = pick_engine(*p);
+  rc = check_engine(*p, engine);
+  if (rc) return rc;
+  p->r.engine = engine;
   return REN_OK;
+}
+// tcgen05 tangent layouts (bytes).  stash: [value stash | tangent stash].  backward workspace:
+// [delta_val mats | graw_val | gmax 256 | delta_dot mats | graw_dot | extra mats | packed weights]
+static size_t tct_mats(const RenPlan& p, long long S) { return (size_t)2 * p.act_floats * ren_pad128(S); }
+static size_t tct_graw(const RenPlan& p, long long S) { return (size_t)4 * (1 + p.C) * ren_pad128(S); }
+static size_t tct_bwd_bytes(const RenPlan& p, long long S) {
+  return 3 * tct_mats(p, S) + 2 * tct_graw(p, S) + 256 + 1024;
 }
 
 extern "C" int ren_tangent_stash_bytes(const RenFieldDesc* f, const RenRenderDesc* r, int64_t n_rays, int32_t K,
@@ -455,7 +472,9 @@ extern "C" int ren_tangent_stash_bytes(const RenFieldDesc* f, const RenRenderDes
   RenPlan p;
   int rc = tangent_plan(f, r, n_rays, K, &p);
   if (rc) return rc;
-  *bytes = sizeof(float) * (size_t)ren_stash_floats(p, 2 * (long long)n_rays * K);
+  const long long S = (long long)n_rays * K;
+  *bytes = p.r.engine == REN_ENGINE_SIMT_FP32 ? sizeof(float) * (size_t)ren_stash_floats(p, 2 * S)
+                                               : 2 * tcs_bytes(p, S) + 512;
   return REN_OK;
 }
 
@@ -464,9 +483,16 @@ extern "C" int ren_tangent_workspace_bytes(const RenFieldDesc* f, const RenRende
   RenPlan p;
   int rc = tangent_plan(f, r, n_rays, K, &p);
   if (rc) return rc;
-  const long long S2 = 2 * (long long)n_rays * K;
-  const size_t n = for_backward ? sizeof(float) * (size_t)ren_delta_floats(p, S2)
-                                : (has_stash ? 0 : sizeof(float) * (size_t)((1 + p.C) * ren_pad128(S2)));
+  const long long S = (long long)n_rays * K;
+  size_t n;
+  if (p.r.engine == REN_ENGINE_SIMT_FP32) {
+    n = for_backward ? sizeof(float) * (size_t)ren_delta_floats(p, 2 * S)
+                     : (has_stash ? 0 : sizeof(float) * (size_t)((1 + p.C) * ren_pad128(2 * S)));
+  } else {
+    // without a caller stash the forward still needs both stashes (the tangent pass reads the value pass')
+    n = for_backward ? tct_bwd_bytes(p, S) + ren_tc_bwd_pack_bytes(p)
+                     : (has_stash ? 0 : 2 * tcs_bytes(p, S) + 512) + ren_tc_fwd_workspace_bytes(p);
+  }
   *bytes = n + 2048;
   return REN_OK;
 }
@@ -488,22 +514,47 @@ extern "C" int ren_render_tangent_forward(const RenFieldDesc* f, const RenRender
     return REN_E_INVALID;
   }
   if (r->stratified && jitter == nullptr) { ren_set_error("stratified marching needs a jitter buffer"); return REN_E_INVALID; }
-  const long long S2 = 2 * (long long)n_rays * K;
+  const long long S = (long long)n_rays * K;
   cudaStream_t st = (cudaStream_t)stream;
+  char* ws = (char*)align256(workspace);
+  size_t ws_left = workspace ? workspace_bytes - (size_t)(ws - (char*)workspace) : 0;
+  if (p.r.engine != REN_ENGINE_SIMT_FP32) {
+    const size_t one = (tcs_bytes(p, S) + 255) & ~(size_t)255;
+    char* sv;
+    if (stash) {
+      if (stash_bytes < 2 * tcs_bytes(p, S) + 512) { ren_set_error("stash too small"); return REN_E_WORKSPACE; }
+      sv = (char*)align256(stash);
+    } else {
+      if (!workspace || ws_left < 2 * one) { ren_set_error("workspace too small for the tangent stashes"); return REN_E_WORKSPACE; }
+      sv = ws;
+      ws += 2 * one;
+      ws_left -= 2 * one;
+    }
+    char* sd = sv + one;
+    float* raw_val = (float*)(sv + tcs_raw(p, S));
+    float* raw_dot = (float*)(sd + tcs_raw(p, S));
+    rc = ren_tc_launch_fwd(p, n_rays, K, rays_o, rays_d, nullptr, nullptr, nullptr, jitter, params, sv, raw_val, ws,
+                           ws_left, st);
+    if (rc) return rc;
+    rc = ren_tc_launch_fwd(p, n_rays, K, rays_o, rays_d, rays_o_dot, rays_d_dot, sv, jitter, params, sd, raw_dot, ws,
+                           ws_left, st);
+    if (rc) return rc;
+    return ren_launch_composite_tan(p, n_rays, K, rays_o, rays_d, jitter, raw_val, raw_dot, bkgd, radiance, opacity,
+                                    depth, radiance_dot, opacity_dot, n_kept, st);
+  }
+  const long long S2 = 2 * S;
   float* raw;
   if (stash) {
     if (stash_bytes < sizeof(float) * (size_t)ren_stash_floats(p, S2)) { ren_set_error("stash too small"); return REN_E_WORKSPACE; }
     raw = (float*)stash + ren_stash_raw(p, S2);
   } else {
-    char* ws = (char*)align256(workspace);
-    const size_t ws_left = workspace ? workspace_bytes - (size_t)(ws - (char*)workspace) : 0;
     const size_t need = sizeof(float) * (size_t)((1 + p.C) * ren_pad128(S2));
     if (!workspace || ws_left < need) { ren_set_error("workspace too small for raw samples (%zu < %zu)", ws_left, need); return REN_E_WORKSPACE; }
     raw = (float*)ws;
   }
   rc = ren_simt_launch_fwd(p, n_rays, K, rays_o, rays_d, rays_o_dot, rays_d_dot, jitter, params, (float*)stash, raw, st);
   if (rc) return rc;
-  return ren_launch_composite_tan(p, n_rays, K, rays_o, rays_d, jitter, raw, bkgd, radiance, opacity, depth,
+  return ren_launch_composite_tan(p, n_rays, K, rays_o, rays_d, jitter, raw, nullptr, bkgd, radiance, opacity, depth,
                                   radiance_dot, opacity_dot, n_kept, st);
 }
 
@@ -523,19 +574,54 @@ extern "C" int ren_render_tangent_backward(const RenFieldDesc* f, const RenRende
     ren_set_error("ren_render_tangent_backward: null pointer argument");
     return REN_E_INVALID;
   }
-  const long long S2 = 2 * (long long)n_rays * K;
-  if (stash_bytes < sizeof(float) * (size_t)ren_stash_floats(p, S2)) { ren_set_error("stash too small"); return REN_E_WORKSPACE; }
+  const long long S = (long long)n_rays * K;
   char* ws = (char*)align256(workspace);
   const size_t ws_left = workspace_bytes - (size_t)(ws - (char*)workspace);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (p.r.engine != REN_ENGINE_SIMT_FP32) {
+    if (g_rays) {
+      ren_set_error("ray gradients (trainable refractory period) are provided by the simt_fp32 engine only");
+      return REN_E_UNSUPPORTED;
+    }
+    if (stash_bytes < 2 * tcs_bytes(p, S) + 512) { ren_set_error("stash too small"); return REN_E_WORKSPACE; }
+    const size_t need = tct_bwd_bytes(p, S);
+    if (ws_left < need) { ren_set_error("workspace too small for backward (%zu < %zu)", ws_left, need); return REN_E_WORKSPACE; }
+    const size_t one = (tcs_bytes(p, S) + 255) & ~(size_t)255;
+    const char* sv = (const char*)align256((void*)stash);
+    const char* sd = sv + one;
+    const float* raw_val = (const float*)(sv + tcs_raw(p, S));
+    const float* raw_dot = (const float*)(sd + tcs_raw(p, S));
+    char* delta_val = ws;
+    float* graw_val = (float*)(delta_val + tct_mats(p, S));
+    unsigned int* gmax = (unsigned int*)((char*)graw_val + tct_graw(p, S));
+    char* delta_dot = (char*)gmax + 256;
+    float* graw_dot = (float*)(delta_dot + tct_mats(p, S));
+    char* extra = (char*)graw_dot + tct_graw(p, S);
+    char* pack_ws = (char*)align256(extra + tct_mats(p, S));
+    const size_t pack_left = workspace_bytes - (size_t)(pack_ws - (char*)workspace);
+    if (cudaMemsetAsync(gmax, 0, 256, st) != cudaSuccess) { ren_set_error("gmax memset failed"); return REN_E_CUDA; }
+    rc = ren_launch_composite_tan_bwd(p, n_rays, K, rays_o, rays_d, jitter, raw_val, raw_dot, bkgd, g_radiance,
+                                      g_opacity, g_depth, g_radiance_dot, g_opacity_dot, graw_val, graw_dot, g_bkgd,
+                                      gmax, st);
+    if (rc) return rc;
+    rc = ren_tc_launch_dgrad(p, S, params, sv, graw_dot, gmax, delta_dot, 1, sd, extra, pack_ws, pack_left, st);
+    if (rc) return rc;
+    rc = ren_tc_launch_dgrad(p, S, params, sv, graw_val, gmax, delta_val, 2, nullptr, extra, pack_ws, pack_left, st);
+    if (rc) return rc;
+    rc = ren_tc_launch_wgrad(p, S, sv, delta_val, graw_val, gmax, g_params, 1, st);
+    if (rc) return rc;
+    return ren_tc_launch_wgrad(p, S, sd, delta_dot, graw_dot, gmax, g_params, 0, st);
+  }
+  const long long S2 = 2 * S;
+  if (stash_bytes < sizeof(float) * (size_t)ren_stash_floats(p, S2)) { ren_set_error("stash too small"); return REN_E_WORKSPACE; }
   const size_t need = sizeof(float) * (size_t)ren_delta_floats(p, S2);
   if (ws_left < need) { ren_set_error("workspace too small for backward (%zu < %zu)", ws_left, need); return REN_E_WORKSPACE; }
-  cudaStream_t st = (cudaStream_t)stream;
   float* delta = (float*)ws;
   float* graw = delta + p.act_floats * ren_pad128(S2);
   const float* st_f = (const float*)stash;
   const float* raw = st_f + ren_stash_raw(p, S2);
-  rc = ren_launch_composite_tan_bwd(p, n_rays, K, rays_o, rays_d, jitter, raw, bkgd, g_radiance, g_opacity, g_depth,
-                                    g_radiance_dot, g_opacity_dot, graw, g_bkgd, st);
+  rc = ren_launch_composite_tan_bwd(p, n_rays, K, rays_o, rays_d, jitter, raw, nullptr, bkgd, g_radiance, g_opacity,
+                                    g_depth, g_radiance_dot, g_opacity_dot, graw, nullptr, g_bkgd, nullptr, st);
   if (rc) return rc;
   rc = ren_simt_launch_dgrad(p, S2, params, st_f, graw, delta, 1, st);
   if (rc) return rc;

@@ -30,8 +30,11 @@ struct CompArgs {
   float* graw;           // [S][1+C]
   float* g_bkgd;         // [C] or NULL
   unsigned int* gmax;    // max |graw| as float bits (tcgen05 backward loss scaling) or NULL
-  // tangent mode: raw / graw have 2 rows per sample (value, d/dw)
+  // tangent mode: raw / graw have 2 rows per sample (value, d/dw) -- or, when raw_dot / graw_dot are
+  // given (tcgen05 engine), the d/dw rows live in their own [S][1+C] arrays
   int tangent;
+  const float* raw_dot;
+  float* graw_dot;
   float* radiance_dot;   // [n_rays][C]
   float* opacity_dot;    // [n_rays]
   const float* g_radiance_dot;
@@ -92,7 +95,7 @@ __device__ __forceinline__ void walk_ray(const CompArgs& a, long long r, int lan
     b.c[0] = b.c[1] = b.c[2] = 0.f;
     b.dact_c[0] = b.dact_c[1] = b.dact_c[2] = 0.f;
     if (b.alive) {
-      const float* rw = a.raw + (r * a.K + k) * (a.tangent ? 2 : 1) * C1;
+      const float* rw = a.raw + (r * a.K + k) * ((a.tangent && !a.raw_dot) ? 2 : 1) * C1;
       sraw = rw[0];
       for (int c = 0; c < p.C; ++c) b.c[c] = ren_radiance_act(p.f.radiance_activation, rw[1 + c], &b.dact_c[c]);
     }
@@ -281,7 +284,7 @@ __device__ __forceinline__ TanBlk tan_block(const CompArgs& a, long long r, int 
   t.sdot_raw = 0.f;
   t.cdot_raw[0] = t.cdot_raw[1] = t.cdot_raw[2] = 0.f;
   if (b.keep) {
-    const float* rw = a.raw + ((r * a.K + k) * 2 + 1) * C1;
+    const float* rw = a.raw_dot ? a.raw_dot + (r * a.K + k) * C1 : a.raw + ((r * a.K + k) * 2 + 1) * C1;
     t.sdot_raw = rw[0];
     for (int c = 0; c < p.C; ++c) t.cdot_raw[c] = rw[1 + c];
   }
@@ -352,6 +355,7 @@ extern "C" __global__ void __launch_bounds__(128) ren_composite_tan_bwd(const Co
   const RenPlan& p = a.p;
   const int C1 = 1 + p.C;
   float gb_acc[3] = {0.f, 0.f, 0.f};
+  float gabs = 0.f;
   for (long long r = warp; r < a.n_rays; r += n_warps) {
     float gC[3] = {0.f, 0.f, 0.f}, gCd[3] = {0.f, 0.f, 0.f}, bk[3] = {0.f, 0.f, 0.f};
     for (int c = 0; c < p.C; ++c) {
@@ -414,24 +418,26 @@ extern "C" __global__ void __launch_bounds__(128) ren_composite_tan_bwd(const Co
       prefA += __shfl_sync(0xffffffffu, inclA, 31);
       prefB += __shfl_sync(0xffffffffu, inclB, 31);
       if (k < a.K) {
-        float* gv = a.graw + ((r * a.K + k) * 2) * C1;
-        float* gt = gv + C1;
+        const long long vrow = (r * a.K + k) * (a.raw_dot ? 1 : 2);
+        float* gv = a.graw + (a.graw_dot ? (r * a.K + k) : (r * a.K + k) * 2) * C1;
+        float* gt = a.graw_dot ? a.graw_dot + (r * a.K + k) * C1 : gv + C1;
         float gs = 0.f, gsd = 0.f;
         if (b.keep) {
           const float dt = __fsub_rn(b.t1, b.t0);
           const float Tb = b.Texcl * expf(-b.sdt);
           const float dadot = Wt * Tb - (float)sufB;
           const float da = Wv * Tb - Wt * Tb * (t.Edot + t.adot) - (float)sufA;
-          const float sraw = a.raw[((r * a.K + k) * 2) * C1];
+          const float sraw = a.raw[vrow * C1];
           gsd = dadot * dt * b.dact_s;
           gs = da * dt * b.dact_s + dadot * dt * ren_density_act2(p.f.density_activation, sraw) * t.sdot_raw;
         }
         gv[0] = gs;
         gt[0] = gsd;
+        gabs = fmaxf(gabs, fmaxf(fabsf(gs), fabsf(gsd)));
         for (int c = 0; c < p.C; ++c) {
           float gcv = 0.f, gcd = 0.f;
           if (b.keep) {
-            const float craw = a.raw[((r * a.K + k) * 2) * C1 + 1 + c];
+            const float craw = a.raw[vrow * C1 + 1 + c];
             const float dc = gC[c] * b.w + gCd[c] * t.wdot;
             const float dcd = gCd[c] * b.w;
             gcd = dcd * b.dact_c[c];
@@ -439,6 +445,7 @@ extern "C" __global__ void __launch_bounds__(128) ren_composite_tan_bwd(const Co
           }
           gv[1 + c] = gcv;
           gt[1 + c] = gcd;
+          gabs = fmaxf(gabs, fmaxf(fabsf(gcv), fabsf(gcd)));
         }
       }
     });
@@ -446,17 +453,22 @@ extern "C" __global__ void __launch_bounds__(128) ren_composite_tan_bwd(const Co
   if (a.g_bkgd && a.bkgd && lane == 0)
     for (int c = 0; c < p.C; ++c)
       if (gb_acc[c] != 0.f) atomicAdd(a.g_bkgd + c, gb_acc[c]);
+  if (a.gmax != nullptr) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) gabs = fmaxf(gabs, __shfl_xor_sync(0xffffffffu, gabs, o));
+    if (lane == 0 && gabs > 0.f && gabs < INFINITY) atomicMax(a.gmax, __float_as_uint(gabs));
+  }
 }
 
 int ren_launch_composite_tan(const RenPlan& p, long long n_rays, int K, const float* o, const float* d,
-                             const float* jitter, const float* raw, const float* bkgd, float* radiance,
+                             const float* jitter, const float* raw, const float* raw_dot, const float* bkgd, float* radiance,
                              float* opacity, float* depth, float* radiance_dot, float* opacity_dot,
                              int* n_kept, cudaStream_t st) {
   if (n_rays <= 0) return REN_OK;
   CompArgs a = {};
   a.p = p; a.n_rays = n_rays; a.K = K; a.rays_o = o; a.rays_d = d; a.jitter = jitter; a.raw = raw;
   a.bkgd = bkgd; a.radiance = radiance; a.opacity = opacity; a.depth = depth; a.n_kept = n_kept;
-  a.tangent = 1; a.radiance_dot = radiance_dot; a.opacity_dot = opacity_dot;
+  a.tangent = 1; a.radiance_dot = radiance_dot; a.opacity_dot = opacity_dot; a.raw_dot = raw_dot;
   long long blocks = (n_rays + 3) / 4;
   if (blocks > 148 * 64) blocks = 148 * 64;
   ren_prof_begin(REN_K_COMPOSITE_FWD, st);
@@ -468,16 +480,16 @@ int ren_launch_composite_tan(const RenPlan& p, long long n_rays, int K, const fl
 }
 
 int ren_launch_composite_tan_bwd(const RenPlan& p, long long n_rays, int K, const float* o, const float* d,
-                                 const float* jitter, const float* raw, const float* bkgd,
+                                 const float* jitter, const float* raw, const float* raw_dot, const float* bkgd,
                                  const float* g_radiance, const float* g_opacity, const float* g_depth,
                                  const float* g_radiance_dot, const float* g_opacity_dot, float* graw,
-                                 float* g_bkgd, cudaStream_t st) {
+                                 float* graw_dot, float* g_bkgd, unsigned int* gmax, cudaStream_t st) {
   if (n_rays <= 0) return REN_OK;
   CompArgs a = {};
   a.p = p; a.n_rays = n_rays; a.K = K; a.rays_o = o; a.rays_d = d; a.jitter = jitter; a.raw = raw;
   a.bkgd = bkgd; a.g_radiance = g_radiance; a.g_opacity = g_opacity; a.g_depth = g_depth;
   a.g_radiance_dot = g_radiance_dot; a.g_opacity_dot = g_opacity_dot;
-  a.graw = graw; a.g_bkgd = g_bkgd; a.tangent = 1;
+  a.graw = graw; a.g_bkgd = g_bkgd; a.tangent = 1; a.raw_dot = raw_dot; a.graw_dot = graw_dot; a.gmax = gmax;
   long long blocks = (n_rays + 3) / 4;
   if (blocks > 148 * 64) blocks = 148 * 64;
   ren_prof_begin(REN_K_COMPOSITE_BWD, st);

@@ -32,6 +32,7 @@
 #include <string.h>
 
 #include "ren_tc.cuh"
+#include "ren_dual.cuh"
 
 #define TC_EPI_WARPS 16
 #define TC_PRO_WARPS 4                         // forward prologue warps: one thread per sample row
@@ -120,6 +121,15 @@ struct TcArgs {
   float* raw;                    // fwd: [S][1+C] raw sigma / radiance
   const float* graw;             // dgrad: [S][1+C] d loss / d raw
   const unsigned int* gmax;      // dgrad: max |graw| (float bits) -> power-of-two delta scale
+  // tangent render (d/dw rows): three more passes of the same chain
+  int tan;                       // fwd: tangent pass -- A = d enc/dw, epilogue = act'(value stash) * acc, no biases
+  int pass;                      // dgrad: 0 plain, 1 tangent adjoint (also writes E = abar_dot * act'' * pre_dot),
+                                 //        2 value adjoint (adds E)
+  const float* rays_o_dot;
+  const float* rays_d_dot;
+  const unsigned char* stash_val;   // fwd tangent pass: the value pass' stash (read)
+  const unsigned char* stash_dot;   // dgrad pass 1: the tangent pass' stash (read)
+  unsigned char* extra;             // dgrad: E matrices (fp16 blocked; written by pass 1, read by pass 2)
 };
 
 __device__ __forceinline__ float ex2_ftz(float x) {
@@ -136,6 +146,16 @@ __device__ __forceinline__ float lg2_ftz(float x) {
 __device__ __forceinline__ float softplus_log2(float u) { return fmaxf(u, 0.f) + lg2_ftz(1.f + ex2_ftz(-fabsf(u))); }
 // d softplus / dx from g = 100 log2e * softplus_100(x): sigmoid(100 x) = 1 - 2^-g
 __device__ __forceinline__ float softplus_grad_log2(float g) { return 1.f - ex2_ftz(-g); }
+
+// dgrad through one hidden activation, from the stashed log2-domain output g (and, for the tangent render,
+// the stashed tangent gdot):  pass 0/1: y = v act'(g);  pass 1 also E = v act''(pre) pre_dot = v ln2 2^-g gdot;
+// pass 2: y = v act'(g) + E (x = E).
+__device__ __forceinline__ float dgrad_act(int softplus, int pass, float v, float g, float x, float* e) {
+  float s, e2 = 0.f;
+  if (softplus) { e2 = ex2_ftz(-g); s = 1.f - e2; } else { s = g > 0.f ? 1.f : 0.f; }
+  *e = pass == 1 ? v * (0.6931471805599453f * e2 * x) : 0.f;
+  return pass == 2 ? fmaf(v, s, x) : v * s;
+}
 
 __device__ __forceinline__ void tc_mma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
                                               uint32_t accumulate) {
@@ -173,15 +193,31 @@ __device__ __forceinline__ float enc_feature(const float* x, int deg, int j) {
   const float xb = __fmul_rn(xa, __int_as_float((127 + i) << 23));     // exact 2^i
   return ren_sinf(shifted ? __fadd_rn(xb, 1.5707963267948966f) : xb);
 }
+__device__ __noinline__ float ren_cosf(float x) { return cosf(x); }
+// d/dw of the same feature given xdot = dx/dw
+__device__ __forceinline__ float enc_feature_tan(const float* x, const float* xd, int deg, int j) {
+  if (j < 3) return j == 0 ? xd[0] : (j == 1 ? xd[1] : xd[2]);
+  if (j >= 3 + 6 * deg) return 0.f;
+  const int jj = j - 3;
+  const bool shifted = jj >= 3 * deg;
+  const int q = shifted ? jj - 3 * deg : jj;
+  const int i = q / 3, a = q - 3 * i;
+  const float xa = a == 0 ? x[0] : (a == 1 ? x[1] : x[2]);
+  const float xda = a == 0 ? xd[0] : (a == 1 ? xd[1] : xd[2]);
+  const float sc = __int_as_float((127 + i) << 23);
+  const float xb = __fmul_rn(xa, sc);
+  return ren_cosf(shifted ? __fadd_rn(xb, 1.5707963267948966f) : xb) * sc * xda;
+}
 // encode k-cores [c0, c1) of an encoding into an operand region (+ fp16 stash)
-__device__ __forceinline__ void encode_cores(const float* x, int deg, int kp, int c0, int c1, bool valid,
-                                             unsigned char* smem, uint32_t hi_off, uint32_t lo_off, int m,
+__device__ __forceinline__ void encode_cores(const float* x, const float* xd, int deg, int kp, int c0, int c1,
+                                             bool valid, unsigned char* smem, uint32_t hi_off, uint32_t lo_off, int m,
                                              unsigned char* stash_mat, long long sidx) {
 #pragma unroll 1
   for (int c = c0; c < c1; ++c) {
     float f[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) f[j] = valid ? enc_feature(x, deg, c * 8 + j) : 0.f;
+    for (int j = 0; j < 8; ++j)
+      f[j] = !valid ? 0.f : (xd ? enc_feature_tan(x, xd, deg, c * 8 + j) : enc_feature(x, deg, c * 8 + j));
     uint4 hi, lo;
     split8(f, &hi, &lo);
     *reinterpret_cast<uint4*>(smem + hi_off + c * (TC_M * 16) + m * 16) = hi;
@@ -208,8 +244,11 @@ __device__ __forceinline__ uint64_t mk_desc(uint32_t lo32) {
   return d;
 }
 
-template <int MODE, bool STASH>   // MODE 0: forward, 1: dgrad
+// MODE 0: forward (VAR 0 value pass, 1 tangent pass); MODE 1: dgrad (VAR = pass 0 / 1 / 2)
+template <int MODE, bool STASH, int VAR>
 __global__ void __launch_bounds__(MODE == 0 ? TC_THREADS_FWD : TC_THREADS_BWD, 1) ren_tc_chain(const TcArgs a) {
+  constexpr bool TAN = MODE == 0 && VAR == 1;
+  constexpr int PASS = MODE == 1 ? VAR : 0;
   extern __shared__ __align__(1024) unsigned char smem[];
   const RenPlan& p = a.p;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -376,10 +415,32 @@ __global__ void __launch_bounds__(MODE == 0 ? TC_THREADS_FWD : TC_THREADS_BWD, 1
         }
         const float dz[3] = {__fmul_rn(d[0], 3.141592653589793f), __fmul_rn(d[1], 3.141592653589793f),
                              __fmul_rn(d[2], 3.141592653589793f)};
+        float zdot[3] = {0.f, 0.f, 0.f}, dzdot[3] = {0.f, 0.f, 0.f};
+        if (TAN && valid) {
+          // x = o + d tm, xdot = odot + ddot tm (the march carries no gradient); zdot = J_contract(x) xdot
+          const long long r = sidx / a.K;
+          const int k = (int)(sidx - r * a.K);
+          float t_min, t_max, t0, t1;
+          ren_ray_range(p.f, p.r, o, d, a.jitter ? a.jitter[r] : 0.f, &t_min, &t_max);
+          ren_march_to(p.r, t_min, k, &t0, &t1);
+          const float tm = __fmul_rn(__fadd_rn(t0, t1), 0.5f);
+          Dual pd[3], zd[3];
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const float od = a.rays_o_dot[r * 3 + c], dd = a.rays_d_dot[r * 3 + c];
+            pd[c] = Dual(__fadd_rn(o[c], __fmul_rn(__fmul_rn(d[c], __fadd_rn(t0, t1)), 0.5f)), fmaf(dd, tm, od));
+            dzdot[c] = dd * 3.141592653589793f;
+          }
+          ren_contract_t<Dual>(p.f, pd, zd);
+#pragma unroll
+          for (int c = 0; c < 3; ++c) zdot[c] = zd[c].d;
+        }
         mbar_wait(bar_pfree + 8 * eb, ((n_t >> 1) & 1u) ^ 1u);       // the MMAs of tile n_t - 2 are done with it
         unsigned char* buf = smem + eb * SM_ENC_BYTES;
-        encode_cores(z, 10, 64, 0, 8, valid, buf, SM_P_HI, SM_P_LO, m, STASH ? a.stash + tcs_encp(p, S) : nullptr, sidx);
-        encode_cores(dz, 4, 32, 0, 4, valid, buf, SM_D_HI, SM_D_LO, m, STASH ? a.stash + tcs_encd(p, S) : nullptr, sidx);
+        encode_cores(z, TAN ? zdot : nullptr, 10, 64, 0, 8, valid, buf, SM_P_HI, SM_P_LO, m,
+                     STASH ? a.stash + tcs_encp(p, S) : nullptr, sidx);
+        encode_cores(dz, TAN ? dzdot : nullptr, 4, 32, 0, 4, valid, buf, SM_D_HI, SM_D_LO, m,
+                     STASH ? a.stash + tcs_encd(p, S) : nullptr, sidx);
         sel[eb * 128 + m] = selector ? 1.f : 0.f;
         fence_proxy_async();
         __syncwarp();
@@ -409,11 +470,16 @@ __global__ void __launch_bounds__(MODE == 0 ? TC_THREADS_FWD : TC_THREADS_BWD, 1
         const TcStep& st0 = a.steps[0];
         const int mat = p.cond[0].mat;
         const size_t tile_off = (size_t)tile * (size_t)(p.WC >> 3) * 2048 + (size_t)m * 16 + (size_t)(cg * 4) * 2048;
-        uint4 act[4];
+        uint4 act[4], aux[4];          // aux: tangent activations (pass 1) or E (pass 2)
         if (valid) {
           const unsigned char* am = a.stash + tcs_mat(p, S, mat) + tile_off;
 #pragma unroll
           for (int i = 0; i < 4; ++i) act[i] = __ldg(reinterpret_cast<const uint4*>(am + i * 2048));
+          if (PASS) {
+            const unsigned char* xm = (PASS == 1 ? a.stash_dot : a.extra) + tcs_mat(p, S, mat) + tile_off;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) aux[i] = __ldg(reinterpret_cast<const uint4*>(xm + i * 2048));
+          }
         }
         float gc[3] = {0.f, 0.f, 0.f};
         if (valid) {
@@ -425,22 +491,27 @@ __global__ void __launch_bounds__(MODE == 0 ? TC_THREADS_FWD : TC_THREADS_BWD, 1
         unsigned char* dm = a.delta + tcs_mat(p, S, mat) + tile_off;
 #pragma unroll
         for (int j8 = 0; j8 < 4; ++j8) {
-          float av[8], y[8];
+          float av[8], xv[8], y[8], e[8];
           unpack8(act[j8], av);
+          if (PASS) unpack8(aux[j8], xv);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const int n = cg * 32 + j8 * 8 + j;
             float v = gc[0] * vec[VEC_WO + n];
             if (p.C > 1) v = fmaf(gc[1], vec[VEC_WO + 128 + n], v);
             if (p.C > 2) v = fmaf(gc[2], vec[VEC_WO + 256 + n], v);
-            v *= a.softplus ? softplus_grad_log2(av[j]) : (av[j] > 0.f ? 1.f : 0.f);
-            y[j] = valid ? v : 0.f;
+            y[j] = valid ? dgrad_act(a.softplus, PASS, v, av[j], xv[j], &e[j]) : 0.f;
+            if (!valid) e[j] = 0.f;
           }
           uint4 hi, lo;
           split8(y, &hi, &lo);
           hi16[j8 * 4 + 0] = hi.x; hi16[j8 * 4 + 1] = hi.y; hi16[j8 * 4 + 2] = hi.z; hi16[j8 * 4 + 3] = hi.w;
           lo16[j8 * 4 + 0] = lo.x; lo16[j8 * 4 + 1] = lo.y; lo16[j8 * 4 + 2] = lo.z; lo16[j8 * 4 + 3] = lo.w;
           *reinterpret_cast<uint4*>(dm + j8 * 2048) = hi;
+          if (PASS == 1) {
+            split8(e, &hi, &lo);
+            *reinterpret_cast<uint4*>(a.extra + tcs_mat(p, S, mat) + tile_off + j8 * 2048) = hi;
+          }
         }
         const uint32_t tcol = tmem_lane + (uint32_t)(st0.a_col + 32 * cg);
         tc_st16(tcol, hi16);
@@ -459,10 +530,21 @@ __global__ void __launch_bounds__(MODE == 0 ? TC_THREADS_FWD : TC_THREADS_BWD, 1
           const int n0 = 128 * h + 32 * cg;            // first of this thread's 32 features
           // byte offset of this thread's first 8-feature group inside a blocked fp16 matrix of width N
           const size_t tile_off = (size_t)tile * (size_t)(st.N >> 3) * 2048 + (size_t)m * 16 + (size_t)(n0 >> 3) * 2048;
-          uint4 act[4];
+          uint4 act[4], aux[4];
           if (MODE == 1 && st.epi == EPI_D_ACT && valid) {
             // prefetch this thread's slice of the activation stash while the MMAs run
             const unsigned char* am = a.stash + tcs_mat(p, S, st.act_mat) + tile_off;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) act[i] = __ldg(reinterpret_cast<const uint4*>(am + i * 2048));
+            if (PASS) {
+              const unsigned char* xm = (PASS == 1 ? a.stash_dot : a.extra) + tcs_mat(p, S, st.act_mat) + tile_off;
+#pragma unroll
+              for (int i = 0; i < 4; ++i) aux[i] = __ldg(reinterpret_cast<const uint4*>(xm + i * 2048));
+            }
+          }
+          if (MODE == 0 && TAN && st.epi != EPI_F_LINEAR && valid) {
+            // tangent pass: act'(pre) comes from the value pass' stash of this layer's output
+            const unsigned char* am = a.stash_val + tcs_mat(p, S, st.out_mat) + tile_off;
 #pragma unroll
             for (int i = 0; i < 4; ++i) act[i] = __ldg(reinterpret_cast<const uint4*>(am + i * 2048));
           }
@@ -493,7 +575,18 @@ __global__ void __launch_bounds__(MODE == 0 ? TC_THREADS_FWD : TC_THREADS_BWD, 1
 #pragma unroll
           for (int j8 = 0; j8 < 4; ++j8) {
             float y[8];
-            if (MODE == 0) {
+            float e8[8];
+            if (MODE == 0 && TAN) {
+              // d/dw rows: no bias; gdot = act'(pre) * (W gdot_prev) with act' from the value stash
+              float av[8];
+              if (st.epi != EPI_F_LINEAR) unpack8(act[j8], av);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float x = __uint_as_float(r[j8 * 8 + j]);
+                if (st.epi == EPI_F_LINEAR) y[j] = x * st.acc_scale;
+                else y[j] = valid ? x * (a.softplus ? softplus_grad_log2(av[j]) : (av[j] > 0.f ? 1.f : 0.f)) : 0.f;
+              }
+            } else if (MODE == 0) {
               const float4 b0 = *reinterpret_cast<const float4*>(bias + j8 * 8);
               const float4 b1 = *reinterpret_cast<const float4*>(bias + j8 * 8 + 4);
               const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
@@ -506,6 +599,8 @@ __global__ void __launch_bounds__(MODE == 0 ? TC_THREADS_FWD : TC_THREADS_BWD, 1
                   y[j] = (a.dbg & 1) ? x : (a.softplus ? softplus_log2(x) : fmaxf(x, 0.f));
                 }
               }
+            }
+            if (MODE == 0) {
               if (st.sig_head) {
                 const float4 w0 = *reinterpret_cast<const float4*>(vec + VEC_WSIG + n0 + j8 * 8);
                 const float4 w1 = *reinterpret_cast<const float4*>(vec + VEC_WSIG + n0 + j8 * 8 + 4);
@@ -521,15 +616,19 @@ __global__ void __launch_bounds__(MODE == 0 ? TC_THREADS_FWD : TC_THREADS_BWD, 1
                 }
               }
             } else {
-              float av[8];
-              if (st.epi == EPI_D_ACT) unpack8(act[j8], av);
+              float av[8], xv[8];
+              if (st.epi == EPI_D_ACT) {
+                unpack8(act[j8], av);
+                if (PASS) unpack8(aux[j8], xv);
+              }
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
                 float v = __uint_as_float(r[j8 * 8 + j]);
                 if (st.rank1) v = fmaf(gs, vec[VEC_WSIG + n0 + j8 * 8 + j], v);
-                if (st.epi == EPI_D_ACT)
-                  v *= a.softplus ? softplus_grad_log2(av[j]) : (av[j] > 0.f ? 1.f : 0.f);
+                e8[j] = 0.f;
+                if (st.epi == EPI_D_ACT) v = dgrad_act(a.softplus, PASS, v, av[j], xv[j], &e8[j]);
                 y[j] = valid ? v : 0.f;
+                if (!valid) e8[j] = 0.f;
               }
             }
             uint4 hi, lo;
@@ -537,6 +636,11 @@ __global__ void __launch_bounds__(MODE == 0 ? TC_THREADS_FWD : TC_THREADS_BWD, 1
             hi16[j8 * 4 + 0] = hi.x; hi16[j8 * 4 + 1] = hi.y; hi16[j8 * 4 + 2] = hi.z; hi16[j8 * 4 + 3] = hi.w;
             lo16[j8 * 4 + 0] = lo.x; lo16[j8 * 4 + 1] = lo.y; lo16[j8 * 4 + 2] = lo.z; lo16[j8 * 4 + 3] = lo.w;
             if (out_mat != nullptr) *reinterpret_cast<uint4*>(out_mat + j8 * 2048) = hi;
+            if (MODE == 1 && PASS == 1 && st.epi == EPI_D_ACT && st.out_mat >= 0) {
+              uint4 eh, el;
+              split8(e8, &eh, &el);
+              *reinterpret_cast<uint4*>(a.extra + tcs_mat(p, S, st.out_mat) + tile_off + j8 * 2048) = eh;
+            }
           }
           if (st.write_a) {
             tc_st16(tcol, hi16);
@@ -554,11 +658,12 @@ __global__ void __launch_bounds__(MODE == 0 ? TC_THREADS_FWD : TC_THREADS_BWD, 1
         asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");
         if (cg == 0 && sidx < S) {
           const float4 p0 = part[m], p1 = part[128 + m], p2 = part[256 + m], p3 = part[384 + m];
-          const float sraw = (p0.x + p1.x) + (p2.x + p3.x) + vec[VEC_HB];
-          a.raw[sidx * C1] = selector ? sraw : -INFINITY;
-          a.raw[sidx * C1 + 1] = (p0.y + p1.y) + (p2.y + p3.y) + vec[VEC_HB + 1];
-          if (p.C > 1) a.raw[sidx * C1 + 2] = (p0.z + p1.z) + (p2.z + p3.z) + vec[VEC_HB + 2];
-          if (p.C > 2) a.raw[sidx * C1 + 3] = (p0.w + p1.w) + (p2.w + p3.w) + vec[VEC_HB + 3];
+          const float hb = TAN ? 0.f : 1.f;          // the d/dw rows carry no bias
+          const float sraw = (p0.x + p1.x) + (p2.x + p3.x) + hb * vec[VEC_HB];
+          a.raw[sidx * C1] = (selector || TAN) ? sraw : -INFINITY;
+          a.raw[sidx * C1 + 1] = (p0.y + p1.y) + (p2.y + p3.y) + hb * vec[VEC_HB + 1];
+          if (p.C > 1) a.raw[sidx * C1 + 2] = (p0.z + p1.z) + (p2.z + p3.z) + hb * vec[VEC_HB + 2];
+          if (p.C > 2) a.raw[sidx * C1 + 3] = (p0.w + p1.w) + (p2.w + p3.w) + hb * vec[VEC_HB + 3];
         }
         asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");
       }
@@ -839,17 +944,17 @@ static int run_pack(const TcProgram& P, int mode, const float* params, unsigned 
   return REN_OK;
 }
 
-template <int MODE, bool STASH>
+template <int MODE, bool STASH, int VAR>
 static int launch_chain(const TcArgs& a, long long n_tiles, int kind, cudaStream_t st) {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = (int)(n_tiles < sms ? n_tiles : sms);
   if (grid < 1) return REN_OK;
-  cudaError_t e = cudaFuncSetAttribute(ren_tc_chain<MODE, STASH>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
+  cudaError_t e = cudaFuncSetAttribute(ren_tc_chain<MODE, STASH, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
   if (e != cudaSuccess) { ren_set_error("tc chain smem attr: %s", cudaGetErrorString(e)); return REN_E_CUDA; }
   ren_prof_begin(kind, st);
-  ren_tc_chain<MODE, STASH><<<grid, MODE == 0 ? TC_THREADS_FWD : TC_THREADS_BWD, SM_TOTAL, st>>>(a);
+  ren_tc_chain<MODE, STASH, VAR><<<grid, MODE == 0 ? TC_THREADS_FWD : TC_THREADS_BWD, SM_TOTAL, st>>>(a);
   ren_prof_end(kind, st);
   e = cudaGetLastError();
   if (e != cudaSuccess) { ren_set_error("tc chain launch: %s", cudaGetErrorString(e)); return REN_E_CUDA; }
@@ -883,7 +988,9 @@ static void fill_args(TcArgs& a, const RenPlan& p, const TcProgram& P) {
   a.dbg = dbg ? atoi(dbg) : 0;
 }
 
+// o_dot / d_dot / stash_val != NULL: the tangent pass of the tangent render (stash = its own stash, raw = raw_dot)
 int ren_tc_launch_fwd(const RenPlan& p, long long n_rays, int K, const float* o, const float* d,
+                      const float* o_dot, const float* d_dot, const void* stash_val,
                       const float* jitter, const float* params, void* stash, float* raw, void* ws,
                       size_t ws_bytes, cudaStream_t st) {
   TcProgram P;
@@ -898,14 +1005,19 @@ int ren_tc_launch_fwd(const RenPlan& p, long long n_rays, int K, const float* o,
   fill_args(a, p, P);
   a.n_rays = n_rays; a.K = K; a.rays_o = o; a.rays_d = d; a.jitter = jitter;
   a.pack = pack; a.vec = vec; a.prog = prog; a.n_ops = P.n_ops; a.stash = (unsigned char*)stash; a.raw = raw;
+  a.tan = o_dot != nullptr ? 1 : 0; a.rays_o_dot = o_dot; a.rays_d_dot = d_dot;
+  a.stash_val = (const unsigned char*)stash_val;
   const long long n_tiles = (n_rays * K + TC_M - 1) / TC_M;
-  return stash ? launch_chain<0, true>(a, n_tiles, REN_K_FIELD_FWD, st)
-               : launch_chain<0, false>(a, n_tiles, REN_K_FIELD_FWD, st);
+  if (a.tan) return launch_chain<0, true, 1>(a, n_tiles, REN_K_FIELD_FWD, st);     // the tangent pass always stashes
+  return stash ? launch_chain<0, true, 0>(a, n_tiles, REN_K_FIELD_FWD, st)
+               : launch_chain<0, false, 0>(a, n_tiles, REN_K_FIELD_FWD, st);
 }
 
+// pass 0: plain dgrad; 1: tangent-adjoint chain of the tangent render (reads stash_dot, writes extra);
+// 2: its value-adjoint chain (reads extra)
 int ren_tc_launch_dgrad(const RenPlan& p, long long S, const float* params, const void* stash,
-                        const float* graw, const unsigned int* gmax, void* delta, void* ws, size_t ws_bytes,
-                        cudaStream_t st) {
+                        const float* graw, const unsigned int* gmax, void* delta, int pass, const void* stash_dot,
+                        void* extra, void* ws, size_t ws_bytes, cudaStream_t st) {
   TcProgram P;
   build_dgrad(p, P);
   unsigned char* pack; float* vec; StageOp* prog;
@@ -919,6 +1031,9 @@ int ren_tc_launch_dgrad(const RenPlan& p, long long S, const float* params, cons
   a.n_rays = S; a.K = 1;            // dgrad only needs the flat sample count
   a.pack = pack; a.vec = vec; a.prog = prog; a.n_ops = P.n_ops;
   a.stash = (unsigned char*)stash; a.delta = (unsigned char*)delta; a.graw = graw; a.gmax = gmax;
+  a.pass = pass; a.stash_dot = (const unsigned char*)stash_dot; a.extra = (unsigned char*)extra;
   const long long n_tiles = (S + TC_M - 1) / TC_M;
-  return launch_chain<1, false>(a, n_tiles, REN_K_FIELD_DGRAD, st);
+  if (pass == 1) return launch_chain<1, false, 1>(a, n_tiles, REN_K_FIELD_DGRAD, st);
+  if (pass == 2) return launch_chain<1, false, 2>(a, n_tiles, REN_K_FIELD_DGRAD, st);
+  return launch_chain<1, false, 0>(a, n_tiles, REN_K_FIELD_DGRAD, st);
 }

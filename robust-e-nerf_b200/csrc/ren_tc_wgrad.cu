@@ -234,13 +234,15 @@ extern "C" __global__ void __launch_bounds__(256) ren_tc_head_wgrad(const HeadAr
     float b = bsum[c];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) b += __shfl_xor_sync(0xffffffffu, b, o);
-    if (lane == 0 && fg == 0) atomicAdd(a.g_params + a.b_off[which] + c, b);
+    if (lane == 0 && fg == 0 && a.b_off[which] >= 0) atomicAdd(a.g_params + a.b_off[which] + c, b);
   }
 }
 
 // ------------------------------------------------------------------ host side
+// with_bias = 0: the tangent rows of the tangent render (d/dw activations carry no bias)
 int ren_tc_launch_wgrad(const RenPlan& p, long long S, const void* stash, const void* delta,
-                        const float* graw, const unsigned int* gmax, float* g_params, cudaStream_t st) {
+                        const float* graw, const unsigned int* gmax, float* g_params, int with_bias,
+                        cudaStream_t st) {
   WgArgs a;
   static_assert(sizeof(WgArgs) <= 4000, "kernel parameter block too large");
   memset(&a, 0, sizeof(a));
@@ -251,7 +253,8 @@ int ren_tc_launch_wgrad(const RenPlan& p, long long S, const void* stash, const 
     for (int h = 0; h < Nd / 128; ++h) {
       WgMat& m = a.mats[n++];
       m.d_off = (long long)tcs_mat(p, S, dmat); m.Nd = Nd; m.n_half = h; m.h_off = h_off; m.Hw = Hw;
-      m.w_off = w_off; m.ldw = ldw; m.col0 = col0; m.Ktrue = Ktrue; m.b_off = b_off; m.h_scale = h_scale;
+      m.w_off = w_off; m.ldw = ldw; m.col0 = col0; m.Ktrue = Ktrue; m.b_off = with_bias ? b_off : -1;
+      m.h_scale = h_scale;
     }
   };
   // prev_scale: scale of the stashed main input (hidden activations are kept in the log2 domain)
@@ -297,9 +300,9 @@ int ren_tc_launch_wgrad(const RenPlan& p, long long S, const void* stash, const 
   HeadArgs h;
   memset(&h, 0, sizeof(h));
   h.h[0] = (const unsigned char*)stash + tcs_mat(p, S, last_trunk); h.N[0] = p.W;
-  h.w_off[0] = p.sig_w; h.b_off[0] = p.sig_b; h.n_ch[0] = 1; h.g_col[0] = 0;
+  h.w_off[0] = p.sig_w; h.b_off[0] = with_bias ? p.sig_b : -1; h.n_ch[0] = 1; h.g_col[0] = 0;
   h.h[1] = (const unsigned char*)stash + tcs_mat(p, S, p.cond[0].mat); h.N[1] = p.WC;
-  h.w_off[1] = p.rgb_w; h.b_off[1] = p.rgb_b; h.n_ch[1] = p.C; h.g_col[1] = 1;
+  h.w_off[1] = p.rgb_w; h.b_off[1] = with_bias ? p.rgb_b : -1; h.n_ch[1] = p.C; h.g_col[1] = 1;
   h.graw = graw; h.C1 = 1 + p.C; h.S = S; h.n_tiles = a.n_tiles; h.g_params = g_params; h.h_scale = kap;
   ren_prof_begin(REN_K_WGRAD, st);
   ren_tc_head_wgrad<<<dim3(sms * 2, 2), 256, 0, st>>>(h);

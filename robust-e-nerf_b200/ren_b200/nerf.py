@@ -144,9 +144,11 @@ class RenderTangentFunction(torch.autograd.Function):
             raise RuntimeError("ren_b200 renders on CUDA tensors only (no CPU fallback)")
         B = o.shape[0]
         C_ = owner.radiance_dim
-        fdesc, rdesc, K = owner._descs("simt_fp32")
-        flat = owner.flat_params()
         ray_grad = bool(want_grad) and any(ctx.needs_input_grad[2:6])
+        # ray gradients (trainable refractory period) come from the fp32 engine; otherwise the tcgen05 engine
+        # runs value and tangent passes of the same chain kernel
+        fdesc, rdesc, K = owner._descs("simt_fp32" if ray_grad else None)
+        flat = owner.flat_params()
         need_grad = bool(want_grad) and (ray_grad or any(ctx.needs_input_grad[7:]))
         dev = o.device
         o, d, o_dot, d_dot = (t.contiguous().float() for t in (o, d, o_dot, d_dot))
