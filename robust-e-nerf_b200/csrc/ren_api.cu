@@ -25,7 +25,8 @@ int ren_launch_composite_tan_bwd(const RenPlan& p, long long n_rays, int K, cons
                                  float* graw_dot, float* g_bkgd, unsigned int* gmax, cudaStream_t st);
 int ren_launch_raygrad(const RenPlan& p, long long n_rays, int K, const float* o, const float* d,
                        const float* o_dot, const float* d_dot, const float* jitter, const float* params,
-                       const float* delta, float* g_rays, cudaStream_t st);
+                       const void* delta, const void* delta_dot, int fp16, const unsigned int* gmax, float* g_rays,
+                       cudaStream_t st);
 int ren_launch_composite(const RenPlan& p, long long n_rays, int K, const float* o, const float* d,
                          const float* jitter, const float* raw, const float* bkgd, float* radiance,
                          float* opacity, float* depth, int* n_kept, cudaStream_t st);
@@ -416,14 +417,11 @@ extern "C" int ren_render_backward(const RenFieldDesc* f, const RenRenderDesc* r
     rc = ren_simt_launch_dgrad(p, S, params, st_f, graw, delta, 0, st);
     if (rc) return rc;
     if (g_rays) {
-      rc = ren_launch_raygrad(p, n_rays, K, rays_o, rays_d, nullptr, nullptr, jitter, params, delta, g_rays, st);
+      rc = ren_launch_raygrad(p, n_rays, K, rays_o, rays_d, nullptr, nullptr, jitter, params, delta, nullptr, 0,
+                              nullptr, g_rays, st);
       if (rc) return rc;
     }
     return ren_simt_launch_wgrad(p, S, st_f, delta, graw, g_params, 0, st);
-  }
-  if (g_rays) {
-    ren_set_error("ray gradients (trainable refractory period) are provided by the simt_fp32 engine only");
-    return REN_E_UNSUPPORTED;
   }
   const size_t need = tcd_bytes(p, S);
   if (ws_left < need + 1024) { ren_set_error("workspace too small for backward (%zu < %zu)", ws_left, need); return REN_E_WORKSPACE; }
@@ -439,6 +437,11 @@ extern "C" int ren_render_backward(const RenFieldDesc* f, const RenRenderDesc* r
   if (rc) return rc;
   rc = ren_tc_launch_dgrad(p, S, params, stash, graw, gmax, delta, 0, nullptr, nullptr, pack_ws, pack_left, st);
   if (rc) return rc;
+  if (g_rays) {
+    rc = ren_launch_raygrad(p, n_rays, K, rays_o, rays_d, nullptr, nullptr, jitter, params, delta, nullptr, 1, gmax,
+                            g_rays, st);
+    if (rc) return rc;
+  }
   return ren_tc_launch_wgrad(p, S, stash, delta, graw, gmax, g_params, 1, st);
 }
 
@@ -446,7 +449,7 @@ extern "C" int ren_render_backward(const RenFieldDesc* f, const RenRenderDesc* r
 // fp32 FFMA engine: (value, d/dw) row pairs through one pass.  tcgen05 engine: the value pass, then a
 // tangent pass of the same chain kernel whose epilogue multiplies by act'(pre) from the value stash; the
 // reverse is two dgrad passes (tangent adjoint, which also emits E = abar_dot act'' pre_dot, then value
-// adjoint, which adds E) and two weight-gradient passes.  Ray gradients come from the fp32 engine only.
+// adjoint, which adds E) and two weight-gradient passes.
 static int tangent_plan(const RenFieldDesc* f, const RenRenderDesc* r, int64_t n_rays, int32_t K, RenPlan* p) {
   int rc = ren_build_plan(f, r, p);
   if (rc) return rc;
@@ -579,10 +582,6 @@ extern "C" int ren_render_tangent_backward(const RenFieldDesc* f, const RenRende
   const size_t ws_left = workspace_bytes - (size_t)(ws - (char*)workspace);
   cudaStream_t st = (cudaStream_t)stream;
   if (p.r.engine != REN_ENGINE_SIMT_FP32) {
-    if (g_rays) {
-      ren_set_error("ray gradients (trainable refractory period) are provided by the simt_fp32 engine only");
-      return REN_E_UNSUPPORTED;
-    }
     if (stash_bytes < 2 * tcs_bytes(p, S) + 512) { ren_set_error("stash too small"); return REN_E_WORKSPACE; }
     const size_t need = tct_bwd_bytes(p, S);
     if (ws_left < need) { ren_set_error("workspace too small for backward (%zu < %zu)", ws_left, need); return REN_E_WORKSPACE; }
@@ -608,6 +607,11 @@ extern "C" int ren_render_tangent_backward(const RenFieldDesc* f, const RenRende
     if (rc) return rc;
     rc = ren_tc_launch_dgrad(p, S, params, sv, graw_val, gmax, delta_val, 2, nullptr, extra, pack_ws, pack_left, st);
     if (rc) return rc;
+    if (g_rays) {
+      rc = ren_launch_raygrad(p, n_rays, K, rays_o, rays_d, rays_o_dot, rays_d_dot, jitter, params, delta_val,
+                              delta_dot, 1, gmax, g_rays, st);
+      if (rc) return rc;
+    }
     rc = ren_tc_launch_wgrad(p, S, sv, delta_val, graw_val, gmax, g_params, 1, st);
     if (rc) return rc;
     return ren_tc_launch_wgrad(p, S, sd, delta_dot, graw_dot, gmax, g_params, 0, st);
@@ -626,7 +630,8 @@ extern "C" int ren_render_tangent_backward(const RenFieldDesc* f, const RenRende
   rc = ren_simt_launch_dgrad(p, S2, params, st_f, graw, delta, 1, st);
   if (rc) return rc;
   if (g_rays) {
-    rc = ren_launch_raygrad(p, n_rays, K, rays_o, rays_d, rays_o_dot, rays_d_dot, jitter, params, delta, g_rays, st);
+    rc = ren_launch_raygrad(p, n_rays, K, rays_o, rays_d, rays_o_dot, rays_d_dot, jitter, params, delta, nullptr, 0,
+                            nullptr, g_rays, st);
     if (rc) return rc;
   }
   return ren_simt_launch_wgrad(p, S2, st_f, delta, graw, g_params, 1, st);

@@ -11,7 +11,7 @@
 // reduces it to d loss / d (o, d); tangent mode (rows = (value, d/dw) pairs) also needs the second
 // derivative of the contraction, taken with hyper-dual numbers, and returns
 // d loss / d (o, d, o_dot, d_dot).
-#include "ren_common.cuh"
+#include "ren_tc.cuh"
 #include "ren_dual.cuh"
 
 #define RG_ROWS 4
@@ -19,13 +19,15 @@
 #define RG_MAX_SRC 8
 
 struct RgSource {
-  const float* D;   // Delta matrix (blocked [rows x N]) or graw (row-major [rows][ldd])
-  int N;            // rows of W feeding (== width of D)
-  int ldd;          // blocked: N; row-major: 1 + C
+  const void* D;      // Delta matrix of the value rows (blocked [rows x N], fp32 or fp16) or graw (row-major fp32)
+  const void* D_dot;  // tcgen05 tangent render: Delta of the d/dw rows in its own matrix (else NULL: the fp32
+                      // engine interleaves (value, d/dw) rows in D)
+  int N;              // rows of W feeding (== width of D)
+  int ldd;            // blocked: N; row-major: 1 + C
   int rowmajor;
-  const float* W;   // params + w_off + column offset of the encoding segment
+  const float* W;     // params + w_off + column offset of the encoding segment
   int ldw;
-  int enc;          // 1 positional, 2 direction
+  int enc;            // 1 positional, 2 direction
 };
 struct RgArgs {
   RenPlan p;
@@ -34,6 +36,8 @@ struct RgArgs {
   long long n_rays;
   int K;
   int tangent;
+  int fp16;                    // Delta matrices are fp16 blocked, scaled by delta_scale(gmax) (tcgen05 engine)
+  const unsigned int* gmax;
   const float* rays_o;
   const float* rays_d;
   const float* rays_o_dot;
@@ -71,8 +75,9 @@ extern "C" __global__ void __launch_bounds__(RG_THREADS) ren_raygrad_kernel(cons
   __shared__ float gP[RG_ROWS][REN_PE_MAX];
   __shared__ float gD[RG_ROWS][REN_DE_MAX];
   const RenPlan& p = a.p;
-  const long long S = a.n_rays * a.K * (a.tangent ? 2 : 1);     // rows
+  const long long S = a.n_rays * a.K * (a.tangent ? 2 : 1);     // rows (value and d/dw rows counted separately)
   const int j = threadIdx.x & 63, lr = threadIdx.x >> 6;
+  const float unscale = a.fp16 ? 1.f / delta_scale(a.gmax) : 1.f;
   for (long long row0 = (long long)blockIdx.x * RG_ROWS; row0 < S; row0 += (long long)gridDim.x * RG_ROWS) {
     const long long row = row0 + lr;
     float accP = 0.f, accD = 0.f;
@@ -81,11 +86,22 @@ extern "C" __global__ void __launch_bounds__(RG_THREADS) ren_raygrad_kernel(cons
         const RgSource& sc = a.src[si];
         const int width = sc.enc == 1 ? p.PE : p.DE;
         if (j >= width) continue;
+        // matrix and row inside it: separate d/dw matrix (tcgen05) or interleaved rows (fp32 engine)
+        const void* D = sc.D;
+        long long mrow = row;
+        if (a.tangent && sc.D_dot != nullptr) {
+          D = (row & 1) ? sc.D_dot : sc.D;
+          mrow = row >> 1;
+        }
         float acc = 0.f;
         for (int n = 0; n < sc.N; ++n) {
-          const float dv = sc.rowmajor ? sc.D[row * sc.ldd + n] : sc.D[ren_blk(row, n, sc.ldd)];
+          float dv;
+          if (sc.rowmajor) dv = reinterpret_cast<const float*>(D)[mrow * sc.ldd + n];
+          else if (a.fp16) dv = __half2float(reinterpret_cast<const __half*>(D)[ren_blk(mrow, n, sc.ldd)]);
+          else dv = reinterpret_cast<const float*>(D)[ren_blk(mrow, n, sc.ldd)];
           acc = fmaf(dv, __ldg(sc.W + (long long)n * sc.ldw + j), acc);
         }
+        if (!sc.rowmajor) acc *= unscale;
         if (sc.enc == 1) accP += acc; else accD += acc;
       }
     }
@@ -162,37 +178,47 @@ extern "C" __global__ void __launch_bounds__(RG_THREADS) ren_raygrad_kernel(cons
   }
 }
 
-// delta: fp32 blocked delta workspace (mats mirror of the stash) followed by graw [rows][1+C]
+// fp32 engine: delta = fp32 blocked delta workspace (mats mirror of the stash) followed by graw [rows][1+C];
+// tcgen05 engine (fp16 != 0): delta / delta_dot = fp16 blocked delta matrices of the value / d/dw rows
 int ren_launch_raygrad(const RenPlan& p, long long n_rays, int K, const float* o, const float* d,
                        const float* o_dot, const float* d_dot, const float* jitter, const float* params,
-                       const float* delta, float* g_rays, cudaStream_t st) {
+                       const void* delta, const void* delta_dot, int fp16, const unsigned int* gmax, float* g_rays,
+                       cudaStream_t st) {
   if (n_rays <= 0) return REN_OK;
   RgArgs a;
-  a.p = p; a.n_rays = n_rays; a.K = K; a.tangent = o_dot != nullptr ? 1 : 0;
+  a.p = p; a.n_rays = n_rays; a.K = K; a.tangent = o_dot != nullptr ? 1 : 0; a.fp16 = fp16; a.gmax = gmax;
   a.rays_o = o; a.rays_d = d; a.rays_o_dot = o_dot; a.rays_d_dot = d_dot; a.jitter = jitter; a.g_rays = g_rays;
-  const long long S = n_rays * K * (a.tangent ? 2 : 1);
-  const float* graw = delta + p.act_floats * ren_pad128(S);
+  const long long S = n_rays * K * (a.tangent ? 2 : 1);          // rows
+  const long long Sm = fp16 ? n_rays * K : S;                    // rows of one delta matrix
+  const float* graw = fp16 ? nullptr : (const float*)delta + p.act_floats * ren_pad128(S);
   int n = 0;
-  auto add = [&](const float* D, int N, int ldd, int rowmajor, const float* W, int ldw, int enc) {
+  auto add = [&](const void* D, const void* Dd, int N, int ldd, int rowmajor, const float* W, int ldw, int enc) {
     if (n < RG_MAX_SRC) {
       RgSource& s = a.src[n];
-      s.D = D; s.N = N; s.ldd = ldd; s.rowmajor = rowmajor; s.W = W; s.ldw = ldw; s.enc = enc;
+      s.D = D; s.D_dot = Dd; s.N = N; s.ldd = ldd; s.rowmajor = rowmajor; s.W = W; s.ldw = ldw; s.enc = enc;
     }
     ++n;
   };
+  auto mat = [&](const void* base, int m) -> const void* {
+    if (base == nullptr) return nullptr;
+    return fp16 ? (const void*)((const char*)base + tcs_mat(p, Sm, m))
+                : (const void*)((const float*)base + ren_stash_mat(p, S, m));
+  };
   auto add_layer = [&](const RenLayer& L) {
-    const float* D = delta + ren_stash_mat(p, S, L.mat);
     const int ldw = L.K0 + L.K1;
-    if (L.src0 == 1) add(D, L.N, L.N, 0, params + L.w_off, ldw, 1);
-    if (L.K1 > 0) add(D, L.N, L.N, 0, params + L.w_off + L.K0, ldw, L.src1 == 1 ? 1 : 2);
+    if (L.src0 == 1) add(mat(delta, L.mat), mat(delta_dot, L.mat), L.N, L.N, 0, params + L.w_off, ldw, 1);
+    if (L.K1 > 0)
+      add(mat(delta, L.mat), mat(delta_dot, L.mat), L.N, L.N, 0, params + L.w_off + L.K0, ldw, L.src1 == 1 ? 1 : 2);
   };
   for (int i = 0; i < p.D; ++i) add_layer(p.trunk[i]);
   add_layer(p.bott);
   for (int jj = 0; jj < p.CD; ++jj) add_layer(p.cond[jj]);
   const int C1 = 1 + p.C;
-  if (p.D == 0) add(graw, 1, C1, 1, params + p.sig_w, p.hid_K0 + p.hid_K1, 1);
-  else if (p.hid_K1 > 0) add(graw, 1, C1, 1, params + p.sig_w + p.hid_K0, p.hid_K0 + p.hid_K1, 1);
-  if (p.CD == 0) add(graw + 1, p.C, C1, 1, params + p.rgb_w + p.W, p.W + p.DE, 2);
+  if (!fp16) {      // head layers that consume an encoding directly: shapes the tcgen05 engine does not cover
+    if (p.D == 0) add(graw, nullptr, 1, C1, 1, params + p.sig_w, p.hid_K0 + p.hid_K1, 1);
+    else if (p.hid_K1 > 0) add(graw, nullptr, 1, C1, 1, params + p.sig_w + p.hid_K0, p.hid_K0 + p.hid_K1, 1);
+    if (p.CD == 0) add(graw + 1, nullptr, p.C, C1, 1, params + p.rgb_w + p.W, p.W + p.DE, 2);
+  }
   if (n > RG_MAX_SRC) { ren_set_error("ray gradient: too many encoding consumers (%d)", n); return REN_E_UNSUPPORTED; }
   a.n_src = n;
   cudaError_t e = cudaMemsetAsync(g_rays, 0, sizeof(float) * (size_t)n_rays * (a.tangent ? 12 : 6), st);

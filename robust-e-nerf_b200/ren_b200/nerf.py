@@ -48,8 +48,7 @@ class RenderFunction(torch.autograd.Function):
              jitter (B)|None, bkgd (C)|None, *params
     outputs: radiance (B,C), opacity (B), depth_raw (B), n_kept (B) int32
     Gradients flow to the MLP parameters and `bkgd`; when `o` / `d` require grad (trainable
-    refractory period) the reverse pass also returns d loss / d (o, d) -- the
-    fp32 FFMA engine computes them, so such a call is routed to `simt_fp32`.
+    refractory period) the reverse pass also returns d loss / d (o, d).
     """
 
     @staticmethod
@@ -60,7 +59,7 @@ class RenderFunction(torch.autograd.Function):
         B = o.shape[0]
         C_ = owner.radiance_dim
         ray_grad = bool(want_grad) and (ctx.needs_input_grad[2] or ctx.needs_input_grad[3])
-        fdesc, rdesc, K = owner._descs("simt_fp32" if ray_grad else None)
+        fdesc, rdesc, K = owner._descs()
         flat = owner.flat_params()
         need_grad = bool(want_grad) and (ray_grad or any(ctx.needs_input_grad[5:]))
         dev = o.device
@@ -145,9 +144,7 @@ class RenderTangentFunction(torch.autograd.Function):
         B = o.shape[0]
         C_ = owner.radiance_dim
         ray_grad = bool(want_grad) and any(ctx.needs_input_grad[2:6])
-        # ray gradients (trainable refractory period) come from the fp32 engine; otherwise the tcgen05 engine
-        # runs value and tangent passes of the same chain kernel
-        fdesc, rdesc, K = owner._descs("simt_fp32" if ray_grad else None)
+        fdesc, rdesc, K = owner._descs()
         flat = owner.flat_params()
         need_grad = bool(want_grad) and (ray_grad or any(ctx.needs_input_grad[7:]))
         dev = o.device
