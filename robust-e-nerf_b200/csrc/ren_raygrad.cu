@@ -14,8 +14,8 @@
 #include "ren_tc.cuh"
 #include "ren_dual.cuh"
 
-#define RG_ROWS 4
-#define RG_THREADS (64 * RG_ROWS)
+#define RG_ROWS 64
+#define RG_THREADS 256
 #define RG_MAX_SRC 8
 
 struct RgSource {
@@ -71,42 +71,94 @@ __device__ __forceinline__ void enc_backward(const float* x, const float* xdot, 
   }
 }
 
+// value of Delta[row][n] of one source: separate d/dw matrix (tcgen05) or interleaved rows (fp32 engine)
+__device__ __forceinline__ float rg_load(const RgArgs& a, const RgSource& sc, long long row, int n) {
+  const void* D = sc.D;
+  long long mrow = row;
+  if (a.tangent && sc.D_dot != nullptr) {
+    D = (row & 1) ? sc.D_dot : sc.D;
+    mrow = row >> 1;
+  }
+  if (sc.rowmajor) return reinterpret_cast<const float*>(D)[mrow * sc.ldd + n];
+  if (a.fp16) return __half2float(reinterpret_cast<const __half*>(D)[ren_blk(mrow, n, sc.ldd)]);
+  return reinterpret_cast<const float*>(D)[ren_blk(mrow, n, sc.ldd)];
+}
+
+// Tile = 64 rows.  Phase 1: dEnc[64 x (64 | 32)] = sum over sources of Delta[64 x N] W[N x enc cols] as a
+// register-blocked fp32 GEMM (thread = 4 rows x 4 positional + 2 direction columns, K chunks of 16 staged in
+// shared memory).  Phase 2: one thread per sample reduces dEnc through the encoder and the contraction.
 extern "C" __global__ void __launch_bounds__(RG_THREADS) ren_raygrad_kernel(const RgArgs a) {
-  __shared__ float gP[RG_ROWS][REN_PE_MAX];
-  __shared__ float gD[RG_ROWS][REN_DE_MAX];
+  __shared__ __align__(16) float gP[RG_ROWS][REN_PE_MAX];
+  __shared__ __align__(16) float gD[RG_ROWS][REN_DE_MAX];
+  __shared__ __align__(16) float As[16][RG_ROWS];        // Delta chunk, k-major
+  __shared__ __align__(16) float Ws[16][64];             // weight chunk [k][enc col]
   const RenPlan& p = a.p;
   const long long S = a.n_rays * a.K * (a.tangent ? 2 : 1);     // rows (value and d/dw rows counted separately)
-  const int j = threadIdx.x & 63, lr = threadIdx.x >> 6;
+  const int tid = threadIdx.x;
+  const int ty = tid >> 4, tx = tid & 15;                // rows 4 ty .. 4 ty + 3; columns 4 tx .. (P), 2 tx .. (D)
   const float unscale = a.fp16 ? 1.f / delta_scale(a.gmax) : 1.f;
   for (long long row0 = (long long)blockIdx.x * RG_ROWS; row0 < S; row0 += (long long)gridDim.x * RG_ROWS) {
-    const long long row = row0 + lr;
-    float accP = 0.f, accD = 0.f;
-    if (row < S) {
-      for (int si = 0; si < a.n_src; ++si) {
-        const RgSource& sc = a.src[si];
-        const int width = sc.enc == 1 ? p.PE : p.DE;
-        if (j >= width) continue;
-        // matrix and row inside it: separate d/dw matrix (tcgen05) or interleaved rows (fp32 engine)
-        const void* D = sc.D;
-        long long mrow = row;
-        if (a.tangent && sc.D_dot != nullptr) {
-          D = (row & 1) ? sc.D_dot : sc.D;
-          mrow = row >> 1;
+    float accP[4][4], accD[4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) accP[i][c] = 0.f;
+      accD[i][0] = accD[i][1] = 0.f;
+    }
+    for (int si = 0; si < a.n_src; ++si) {
+      const RgSource& sc = a.src[si];
+      const int width = sc.enc == 1 ? p.PE : p.DE;
+      const float scale = sc.rowmajor ? 1.f : unscale;
+      for (int k0 = 0; k0 < sc.N; k0 += 16) {
+        // stage: 64 rows x 16 k of Delta (4 per thread), 16 k x 64 columns of W (4 per thread)
+        {
+          const int lrow = tid >> 2, kq = (tid & 3) * 4;
+          const long long row = row0 + lrow;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int n = k0 + kq + e;
+            As[kq + e][lrow] = (row < S && n < sc.N) ? rg_load(a, sc, row, n) * scale : 0.f;
+          }
+          const int wk = tid >> 4, wc = (tid & 15) * 4;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int n = k0 + wk, c = wc + e;
+            Ws[wk][c] = (n < sc.N && c < width) ? __ldg(sc.W + (long long)n * sc.ldw + c) : 0.f;
+          }
         }
-        float acc = 0.f;
-        for (int n = 0; n < sc.N; ++n) {
-          float dv;
-          if (sc.rowmajor) dv = reinterpret_cast<const float*>(D)[mrow * sc.ldd + n];
-          else if (a.fp16) dv = __half2float(reinterpret_cast<const __half*>(D)[ren_blk(mrow, n, sc.ldd)]);
-          else dv = reinterpret_cast<const float*>(D)[ren_blk(mrow, n, sc.ldd)];
-          acc = fmaf(dv, __ldg(sc.W + (long long)n * sc.ldw + j), acc);
+        __syncthreads();
+        if (sc.enc == 1) {
+#pragma unroll
+          for (int kk = 0; kk < 16; ++kk) {
+            const float4 av = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+            const float4 wv = *reinterpret_cast<const float4*>(&Ws[kk][tx * 4]);
+            const float ar[4] = {av.x, av.y, av.z, av.w}, wr[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+              for (int c = 0; c < 4; ++c) accP[i][c] = fmaf(ar[i], wr[c], accP[i][c]);
+          }
+        } else {
+#pragma unroll
+          for (int kk = 0; kk < 16; ++kk) {
+            const float4 av = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+            const float2 wv = *reinterpret_cast<const float2*>(&Ws[kk][tx * 2]);
+            const float ar[4] = {av.x, av.y, av.z, av.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              accD[i][0] = fmaf(ar[i], wv.x, accD[i][0]);
+              accD[i][1] = fmaf(ar[i], wv.y, accD[i][1]);
+            }
+          }
         }
-        if (!sc.rowmajor) acc *= unscale;
-        if (sc.enc == 1) accP += acc; else accD += acc;
+        __syncthreads();
       }
     }
-    gP[lr][j] = accP;
-    if (j < REN_DE_MAX) gD[lr][j] = accD;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      *reinterpret_cast<float4*>(&gP[ty * 4 + i][tx * 4]) = make_float4(accP[i][0], accP[i][1], accP[i][2], accP[i][3]);
+      *reinterpret_cast<float2*>(&gD[ty * 4 + i][tx * 2]) = make_float2(accD[i][0], accD[i][1]);
+    }
     __syncthreads();
     const int per = a.tangent ? 2 : 1;
     if (threadIdx.x < RG_ROWS / per) {
