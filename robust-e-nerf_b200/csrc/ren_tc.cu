@@ -585,6 +585,8 @@ __global__ void __launch_bounds__(MODE == 0 ? TC_THREADS_FWD : TC_THREADS_BWD, 1
                 const float x = __uint_as_float(r[j8 * 8 + j]);
                 if (st.epi == EPI_F_LINEAR) y[j] = x * st.acc_scale;
                 else y[j] = valid ? x * (a.softplus ? softplus_grad_log2(av[j]) : (av[j] > 0.f ? 1.f : 0.f)) : 0.f;
+                // d/dw activations scale with the camera speed: keep them inside fp16 (the hi part is the operand)
+                y[j] = fminf(fmaxf(y[j], -60000.f), 60000.f);
               }
             } else if (MODE == 0) {
               const float4 b0 = *reinterpret_cast<const float4*>(bias + j8 * 8);

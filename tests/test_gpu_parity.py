@@ -248,6 +248,44 @@ def test_real_sequence_like_configs(aabb, near, far, built_lib, dataset_dir):
     assert abs(spp - spp_ref) <= 1e-3 * spp_ref + 0.5
 
 
+@pytest.mark.parametrize("engine", ENGINES)
+def test_three_channel_radiance_matches_oracle(engine, built_lib, dataset_dir):
+    """Bayer sensors render radiance_dim = 3 (robust_e_nerf.py:230-233, `bayering` :887-890): `NeRF.forward`
+    and its backward with C = 3 against the oracle (per-channel radiance, background vector, MLP gradients)."""
+    from ren_b200 import NeRF
+    g = dict(H.load_golden("step_8x256"))
+    fcfg, rcfg, _ = H.golden_configs(g)
+    fcfg.radiance_dim = 3
+    cfgp = H.product_config(g)["nerf"]
+    torch.manual_seed(3)
+    nerf = NeRF(cfgp["aabb"], cfgp["contraction_type"], cfgp["occ_grid"], cfgp["near_plane"], cfgp["far_plane"],
+                cfgp["render_step_size"], "parameter", cfgp["cone_angle"], cfgp["early_stop_eps"],
+                cfgp["alpha_thre"], cfgp["test_chunk_size"], "mlp", arch_config=cfgp["mlp"], radiance_dim=3,
+                engine=engine).cuda().train()
+    params = {k[len("radiance_field."):]: v.detach().cpu().clone().requires_grad_(True)
+              for k, v in nerf.state_dict().items() if k.startswith("radiance_field.mlp.")}
+    B = 48
+    gen = torch.Generator().manual_seed(9)
+    ang = torch.rand(B, generator=gen) * 6.2831853
+    o = torch.stack([3 * torch.cos(ang), 3 * torch.sin(ang), 0.2 * torch.sin(3 * ang)], -1)
+    d = torch.nn.functional.normalize(-o + 0.4 * torch.randn(B, 3, generator=gen), dim=-1)
+    u = torch.rand(B, generator=gen)
+    wts = torch.randn(B, 3, generator=gen)
+    rad, opac, depth, spp = nerf(o.cuda(), d.cuda(), u.cuda())
+    assert rad.shape == (B, 3)
+    (rad * wts.cuda()).sum().backward()
+    th_b = nerf.parametrizations.render_bkgd.original.detach().cpu().clone().requires_grad_(True)
+    rad_o, opac_o, depth_o, _ = R.render(params, fcfg, rcfg, o, d, u, R.softplus(th_b, 1.0))
+    (rad_o * wts).sum().backward()
+    nw, ma, _ = H.rel_err(_log_i(rad), _log_i(rad_o))
+    print(f"[C=3/{engine}] logI normwise={nw:.2e} maxabs={ma:.2e}")
+    assert nw < REL_BAR and ma < 3e-4 and H.rel_err(opac, opac_o)[1] < 1e-4
+    assert H.rel_err(nerf.parametrizations.render_bkgd.original.grad, th_b.grad)[0] < 1e-3
+    named = dict(nerf.named_parameters())
+    for k, v in params.items():
+        _grad_cmp(k, named["radiance_field." + k].grad, v.grad, cos_bar=0.9999, nw_bar=1e-2)
+
+
 def test_edge_cases(built_lib, dataset_dir):
     """Empty and ragged inputs: zero rays, a single ray, a ray count whose samples do not fill a tile."""
     g = dict(H.load_golden("step_8x256"))
