@@ -35,8 +35,9 @@
 #include "ren_dual.cuh"
 
 #define TC_EPI_WARPS 16
-#define TC_PRO_WARPS 4                         // forward prologue warps: one thread per sample row
-#define TC_THREADS_FWD (64 + 32 * TC_EPI_WARPS + 32 * TC_PRO_WARPS)   // 704
+#define TC_PRO_WARPS 2                         // forward prologue warps: two sample rows per thread (640 threads keep
+                                               // 96 registers for the epilogue warps)
+#define TC_THREADS_FWD (64 + 32 * TC_EPI_WARPS + 32 * TC_PRO_WARPS)   // 640
 #define TC_THREADS_BWD (64 + 32 * TC_EPI_WARPS)                       // 576: dgrad has no prologue warps
 #define TC_STAGES 3            // ring stages of up to TC_STAGE_KS K steps (32 KB)
 #define TC_STAGE_KS 4
@@ -390,11 +391,13 @@ __global__ void __launch_bounds__(MODE == 0 ? TC_THREADS_FWD : TC_THREADS_BWD, 1
     // march -> sample position -> contraction -> sin/cos encodings of one sample row per thread, written
     // as fp16 hi/lo K-major operands into the free encoding buffer (+ the fp16 stash when training)
     if (MODE == 0) {
-      const int m = (warp - 2 - TC_EPI_WARPS) * 32 + lane;
       float* sel = reinterpret_cast<float*>(smem + SM_SEL);
       uint32_t n_t = 0;
       for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n_t) {
         const uint32_t eb = n_t & 1u;
+        mbar_wait(bar_pfree + 8 * eb, ((n_t >> 1) & 1u) ^ 1u);       // the MMAs of tile n_t - 2 are done with it
+#pragma unroll 1
+        for (int m = (warp - 2 - TC_EPI_WARPS) * 32 + lane; m < TC_M; m += 32 * TC_PRO_WARPS) {
         const long long sidx = tile * TC_M + m;
         const bool valid = sidx < S && !(a.dbg & 4);
         float o[3] = {0.f, 0.f, 0.f}, d[3] = {0.f, 0.f, 1.f}, z[3] = {0.f, 0.f, 0.f};
@@ -435,13 +438,13 @@ __global__ void __launch_bounds__(MODE == 0 ? TC_THREADS_FWD : TC_THREADS_BWD, 1
 #pragma unroll
           for (int c = 0; c < 3; ++c) zdot[c] = zd[c].d;
         }
-        mbar_wait(bar_pfree + 8 * eb, ((n_t >> 1) & 1u) ^ 1u);       // the MMAs of tile n_t - 2 are done with it
         unsigned char* buf = smem + eb * SM_ENC_BYTES;
         encode_cores(z, TAN ? zdot : nullptr, 10, 64, 0, 8, valid, buf, SM_P_HI, SM_P_LO, m,
                      STASH ? a.stash + tcs_encp(p, S) : nullptr, sidx);
         encode_cores(dz, TAN ? dzdot : nullptr, 4, 32, 0, 4, valid, buf, SM_D_HI, SM_D_LO, m,
                      STASH ? a.stash + tcs_encd(p, S) : nullptr, sidx);
         sel[eb * 128 + m] = selector ? 1.f : 0.f;
+        }
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_p + 8 * eb);
