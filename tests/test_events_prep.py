@@ -67,3 +67,40 @@ def test_event_queue_full_size_vs_oracle(built_lib):
              "polarity": np.zeros((0,), bool)}
     q0, m0 = E._run(empty, calib, "cuda")
     assert q0["end_ts"].numel() == 0 and m0 == np.iinfo(np.int64).max
+
+
+@pytest.mark.gpu
+def test_raw_events_to_training_steps(built_lib, dataset_dir):
+    """The rows either side of the hot path in one flow, all on the device: `raw_events.npz` -> `ren_event_queue`
+    -> `DeviceEventSampler` (randint-with-replacement gather + normalised timestamp samplers) ->
+    `RobustENeRF.training_step` + backward + Adam for a few steps."""
+    import helpers as H
+    from oracle import synth
+    from ren_b200 import events as E
+    from ren_b200.data import DeviceEventSampler
+    from ren_b200.trainer import FlatTrainer
+    scene = synth.load_scene(dataset_dir)
+    T = scene["T_wc_timestamp"]
+    raw = EP.synth_raw_events(300_000, 640, 480, seed=21)
+    # spread the stream over the interior of the pose track
+    span = int(T[-6] - T[5])
+    raw["timestamp"] = (int(T[5]) + (raw["timestamp"] - raw["timestamp"][0]) % span).astype(np.int64)
+    raw["timestamp"].sort()
+    calib = {"img_width": 640, "img_height": 480, "bayer_pattern": ""}
+    q, tau_max = E._run(raw, calib, "cuda")
+    assert q["end_ts"].numel() > 1000 and tau_max > 0
+    # the sensor model needs refractory period < every interval (event_generation_params.py:117-131 redefines
+    # tau from the extracted maximum); this synthetic stream is denser than the calibrated tau, so keep the
+    # intervals that respect it
+    keep = (q["end_ts"] - q["start_ts"]) > 100_000
+    q = {k: v[keep] for k, v in q.items()}
+    g = dict(H.load_golden("step_8x256"))
+    g["rcfg"] = dict(g["rcfg"], render_step_size=4.0 / 32, far_plane=0.5 + 32.5 * (4.0 / 32))
+    m = H.build_product(g, dataset_dir, "cuda")
+    tr = FlatTrainer(m)
+    sampler = DeviceEventSampler(q, 512, device="cuda", seed=1)
+    losses = []
+    for i, batch in zip(range(4), sampler):
+        losses.append(float(tr.step(batch, i)))
+    assert all(np.isfinite(losses)), losses
+    assert int(m.logged["train/batch_size"]) == 512

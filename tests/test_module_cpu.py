@@ -114,3 +114,27 @@ def test_unsupported_configurations_raise(built_lib, dataset_dir):
     with pytest.raises(NotImplementedError):
         NeRF(cfg["aabb"], "sphere", cfg["occ_grid"], 0.5, 4.5, 0.03, None, 0.0, 0.0, 0.0, 16384, "ngp",
              arch_config=cfg["mlp"])
+
+
+def test_device_sampler_distributions():
+    """`ren_b200.data.DeviceEventSampler` (on CPU here: same code path, `device` argument only): batch layout,
+    dtypes and the three normalised-timestamp distributions of data/datamodule.py:149-196."""
+    from ren_b200.data import DeviceEventSampler, trunc_normal
+    M = 1000
+    ev = {"position": torch.randint(0, 64, (M, 2)), "start_ts": torch.arange(M) * 10, "end_ts": torch.arange(M) * 10 + 5,
+          "num_pos": torch.ones(M, dtype=torch.int64), "num_neg": torch.zeros(M, dtype=torch.int64)}
+    s = DeviceEventSampler(ev, 4096, device="cpu", seed=3, rank=1)
+    b = next(iter(s))
+    assert b["event"]["position"].shape == (1, 4096, 2) and b["event"]["position"].dtype == torch.float32
+    assert b["event"]["start_ts"].dtype == torch.int64 and b["event"]["end_ts"].shape == (1, 4096)
+    assert bool((b["event"]["end_ts"] - b["event"]["start_ts"] == 5).all())        # rows stay aligned
+    nz = b["normalized"]
+    assert all(v.dtype == torch.float64 and v.shape == (1, 4096) for v in nz.values())
+    assert bool((nz["ts_diff"] == 1).all())
+    assert 0.45 < float(nz["diff_start_ts"].mean()) < 0.55 and float(nz["diff_start_ts"].min()) >= 0
+    g = nz["grad_ts"]
+    assert float(g.min()) >= 0 and float(g.max()) <= 1 and abs(float(g.mean()) - 0.5) < 0.02
+    assert 0.18 < float(g.std()) < 0.24                       # N(0.5, 0.25) truncated to +-2 sigma: std ~0.22
+    s.batch_size = 17                                          # dynamic batch size
+    assert next(s)["event"]["end_ts"].shape == (1, 17)
+    assert float(trunc_normal(0, 1, (10,), 0.5, 0.25, dtype=torch.float64).max()) <= 1
