@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define REN_ABI_VERSION 2
+#define REN_ABI_VERSION 3
 
 enum {
   REN_OK = 0,
@@ -86,6 +86,14 @@ typedef struct RenRenderDesc {
   int32_t has_far;
   int32_t stratified;    /* training: t_min += u*step, one u per ray */
   int32_t engine;        /* REN_ENGINE_* */
+  /* nerfacc.OccupancyGrid binary grid (models/nerf.py:98-102, external/utils.py:106-119): device pointer to
+   * occ_res[0]*occ_res[1]*occ_res[2] bytes (0 / 1), index (ix*res_y + iy)*res_z + iz over the contracted unit
+   * cube of the field's aabb / contraction; NULL = every cell occupied.  Marching steps whose midpoint falls
+   * in an unoccupied cell emit no sample.  Supported for the sphere / tanh contractions (nerfacc advances by
+   * voxel traversal instead of fixed steps for `aabb`, which needs the packed-sample marcher). */
+  const uint8_t* occ_binary;
+  int32_t occ_res[3];
+  int32_t reserved;
 } RenRenderDesc;
 
 int ren_version(void);
@@ -138,6 +146,13 @@ int ren_render_forward(const RenFieldDesc* f, const RenRenderDesc* r, int64_t n_
                        const float* params, const float* bkgd, float* radiance, float* opacity,
                        float* depth, int32_t* n_kept, void* stash, size_t stash_bytes,
                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* Replaces `VanillaNeRFRadianceField.query_density` (external/mlp.py:344-348) on free points, as the occupancy
+ * grid update evaluates it (models/nerf.py:171-198): sigma (n_points) f32 = density_activation(sigma_raw) *
+ * selector.  points (n_points,3) f32.  workspace: ren_density_workspace_bytes. */
+int ren_density_workspace_bytes(const RenFieldDesc* f, const RenRenderDesc* r, int64_t n_points, size_t* bytes);
+int ren_field_density(const RenFieldDesc* f, const RenRenderDesc* r, int64_t n_points, const float* points,
+                      const float* params, float* sigma, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Reverse pass of the above (replaces autograd through the same reference files).
  *   g_radiance (n_rays,C), g_opacity (n_rays), g_depth (n_rays): upstream grads (NULL = 0)

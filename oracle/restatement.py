@@ -141,6 +141,45 @@ def radiance_act(cfg, x):
 
 
 # ----------------------------------------------------------------------------- field
+def contract_unit(cfg: FieldConfig, x):
+    """World -> unit cube [0,1]^3 part of `contract_input_space` (also what nerfacc's grid lookup applies)."""
+    return (contract_input_space(cfg, x)[0] / (2 * math.pi)) + 0.5
+
+
+def contract_inv(cfg: FieldConfig, u):
+    """Unit cube -> world: inverse of the above (nerfacc `contract_inv`, used by OccupancyGrid._update)."""
+    aabb = torch.tensor(cfg.aabb, dtype=u.dtype)
+    a_min, a_max = aabb[:3], aabb[3:]
+    if cfg.contraction == "sphere":
+        y = u * 4 - 2
+        mag = y.norm(dim=-1, keepdim=True)
+        y = torch.where(mag > 1, y / mag / (2 - mag), y)
+        u = y * 0.5 + 0.5
+    elif cfg.contraction == "tanh":
+        u = torch.atanh((u * 2 - 1).clamp(-1 + 1e-6, 1 - 1e-6)) + 0.5
+    return u * (a_max - a_min) + a_min
+
+
+@torch.no_grad()
+def grid_occupied(cfg: FieldConfig, grid_binary, x):
+    """nerfacc `grid_occupied_at` (ray_marching kernel): cell = floor(unit position * resolution), clamped."""
+    # same op order as the field input: normalise, contract (no 2 pi round trip)
+    aabb = torch.tensor(cfg.aabb, dtype=x.dtype)
+    a_min, a_max = aabb[:3], aabb[3:]
+    u = (x - a_min) / (a_max - a_min)
+    if cfg.contraction == "sphere":
+        u = u * 2 - 1
+        mag = u.norm(dim=-1, keepdim=True)
+        u = torch.where(mag > 1, (2 - 1 / mag) * (u / mag), u)
+        u = u / 4 + 0.5
+    elif cfg.contraction == "tanh":
+        u = (torch.tanh(u - 0.5) + 1) / 2
+    res = torch.tensor(grid_binary.shape)
+    idx = torch.floor(u * res).long()
+    idx = torch.minimum(torch.maximum(idx, torch.zeros_like(idx)), res - 1)
+    return grid_binary[idx[..., 0], idx[..., 1], idx[..., 2]]
+
+
 def contract_input_space(cfg: FieldConfig, x):
     """external/mlp.py:321-335 + external/ngp.py:68-106."""
     aabb = torch.tensor(cfg.aabb, dtype=x.dtype)
@@ -282,13 +321,18 @@ def visibility(alpha, alive, early_stop_eps, alpha_thre):
 
 # ------------------------------------------------------------------------ rendering
 def render(params, cfg: FieldConfig, rcfg: RenderConfig, o, d, jitter, bkgd=None,
-           return_aux=False):
+           return_aux=False, grid_binary=None):
     """`NeRF.forward` (models/nerf.py:230-286) -> `render_image`
     (external/utils.py:38-140) -> `rendering` (external/vol_rendering.py:82-126).
     Returns radiance (B[,C]), opacity (B), depth (B), mean samples per ray."""
     B = o.shape[0]
     t0, t1, alive = march(cfg, rcfg, o.detach(), d.detach(), jitter)
     K = t0.shape[1]
+    if grid_binary is not None and K > 0:
+        # marching steps whose midpoint lies in an unoccupied cell emit no sample (non-aabb grid types advance by
+        # fixed steps, so the surviving samples stay on the same lattice)
+        assert cfg.contraction != "aabb"
+        alive = alive & grid_occupied(cfg, grid_binary, sample_positions(o.detach(), d.detach(), t0, t1))
     if K == 0:
         keep = alive
     else:

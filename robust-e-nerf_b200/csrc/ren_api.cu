@@ -222,6 +222,20 @@ static int validate_render(const RenRenderDesc* r) {
   if (!(r->render_step_size > 0.f)) { ren_set_error("render_step_size must be > 0"); return REN_E_INVALID; }
   if (r->cone_angle < 0.f) { ren_set_error("cone_angle must be >= 0"); return REN_E_INVALID; }
   if (r->engine < 0 || r->engine > 3) { ren_set_error("engine id out of range"); return REN_E_INVALID; }
+  if (r->occ_binary != nullptr && (r->occ_res[0] < 1 || r->occ_res[1] < 1 || r->occ_res[2] < 1)) {
+    ren_set_error("occupancy grid resolution must be positive");
+    return REN_E_INVALID;
+  }
+  return REN_OK;
+}
+// nerfacc skips unoccupied space by voxel traversal for the `aabb` grid type: sample positions leave the
+// fixed-step lattice the dense layout assumes
+static int check_occupancy(const RenFieldDesc* f, const RenRenderDesc* r) {
+  if (r->occ_binary != nullptr && f->contraction == REN_CONTRACT_AABB) {
+    ren_set_error("occupancy-grid skipping with contraction_type aabb needs the packed-sample marcher; "
+                  "sphere / tanh contractions are supported");
+    return REN_E_UNSUPPORTED;
+  }
   return REN_OK;
 }
 
@@ -348,6 +362,8 @@ extern "C" int ren_render_forward(const RenFieldDesc* f, const RenRenderDesc* r,
     return REN_E_INVALID;
   }
   if (r->stratified && jitter == nullptr) { ren_set_error("stratified marching needs a jitter buffer"); return REN_E_INVALID; }
+  rc = check_occupancy(f, r);
+  if (rc) return rc;
   const int engine = pick_engine(p);
   rc = check_engine(p, engine);
   if (rc) return rc;
@@ -454,6 +470,8 @@ static int tangent_plan(const RenFieldDesc* f, const RenRenderDesc* r, int64_t n
   int rc = ren_build_plan(f, r, p);
   if (rc) return rc;
   rc = validate_render(r);
+  if (rc) return rc;
+  rc = check_occupancy(f, r);
   if (rc) return rc;
   if (n_rays < 0 || K < 1) { ren_set_error("bad n_rays/K"); return REN_E_INVALID; }
   const int engine = pick_engine(*p);
@@ -635,4 +653,84 @@ extern "C" int ren_render_tangent_backward(const RenFieldDesc* f, const RenRende
     if (rc) return rc;
   }
   return ren_simt_launch_wgrad(p, S2, st_f, delta, graw, g_params, 1, st);
+}
+
+// ------------------------------------------------------------------ density at free points
+// The field kernels take rays; a point is the ray (o = x, d = 0): every marching step then sits at x exactly.
+// One sample per point, no jitter, no grid, planes wide open; the raw sigma column becomes the density.
+struct DensityArgs {
+  long long n;
+  int C1, density_activation;
+  const float* raw;
+  float* sigma;
+};
+extern "C" __global__ void ren_density_finish(const DensityArgs a) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.n) return;
+  const float sraw = a.raw[i * a.C1];
+  float dact;
+  float s = ren_density_act(a.density_activation, sraw, &dact);
+  if (sraw == -INFINITY || sraw != sraw) s = 0.f;
+  a.sigma[i] = s;
+}
+static void density_descs(const RenRenderDesc* r, RenRenderDesc* rr) {
+  *rr = *r;
+  rr->has_near = 1; rr->near_plane = 0.f; rr->has_far = 1; rr->far_plane = 1e9f;
+  rr->render_step_size = 1.f; rr->cone_angle = 0.f; rr->early_stop_eps = 0.f; rr->alpha_thre = 0.f;
+  rr->stratified = 0; rr->occ_binary = nullptr;
+}
+extern "C" int ren_density_workspace_bytes(const RenFieldDesc* f, const RenRenderDesc* r, int64_t n_points,
+                                           size_t* bytes) {
+  if (!r || !bytes || n_points < 0) { ren_set_error("ren_density_workspace_bytes: bad arguments"); return REN_E_INVALID; }
+  RenRenderDesc rr;
+  density_descs(r, &rr);
+  size_t ws = 0;
+  int rc = ren_workspace_bytes(f, &rr, n_points, 1, 0, 0, &ws);
+  if (rc) return rc;
+  *bytes = ws + sizeof(float) * 3 * (size_t)(n_points + 64) + 1024;
+  return REN_OK;
+}
+extern "C" int ren_field_density(const RenFieldDesc* f, const RenRenderDesc* r, int64_t n_points, const float* points,
+                                 const float* params, float* sigma, void* workspace, size_t workspace_bytes,
+                                 void* stream) {
+  if (!r) { ren_set_error("null RenRenderDesc"); return REN_E_INVALID; }
+  RenRenderDesc rr;
+  density_descs(r, &rr);
+  RenPlan p;
+  int rc = ren_build_plan(f, &rr, &p);
+  if (rc) return rc;
+  rc = validate_render(&rr);
+  if (rc) return rc;
+  if (n_points < 0) { ren_set_error("bad n_points"); return REN_E_INVALID; }
+  if (n_points == 0) return REN_OK;
+  if (!points || !params || !sigma || !workspace) { ren_set_error("ren_field_density: null pointer argument"); return REN_E_INVALID; }
+  const int engine = pick_engine(p);
+  rc = check_engine(p, engine);
+  if (rc) return rc;
+  p.r.engine = engine;
+  cudaStream_t st = (cudaStream_t)stream;
+  char* ws = (char*)align256(workspace);
+  size_t ws_left = workspace_bytes - (size_t)(ws - (char*)workspace);
+  const size_t zero_bytes = sizeof(float) * 3 * (size_t)n_points;
+  const size_t raw_bytes = sizeof(float) * (size_t)((1 + p.C) * ren_pad128(n_points));
+  if (ws_left < zero_bytes + raw_bytes + 512) { ren_set_error("ren_field_density: workspace too small"); return REN_E_WORKSPACE; }
+  float* zeros = (float*)ws;
+  if (cudaMemsetAsync(zeros, 0, zero_bytes, st) != cudaSuccess) { ren_set_error("density memset failed"); return REN_E_CUDA; }
+  float* raw = (float*)align256(ws + zero_bytes);
+  char* rest = (char*)align256((char*)raw + raw_bytes);
+  ws_left = workspace_bytes - (size_t)(rest - (char*)workspace);
+  if (engine == REN_ENGINE_SIMT_FP32)
+    rc = ren_simt_launch_fwd(p, n_points, 1, points, zeros, nullptr, nullptr, nullptr, params, nullptr, raw, st);
+  else
+    rc = ren_tc_launch_fwd(p, n_points, 1, points, zeros, nullptr, nullptr, nullptr, nullptr, params, nullptr, raw,
+                           rest, ws_left, st);
+  if (rc) return rc;
+  DensityArgs da;
+  da.n = n_points; da.C1 = 1 + p.C; da.density_activation = f->density_activation; da.raw = raw; da.sigma = sigma;
+  ren_prof_begin(REN_K_COMPOSITE_FWD, st);
+  ren_density_finish<<<(unsigned)((n_points + 255) / 256), 256, 0, st>>>(da);
+  ren_prof_end(REN_K_COMPOSITE_FWD, st);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { ren_set_error("ren_field_density launch: %s", cudaGetErrorString(e)); return REN_E_CUDA; }
+  return REN_OK;
 }

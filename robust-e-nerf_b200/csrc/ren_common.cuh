@@ -205,10 +205,9 @@ __device__ __forceinline__ bool ren_alive(float t0, float t1, float t_max) {
 // ------------------------------------------------------------------ field input
 // positions = o + d*(t0+t1)/2 (external/utils.py:87), contraction to [0,1]^3 + selector,
 // then 2*pi*(x-0.5) (external/mlp.py:321-335).  Returns selector.
-__device__ __forceinline__ bool ren_field_input(const RenFieldDesc& f, const float* o,
-                                                const float* d, float t0, float t1, float* z) {
+__device__ __forceinline__ void ren_unit_position(const RenFieldDesc& f, const float* o, const float* d,
+                                                  float t0, float t1, float* x) {
   float tm2 = __fadd_rn(t0, t1);
-  float x[3];
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
     float p = __fadd_rn(o[a], __fmul_rn(__fmul_rn(d[a], tm2), 0.5f));
@@ -231,6 +230,11 @@ __device__ __forceinline__ bool ren_field_input(const RenFieldDesc& f, const flo
     for (int a = 0; a < 3; ++a)
       x[a] = __fmul_rn(__fadd_rn(tanhf(__fsub_rn(x[a], 0.5f)), 1.f), 0.5f);
   }
+}
+__device__ __forceinline__ bool ren_field_input(const RenFieldDesc& f, const float* o,
+                                                const float* d, float t0, float t1, float* z) {
+  float x[3];
+  ren_unit_position(f, o, d, t0, t1, x);
   bool sel = true;
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
@@ -238,6 +242,22 @@ __device__ __forceinline__ bool ren_field_input(const RenFieldDesc& f, const flo
     z[a] = __fmul_rn(6.283185307179586f, __fsub_rn(x[a], 0.5f));
   }
   return sel;
+}
+// nerfacc grid_occupied_at (ray_marching kernel, call site external/utils.py:106-119): the marching step's
+// midpoint, contracted to the unit cube, looked up in the binary grid (cell = floor(x * res), clamped).
+__device__ __forceinline__ bool ren_occupied(const RenFieldDesc& f, const RenRenderDesc& r, const float* o,
+                                             const float* d, float t0, float t1) {
+  if (r.occ_binary == nullptr) return true;
+  float x[3];
+  ren_unit_position(f, o, d, t0, t1, x);
+  int idx = 0;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    int i = (int)floorf(x[a] * (float)r.occ_res[a]);
+    i = i < 0 ? 0 : (i > r.occ_res[a] - 1 ? r.occ_res[a] - 1 : i);
+    idx = idx * r.occ_res[a] + i;
+  }
+  return r.occ_binary[idx] != 0;
 }
 
 // SinusoidalEncoder.forward (external/mlp.py:227-243): [x | sin(2^i x) | sin(2^i x + pi/2)],

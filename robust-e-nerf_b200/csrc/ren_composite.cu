@@ -90,14 +90,20 @@ __device__ __forceinline__ void walk_ray(const CompArgs& a, long long r, int lan
     const int k = kb + lane;
     SampleBlk b;
     b.t0 = t0; b.t1 = t1;
-    b.alive = (k < a.K) && ren_alive(t0, t1, t_max);
+    const bool in_range = (k < a.K) && ren_alive(t0, t1, t_max);   // geometric: midpoint before t_max
+    b.alive = in_range;
     float sraw = -INFINITY;
     b.c[0] = b.c[1] = b.c[2] = 0.f;
     b.dact_c[0] = b.dact_c[1] = b.dact_c[2] = 0.f;
     if (b.alive) {
       const float* rw = a.raw + (r * a.K + k) * ((a.tangent && !a.raw_dot) ? 2 : 1) * C1;
       sraw = rw[0];
-      for (int c = 0; c < p.C; ++c) b.c[c] = ren_radiance_act(p.f.radiance_activation, rw[1 + c], &b.dact_c[c]);
+      if (sraw != sraw) {            // NaN: the marching step fell into an unoccupied grid cell -> no sample
+        b.alive = false;
+        sraw = -INFINITY;
+      } else {
+        for (int c = 0; c < p.C; ++c) b.c[c] = ren_radiance_act(p.f.radiance_activation, rw[1 + c], &b.dact_c[c]);
+      }
     }
     float sigma = ren_density_act(p.f.density_activation, sraw, &b.dact_s);
     if (!b.alive || sraw == -INFINITY) { sigma = 0.f; b.dact_s = 0.f; }
@@ -144,7 +150,7 @@ __device__ __forceinline__ void walk_ray(const CompArgs& a, long long r, int lan
       t0 = t1;
       t1 = __fadd_rn(t0, ren_dt(p.r, t0));
     }
-    if (__ballot_sync(0xffffffffu, b.alive) == 0u) {
+    if (__ballot_sync(0xffffffffu, in_range) == 0u) {
       // the whole block is past t_max: remaining samples are dead too; still let the body
       // see them (backward must zero their grads)
       for (int kb2 = kb + 32; kb2 < a.K; kb2 += 32) {

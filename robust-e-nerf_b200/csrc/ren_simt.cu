@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ren_simt_field_fwd(const FwdArgs 
       const long long sidx = s0 + tid;     // row
       float* eP = s.encP + tid * REN_PE_MAX;
       float* eD = s.encD + tid * REN_DE_MAX;
-      bool selector = false;
+      bool selector = false, skipped = false;
       if (sidx < S) {
         const long long smp = TAN ? (sidx >> 1) : sidx;
         const bool tan_row = TAN && (sidx & 1);
@@ -264,6 +264,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ren_simt_field_fwd(const FwdArgs 
         ren_march_to(p.r, t_min, k, &t0, &t1);
         selector = ren_field_input(p.f, o, d, t0, t1, z);
         if (!ren_alive(t0, t1, t_max)) selector = false;  // dead tail sample: masked anyway
+        skipped = !ren_occupied(p.f, p.r, o, d, t0, t1);  // unoccupied cell: the marcher emits no sample
         float dz[3] = {__fmul_rn(d[0], 3.141592653589793f), __fmul_rn(d[1], 3.141592653589793f),
                        __fmul_rn(d[2], 3.141592653589793f)};
         if (!tan_row) {
@@ -297,7 +298,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ren_simt_field_fwd(const FwdArgs 
         for (int j = 0; j < REN_PE_MAX; ++j) eP[j] = 0.f;
         for (int j = 0; j < REN_DE_MAX; ++j) eD[j] = 0.f;
       }
-      sel[tid] = selector ? 1.f : 0.f;
+      sel[tid] = skipped ? 2.f : (selector ? 1.f : 0.f);
     }
     __syncthreads();
     // ---- trunk
@@ -320,7 +321,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) ren_simt_field_fwd(const FwdArgs 
           a.raw[(s0 + m) * (1 + p.C)] = v;                 // d sigma_raw / d w (no bias)
         } else {
           v += a.params[p.sig_b];
-          a.raw[(s0 + m) * (1 + p.C)] = sel[m] != 0.f ? v : -INFINITY;
+          // -inf: outside the contracted box (sigma = 0, still a sample); NaN: no sample at all
+          a.raw[(s0 + m) * (1 + p.C)] = sel[m] == 2.f ? __int_as_float(0x7fc00000) : (sel[m] != 0.f ? v : -INFINITY);
         }
       }
     }

@@ -401,7 +401,7 @@ __global__ void __launch_bounds__(MODE == 0 ? TC_THREADS_FWD : TC_THREADS_BWD, 1
         const long long sidx = tile * TC_M + m;
         const bool valid = sidx < S && !(a.dbg & 4);
         float o[3] = {0.f, 0.f, 0.f}, d[3] = {0.f, 0.f, 1.f}, z[3] = {0.f, 0.f, 0.f};
-        bool selector = false;
+        bool selector = false, skipped = false;
         if (valid) {
           const long long r = sidx / a.K;
           const int k = (int)(sidx - r * a.K);
@@ -415,6 +415,7 @@ __global__ void __launch_bounds__(MODE == 0 ? TC_THREADS_FWD : TC_THREADS_BWD, 1
           ren_march_to(p.r, t_min, k, &t0, &t1);
           selector = ren_field_input(p.f, o, d, t0, t1, z);
           if (!ren_alive(t0, t1, t_max)) selector = false;
+          skipped = !ren_occupied(p.f, p.r, o, d, t0, t1);      // unoccupied cell: the marcher emits no sample
         }
         const float dz[3] = {__fmul_rn(d[0], 3.141592653589793f), __fmul_rn(d[1], 3.141592653589793f),
                              __fmul_rn(d[2], 3.141592653589793f)};
@@ -443,7 +444,7 @@ __global__ void __launch_bounds__(MODE == 0 ? TC_THREADS_FWD : TC_THREADS_BWD, 1
                      STASH ? a.stash + tcs_encp(p, S) : nullptr, sidx);
         encode_cores(dz, TAN ? dzdot : nullptr, 4, 32, 0, 4, valid, buf, SM_D_HI, SM_D_LO, m,
                      STASH ? a.stash + tcs_encd(p, S) : nullptr, sidx);
-        sel[eb * 128 + m] = selector ? 1.f : 0.f;
+        sel[eb * 128 + m] = skipped ? 2.f : (selector ? 1.f : 0.f);
         }
         fence_proxy_async();
         __syncwarp();
@@ -462,7 +463,7 @@ __global__ void __launch_bounds__(MODE == 0 ? TC_THREADS_FWD : TC_THREADS_BWD, 1
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n_t) {
       const long long sidx = tile * TC_M + m;
       const bool valid = sidx < S && !(MODE == 0 && (a.dbg & 4));
-      bool selector = false;
+      float selector_code = 0.f;             // 0 outside the contracted box, 1 inside, 2 unoccupied cell (no sample)
       float gs = 0.f;                        // dgrad: scaled d loss / d sigma_raw of this row
       float head_acc[4] = {0.f, 0.f, 0.f, 0.f};
       if (MODE == 0) {
@@ -557,7 +558,7 @@ __global__ void __launch_bounds__(MODE == 0 ? TC_THREADS_FWD : TC_THREADS_BWD, 1
           // the prologue warps published the selector before bar_p of this tile, which the first MMA waited
           // for; read it now -- the buffer may be recycled as soon as the tile's last MMA completes
           if (MODE == 0 && g == 0 && h == 0)
-            selector = reinterpret_cast<const volatile float*>(smem + SM_SEL)[(n_t & 1u) * 128 + m] != 0.f;
+            selector_code = reinterpret_cast<const volatile float*>(smem + SM_SEL)[(n_t & 1u) * 128 + m];
           const uint32_t tcol = tmem_lane + (uint32_t)(st.acc_col + n0);
           uint32_t r[32];
           if (a.dbg & 16) {
@@ -665,7 +666,9 @@ __global__ void __launch_bounds__(MODE == 0 ? TC_THREADS_FWD : TC_THREADS_BWD, 1
           const float4 p0 = part[m], p1 = part[128 + m], p2 = part[256 + m], p3 = part[384 + m];
           const float hb = TAN ? 0.f : 1.f;          // the d/dw rows carry no bias
           const float sraw = (p0.x + p1.x) + (p2.x + p3.x) + hb * vec[VEC_HB];
-          a.raw[sidx * C1] = (selector || TAN) ? sraw : -INFINITY;
+          a.raw[sidx * C1] = TAN ? sraw
+                                 : (selector_code == 2.f ? __int_as_float(0x7fc00000)
+                                                         : (selector_code != 0.f ? sraw : -INFINITY));
           a.raw[sidx * C1 + 1] = (p0.y + p1.y) + (p2.y + p3.y) + hb * vec[VEC_HB + 1];
           if (p.C > 1) a.raw[sidx * C1 + 2] = (p0.z + p1.z) + (p2.z + p3.z) + hb * vec[VEC_HB + 2];
           if (p.C > 2) a.raw[sidx * C1 + 3] = (p0.w + p1.w) + (p2.w + p3.w) + hb * vec[VEC_HB + 3];

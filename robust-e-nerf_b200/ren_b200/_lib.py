@@ -17,7 +17,7 @@ DENSITY_ACT = {"shifted_trunc_exp": 0, "softplus": 1, "shifted_softplus": 2}
 RADIANCE_ACT = {"softplus": 0, "sigmoid": 1}
 CONTRACTION = {"aabb": 0, "sphere": 1, "tanh": 2}
 ERROR_FN = {"l1": 0, "mse": 1, "mape": 2}
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class RenFieldDesc(C.Structure):
@@ -37,6 +37,7 @@ class RenRenderDesc(C.Structure):
         ("cone_angle", C.c_float), ("early_stop_eps", C.c_float), ("alpha_thre", C.c_float),
         ("has_near", C.c_int32), ("has_far", C.c_int32), ("stratified", C.c_int32),
         ("engine", C.c_int32),
+        ("occ_binary", C.c_void_p), ("occ_res", C.c_int32 * 3), ("reserved", C.c_int32),
     ]
 
 
@@ -59,6 +60,10 @@ _SIGNATURES = {
     "ren_render_forward": (C.c_int, [C.POINTER(RenFieldDesc), C.POINTER(RenRenderDesc), C.c_int64,
                                      C.c_int32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_size_t,
                                      _P, C.c_size_t, _P]),
+    "ren_density_workspace_bytes": (C.c_int, [C.POINTER(RenFieldDesc), C.POINTER(RenRenderDesc), C.c_int64,
+                                              C.POINTER(C.c_size_t)]),
+    "ren_field_density": (C.c_int, [C.POINTER(RenFieldDesc), C.POINTER(RenRenderDesc), C.c_int64, _P, _P, _P, _P,
+                                    C.c_size_t, _P]),
     "ren_render_backward": (C.c_int, [C.POINTER(RenFieldDesc), C.POINTER(RenRenderDesc), C.c_int64,
                                       C.c_int32, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P,
                                       _P, _P, _P, C.c_size_t, _P]),
@@ -164,7 +169,20 @@ def make_render_desc(near_plane=None, far_plane=None, render_step_size=1e-2, con
     d.cone_angle, d.early_stop_eps, d.alpha_thre = float(cone_angle), float(early_stop_eps), float(alpha_thre)
     d.stratified = int(bool(stratified))
     d.engine = REN_ENGINE[engine] if isinstance(engine, str) else int(engine)
+    d.occ_binary = None
     return d
+
+
+def set_occupancy(rdesc, binary):
+    """Point a render descriptor at a (rx, ry, rz) uint8 device tensor (None = all occupied).  The caller keeps
+    the tensor alive for as long as the descriptor is used."""
+    if binary is None:
+        rdesc.occ_binary = None
+        return
+    assert binary.dtype == __import__("torch").uint8 and binary.is_contiguous() and binary.dim() == 3
+    rdesc.occ_binary = binary.data_ptr()
+    for i in range(3):
+        rdesc.occ_res[i] = int(binary.shape[i])
 
 
 def param_layout(fdesc):

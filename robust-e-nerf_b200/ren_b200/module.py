@@ -303,7 +303,8 @@ class RobustENeRF(LightningModule):
             if _get(self.hparams[c], "load_state_dict"):
                 prefix = c + "."
                 sub = {k[len(prefix):]: v for k, v in ckpt["state_dict"].items() if k.startswith(prefix)}
-                sub = {k: v for k, v in sub.items() if not k.startswith("occupancy_grid.")}
+                if c == "nerf" and getattr(self.nerf, "occupancy_grid", None) is None:
+                    sub = {k: v for k, v in sub.items() if not k.startswith("occupancy_grid.")}
                 getattr(self, c).load_state_dict(sub)
 
     def _freeze_model_components(self):

@@ -41,6 +41,89 @@ class _Encoder(torch.nn.Module):
         self.register_buffer("scales", torch.tensor([2 ** i for i in range(0, max_deg)]))
 
 
+class OccupancyGrid(torch.nn.Module):
+    """`nerfacc.OccupancyGrid` (nerfacc==0.3.1; constructed at robust_e_nerf/models/nerf.py:98-102, updated at
+    :200-204): EMA-max occupancy estimate per cell of the contracted unit cube + its thresholded binary image,
+    which the marcher consults (external/utils.py:106-119).  State-dict keys `_roi_aabb`, `resolution`, `occs`,
+    `_binary` as in nerfacc.  Everything is device-side torch; the density query is `ren_field_density`."""
+
+    NUM_DIM = 3
+
+    def __init__(self, roi_aabb, resolution=128, contraction="aabb"):
+        super().__init__()
+        if isinstance(resolution, int):
+            resolution = [resolution] * self.NUM_DIM
+        self.contraction = contraction
+        self.register_buffer("_roi_aabb", torch.as_tensor(roi_aabb, dtype=torch.float32))
+        self.register_buffer("resolution", torch.as_tensor(resolution, dtype=torch.int32))
+        self.num_cells = int(torch.as_tensor(resolution).prod())
+        self.register_buffer("occs", torch.zeros(self.num_cells))
+        self.register_buffer("_binary", torch.zeros(list(resolution), dtype=torch.bool))
+        self._u8 = None
+        self._u8_version = None
+
+    @property
+    def binary(self):
+        return self._binary
+
+    def binary_u8(self):
+        """Contiguous uint8 image of `_binary` for the kernels (re-made when `_binary` changed)."""
+        key = (self._binary.data_ptr(), self._binary._version, self._binary.device)
+        if self._u8 is None or self._u8_version != key:
+            self._u8 = self._binary.to(torch.uint8).contiguous()
+            self._u8_version = key
+        return self._u8
+
+    def cell_coords(self, indices):
+        ry, rz = int(self.resolution[1]), int(self.resolution[2])
+        return torch.stack((indices // (ry * rz), (indices // rz) % ry, indices % rz), dim=-1)
+
+    def contract_inv(self, x):
+        """Unit cube -> world (inverse of the field's input contraction, external/ngp.py:68-106)."""
+        a_min, a_max = self._roi_aabb[:3], self._roi_aabb[3:]
+        if self.contraction == "sphere":
+            y = x * 4 - 2
+            mag = y.norm(dim=-1, keepdim=True)
+            y = torch.where(mag > 1, y / mag / (2 - mag).clamp(min=1e-12), y)
+            x = y * 0.5 + 0.5
+        elif self.contraction == "tanh":
+            x = torch.atanh((x * 2 - 1).clamp(-1 + 1e-6, 1 - 1e-6)) + 0.5
+        return x * (a_max - a_min) + a_min
+
+    @torch.no_grad()
+    def _sample_uniform_and_occupied_cells(self, n, generator=None):
+        dev = self.occs.device
+        uniform = torch.randint(self.num_cells, (n,), device=dev, generator=generator)
+        occupied = torch.nonzero(self._binary.flatten())[:, 0]
+        if n < len(occupied):
+            occupied = occupied[torch.randint(len(occupied), (n,), device=dev, generator=generator)]
+        return torch.cat([uniform, occupied], dim=0)
+
+    @torch.no_grad()
+    def _update(self, step, occ_eval_fn, occ_thre=0.01, ema_decay=0.95, warmup_steps=256, generator=None):
+        dev = self.occs.device
+        if step < warmup_steps:
+            indices = torch.arange(self.num_cells, device=dev)
+        else:
+            indices = self._sample_uniform_and_occupied_cells(self.num_cells // 4, generator)
+        coords = self.cell_coords(indices)
+        jitter = torch.rand(coords.shape, device=dev, dtype=torch.float32, generator=generator)
+        x = (coords + jitter) / self.resolution
+        if self.contraction == "sphere":                 # only the inscribed ball of the unit cube is ever reached
+            mask = (x - 0.5).norm(dim=1) < 0.5
+            x, indices = x[mask], indices[mask]
+        occ = occ_eval_fn(self.contract_inv(x)).reshape(-1)
+        self.occs[indices] = torch.maximum(self.occs[indices] * ema_decay, occ)
+        self._binary = (self.occs > torch.clamp(self.occs.mean(), max=occ_thre)).view(self._binary.shape)
+
+    @torch.no_grad()
+    def every_n_step(self, step, occ_eval_fn, occ_thre=1e-2, ema_decay=0.95, warmup_steps=256, n=16, generator=None):
+        if not self.training:
+            raise RuntimeError("OccupancyGrid.every_n_step() is a training-time call")
+        if step % n == 0:
+            self._update(step, occ_eval_fn, occ_thre, ema_decay, warmup_steps, generator)
+
+
 class RenderFunction(torch.autograd.Function):
     """ren_render_forward / ren_render_backward as one differentiable op.
 
@@ -247,6 +330,15 @@ class NeRF(torch.nn.Module):
         self.contraction_type = contraction_type
         self.contraction = _contraction_name(contraction_type)
         self.occ_grid_config = occ_grid_config
+        # models/nerf.py:98-102.  `enabled: false` (an extra key, absent from the reference YAMLs) keeps every cell
+        # occupied -- the fixed-N regime of SURVEY.md section 8d that the golden vectors and bench.py use.
+        cfg_get = (lambda k, dflt: occ_grid_config.get(k, dflt)) if isinstance(occ_grid_config, dict) \
+            else (lambda k, dflt: getattr(occ_grid_config, k, dflt))
+        self.occ_grid_enabled = bool(cfg_get("enabled", True)) and occ_grid_config is not None
+        self.occupancy_grid = None
+        if self.occ_grid_enabled and self.contraction != "aabb":
+            self.occupancy_grid = OccupancyGrid(aabb, cfg_get("resolution", 128), self.contraction)
+        self._warned_aabb_grid = False
         self.near_plane = near_plane
         self.far_plane = far_plane
         self.register_buffer("render_step_size", torch.tensor(render_step_size, dtype=torch.float32),
@@ -401,12 +493,54 @@ class NeRF(torch.nn.Module):
             K = _lib.samples_per_ray(self._fdesc, rdesc)
             hit = (self._fdesc, rdesc, K)
             self._desc_cache[key] = hit
+        _lib.set_occupancy(hit[1], None if self.occupancy_grid is None else self.occupancy_grid.binary_u8())
         return hit
 
-    def update_occ_grid(self, step, T_wc_position):
-        """models/nerf.py:170-204.  The dense marcher treats every cell as occupied
-        (exact for the fixed-N regime of SURVEY.md section 8d); grid skipping is section 8(f) #1."""
-        return None
+    def query_density(self, x):
+        """`VanillaNeRFRadianceField.query_density` (external/mlp.py:344-348) at free points (n,3) -> (n,)."""
+        lib = _lib.load()
+        x = x.detach().contiguous().float()
+        n = x.shape[0]
+        fdesc, rdesc, _ = self._descs()
+        sigma = torch.empty((n,), device=x.device, dtype=torch.float32)
+        nb = C.c_size_t(0)
+        _lib.check(lib.ren_density_workspace_bytes(C.byref(fdesc), C.byref(rdesc), n, C.byref(nb)),
+                   "ren_density_workspace_bytes")
+        ws = torch.empty((int(nb.value),), device=x.device, dtype=torch.uint8)
+        _lib.check(lib.ren_field_density(C.byref(fdesc), C.byref(rdesc), n, _lib.ptr(x), _lib.ptr(self.flat_params()),
+                                         _lib.ptr(sigma), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()),
+                   "ren_field_density")
+        return sigma
+
+    @torch.no_grad()
+    def update_occ_grid(self, step, T_wc_position, generator=None):
+        """models/nerf.py:170-204.  sphere / tanh contractions: the nerfacc occupancy-grid update, with the density
+        sweep over the sampled cells on the field kernels.  `aabb` contraction (nerfacc skips empty voxels by DDA
+        traversal there, SURVEY.md section 8f #1) and `occ_grid.enabled: false` keep every cell occupied."""
+        if self.occupancy_grid is None:
+            if self.occ_grid_enabled and not self._warned_aabb_grid:
+                import warnings
+                warnings.warn("ren_b200: occupancy-grid skipping is not implemented for contraction_type 'aabb'; "
+                              "every marching step is evaluated (a superset of the reference's samples)")
+                self._warned_aabb_grid = True
+            return None
+        cfg = self.occ_grid_config
+        get = (lambda k: cfg[k]) if isinstance(cfg, dict) else (lambda k: getattr(cfg, k))
+        step_size = float(self.render_step_size)
+
+        def occ_eval_fn(x):
+            if self.cone_angle > 0.0:
+                cam = torch.randint(0, len(T_wc_position), (x.shape[0],), device=x.device, generator=generator)
+                t = (T_wc_position.to(x.device)[cam, :] - x).norm(dim=-1)
+                ss = torch.clamp(t * self.cone_angle, min=step_size)
+                if (self.near_plane is not None) and (self.far_plane is not None):
+                    ss = torch.where((t > self.near_plane) & (t < self.far_plane), ss, torch.zeros_like(ss))
+            else:
+                ss = step_size
+            return self.query_density(x) * ss
+
+        self.occupancy_grid.every_n_step(step, occ_eval_fn, get("occ_thre"), get("ema_decay"), get("warmup_steps"),
+                                         get("n"), generator=generator)
 
     @staticmethod
     def pixel_params_to_ray(intrinsics_inverse, pixel_position, T_wc_position, T_wc_orientation):

@@ -124,7 +124,7 @@ def default_config(net_depth=8, net_width=256, n_samples=128, learn_bkgd=False, 
     step = span / n_samples
     nerf = dict(
         aabb=list(aabb), contraction_type="sphere",
-        occ_grid=dict(resolution=128, occ_thre=1e-2, ema_decay=0.95, warmup_steps=256, n=16),
+        occ_grid=dict(resolution=128, occ_thre=1e-2, ema_decay=0.95, warmup_steps=256, n=16, enabled=False),
         near_plane=near, far_plane=near + (n_samples + 0.5) * step, render_step_size=step,
         cone_angle=0.0, early_stop_eps=0.0, alpha_thre=0.0, test_chunk_size=16384, arch="mlp",
         load_state_dict=False, freeze=False,

@@ -41,7 +41,7 @@ def product_config(g):
     f, r, s = g["fcfg"], g["rcfg"], g["scfg"]
     nerf = dict(
         aabb=list(f["aabb"]), contraction_type=f["contraction"],
-        occ_grid=dict(resolution=8, occ_thre=1e-2, ema_decay=0.95, warmup_steps=256, n=16),
+        occ_grid=dict(resolution=8, occ_thre=1e-2, ema_decay=0.95, warmup_steps=256, n=16, enabled=False),
         near_plane=r["near_plane"], far_plane=r["far_plane"], render_step_size=r["render_step_size"],
         cone_angle=r["cone_angle"], early_stop_eps=r["early_stop_eps"], alpha_thre=r["alpha_thre"],
         test_chunk_size=16384, arch="mlp", load_state_dict=False, freeze=False,

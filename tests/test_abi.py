@@ -29,7 +29,7 @@ def test_header_symbols_exported(built_lib):
 def test_binding_covers_header(built_lib):
     from ren_b200 import _lib
     assert _lib.exported_symbols() == _declared_symbols()
-    assert _lib.load().ren_version() == 2
+    assert _lib.load().ren_version() == 3
 
 
 @pytest.mark.parametrize("kw", [
