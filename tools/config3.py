@@ -1,7 +1,7 @@
 """GPU timing of BASELINE config 3 ("ficus hard": 16384-ray batch x 128 samples, 8x256 MLP, l_diff + l_grad,
 C_p and tau trainable with a poor initialisation): 2 value renders + 1 tangent render per step, fwd+bwd+Adam."""
 import json, os, sys, time
-ROOT = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (os.path.join(ROOT, "robust-e-nerf_b200"), ROOT):
     sys.path.insert(0, p)
 import torch

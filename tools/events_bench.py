@@ -1,6 +1,6 @@
 """GPU timing of the raw-event conversion (ren_event_queue) next to the oracle and the reference loop rate."""
 import os, sys, time
-ROOT = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (os.path.join(ROOT, "robust-e-nerf_b200"), ROOT):
     sys.path.insert(0, p)
 import numpy as np, torch

@@ -1,6 +1,6 @@
 """compute-sanitizer target: one small training step per engine (value + tangent renders) and the event prep."""
 import os, sys
-ROOT = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (os.path.join(ROOT, "robust-e-nerf_b200"), ROOT, os.path.join(ROOT, "tests")):
     sys.path.insert(0, p)
 import numpy as np, torch

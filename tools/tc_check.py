@@ -1,6 +1,6 @@
 """GPU diagnostic: tcgen05 engine vs SIMT engine vs reference golden on one render."""
 import os, sys, time
-ROOT = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (os.path.join(ROOT, "robust-e-nerf_b200"), ROOT, os.path.join(ROOT, "tests")):
     sys.path.insert(0, p)
 import torch

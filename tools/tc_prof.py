@@ -1,6 +1,6 @@
 """GPU profiling target: a few no-grad renders (config-2 size) with one engine."""
 import os, sys
-ROOT = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (os.path.join(ROOT, "robust-e-nerf_b200"), ROOT, os.path.join(ROOT, "tests")):
     sys.path.insert(0, p)
 import torch
