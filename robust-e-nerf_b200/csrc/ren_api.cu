@@ -25,8 +25,8 @@ int ren_launch_composite_tan_bwd(const RenPlan& p, long long n_rays, int K, cons
                                  float* graw_dot, float* g_bkgd, unsigned int* gmax, cudaStream_t st);
 int ren_launch_raygrad(const RenPlan& p, long long n_rays, int K, const float* o, const float* d,
                        const float* o_dot, const float* d_dot, const float* jitter, const float* params,
-                       const void* delta, const void* delta_dot, int fp16, const unsigned int* gmax, float* g_rays,
-                       cudaStream_t st);
+                       const void* delta, const void* delta_dot, int fp16, const unsigned int* gmax,
+                       const unsigned char* tile_live, float* g_rays, cudaStream_t st);
 int ren_launch_composite(const RenPlan& p, long long n_rays, int K, const float* o, const float* d,
                          const float* jitter, const float* raw, const float* bkgd, float* radiance,
                          float* opacity, float* depth, int* n_kept, cudaStream_t st);
@@ -40,14 +40,16 @@ size_t ren_tc_fwd_workspace_bytes(const RenPlan& p);
 size_t ren_tc_bwd_pack_bytes(const RenPlan& p);
 int ren_tc_launch_fwd(const RenPlan& p, long long n_rays, int K, const float* o, const float* d,
                       const float* o_dot, const float* d_dot, const void* stash_val,
-                      const float* jitter, const float* params, void* stash, float* raw, void* ws,
-                      size_t ws_bytes, cudaStream_t st);
+                      const float* jitter, const float* params, void* stash, float* raw, const unsigned char* tile_live,
+                      void* ws, size_t ws_bytes, cudaStream_t st);
 int ren_tc_launch_dgrad(const RenPlan& p, long long S, const float* params, const void* stash,
                         const float* graw, const unsigned int* gmax, void* delta, int pass, const void* stash_dot,
-                        void* extra, void* ws, size_t ws_bytes, cudaStream_t st);
+                        void* extra, const unsigned char* tile_live, void* ws, size_t ws_bytes, cudaStream_t st);
 int ren_tc_launch_wgrad(const RenPlan& p, long long S, const void* stash, const void* delta,
                         const float* graw, const unsigned int* gmax, float* g_params, int with_bias,
-                        cudaStream_t st);
+                        const unsigned char* tile_live, cudaStream_t st);
+int ren_launch_tile_live(const RenPlan& p, long long n_rays, int K, const float* o, const float* d,
+                         const float* jitter, unsigned char* live, cudaStream_t st);
 
 static thread_local char g_err[512] = "";
 
@@ -334,7 +336,8 @@ extern "C" int ren_workspace_bytes(const RenFieldDesc* f, const RenRenderDesc* r
                      : (has_stash ? 0 : sizeof(float) * (size_t)((1 + p.C) * ren_pad128(S)));
   } else {
     n = for_backward ? tcd_bytes(p, S) + ren_tc_bwd_pack_bytes(p)
-                     : (has_stash ? 0 : sizeof(float) * (size_t)((1 + p.C) * ren_pad128(S))) +
+                     : (has_stash ? 0 : sizeof(float) * (size_t)((1 + p.C) * ren_pad128(S)) +
+                                            (size_t)(ren_pad128(S) >> 7) + 512) +
                            ren_tc_fwd_workspace_bytes(p);
   }
   *bytes = n + 2048;
@@ -386,9 +389,24 @@ extern "C" int ren_render_forward(const RenFieldDesc* f, const RenRenderDesc* r,
   }
   if (engine == REN_ENGINE_SIMT_FP32)
     rc = ren_simt_launch_fwd(p, n_rays, K, rays_o, rays_d, nullptr, nullptr, jitter, params, (float*)stash, raw, st);
-  else
-    rc = ren_tc_launch_fwd(p, n_rays, K, rays_o, rays_d, nullptr, nullptr, nullptr, jitter, params, stash, raw, ws,
-                           ws_left, st);
+  else {
+    unsigned char* live = nullptr;
+    if (r->occ_binary != nullptr) {       // occupancy-grid marching: find the tiles that emit no sample at all
+      if (stash) {
+        live = (unsigned char*)stash + tcs_live(p, S);
+      } else {
+        const size_t lb = (((size_t)(ren_pad128(S) >> 7)) + 255) & ~(size_t)255;
+        if (ws_left < lb) { ren_set_error("workspace too small for the live-tile flags"); return REN_E_WORKSPACE; }
+        live = (unsigned char*)ws;
+        ws += lb;
+        ws_left -= lb;
+      }
+      rc = ren_launch_tile_live(p, n_rays, K, rays_o, rays_d, jitter, live, st);
+      if (rc) return rc;
+    }
+    rc = ren_tc_launch_fwd(p, n_rays, K, rays_o, rays_d, nullptr, nullptr, nullptr, jitter, params, stash, raw, live,
+                           ws, ws_left, st);
+  }
   if (rc) return rc;
   return ren_launch_composite(p, n_rays, K, rays_o, rays_d, jitter, raw, bkgd, radiance, opacity, depth,
                               n_kept, st);
@@ -434,7 +452,7 @@ extern "C" int ren_render_backward(const RenFieldDesc* f, const RenRenderDesc* r
     if (rc) return rc;
     if (g_rays) {
       rc = ren_launch_raygrad(p, n_rays, K, rays_o, rays_d, nullptr, nullptr, jitter, params, delta, nullptr, 0,
-                              nullptr, g_rays, st);
+                              nullptr, nullptr, g_rays, st);
       if (rc) return rc;
     }
     return ren_simt_launch_wgrad(p, S, st_f, delta, graw, g_params, 0, st);
@@ -451,14 +469,15 @@ extern "C" int ren_render_backward(const RenFieldDesc* f, const RenRenderDesc* r
   rc = ren_launch_composite_bwd(p, n_rays, K, rays_o, rays_d, jitter, raw, bkgd, g_radiance, g_opacity,
                                 g_depth, graw, g_bkgd, gmax, st);
   if (rc) return rc;
-  rc = ren_tc_launch_dgrad(p, S, params, stash, graw, gmax, delta, 0, nullptr, nullptr, pack_ws, pack_left, st);
+  const unsigned char* live = r->occ_binary != nullptr ? (const unsigned char*)stash + tcs_live(p, S) : nullptr;
+  rc = ren_tc_launch_dgrad(p, S, params, stash, graw, gmax, delta, 0, nullptr, nullptr, live, pack_ws, pack_left, st);
   if (rc) return rc;
   if (g_rays) {
     rc = ren_launch_raygrad(p, n_rays, K, rays_o, rays_d, nullptr, nullptr, jitter, params, delta, nullptr, 1, gmax,
-                            g_rays, st);
+                            live, g_rays, st);
     if (rc) return rc;
   }
-  return ren_tc_launch_wgrad(p, S, stash, delta, graw, gmax, g_params, 1, st);
+  return ren_tc_launch_wgrad(p, S, stash, delta, graw, gmax, g_params, 1, live, st);
 }
 
 // ------------------------------------------------------------------ tangent mode
@@ -554,11 +573,17 @@ extern "C" int ren_render_tangent_forward(const RenFieldDesc* f, const RenRender
     char* sd = sv + one;
     float* raw_val = (float*)(sv + tcs_raw(p, S));
     float* raw_dot = (float*)(sd + tcs_raw(p, S));
-    rc = ren_tc_launch_fwd(p, n_rays, K, rays_o, rays_d, nullptr, nullptr, nullptr, jitter, params, sv, raw_val, ws,
-                           ws_left, st);
+    unsigned char* live = nullptr;
+    if (r->occ_binary != nullptr) {
+      live = (unsigned char*)sv + tcs_live(p, S);
+      rc = ren_launch_tile_live(p, n_rays, K, rays_o, rays_d, jitter, live, st);
+      if (rc) return rc;
+    }
+    rc = ren_tc_launch_fwd(p, n_rays, K, rays_o, rays_d, nullptr, nullptr, nullptr, jitter, params, sv, raw_val, live,
+                           ws, ws_left, st);
     if (rc) return rc;
-    rc = ren_tc_launch_fwd(p, n_rays, K, rays_o, rays_d, rays_o_dot, rays_d_dot, sv, jitter, params, sd, raw_dot, ws,
-                           ws_left, st);
+    rc = ren_tc_launch_fwd(p, n_rays, K, rays_o, rays_d, rays_o_dot, rays_d_dot, sv, jitter, params, sd, raw_dot, live,
+                           ws, ws_left, st);
     if (rc) return rc;
     return ren_launch_composite_tan(p, n_rays, K, rays_o, rays_d, jitter, raw_val, raw_dot, bkgd, radiance, opacity,
                                     depth, radiance_dot, opacity_dot, n_kept, st);
@@ -621,18 +646,20 @@ extern "C" int ren_render_tangent_backward(const RenFieldDesc* f, const RenRende
                                       g_opacity, g_depth, g_radiance_dot, g_opacity_dot, graw_val, graw_dot, g_bkgd,
                                       gmax, st);
     if (rc) return rc;
-    rc = ren_tc_launch_dgrad(p, S, params, sv, graw_dot, gmax, delta_dot, 1, sd, extra, pack_ws, pack_left, st);
+    const unsigned char* live = r->occ_binary != nullptr ? (const unsigned char*)sv + tcs_live(p, S) : nullptr;
+    rc = ren_tc_launch_dgrad(p, S, params, sv, graw_dot, gmax, delta_dot, 1, sd, extra, live, pack_ws, pack_left, st);
     if (rc) return rc;
-    rc = ren_tc_launch_dgrad(p, S, params, sv, graw_val, gmax, delta_val, 2, nullptr, extra, pack_ws, pack_left, st);
+    rc = ren_tc_launch_dgrad(p, S, params, sv, graw_val, gmax, delta_val, 2, nullptr, extra, live, pack_ws, pack_left,
+                             st);
     if (rc) return rc;
     if (g_rays) {
       rc = ren_launch_raygrad(p, n_rays, K, rays_o, rays_d, rays_o_dot, rays_d_dot, jitter, params, delta_val,
-                              delta_dot, 1, gmax, g_rays, st);
+                              delta_dot, 1, gmax, live, g_rays, st);
       if (rc) return rc;
     }
-    rc = ren_tc_launch_wgrad(p, S, sv, delta_val, graw_val, gmax, g_params, 1, st);
+    rc = ren_tc_launch_wgrad(p, S, sv, delta_val, graw_val, gmax, g_params, 1, live, st);
     if (rc) return rc;
-    return ren_tc_launch_wgrad(p, S, sd, delta_dot, graw_dot, gmax, g_params, 0, st);
+    return ren_tc_launch_wgrad(p, S, sd, delta_dot, graw_dot, gmax, g_params, 0, live, st);
   }
   const long long S2 = 2 * S;
   if (stash_bytes < sizeof(float) * (size_t)ren_stash_floats(p, S2)) { ren_set_error("stash too small"); return REN_E_WORKSPACE; }
@@ -649,7 +676,7 @@ extern "C" int ren_render_tangent_backward(const RenFieldDesc* f, const RenRende
   if (rc) return rc;
   if (g_rays) {
     rc = ren_launch_raygrad(p, n_rays, K, rays_o, rays_d, rays_o_dot, rays_d_dot, jitter, params, delta, nullptr, 0,
-                            nullptr, g_rays, st);
+                            nullptr, nullptr, g_rays, st);
     if (rc) return rc;
   }
   return ren_simt_launch_wgrad(p, S2, st_f, delta, graw, g_params, 1, st);
@@ -723,7 +750,7 @@ extern "C" int ren_field_density(const RenFieldDesc* f, const RenRenderDesc* r, 
     rc = ren_simt_launch_fwd(p, n_points, 1, points, zeros, nullptr, nullptr, nullptr, params, nullptr, raw, st);
   else
     rc = ren_tc_launch_fwd(p, n_points, 1, points, zeros, nullptr, nullptr, nullptr, nullptr, params, nullptr, raw,
-                           rest, ws_left, st);
+                           nullptr, rest, ws_left, st);
   if (rc) return rc;
   DensityArgs da;
   da.n = n_points; da.C1 = 1 + p.C; da.density_activation = f->density_activation; da.raw = raw; da.sigma = sigma;

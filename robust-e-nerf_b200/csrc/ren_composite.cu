@@ -466,6 +466,62 @@ extern "C" __global__ void __launch_bounds__(128) ren_composite_tan_bwd(const Co
   }
 }
 
+// ------------------------------------------------------------------ live tiles (occupancy-grid marching)
+// live[t] = 1 iff any of the 128 dense marching steps of tile t emits a sample (midpoint before t_max and in an
+// occupied cell).  The tcgen05 kernels skip dead tiles entirely.
+struct LiveArgs {
+  RenPlan p;
+  long long n_rays;
+  int K;
+  const float* rays_o;
+  const float* rays_d;
+  const float* jitter;
+  unsigned char* live;
+};
+extern "C" __global__ void __launch_bounds__(128) ren_tile_live_kernel(const LiveArgs a) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const RenPlan& p = a.p;
+  for (long long r = warp; r < a.n_rays; r += n_warps) {
+    float o[3], d[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      o[c] = a.rays_o[r * 3 + c];
+      d[c] = a.rays_d[r * 3 + c];
+    }
+    float t_min, t_max, t0, t1;
+    ren_ray_range(p.f, p.r, o, d, a.jitter ? a.jitter[r] : 0.f, &t_min, &t_max);
+    ren_march_to(p.r, t_min, lane, &t0, &t1);
+    for (int kb = 0; kb < a.K; kb += 32) {
+      const int k = kb + lane;
+      const bool in_range = (k < a.K) && ren_alive(t0, t1, t_max);
+      if (in_range && ren_occupied(p.f, p.r, o, d, t0, t1)) a.live[(r * a.K + k) >> 7] = 1;
+      if (__ballot_sync(0xffffffffu, in_range) == 0u) break;
+      for (int i = 0; i < 32; ++i) {
+        t0 = t1;
+        t1 = __fadd_rn(t0, ren_dt(p.r, t0));
+      }
+    }
+  }
+}
+int ren_launch_tile_live(const RenPlan& p, long long n_rays, int K, const float* o, const float* d,
+                         const float* jitter, unsigned char* live, cudaStream_t st) {
+  if (n_rays <= 0) return REN_OK;
+  const long long n_tiles = (n_rays * K + 127) >> 7;
+  if (cudaMemsetAsync(live, 0, (size_t)n_tiles, st) != cudaSuccess) { ren_set_error("live-tile memset failed"); return REN_E_CUDA; }
+  LiveArgs a;
+  a.p = p; a.n_rays = n_rays; a.K = K; a.rays_o = o; a.rays_d = d; a.jitter = jitter; a.live = live;
+  long long blocks = (n_rays + 3) / 4;
+  if (blocks > 148 * 64) blocks = 148 * 64;
+  ren_prof_begin(REN_K_COMPOSITE_FWD, st);
+  ren_tile_live_kernel<<<(unsigned)blocks, 128, 0, st>>>(a);
+  ren_prof_end(REN_K_COMPOSITE_FWD, st);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { ren_set_error("live-tile launch: %s", cudaGetErrorString(e)); return REN_E_CUDA; }
+  return REN_OK;
+}
+
 int ren_launch_composite_tan(const RenPlan& p, long long n_rays, int K, const float* o, const float* d,
                              const float* jitter, const float* raw, const float* raw_dot, const float* bkgd, float* radiance,
                              float* opacity, float* depth, float* radiance_dot, float* opacity_dot,

@@ -38,6 +38,7 @@ struct RgArgs {
   int tangent;
   int fp16;                    // Delta matrices are fp16 blocked, scaled by delta_scale(gmax) (tcgen05 engine)
   const unsigned int* gmax;
+  const unsigned char* tile_live;   // per-128-sample-tile flags or NULL: dead tiles hold no data
   const float* rays_o;
   const float* rays_d;
   const float* rays_o_dot;
@@ -98,6 +99,7 @@ extern "C" __global__ void __launch_bounds__(RG_THREADS) ren_raygrad_kernel(cons
   const int ty = tid >> 4, tx = tid & 15;                // rows 4 ty .. 4 ty + 3; columns 4 tx .. (P), 2 tx .. (D)
   const float unscale = a.fp16 ? 1.f / delta_scale(a.gmax) : 1.f;
   for (long long row0 = (long long)blockIdx.x * RG_ROWS; row0 < S; row0 += (long long)gridDim.x * RG_ROWS) {
+    if (a.tile_live != nullptr && !__ldg(a.tile_live + ((a.tangent ? (row0 >> 1) : row0) >> 7))) continue;
     float accP[4][4], accD[4][2];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -234,10 +236,11 @@ extern "C" __global__ void __launch_bounds__(RG_THREADS) ren_raygrad_kernel(cons
 // tcgen05 engine (fp16 != 0): delta / delta_dot = fp16 blocked delta matrices of the value / d/dw rows
 int ren_launch_raygrad(const RenPlan& p, long long n_rays, int K, const float* o, const float* d,
                        const float* o_dot, const float* d_dot, const float* jitter, const float* params,
-                       const void* delta, const void* delta_dot, int fp16, const unsigned int* gmax, float* g_rays,
-                       cudaStream_t st) {
+                       const void* delta, const void* delta_dot, int fp16, const unsigned int* gmax,
+                       const unsigned char* tile_live, float* g_rays, cudaStream_t st) {
   if (n_rays <= 0) return REN_OK;
   RgArgs a;
+  a.tile_live = tile_live;
   a.p = p; a.n_rays = n_rays; a.K = K; a.tangent = o_dot != nullptr ? 1 : 0; a.fp16 = fp16; a.gmax = gmax;
   a.rays_o = o; a.rays_d = d; a.rays_o_dot = o_dot; a.rays_d_dot = d_dot; a.jitter = jitter; a.g_rays = g_rays;
   const long long S = n_rays * K * (a.tangent ? 2 : 1);          // rows

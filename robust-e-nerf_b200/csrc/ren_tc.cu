@@ -131,6 +131,7 @@ struct TcArgs {
   const unsigned char* stash_val;   // fwd tangent pass: the value pass' stash (read)
   const unsigned char* stash_dot;   // dgrad pass 1: the tangent pass' stash (read)
   unsigned char* extra;             // dgrad: E matrices (fp16 blocked; written by pass 1, read by pass 2)
+  const unsigned char* tile_live;   // per-tile flags (occupancy-grid marching) or NULL: dead tiles are skipped by all roles
 };
 
 __device__ __forceinline__ float ex2_ftz(float x) {
@@ -299,6 +300,7 @@ __global__ void __launch_bounds__(MODE == 0 ? TC_THREADS_FWD : TC_THREADS_BWD, 1
       const uint4* prog = reinterpret_cast<const uint4*>(smem + SM_PROG);
       uint32_t it = 0;
       for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        if (a.tile_live != nullptr && !__ldg(a.tile_live + tile)) continue;
         for (int i = 0; i < a.n_ops; ++i, ++it) {
           const uint4 o0 = prog[2 * i];
           const uint32_t s = it % TC_STAGES, ph = (it / TC_STAGES) & 1u;
@@ -322,7 +324,8 @@ __global__ void __launch_bounds__(MODE == 0 ? TC_THREADS_FWD : TC_THREADS_BWD, 1
       // low words of the shared-memory descriptors are linear in the address (all < 256 KB)
       const uint32_t ring_lo = ((sbase + SM_RING) >> 4) & 0x3FFFu;
       const uint32_t smem_lo = ((sbase >> 4) & 0x3FFFu) | (128u << 16);      // encodings: K-core stride 2048 B
-      for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n_p) {
+      for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        if (a.tile_live != nullptr && !__ldg(a.tile_live + tile)) continue;
         const uint32_t eb = n_p & 1u;                                   // encoding buffer of this tile
         const uint32_t enc_lo = smem_lo + eb * (SM_ENC_BYTES >> 4);
         uint4 o0 = prog[0], o1 = prog[1];
@@ -384,6 +387,7 @@ __global__ void __launch_bounds__(MODE == 0 ? TC_THREADS_FWD : TC_THREADS_BWD, 1
           o0 = p0; o1 = p1;
         }
         if (MODE == 0) tc_commit(bar_pfree + 8 * eb);   // every MMA reading this tile's encodings is done
+        ++n_p;                                          // live tiles only
       }
     }
   } else if (warp >= 2 + TC_EPI_WARPS) {
@@ -393,7 +397,8 @@ __global__ void __launch_bounds__(MODE == 0 ? TC_THREADS_FWD : TC_THREADS_BWD, 1
     if (MODE == 0) {
       float* sel = reinterpret_cast<float*>(smem + SM_SEL);
       uint32_t n_t = 0;
-      for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n_t) {
+      for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        if (a.tile_live != nullptr && !__ldg(a.tile_live + tile)) continue;
         const uint32_t eb = n_t & 1u;
         mbar_wait(bar_pfree + 8 * eb, ((n_t >> 1) & 1u) ^ 1u);       // the MMAs of tile n_t - 2 are done with it
 #pragma unroll 1
@@ -449,6 +454,7 @@ __global__ void __launch_bounds__(MODE == 0 ? TC_THREADS_FWD : TC_THREADS_BWD, 1
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_p + 8 * eb);
+        ++n_t;                                          // live tiles only
       }
     }
   } else {
@@ -460,8 +466,14 @@ __global__ void __launch_bounds__(MODE == 0 ? TC_THREADS_FWD : TC_THREADS_BWD, 1
     float4* part = reinterpret_cast<float4*>(smem + SM_PART);   // [4][128]
     uint32_t n_acc[2] = {0u, 0u};
     uint32_t n_t = 0;
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n_t) {
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const long long sidx = tile * TC_M + m;
+      if (a.tile_live != nullptr && !__ldg(a.tile_live + tile)) {
+        // dead tile: no marching step of it emits a sample -- NaN in the raw sigma column means "no sample" to
+        // the compositing kernels; stash / delta tiles stay untouched and are skipped by every consumer
+        if (MODE == 0 && !TAN && cg == 0 && sidx < S) a.raw[sidx * C1] = __int_as_float(0x7fc00000);
+        continue;
+      }
       const bool valid = sidx < S && !(MODE == 0 && (a.dbg & 4));
       float selector_code = 0.f;             // 0 outside the contracted box, 1 inside, 2 unoccupied cell (no sample)
       float gs = 0.f;                        // dgrad: scaled d loss / d sigma_raw of this row
@@ -675,6 +687,7 @@ __global__ void __launch_bounds__(MODE == 0 ? TC_THREADS_FWD : TC_THREADS_BWD, 1
         }
         asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");
       }
+      ++n_t;                                            // live tiles only
     }
   }
   tc_fence_before();
@@ -999,8 +1012,8 @@ static void fill_args(TcArgs& a, const RenPlan& p, const TcProgram& P) {
 // o_dot / d_dot / stash_val != NULL: the tangent pass of the tangent render (stash = its own stash, raw = raw_dot)
 int ren_tc_launch_fwd(const RenPlan& p, long long n_rays, int K, const float* o, const float* d,
                       const float* o_dot, const float* d_dot, const void* stash_val,
-                      const float* jitter, const float* params, void* stash, float* raw, void* ws,
-                      size_t ws_bytes, cudaStream_t st) {
+                      const float* jitter, const float* params, void* stash, float* raw, const unsigned char* tile_live,
+                      void* ws, size_t ws_bytes, cudaStream_t st) {
   TcProgram P;
   build_forward(p, P);
   unsigned char* pack; float* vec; StageOp* prog;
@@ -1014,7 +1027,7 @@ int ren_tc_launch_fwd(const RenPlan& p, long long n_rays, int K, const float* o,
   a.n_rays = n_rays; a.K = K; a.rays_o = o; a.rays_d = d; a.jitter = jitter;
   a.pack = pack; a.vec = vec; a.prog = prog; a.n_ops = P.n_ops; a.stash = (unsigned char*)stash; a.raw = raw;
   a.tan = o_dot != nullptr ? 1 : 0; a.rays_o_dot = o_dot; a.rays_d_dot = d_dot;
-  a.stash_val = (const unsigned char*)stash_val;
+  a.stash_val = (const unsigned char*)stash_val; a.tile_live = tile_live;
   const long long n_tiles = (n_rays * K + TC_M - 1) / TC_M;
   if (a.tan) return launch_chain<0, true, 1>(a, n_tiles, REN_K_FIELD_FWD, st);     // the tangent pass always stashes
   return stash ? launch_chain<0, true, 0>(a, n_tiles, REN_K_FIELD_FWD, st)
@@ -1025,7 +1038,7 @@ int ren_tc_launch_fwd(const RenPlan& p, long long n_rays, int K, const float* o,
 // 2: its value-adjoint chain (reads extra)
 int ren_tc_launch_dgrad(const RenPlan& p, long long S, const float* params, const void* stash,
                         const float* graw, const unsigned int* gmax, void* delta, int pass, const void* stash_dot,
-                        void* extra, void* ws, size_t ws_bytes, cudaStream_t st) {
+                        void* extra, const unsigned char* tile_live, void* ws, size_t ws_bytes, cudaStream_t st) {
   TcProgram P;
   build_dgrad(p, P);
   unsigned char* pack; float* vec; StageOp* prog;
@@ -1040,6 +1053,7 @@ int ren_tc_launch_dgrad(const RenPlan& p, long long S, const float* params, cons
   a.pack = pack; a.vec = vec; a.prog = prog; a.n_ops = P.n_ops;
   a.stash = (unsigned char*)stash; a.delta = (unsigned char*)delta; a.graw = graw; a.gmax = gmax;
   a.pass = pass; a.stash_dot = (const unsigned char*)stash_dot; a.extra = (unsigned char*)extra;
+  a.tile_live = tile_live;
   const long long n_tiles = (S + TC_M - 1) / TC_M;
   if (pass == 1) return launch_chain<1, false, 1>(a, n_tiles, REN_K_FIELD_DGRAD, st);
   if (pass == 2) return launch_chain<1, false, 2>(a, n_tiles, REN_K_FIELD_DGRAD, st);

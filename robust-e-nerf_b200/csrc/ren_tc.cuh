@@ -28,8 +28,13 @@ __host__ __device__ inline size_t tcs_encd(const RenPlan& p, long long S) {
 __host__ __device__ inline size_t tcs_raw(const RenPlan& p, long long S) {
   return (size_t)2 * (p.act_floats + REN_PE_MAX + REN_DE_MAX) * ren_pad128(S);
 }
-__host__ __device__ inline size_t tcs_bytes(const RenPlan& p, long long S) {
+// per-tile "live" bytes (occupancy-grid marching): a tile none of whose 128 marching steps emits a sample is
+// skipped by every kernel of the step
+__host__ __device__ inline size_t tcs_live(const RenPlan& p, long long S) {
   return tcs_raw(p, S) + (size_t)4 * (1 + p.C) * ren_pad128(S);
+}
+__host__ __device__ inline size_t tcs_bytes(const RenPlan& p, long long S) {
+  return tcs_live(p, S) + (((size_t)(ren_pad128(S) >> 7) + 255) & ~(size_t)255);
 }
 // backward workspace: delta mats (fp16 blocked) then graw (f32 [Sp][1+C])
 __host__ __device__ inline size_t tcd_graw(const RenPlan& p, long long S) {

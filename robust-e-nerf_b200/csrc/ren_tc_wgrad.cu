@@ -25,6 +25,7 @@
 #define SMW_ONES (WG_STAGES * SMW_STAGE)        // 196608
 #define SMW_BAR (SMW_ONES + 4096)
 #define SMW_TMEM_PTR (SMW_BAR + 64)
+#define SMW_EMPTY (SMW_BAR + 96)               // the job in the accumulator saw no live tile
 #define SMW_TOTAL (SMW_BAR + 128)
 #define WG_TMEM_ONES 256
 
@@ -44,6 +45,7 @@ struct WgArgs {
   const unsigned char* delta;
   const unsigned int* gmax;    // deltas carry the power-of-two scale delta_scale(gmax)
   float* g_params;
+  const unsigned char* tile_live;   // per-tile flags or NULL (occupancy-grid marching): dead tiles hold no data
 };
 
 extern "C" __global__ void __launch_bounds__(WG_THREADS, 1) ren_tc_wgrad(const WgArgs a) {
@@ -88,8 +90,10 @@ extern "C" __global__ void __launch_bounds__(WG_THREADS, 1) ren_tc_wgrad(const W
         const int split = job % a.splits;
         const long long t0 = split * tiles_per, t1 = min(a.n_tiles, t0 + tiles_per);
         const uint32_t hbytes = (uint32_t)mt.Hw * 256u;
-        for (long long t = t0; t < t1; ++t, ++it) {
+        for (long long t = t0; t < t1; ++t) {
+          if (a.tile_live != nullptr && !__ldg(a.tile_live + t)) continue;
           const uint32_t s = it % WG_STAGES, ph = (it / WG_STAGES) & 1u;
+          ++it;
           mbar_wait(bar_empty + 8 * s, ph ^ 1u);
           mbar_arrive_expect_tx(bar_full + 8 * s, SMW_D_BYTES + hbytes);
           const unsigned char* dsrc = a.delta + mt.d_off + (size_t)t * mt.Nd * 256 + (size_t)mt.n_half * SMW_D_BYTES;
@@ -112,8 +116,10 @@ extern "C" __global__ void __launch_bounds__(WG_THREADS, 1) ren_tc_wgrad(const W
         tc_fence_after();
         const uint32_t idesc = umma_idesc(mt.Hw, 1, 1);
         uint32_t first = 1;
-        for (long long t = t0; t < t1; ++t, ++it) {
+        for (long long t = t0; t < t1; ++t) {
+          if (a.tile_live != nullptr && !__ldg(a.tile_live + t)) continue;
           const uint32_t s = it % WG_STAGES, ph = (it / WG_STAGES) & 1u;
+          ++it;
           mbar_wait(bar_full + 8 * s, ph);
           tc_fence_after();
           const uint32_t db = sbase + s * SMW_STAGE, hb = db + SMW_D_BYTES;
@@ -129,6 +135,8 @@ extern "C" __global__ void __launch_bounds__(WG_THREADS, 1) ren_tc_wgrad(const W
           }
           tc_commit(bar_empty + 8 * s);
         }
+        *reinterpret_cast<volatile uint32_t*>(smem + SMW_EMPTY) = first;   // nothing accumulated: skip the epilogue
+        __threadfence_block();
         tc_commit(bar_accfull);
         ++jn;
       }
@@ -146,9 +154,10 @@ extern "C" __global__ void __launch_bounds__(WG_THREADS, 1) ren_tc_wgrad(const W
       if (t0 >= t1) continue;
       mbar_wait(bar_accfull, jn & 1u);
       tc_fence_after();
+      const bool empty_job = *reinterpret_cast<volatile uint32_t*>(smem + SMW_EMPTY) != 0u;
       const int n = mt.n_half * 128 + nl;
       float* row = a.g_params + mt.w_off + (long long)n * mt.ldw + mt.col0;
-      for (int cb = 0; cb < mt.Hw; cb += 16) {
+      for (int cb = 0; cb < (empty_job ? 0 : mt.Hw); cb += 16) {
         uint32_t r[16];
         tc_ld16(tmem_lane + (uint32_t)cb, r);
         tc_ld_wait();
@@ -158,7 +167,7 @@ extern "C" __global__ void __launch_bounds__(WG_THREADS, 1) ren_tc_wgrad(const W
             if (cb + j < mt.Ktrue) atomicAdd(row + cb + j, __uint_as_float(r[j]) * (unscale * mt.h_scale));
         }
       }
-      if (mt.b_off >= 0) {
+      if (mt.b_off >= 0 && !empty_job) {
         uint32_t r[16];
         tc_ld16(tmem_lane + WG_TMEM_ONES, r);
         tc_ld_wait();
@@ -189,6 +198,7 @@ struct HeadArgs {
   long long S, n_tiles;
   float* g_params;
   float h_scale;               // log2-domain stash -> true activations
+  const unsigned char* tile_live;
 };
 
 extern "C" __global__ void __launch_bounds__(256) ren_tc_head_wgrad(const HeadArgs a) {
@@ -207,6 +217,7 @@ extern "C" __global__ void __launch_bounds__(256) ren_tc_head_wgrad(const HeadAr
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[c][j] = 0.f;
   for (long long t = warp / groups; t < a.n_tiles; t += tstride) {
+    if (a.tile_live != nullptr && !__ldg(a.tile_live + t)) continue;
     const uint4* blk = reinterpret_cast<const uint4*>(a.h[which]) + ((size_t)t * groups + fg) * 128;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -242,7 +253,7 @@ extern "C" __global__ void __launch_bounds__(256) ren_tc_head_wgrad(const HeadAr
 // with_bias = 0: the tangent rows of the tangent render (d/dw activations carry no bias)
 int ren_tc_launch_wgrad(const RenPlan& p, long long S, const void* stash, const void* delta,
                         const float* graw, const unsigned int* gmax, float* g_params, int with_bias,
-                        cudaStream_t st) {
+                        const unsigned char* tile_live, cudaStream_t st) {
   WgArgs a;
   static_assert(sizeof(WgArgs) <= 4000, "kernel parameter block too large");
   memset(&a, 0, sizeof(a));
@@ -286,7 +297,7 @@ int ren_tc_launch_wgrad(const RenPlan& p, long long S, const void* stash, const 
   if (splits < 1) splits = 1;
   a.splits = splits;
   a.stash = (const unsigned char*)stash; a.delta = (const unsigned char*)delta; a.g_params = g_params;
-  a.gmax = gmax;
+  a.gmax = gmax; a.tile_live = tile_live;
   const int n_jobs = n * splits;
   const int grid = n_jobs < sms ? n_jobs : sms;
   cudaError_t e = cudaFuncSetAttribute(ren_tc_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, SMW_TOTAL);
@@ -304,6 +315,7 @@ int ren_tc_launch_wgrad(const RenPlan& p, long long S, const void* stash, const 
   h.h[1] = (const unsigned char*)stash + tcs_mat(p, S, p.cond[0].mat); h.N[1] = p.WC;
   h.w_off[1] = p.rgb_w; h.b_off[1] = with_bias ? p.rgb_b : -1; h.n_ch[1] = p.C; h.g_col[1] = 1;
   h.graw = graw; h.C1 = 1 + p.C; h.S = S; h.n_tiles = a.n_tiles; h.g_params = g_params; h.h_scale = kap;
+  h.tile_live = tile_live;
   ren_prof_begin(REN_K_WGRAD, st);
   ren_tc_head_wgrad<<<dim3(sms * 2, 2), 256, 0, st>>>(h);
   ren_prof_end(REN_K_WGRAD, st);

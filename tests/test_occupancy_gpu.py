@@ -145,3 +145,41 @@ def test_training_with_occupancy_grid(built_lib, dataset_dir):
     for k in ("nerf.occupancy_grid._roi_aabb", "nerf.occupancy_grid.resolution", "nerf.occupancy_grid.occs",
               "nerf.occupancy_grid._binary"):
         assert k in sd, k
+
+
+def test_dead_tile_skipping_matches_masked_march(built_lib, dataset_dir):
+    """A sparse grid over long rays (512 marching steps): the tcgen05 engine skips every 128-step tile that emits
+    no sample (forward, both dgrad passes, weight gradients, ray gradients); results must equal the fp32 engine,
+    which evaluates and masks every step -- value render, tangent render and all gradients."""
+    import time
+    grid = torch.zeros(16, 16, 16, dtype=torch.bool)
+    gen = torch.Generator().manual_seed(8)
+    grid.view(-1)[torch.randperm(4096, generator=gen)[:300]] = True           # ~7 % of the cells
+    o, d, u = _rays(192, 3)
+    od = 0.05 * torch.randn(192, 3, generator=gen)
+    dd = 0.05 * torch.randn(192, 3, generator=gen)
+    out = {}
+    for engine in ENGINES:
+        m, g = _model(dataset_dir, engine, "sphere", res=16)
+        m.nerf.render_step_size.fill_(4.0 / 512)
+        m.nerf.far_plane = 0.5 + 512.5 * (4.0 / 512)
+        m.nerf._desc_cache.clear()
+        m.nerf.occupancy_grid._binary = grid.cuda()
+        oc, dc = o.cuda().requires_grad_(True), d.cuda().requires_grad_(True)
+        odc, ddc = od.cuda().requires_grad_(True), dd.cuda().requires_grad_(True)
+        torch.cuda.synchronize(); t = time.perf_counter()
+        rad, opac, dep, rad_dot, opac_dot, nk = m.nerf.render_tangent_raw(oc, dc, odc, ddc, u.cuda())
+        rad2, opac2, _, nk2 = m.nerf.render_raw(oc, dc, u.cuda())
+        ((rad_dot ** 2).sum() + rad.sum() + (rad2 * opac2.unsqueeze(-1)).sum()).backward()
+        torch.cuda.synchronize(); dt = time.perf_counter() - t
+        grads = torch.cat([p.grad.reshape(-1) for p in m.nerf.mlp_parameters()])
+        out[engine] = (rad.detach(), rad_dot.detach(), nk.clone(), grads, oc.grad.clone(), ddc.grad.clone(), dt)
+    a, b = out["auto"], out["simt_fp32"]
+    assert torch.equal(a[2], b[2]) and int(a[2].sum()) < 0.2 * 192 * 512       # same kept samples, sparse
+    for name, x, y, bar in (("radiance", a[0], b[0], 1e-5), ("radiance_dot", a[1], b[1], 2e-4),
+                            ("mlp grads", a[3], b[3], 5e-3), ("d loss/d o", a[4], b[4], 1e-2),
+                            ("d loss/d d_dot", a[5], b[5], 1e-2)):
+        nw = H.rel_err(x, y, floor=1e-9)[0]
+        print(f"[dead tiles] {name}: tcgen05 vs fp32 normwise={nw:.2e}")
+        assert nw < bar, name
+    print(f"[dead tiles] kept {int(a[2].sum())} of {192 * 512} steps; tcgen05 {a[6] * 1e3:.1f} ms, fp32 {b[6] * 1e3:.1f} ms")
