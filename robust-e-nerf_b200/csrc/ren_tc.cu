@@ -464,7 +464,7 @@ __global__ void __launch_bounds__(MODE == 0 ? TC_THREADS_FWD : TC_THREADS_BWD, 1
     const int m = q * 32 + lane;             // row of the tile == TMEM lane
     const uint32_t tmem_lane = tmem_base + ((uint32_t)(q * 32) << 16);
     float4* part = reinterpret_cast<float4*>(smem + SM_PART);   // [4][128]
-    uint32_t n_acc[2] = {0u, 0u};
+    uint32_t n_acc0 = 0u, n_acc1 = 0u;       // scalars: an indexed array would live in local memory
     uint32_t n_t = 0;
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const long long sidx = tile * TC_M + m;
@@ -501,7 +501,9 @@ __global__ void __launch_bounds__(MODE == 0 ? TC_THREADS_FWD : TC_THREADS_BWD, 1
         if (valid) {
           const float sc = delta_scale(a.gmax);
           gs = a.graw[sidx * C1] * sc;
-          for (int c = 0; c < p.C; ++c) gc[c] = a.graw[sidx * C1 + 1 + c] * sc;
+#pragma unroll
+          for (int c = 0; c < 3; ++c)
+            if (c < p.C) gc[c] = a.graw[sidx * C1 + 1 + c] * sc;
         }
         uint32_t hi16[16], lo16[16];
         unsigned char* dm = a.delta + tcs_mat(p, S, mat) + tile_off;
@@ -564,8 +566,8 @@ __global__ void __launch_bounds__(MODE == 0 ? TC_THREADS_FWD : TC_THREADS_BWD, 1
 #pragma unroll
             for (int i = 0; i < 4; ++i) act[i] = __ldg(reinterpret_cast<const uint4*>(am + i * 2048));
           }
-          mbar_wait(bar_acc + 8 * h, n_acc[h] & 1u);
-          ++n_acc[h];
+          if (h == 0) { mbar_wait(bar_acc, n_acc0 & 1u); ++n_acc0; }
+          else { mbar_wait(bar_acc + 8, n_acc1 & 1u); ++n_acc1; }
           tc_fence_after();
           // the prologue warps published the selector before bar_p of this tile, which the first MMA waited
           // for; read it now -- the buffer may be recycled as soon as the tile's last MMA completes
@@ -627,10 +629,13 @@ __global__ void __launch_bounds__(MODE == 0 ? TC_THREADS_FWD : TC_THREADS_BWD, 1
                 for (int j = 0; j < 8; ++j) head_acc[0] = fmaf(y[j], ww[j], head_acc[0]);
               }
               if (st.epi == EPI_F_LAST) {
-                for (int c = 0; c < p.C; ++c) {
-                  const float* wo = vec + VEC_WO + c * 128 + n0 + j8 * 8;
 #pragma unroll
-                  for (int j = 0; j < 8; ++j) head_acc[1 + c] = fmaf(y[j], wo[j], head_acc[1 + c]);
+                for (int c = 0; c < 3; ++c) {
+                  if (c < p.C) {
+                    const float* wo = vec + VEC_WO + c * 128 + n0 + j8 * 8;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) head_acc[1 + c] = fmaf(y[j], wo[j], head_acc[1 + c]);
+                  }
                 }
               }
             } else {
