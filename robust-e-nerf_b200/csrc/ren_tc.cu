@@ -590,11 +590,27 @@ __global__ void __launch_bounds__(MODE == 0 ? TC_THREADS_FWD : TC_THREADS_BWD, 1
           }
           const float* bias = (MODE == 0 && st.bias_idx >= 0) ? vec + VEC_BIAS + st.bias_idx * 256 + n0 : nullptr;
           uint32_t hi16[16], lo16[16];
+          // the common case (hidden softplus layer of the value pass) as ONE flat pass over the thread's 32
+          // columns: 32 independent bias -> ex2 -> lg2 chains in flight instead of 8
+          const bool flat = MODE == 0 && !TAN && st.epi == EPI_F_HIDDEN && a.softplus && !(a.dbg & 1);
+          if (flat) {
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 b4 = *reinterpret_cast<const float4*>(bias + j4 * 4);
+              r[j4 * 4 + 0] = __float_as_uint(softplus_log2(__uint_as_float(r[j4 * 4 + 0]) + b4.x));
+              r[j4 * 4 + 1] = __float_as_uint(softplus_log2(__uint_as_float(r[j4 * 4 + 1]) + b4.y));
+              r[j4 * 4 + 2] = __float_as_uint(softplus_log2(__uint_as_float(r[j4 * 4 + 2]) + b4.z));
+              r[j4 * 4 + 3] = __float_as_uint(softplus_log2(__uint_as_float(r[j4 * 4 + 3]) + b4.w));
+            }
+          }
 #pragma unroll
           for (int j8 = 0; j8 < 4; ++j8) {
             float y[8];
             float e8[8];
-            if (MODE == 0 && TAN) {
+            if (flat) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) y[j] = __uint_as_float(r[j8 * 8 + j]);
+            } else if (MODE == 0 && TAN) {
               // d/dw rows: no bias; gdot = act'(pre) * (W gdot_prev) with act' from the value stash
               float av[8];
               if (st.epi != EPI_F_LINEAR) unpack8(act[j8], av);
