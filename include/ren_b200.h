@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define REN_ABI_VERSION 3
+#define REN_ABI_VERSION 4
 
 enum {
   REN_OK = 0,
@@ -96,6 +96,17 @@ typedef struct RenRenderDesc {
   int32_t reserved;
 } RenRenderDesc;
 
+/* Packed samples of one render call, as nerfacc.ray_marching hands them to the field
+ * (external/utils.py:106-128): only the marching steps that land in occupied grid cells.  Built by
+ * ren_march_count + (host: n_samples = ray_offsets[n_rays]) + ren_march_fill; passed to the four render
+ * entry points (NULL = dense (ray, step) layout).  With it, stash / workspace sizes are those of
+ * (n_rays = n_samples, K = 1).  tcgen05 engine only. */
+typedef struct RenPacked {
+  int64_t n_samples;            /* total emitted samples (host value) */
+  const int32_t* sample_idx;    /* (n_samples) dense index ray*K + step of each sample, ray-major marching order */
+  const int32_t* ray_offsets;   /* (n_rays + 1) exclusive scan of the per-ray counts */
+} RenPacked;
+
 int ren_version(void);
 const char* ren_last_error(void);
 
@@ -129,6 +140,20 @@ int ren_stash_bytes(const RenFieldDesc* f, const RenRenderDesc* r, int64_t n_ray
 int ren_workspace_bytes(const RenFieldDesc* f, const RenRenderDesc* r, int64_t n_rays, int32_t K,
                         int32_t has_stash, int32_t for_backward, size_t* bytes);
 
+/* The engine REN_ENGINE_AUTO resolves to for this network (REN_ENGINE_SIMT_FP32 or REN_ENGINE_TC_F16X3). */
+int ren_resolve_engine(const RenFieldDesc* f, const RenRenderDesc* r, int32_t* engine);
+
+/* Phase 1 / 2 of the packed march (replaces the sample enumeration of `nerfacc.ray_marching`,
+ * external/utils.py:106-119).  ren_march_count: ray_offsets (n_rays + 1) i32 = exclusive scan of the per-ray
+ * emitted-step counts (workspace: ren_march_workspace_bytes).  ren_march_fill: sample_idx (ray_offsets[n_rays]). */
+int ren_march_workspace_bytes(int64_t n_rays, size_t* bytes);
+int ren_march_count(const RenFieldDesc* f, const RenRenderDesc* r, int64_t n_rays, int32_t K,
+                    const float* rays_o, const float* rays_d, const float* jitter, int32_t* ray_offsets,
+                    void* workspace, size_t workspace_bytes, void* stream);
+int ren_march_fill(const RenFieldDesc* f, const RenRenderDesc* r, int64_t n_rays, int32_t K,
+                   const float* rays_o, const float* rays_d, const float* jitter, const int32_t* ray_offsets,
+                   int32_t* sample_idx, void* stream);
+
 /* Replaces `NeRF.forward` (models/nerf.py:230-286) -> `render_image`
  * (external/utils.py:38-140) -> nerfacc.ray_marching + `rendering`
  * (external/vol_rendering.py:16-128) -> `VanillaNeRFRadianceField.forward`
@@ -144,7 +169,7 @@ int ren_workspace_bytes(const RenFieldDesc* f, const RenRenderDesc* r, int64_t n
 int ren_render_forward(const RenFieldDesc* f, const RenRenderDesc* r, int64_t n_rays, int32_t K,
                        const float* rays_o, const float* rays_d, const float* jitter,
                        const float* params, const float* bkgd, float* radiance, float* opacity,
-                       float* depth, int32_t* n_kept, void* stash, size_t stash_bytes,
+                       float* depth, int32_t* n_kept, const RenPacked* packed, void* stash, size_t stash_bytes,
                        void* workspace, size_t workspace_bytes, void* stream);
 
 /* Replaces `VanillaNeRFRadianceField.query_density` (external/mlp.py:344-348) on free points, as the occupancy
@@ -163,8 +188,8 @@ int ren_field_density(const RenFieldDesc* f, const RenRenderDesc* r, int64_t n_p
 int ren_render_backward(const RenFieldDesc* f, const RenRenderDesc* r, int64_t n_rays, int32_t K,
                         const float* rays_o, const float* rays_d, const float* jitter,
                         const float* params, const float* bkgd, const float* g_radiance,
-                        const float* g_opacity, const float* g_depth, const void* stash,
-                        size_t stash_bytes, float* g_params, float* g_bkgd, float* g_rays,
+                        const float* g_opacity, const float* g_depth, const RenPacked* packed,
+                        const void* stash, size_t stash_bytes, float* g_params, float* g_bkgd, float* g_rays,
                         void* workspace, size_t workspace_bytes, void* stream);
 
 /* Tangent-mode render: the same render PLUS its derivative along one scalar per ray (the pose
@@ -184,8 +209,9 @@ int ren_render_tangent_forward(const RenFieldDesc* f, const RenRenderDesc* r, in
                                const float* rays_o, const float* rays_d, const float* rays_o_dot,
                                const float* rays_d_dot, const float* jitter, const float* params,
                                const float* bkgd, float* radiance, float* opacity, float* depth,
-                               float* radiance_dot, float* opacity_dot, int32_t* n_kept, void* stash,
-                               size_t stash_bytes, void* workspace, size_t workspace_bytes, void* stream);
+                               float* radiance_dot, float* opacity_dot, int32_t* n_kept,
+                               const RenPacked* packed, void* stash, size_t stash_bytes, void* workspace,
+                               size_t workspace_bytes, void* stream);
 
 /* Reverse pass of the tangent-mode render (the reference's double-backward through
  * external/mlp.py, external/vol_rendering.py): upstream grads of the five per-ray outputs ->
@@ -196,9 +222,9 @@ int ren_render_tangent_backward(const RenFieldDesc* f, const RenRenderDesc* r, i
                                 const float* rays_d_dot, const float* jitter, const float* params,
                                 const float* bkgd, const float* g_radiance, const float* g_opacity,
                                 const float* g_depth, const float* g_radiance_dot,
-                                const float* g_opacity_dot, const void* stash, size_t stash_bytes,
-                                float* g_params, float* g_bkgd, float* g_rays, void* workspace,
-                                size_t workspace_bytes, void* stream);
+                                const float* g_opacity_dot, const RenPacked* packed, const void* stash,
+                                size_t stash_bytes, float* g_params, float* g_bkgd, float* g_rays,
+                                void* workspace, size_t workspace_bytes, void* stream);
 
 /* Replaces `RefractoryPeriod.forward` (models/event_generation_params.py:196-203), the
  * supervision-timestamp derivation (models/robust_e_nerf.py:322-357),

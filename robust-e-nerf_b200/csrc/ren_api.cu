@@ -15,23 +15,29 @@ int ren_simt_launch_dgrad(const RenPlan& p, long long S, const float* params, co
 int ren_simt_launch_wgrad(const RenPlan& p, long long S, const float* stash, const float* delta,
                           const float* graw, float* g_params, int tangent, cudaStream_t st);
 int ren_launch_composite_tan(const RenPlan& p, long long n_rays, int K, const float* o, const float* d,
-                             const float* jitter, const float* raw, const float* raw_dot, const float* bkgd,
+                             const float* jitter, const int* ray_offsets, const float* raw, const float* raw_dot,
+                             const float* bkgd,
                              float* radiance, float* opacity, float* depth, float* radiance_dot, float* opacity_dot,
                              int* n_kept, cudaStream_t st);
 int ren_launch_composite_tan_bwd(const RenPlan& p, long long n_rays, int K, const float* o, const float* d,
-                                 const float* jitter, const float* raw, const float* raw_dot, const float* bkgd,
+                                 const float* jitter, const int* ray_offsets, const float* raw, const float* raw_dot,
+                                 const float* bkgd,
                                  const float* g_radiance, const float* g_opacity, const float* g_depth,
                                  const float* g_radiance_dot, const float* g_opacity_dot, float* graw,
                                  float* graw_dot, float* g_bkgd, unsigned int* gmax, cudaStream_t st);
 int ren_launch_raygrad(const RenPlan& p, long long n_rays, int K, const float* o, const float* d,
                        const float* o_dot, const float* d_dot, const float* jitter, const float* params,
                        const void* delta, const void* delta_dot, int fp16, const unsigned int* gmax,
-                       const unsigned char* tile_live, float* g_rays, cudaStream_t st);
+                       const unsigned char* tile_live, const int* sample_idx, long long n_samples, float* g_rays,
+                       cudaStream_t st);
 int ren_launch_composite(const RenPlan& p, long long n_rays, int K, const float* o, const float* d,
-                         const float* jitter, const float* raw, const float* bkgd, float* radiance,
-                         float* opacity, float* depth, int* n_kept, cudaStream_t st);
+                         const float* jitter, const int* ray_offsets, const float* raw, const float* bkgd,
+                         float* radiance, float* opacity, float* depth, int* n_kept, cudaStream_t st);
+int ren_launch_march_pack(const RenPlan& p, long long n_rays, int K, const float* o, const float* d,
+                          const float* jitter, int* counts, const int* ray_offsets, int* sample_idx,
+                          cudaStream_t st);
 int ren_launch_composite_bwd(const RenPlan& p, long long n_rays, int K, const float* o, const float* d,
-                             const float* jitter, const float* raw, const float* bkgd,
+                             const float* jitter, const int* ray_offsets, const float* raw, const float* bkgd,
                              const float* g_radiance, const float* g_opacity, const float* g_depth,
                              float* graw, float* g_bkgd, unsigned int* gmax, cudaStream_t st);
 // tcgen05 engine (ren_tc.cu)
@@ -41,7 +47,7 @@ size_t ren_tc_bwd_pack_bytes(const RenPlan& p);
 int ren_tc_launch_fwd(const RenPlan& p, long long n_rays, int K, const float* o, const float* d,
                       const float* o_dot, const float* d_dot, const void* stash_val,
                       const float* jitter, const float* params, void* stash, float* raw, const unsigned char* tile_live,
-                      void* ws, size_t ws_bytes, cudaStream_t st);
+                      const int* sample_idx, long long n_samples, void* ws, size_t ws_bytes, cudaStream_t st);
 int ren_tc_launch_dgrad(const RenPlan& p, long long S, const float* params, const void* stash,
                         const float* graw, const unsigned int* gmax, void* delta, int pass, const void* stash_dot,
                         void* extra, const unsigned char* tile_live, void* ws, size_t ws_bytes, cudaStream_t st);
@@ -344,6 +350,20 @@ extern "C" int ren_workspace_bytes(const RenFieldDesc* f, const RenRenderDesc* r
   return REN_OK;
 }
 
+// packed samples are a tcgen05-engine layout; returns the sample count the field kernels run over
+static int check_packed(const RenPacked* packed, int engine, int64_t n_rays, int32_t K, long long* S) {
+  *S = (long long)n_rays * K;
+  if (packed == nullptr) return REN_OK;
+  if (engine == REN_ENGINE_SIMT_FP32) { ren_set_error("packed samples need a tcgen05 engine"); return REN_E_UNSUPPORTED; }
+  if (packed->n_samples < 0 || packed->n_samples > *S || (packed->n_samples > 0 && !packed->sample_idx) ||
+      !packed->ray_offsets) {
+    ren_set_error("bad RenPacked");
+    return REN_E_INVALID;
+  }
+  *S = packed->n_samples;
+  return REN_OK;
+}
+
 static inline void* align256(void* p) {
   return (void*)(((uintptr_t)p + 255) & ~(uintptr_t)255);
 }
@@ -351,8 +371,8 @@ static inline void* align256(void* p) {
 extern "C" int ren_render_forward(const RenFieldDesc* f, const RenRenderDesc* r, int64_t n_rays, int32_t K,
                                   const float* rays_o, const float* rays_d, const float* jitter,
                                   const float* params, const float* bkgd, float* radiance, float* opacity,
-                                  float* depth, int32_t* n_kept, void* stash, size_t stash_bytes,
-                                  void* workspace, size_t workspace_bytes, void* stream) {
+                                  float* depth, int32_t* n_kept, const RenPacked* packed, void* stash,
+                                  size_t stash_bytes, void* workspace, size_t workspace_bytes, void* stream) {
   RenPlan p;
   int rc = ren_build_plan(f, r, &p);
   if (rc) return rc;
@@ -371,7 +391,10 @@ extern "C" int ren_render_forward(const RenFieldDesc* f, const RenRenderDesc* r,
   rc = check_engine(p, engine);
   if (rc) return rc;
   p.r.engine = engine;
-  const long long S = (long long)n_rays * K;
+  long long S;
+  rc = check_packed(packed, engine, n_rays, K, &S);
+  if (rc) return rc;
+  const int* ray_offsets = packed ? packed->ray_offsets : nullptr;
   cudaStream_t st = (cudaStream_t)stream;
   float* raw;
   char* ws = (char*)align256(workspace);
@@ -391,7 +414,7 @@ extern "C" int ren_render_forward(const RenFieldDesc* f, const RenRenderDesc* r,
     rc = ren_simt_launch_fwd(p, n_rays, K, rays_o, rays_d, nullptr, nullptr, jitter, params, (float*)stash, raw, st);
   else {
     unsigned char* live = nullptr;
-    if (r->occ_binary != nullptr) {       // occupancy-grid marching: find the tiles that emit no sample at all
+    if (r->occ_binary != nullptr && packed == nullptr) {   // dense layout: find the tiles that emit no sample at all
       if (stash) {
         live = (unsigned char*)stash + tcs_live(p, S);
       } else {
@@ -404,20 +427,21 @@ extern "C" int ren_render_forward(const RenFieldDesc* f, const RenRenderDesc* r,
       rc = ren_launch_tile_live(p, n_rays, K, rays_o, rays_d, jitter, live, st);
       if (rc) return rc;
     }
-    rc = ren_tc_launch_fwd(p, n_rays, K, rays_o, rays_d, nullptr, nullptr, nullptr, jitter, params, stash, raw, live,
-                           ws, ws_left, st);
+    if (S > 0)
+      rc = ren_tc_launch_fwd(p, n_rays, K, rays_o, rays_d, nullptr, nullptr, nullptr, jitter, params, stash, raw, live,
+                             packed ? packed->sample_idx : nullptr, S, ws, ws_left, st);
   }
   if (rc) return rc;
-  return ren_launch_composite(p, n_rays, K, rays_o, rays_d, jitter, raw, bkgd, radiance, opacity, depth,
-                              n_kept, st);
+  return ren_launch_composite(p, n_rays, K, rays_o, rays_d, jitter, ray_offsets, raw, bkgd, radiance, opacity,
+                              depth, n_kept, st);
 }
 
 extern "C" int ren_render_backward(const RenFieldDesc* f, const RenRenderDesc* r, int64_t n_rays, int32_t K,
                                    const float* rays_o, const float* rays_d, const float* jitter,
                                    const float* params, const float* bkgd, const float* g_radiance,
-                                   const float* g_opacity, const float* g_depth, const void* stash,
-                                   size_t stash_bytes, float* g_params, float* g_bkgd, float* g_rays,
-                                   void* workspace, size_t workspace_bytes, void* stream) {
+                                   const float* g_opacity, const float* g_depth, const RenPacked* packed,
+                                   const void* stash, size_t stash_bytes, float* g_params, float* g_bkgd,
+                                   float* g_rays, void* workspace, size_t workspace_bytes, void* stream) {
   RenPlan p;
   int rc = ren_build_plan(f, r, &p);
   if (rc) return rc;
@@ -433,7 +457,11 @@ extern "C" int ren_render_backward(const RenFieldDesc* f, const RenRenderDesc* r
   rc = check_engine(p, engine);
   if (rc) return rc;
   p.r.engine = engine;
-  const long long S = (long long)n_rays * K;
+  long long S;
+  rc = check_packed(packed, engine, n_rays, K, &S);
+  if (rc) return rc;
+  const int* ray_offsets = packed ? packed->ray_offsets : nullptr;
+  const int* sample_idx = packed ? packed->sample_idx : nullptr;
   if (stash_bytes < stash_bytes_for(p, engine, S)) { ren_set_error("stash too small"); return REN_E_WORKSPACE; }
   char* ws = (char*)align256(workspace);
   const size_t ws_left = workspace_bytes - (size_t)(ws - (char*)workspace);
@@ -445,14 +473,14 @@ extern "C" int ren_render_backward(const RenFieldDesc* f, const RenRenderDesc* r
     float* graw = delta + p.act_floats * ren_pad128(S);
     const float* st_f = (const float*)stash;
     const float* raw = st_f + ren_stash_raw(p, S);
-    rc = ren_launch_composite_bwd(p, n_rays, K, rays_o, rays_d, jitter, raw, bkgd, g_radiance, g_opacity,
+    rc = ren_launch_composite_bwd(p, n_rays, K, rays_o, rays_d, jitter, nullptr, raw, bkgd, g_radiance, g_opacity,
                                   g_depth, graw, g_bkgd, nullptr, st);
     if (rc) return rc;
     rc = ren_simt_launch_dgrad(p, S, params, st_f, graw, delta, 0, st);
     if (rc) return rc;
     if (g_rays) {
       rc = ren_launch_raygrad(p, n_rays, K, rays_o, rays_d, nullptr, nullptr, jitter, params, delta, nullptr, 0,
-                              nullptr, nullptr, g_rays, st);
+                              nullptr, nullptr, nullptr, 0, g_rays, st);
       if (rc) return rc;
     }
     return ren_simt_launch_wgrad(p, S, st_f, delta, graw, g_params, 0, st);
@@ -466,15 +494,20 @@ extern "C" int ren_render_backward(const RenFieldDesc* f, const RenRenderDesc* r
   const float* raw = (const float*)((const char*)stash + tcs_raw(p, S));
   unsigned int* gmax = (unsigned int*)(ws + tcd_gmax(p, S));
   if (cudaMemsetAsync(gmax, 0, 256, st) != cudaSuccess) { ren_set_error("gmax memset failed"); return REN_E_CUDA; }
-  rc = ren_launch_composite_bwd(p, n_rays, K, rays_o, rays_d, jitter, raw, bkgd, g_radiance, g_opacity,
+  rc = ren_launch_composite_bwd(p, n_rays, K, rays_o, rays_d, jitter, ray_offsets, raw, bkgd, g_radiance, g_opacity,
                                 g_depth, graw, g_bkgd, gmax, st);
   if (rc) return rc;
-  const unsigned char* live = r->occ_binary != nullptr ? (const unsigned char*)stash + tcs_live(p, S) : nullptr;
+  if (S == 0) {
+    if (g_rays && cudaMemsetAsync(g_rays, 0, sizeof(float) * 6 * (size_t)n_rays, st) != cudaSuccess) return REN_E_CUDA;
+    return REN_OK;
+  }
+  const unsigned char* live = (r->occ_binary != nullptr && packed == nullptr)
+                                  ? (const unsigned char*)stash + tcs_live(p, S) : nullptr;
   rc = ren_tc_launch_dgrad(p, S, params, stash, graw, gmax, delta, 0, nullptr, nullptr, live, pack_ws, pack_left, st);
   if (rc) return rc;
   if (g_rays) {
     rc = ren_launch_raygrad(p, n_rays, K, rays_o, rays_d, nullptr, nullptr, jitter, params, delta, nullptr, 1, gmax,
-                            live, g_rays, st);
+                            live, sample_idx, S, g_rays, st);
     if (rc) return rc;
   }
   return ren_tc_launch_wgrad(p, S, stash, delta, graw, gmax, g_params, 1, live, st);
@@ -541,9 +574,9 @@ extern "C" int ren_render_tangent_forward(const RenFieldDesc* f, const RenRender
                                           const float* rays_o, const float* rays_d, const float* rays_o_dot,
                                           const float* rays_d_dot, const float* jitter, const float* params,
                                           const float* bkgd, float* radiance, float* opacity, float* depth,
-                                          float* radiance_dot, float* opacity_dot, int32_t* n_kept, void* stash,
-                                          size_t stash_bytes, void* workspace, size_t workspace_bytes,
-                                          void* stream) {
+                                          float* radiance_dot, float* opacity_dot, int32_t* n_kept,
+                                          const RenPacked* packed, void* stash, size_t stash_bytes, void* workspace,
+                                          size_t workspace_bytes, void* stream) {
   RenPlan p;
   int rc = tangent_plan(f, r, n_rays, K, &p);
   if (rc) return rc;
@@ -554,7 +587,11 @@ extern "C" int ren_render_tangent_forward(const RenFieldDesc* f, const RenRender
     return REN_E_INVALID;
   }
   if (r->stratified && jitter == nullptr) { ren_set_error("stratified marching needs a jitter buffer"); return REN_E_INVALID; }
-  const long long S = (long long)n_rays * K;
+  long long S;
+  rc = check_packed(packed, p.r.engine, n_rays, K, &S);
+  if (rc) return rc;
+  const int* ray_offsets = packed ? packed->ray_offsets : nullptr;
+  const int* sample_idx = packed ? packed->sample_idx : nullptr;
   cudaStream_t st = (cudaStream_t)stream;
   char* ws = (char*)align256(workspace);
   size_t ws_left = workspace ? workspace_bytes - (size_t)(ws - (char*)workspace) : 0;
@@ -574,19 +611,21 @@ extern "C" int ren_render_tangent_forward(const RenFieldDesc* f, const RenRender
     float* raw_val = (float*)(sv + tcs_raw(p, S));
     float* raw_dot = (float*)(sd + tcs_raw(p, S));
     unsigned char* live = nullptr;
-    if (r->occ_binary != nullptr) {
+    if (r->occ_binary != nullptr && packed == nullptr) {
       live = (unsigned char*)sv + tcs_live(p, S);
       rc = ren_launch_tile_live(p, n_rays, K, rays_o, rays_d, jitter, live, st);
       if (rc) return rc;
     }
-    rc = ren_tc_launch_fwd(p, n_rays, K, rays_o, rays_d, nullptr, nullptr, nullptr, jitter, params, sv, raw_val, live,
-                           ws, ws_left, st);
-    if (rc) return rc;
-    rc = ren_tc_launch_fwd(p, n_rays, K, rays_o, rays_d, rays_o_dot, rays_d_dot, sv, jitter, params, sd, raw_dot, live,
-                           ws, ws_left, st);
-    if (rc) return rc;
-    return ren_launch_composite_tan(p, n_rays, K, rays_o, rays_d, jitter, raw_val, raw_dot, bkgd, radiance, opacity,
-                                    depth, radiance_dot, opacity_dot, n_kept, st);
+    if (S > 0) {
+      rc = ren_tc_launch_fwd(p, n_rays, K, rays_o, rays_d, nullptr, nullptr, nullptr, jitter, params, sv, raw_val,
+                             live, sample_idx, S, ws, ws_left, st);
+      if (rc) return rc;
+      rc = ren_tc_launch_fwd(p, n_rays, K, rays_o, rays_d, rays_o_dot, rays_d_dot, sv, jitter, params, sd, raw_dot,
+                             live, sample_idx, S, ws, ws_left, st);
+      if (rc) return rc;
+    }
+    return ren_launch_composite_tan(p, n_rays, K, rays_o, rays_d, jitter, ray_offsets, raw_val, raw_dot, bkgd,
+                                    radiance, opacity, depth, radiance_dot, opacity_dot, n_kept, st);
   }
   const long long S2 = 2 * S;
   float* raw;
@@ -600,8 +639,8 @@ extern "C" int ren_render_tangent_forward(const RenFieldDesc* f, const RenRender
   }
   rc = ren_simt_launch_fwd(p, n_rays, K, rays_o, rays_d, rays_o_dot, rays_d_dot, jitter, params, (float*)stash, raw, st);
   if (rc) return rc;
-  return ren_launch_composite_tan(p, n_rays, K, rays_o, rays_d, jitter, raw, nullptr, bkgd, radiance, opacity, depth,
-                                  radiance_dot, opacity_dot, n_kept, st);
+  return ren_launch_composite_tan(p, n_rays, K, rays_o, rays_d, jitter, nullptr, raw, nullptr, bkgd, radiance, opacity,
+                                  depth, radiance_dot, opacity_dot, n_kept, st);
 }
 
 extern "C" int ren_render_tangent_backward(const RenFieldDesc* f, const RenRenderDesc* r, int64_t n_rays, int32_t K,
@@ -609,9 +648,9 @@ extern "C" int ren_render_tangent_backward(const RenFieldDesc* f, const RenRende
                                            const float* rays_d_dot, const float* jitter, const float* params,
                                            const float* bkgd, const float* g_radiance, const float* g_opacity,
                                            const float* g_depth, const float* g_radiance_dot,
-                                           const float* g_opacity_dot, const void* stash, size_t stash_bytes,
-                                           float* g_params, float* g_bkgd, float* g_rays, void* workspace,
-                                           size_t workspace_bytes, void* stream) {
+                                           const float* g_opacity_dot, const RenPacked* packed, const void* stash,
+                                           size_t stash_bytes, float* g_params, float* g_bkgd, float* g_rays,
+                                           void* workspace, size_t workspace_bytes, void* stream) {
   RenPlan p;
   int rc = tangent_plan(f, r, n_rays, K, &p);
   if (rc) return rc;
@@ -620,7 +659,11 @@ extern "C" int ren_render_tangent_backward(const RenFieldDesc* f, const RenRende
     ren_set_error("ren_render_tangent_backward: null pointer argument");
     return REN_E_INVALID;
   }
-  const long long S = (long long)n_rays * K;
+  long long S;
+  rc = check_packed(packed, p.r.engine, n_rays, K, &S);
+  if (rc) return rc;
+  const int* ray_offsets = packed ? packed->ray_offsets : nullptr;
+  const int* sample_idx = packed ? packed->sample_idx : nullptr;
   char* ws = (char*)align256(workspace);
   const size_t ws_left = workspace_bytes - (size_t)(ws - (char*)workspace);
   cudaStream_t st = (cudaStream_t)stream;
@@ -642,11 +685,16 @@ extern "C" int ren_render_tangent_backward(const RenFieldDesc* f, const RenRende
     char* pack_ws = (char*)align256(extra + tct_mats(p, S));
     const size_t pack_left = workspace_bytes - (size_t)(pack_ws - (char*)workspace);
     if (cudaMemsetAsync(gmax, 0, 256, st) != cudaSuccess) { ren_set_error("gmax memset failed"); return REN_E_CUDA; }
-    rc = ren_launch_composite_tan_bwd(p, n_rays, K, rays_o, rays_d, jitter, raw_val, raw_dot, bkgd, g_radiance,
-                                      g_opacity, g_depth, g_radiance_dot, g_opacity_dot, graw_val, graw_dot, g_bkgd,
-                                      gmax, st);
+    rc = ren_launch_composite_tan_bwd(p, n_rays, K, rays_o, rays_d, jitter, ray_offsets, raw_val, raw_dot, bkgd,
+                                      g_radiance, g_opacity, g_depth, g_radiance_dot, g_opacity_dot, graw_val, graw_dot,
+                                      g_bkgd, gmax, st);
     if (rc) return rc;
-    const unsigned char* live = r->occ_binary != nullptr ? (const unsigned char*)sv + tcs_live(p, S) : nullptr;
+    if (S == 0) {
+      if (g_rays && cudaMemsetAsync(g_rays, 0, sizeof(float) * 12 * (size_t)n_rays, st) != cudaSuccess) return REN_E_CUDA;
+      return REN_OK;
+    }
+    const unsigned char* live = (r->occ_binary != nullptr && packed == nullptr)
+                                    ? (const unsigned char*)sv + tcs_live(p, S) : nullptr;
     rc = ren_tc_launch_dgrad(p, S, params, sv, graw_dot, gmax, delta_dot, 1, sd, extra, live, pack_ws, pack_left, st);
     if (rc) return rc;
     rc = ren_tc_launch_dgrad(p, S, params, sv, graw_val, gmax, delta_val, 2, nullptr, extra, live, pack_ws, pack_left,
@@ -654,7 +702,7 @@ extern "C" int ren_render_tangent_backward(const RenFieldDesc* f, const RenRende
     if (rc) return rc;
     if (g_rays) {
       rc = ren_launch_raygrad(p, n_rays, K, rays_o, rays_d, rays_o_dot, rays_d_dot, jitter, params, delta_val,
-                              delta_dot, 1, gmax, live, g_rays, st);
+                              delta_dot, 1, gmax, live, sample_idx, S, g_rays, st);
       if (rc) return rc;
     }
     rc = ren_tc_launch_wgrad(p, S, sv, delta_val, graw_val, gmax, g_params, 1, live, st);
@@ -669,14 +717,14 @@ extern "C" int ren_render_tangent_backward(const RenFieldDesc* f, const RenRende
   float* graw = delta + p.act_floats * ren_pad128(S2);
   const float* st_f = (const float*)stash;
   const float* raw = st_f + ren_stash_raw(p, S2);
-  rc = ren_launch_composite_tan_bwd(p, n_rays, K, rays_o, rays_d, jitter, raw, nullptr, bkgd, g_radiance, g_opacity,
-                                    g_depth, g_radiance_dot, g_opacity_dot, graw, nullptr, g_bkgd, nullptr, st);
+  rc = ren_launch_composite_tan_bwd(p, n_rays, K, rays_o, rays_d, jitter, nullptr, raw, nullptr, bkgd, g_radiance,
+                                    g_opacity, g_depth, g_radiance_dot, g_opacity_dot, graw, nullptr, g_bkgd, nullptr, st);
   if (rc) return rc;
   rc = ren_simt_launch_dgrad(p, S2, params, st_f, graw, delta, 1, st);
   if (rc) return rc;
   if (g_rays) {
     rc = ren_launch_raygrad(p, n_rays, K, rays_o, rays_d, rays_o_dot, rays_d_dot, jitter, params, delta, nullptr, 0,
-                            nullptr, nullptr, g_rays, st);
+                            nullptr, nullptr, nullptr, 0, g_rays, st);
     if (rc) return rc;
   }
   return ren_simt_launch_wgrad(p, S2, st_f, delta, graw, g_params, 1, st);
@@ -750,7 +798,7 @@ extern "C" int ren_field_density(const RenFieldDesc* f, const RenRenderDesc* r, 
     rc = ren_simt_launch_fwd(p, n_points, 1, points, zeros, nullptr, nullptr, nullptr, params, nullptr, raw, st);
   else
     rc = ren_tc_launch_fwd(p, n_points, 1, points, zeros, nullptr, nullptr, nullptr, nullptr, params, nullptr, raw,
-                           nullptr, rest, ws_left, st);
+                           nullptr, nullptr, 0, rest, ws_left, st);
   if (rc) return rc;
   DensityArgs da;
   da.n = n_points; da.C1 = 1 + p.C; da.density_activation = f->density_activation; da.raw = raw; da.sigma = sigma;
@@ -760,4 +808,65 @@ extern "C" int ren_field_density(const RenFieldDesc* f, const RenRenderDesc* r, 
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { ren_set_error("ren_field_density launch: %s", cudaGetErrorString(e)); return REN_E_CUDA; }
   return REN_OK;
+}
+
+// ------------------------------------------------------------------ packed march
+#include <cub/device/device_scan.cuh>
+extern "C" int ren_resolve_engine(const RenFieldDesc* f, const RenRenderDesc* r, int32_t* engine) {
+  RenPlan p;
+  int rc = ren_build_plan(f, r, &p);
+  if (rc) return rc;
+  rc = validate_render(r);
+  if (rc) return rc;
+  if (!engine) { ren_set_error("ren_resolve_engine: null output"); return REN_E_INVALID; }
+  const int e = pick_engine(p);
+  rc = check_engine(p, e);
+  if (rc) return rc;
+  *engine = e;
+  return REN_OK;
+}
+extern "C" int ren_march_workspace_bytes(int64_t n_rays, size_t* bytes) {
+  if (n_rays < 0 || !bytes) { ren_set_error("ren_march_workspace_bytes: bad arguments"); return REN_E_INVALID; }
+  size_t scan = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, scan, (const int*)nullptr, (int*)nullptr, (int)(n_rays + 1));
+  *bytes = scan + sizeof(int) * (size_t)(n_rays + 1) + 1024;
+  return REN_OK;
+}
+extern "C" int ren_march_count(const RenFieldDesc* f, const RenRenderDesc* r, int64_t n_rays, int32_t K,
+                               const float* rays_o, const float* rays_d, const float* jitter, int32_t* ray_offsets,
+                               void* workspace, size_t workspace_bytes, void* stream) {
+  RenPlan p;
+  int rc = ren_build_plan(f, r, &p);
+  if (rc) return rc;
+  rc = validate_render(r);
+  if (rc) return rc;
+  rc = check_occupancy(f, r);
+  if (rc) return rc;
+  if (n_rays < 0 || K < 1 || (long long)n_rays * K >= (1LL << 31)) { ren_set_error("ren_march_count: bad n_rays/K"); return REN_E_INVALID; }
+  if (!rays_o || !rays_d || !ray_offsets || !workspace) { ren_set_error("ren_march_count: null pointer argument"); return REN_E_INVALID; }
+  cudaStream_t st = (cudaStream_t)stream;
+  char* ws = (char*)align256(workspace);
+  int* counts = (int*)ws;
+  char* scan_ws = (char*)align256(ws + sizeof(int) * (size_t)(n_rays + 1));
+  size_t scan_bytes = workspace_bytes - (size_t)(scan_ws - (char*)workspace);
+  if (cudaMemsetAsync(counts, 0, sizeof(int) * (size_t)(n_rays + 1), st) != cudaSuccess) return REN_E_CUDA;
+  rc = ren_launch_march_pack(p, n_rays, K, rays_o, rays_d, jitter, counts, nullptr, nullptr, st);
+  if (rc) return rc;
+  cudaError_t e = cub::DeviceScan::ExclusiveSum(scan_ws, scan_bytes, counts, ray_offsets, (int)(n_rays + 1), st);
+  if (e != cudaSuccess) { ren_set_error("ren_march_count scan: %s", cudaGetErrorString(e)); return REN_E_CUDA; }
+  return REN_OK;
+}
+extern "C" int ren_march_fill(const RenFieldDesc* f, const RenRenderDesc* r, int64_t n_rays, int32_t K,
+                              const float* rays_o, const float* rays_d, const float* jitter,
+                              const int32_t* ray_offsets, int32_t* sample_idx, void* stream) {
+  RenPlan p;
+  int rc = ren_build_plan(f, r, &p);
+  if (rc) return rc;
+  rc = validate_render(r);
+  if (rc) return rc;
+  if (n_rays < 0 || K < 1) { ren_set_error("ren_march_fill: bad n_rays/K"); return REN_E_INVALID; }
+  if (n_rays == 0) return REN_OK;
+  if (!rays_o || !rays_d || !ray_offsets || !sample_idx) { ren_set_error("ren_march_fill: null pointer argument"); return REN_E_INVALID; }
+  return ren_launch_march_pack(p, n_rays, K, rays_o, rays_d, jitter, nullptr, ray_offsets, sample_idx,
+                               (cudaStream_t)stream);
 }

@@ -35,6 +35,9 @@ struct CompArgs {
   int tangent;
   const float* raw_dot;
   float* graw_dot;
+  // packed samples (occupancy-grid marching on the tcgen05 engine): raw / graw hold only the emitted samples,
+  // ray r owns [ray_offsets[r], ray_offsets[r+1]) in marching order
+  const int* ray_offsets;
   float* radiance_dot;   // [n_rays][C]
   float* opacity_dot;    // [n_rays]
   const float* g_radiance_dot;
@@ -64,6 +67,7 @@ __device__ __forceinline__ double warp_sum_d(double v) {
 struct SampleBlk {
   float t0, t1, sdt, alpha, w, Texcl, dact_s, dact_c[3], c[3];
   bool alive, keep;
+  long long sidx;       // row of this sample in raw / graw (dense r*K + k, or its packed position)
 };
 
 // Walks the ray in blocks of 32 samples.  `Body(k, blk)` is called for every sample index
@@ -86,17 +90,27 @@ __device__ __forceinline__ void walk_ray(const CompArgs& a, long long r, int lan
   float carry_sum = 0.f;    // sum of kept sigma*dt before this block
   float carry_T = 1.f;      // product of (1-alpha) of kept samples before this block (cull rule)
   bool stopped = false;
+  int packed_base = a.ray_offsets ? a.ray_offsets[r] : 0;
   for (int kb = 0; kb < a.K; kb += 32) {
     const int k = kb + lane;
     SampleBlk b;
     b.t0 = t0; b.t1 = t1;
     const bool in_range = (k < a.K) && ren_alive(t0, t1, t_max);   // geometric: midpoint before t_max
     b.alive = in_range;
+    b.sidx = r * a.K + k;
+    if (a.ray_offsets != nullptr) {
+      // packed: only the steps in occupied cells were emitted; rank them in marching order
+      const bool emitted = in_range && ren_occupied(p.f, p.r, o, d, t0, t1);
+      const unsigned em = __ballot_sync(0xffffffffu, emitted);
+      b.sidx = packed_base + __popc(em & ((1u << lane) - 1u));
+      packed_base += __popc(em);
+      b.alive = emitted;
+    }
     float sraw = -INFINITY;
     b.c[0] = b.c[1] = b.c[2] = 0.f;
     b.dact_c[0] = b.dact_c[1] = b.dact_c[2] = 0.f;
     if (b.alive) {
-      const float* rw = a.raw + (r * a.K + k) * ((a.tangent && !a.raw_dot) ? 2 : 1) * C1;
+      const float* rw = a.raw + b.sidx * ((a.tangent && !a.raw_dot) ? 2 : 1) * C1;
       sraw = rw[0];
       if (sraw != sraw) {            // NaN: the marching step fell into an unoccupied grid cell -> no sample
         b.alive = false;
@@ -156,6 +170,7 @@ __device__ __forceinline__ void walk_ray(const CompArgs& a, long long r, int lan
       for (int kb2 = kb + 32; kb2 < a.K; kb2 += 32) {
         SampleBlk z = b;
         z.alive = false; z.keep = false; z.w = 0.f; z.sdt = 0.f;
+        z.sidx = a.ray_offsets ? -1 : r * a.K + kb2 + lane;
         body(kb2 + lane, z);
       }
       break;
@@ -247,8 +262,8 @@ extern "C" __global__ void __launch_bounds__(128) ren_composite_bwd(const CompAr
       }
       const double suffix = tot - (prefix + incl);
       prefix += __shfl_sync(0xffffffffu, incl, 31);
-      if (k < a.K) {
-        float* g = a.graw + (r * a.K + k) * C1;
+      if (k < a.K && (a.ray_offsets == nullptr || b.alive)) {
+        float* g = a.graw + b.sidx * C1;
         float gs = 0.f;
         if (b.keep) {
           const float dsdt = G * b.Texcl * expf(-b.sdt) - (float)suffix;
@@ -290,7 +305,7 @@ __device__ __forceinline__ TanBlk tan_block(const CompArgs& a, long long r, int 
   t.sdot_raw = 0.f;
   t.cdot_raw[0] = t.cdot_raw[1] = t.cdot_raw[2] = 0.f;
   if (b.keep) {
-    const float* rw = a.raw_dot ? a.raw_dot + (r * a.K + k) * C1 : a.raw + ((r * a.K + k) * 2 + 1) * C1;
+    const float* rw = a.raw_dot ? a.raw_dot + b.sidx * C1 : a.raw + (b.sidx * 2 + 1) * C1;
     t.sdot_raw = rw[0];
     for (int c = 0; c < p.C; ++c) t.cdot_raw[c] = rw[1 + c];
   }
@@ -423,10 +438,10 @@ extern "C" __global__ void __launch_bounds__(128) ren_composite_tan_bwd(const Co
       const double sufB = totB - (prefB + inclB);
       prefA += __shfl_sync(0xffffffffu, inclA, 31);
       prefB += __shfl_sync(0xffffffffu, inclB, 31);
-      if (k < a.K) {
-        const long long vrow = (r * a.K + k) * (a.raw_dot ? 1 : 2);
-        float* gv = a.graw + (a.graw_dot ? (r * a.K + k) : (r * a.K + k) * 2) * C1;
-        float* gt = a.graw_dot ? a.graw_dot + (r * a.K + k) * C1 : gv + C1;
+      if (k < a.K && (a.ray_offsets == nullptr || b.alive)) {
+        const long long vrow = b.sidx * (a.raw_dot ? 1 : 2);
+        float* gv = a.graw + (a.graw_dot ? b.sidx : b.sidx * 2) * C1;
+        float* gt = a.graw_dot ? a.graw_dot + b.sidx * C1 : gv + C1;
         float gs = 0.f, gsd = 0.f;
         if (b.keep) {
           const float dt = __fsub_rn(b.t1, b.t0);
@@ -505,6 +520,72 @@ extern "C" __global__ void __launch_bounds__(128) ren_tile_live_kernel(const Liv
     }
   }
 }
+// ------------------------------------------------------------------ packed samples
+// nerfacc.ray_marching emits a packed list of samples (ray_indices, t_starts, t_ends; external/utils.py:106-119).
+// Phase 1 counts the emitted steps per ray, phase 2 (after an exclusive scan of the counts) writes the dense
+// index r*K + k of every emitted step at its packed position.
+struct PackArgs2 {
+  RenPlan p;
+  long long n_rays;
+  int K;
+  const float* rays_o;
+  const float* rays_d;
+  const float* jitter;
+  int* counts;               // phase 1 out: [n_rays]
+  const int* ray_offsets;    // phase 2 in: exclusive scan of counts, [n_rays + 1]
+  int* sample_idx;           // phase 2 out: [total]
+};
+template <bool FILL>
+__global__ void __launch_bounds__(128) ren_march_pack_kernel(const PackArgs2 a) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const RenPlan& p = a.p;
+  for (long long r = warp; r < a.n_rays; r += n_warps) {
+    float o[3], d[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      o[c] = a.rays_o[r * 3 + c];
+      d[c] = a.rays_d[r * 3 + c];
+    }
+    float t_min, t_max, t0, t1;
+    ren_ray_range(p.f, p.r, o, d, a.jitter ? a.jitter[r] : 0.f, &t_min, &t_max);
+    ren_march_to(p.r, t_min, lane, &t0, &t1);
+    int base = FILL ? a.ray_offsets[r] : 0;
+    for (int kb = 0; kb < a.K; kb += 32) {
+      const int k = kb + lane;
+      const bool in_range = (k < a.K) && ren_alive(t0, t1, t_max);
+      const bool emitted = in_range && ren_occupied(p.f, p.r, o, d, t0, t1);
+      const unsigned em = __ballot_sync(0xffffffffu, emitted);
+      if (FILL && emitted) a.sample_idx[base + __popc(em & ((1u << lane) - 1u))] = (int)(r * a.K + k);
+      base += __popc(em);
+      if (__ballot_sync(0xffffffffu, in_range) == 0u) break;
+      for (int i = 0; i < 32; ++i) {
+        t0 = t1;
+        t1 = __fadd_rn(t0, ren_dt(p.r, t0));
+      }
+    }
+    if (!FILL && lane == 0) a.counts[r] = base;
+  }
+}
+int ren_launch_march_pack(const RenPlan& p, long long n_rays, int K, const float* o, const float* d,
+                          const float* jitter, int* counts, const int* ray_offsets, int* sample_idx,
+                          cudaStream_t st) {
+  if (n_rays <= 0) return REN_OK;
+  PackArgs2 a;
+  a.p = p; a.n_rays = n_rays; a.K = K; a.rays_o = o; a.rays_d = d; a.jitter = jitter;
+  a.counts = counts; a.ray_offsets = ray_offsets; a.sample_idx = sample_idx;
+  long long blocks = (n_rays + 3) / 4;
+  if (blocks > 148 * 64) blocks = 148 * 64;
+  ren_prof_begin(REN_K_COMPOSITE_FWD, st);
+  if (sample_idx) ren_march_pack_kernel<true><<<(unsigned)blocks, 128, 0, st>>>(a);
+  else ren_march_pack_kernel<false><<<(unsigned)blocks, 128, 0, st>>>(a);
+  ren_prof_end(REN_K_COMPOSITE_FWD, st);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { ren_set_error("march pack launch: %s", cudaGetErrorString(e)); return REN_E_CUDA; }
+  return REN_OK;
+}
+
 int ren_launch_tile_live(const RenPlan& p, long long n_rays, int K, const float* o, const float* d,
                          const float* jitter, unsigned char* live, cudaStream_t st) {
   if (n_rays <= 0) return REN_OK;
@@ -523,7 +604,8 @@ int ren_launch_tile_live(const RenPlan& p, long long n_rays, int K, const float*
 }
 
 int ren_launch_composite_tan(const RenPlan& p, long long n_rays, int K, const float* o, const float* d,
-                             const float* jitter, const float* raw, const float* raw_dot, const float* bkgd, float* radiance,
+                             const float* jitter, const int* ray_offsets, const float* raw, const float* raw_dot,
+                             const float* bkgd, float* radiance,
                              float* opacity, float* depth, float* radiance_dot, float* opacity_dot,
                              int* n_kept, cudaStream_t st) {
   if (n_rays <= 0) return REN_OK;
@@ -531,6 +613,7 @@ int ren_launch_composite_tan(const RenPlan& p, long long n_rays, int K, const fl
   a.p = p; a.n_rays = n_rays; a.K = K; a.rays_o = o; a.rays_d = d; a.jitter = jitter; a.raw = raw;
   a.bkgd = bkgd; a.radiance = radiance; a.opacity = opacity; a.depth = depth; a.n_kept = n_kept;
   a.tangent = 1; a.radiance_dot = radiance_dot; a.opacity_dot = opacity_dot; a.raw_dot = raw_dot;
+  a.ray_offsets = ray_offsets;
   long long blocks = (n_rays + 3) / 4;
   if (blocks > 148 * 64) blocks = 148 * 64;
   ren_prof_begin(REN_K_COMPOSITE_FWD, st);
@@ -542,7 +625,8 @@ int ren_launch_composite_tan(const RenPlan& p, long long n_rays, int K, const fl
 }
 
 int ren_launch_composite_tan_bwd(const RenPlan& p, long long n_rays, int K, const float* o, const float* d,
-                                 const float* jitter, const float* raw, const float* raw_dot, const float* bkgd,
+                                 const float* jitter, const int* ray_offsets, const float* raw, const float* raw_dot,
+                                 const float* bkgd,
                                  const float* g_radiance, const float* g_opacity, const float* g_depth,
                                  const float* g_radiance_dot, const float* g_opacity_dot, float* graw,
                                  float* graw_dot, float* g_bkgd, unsigned int* gmax, cudaStream_t st) {
@@ -552,6 +636,7 @@ int ren_launch_composite_tan_bwd(const RenPlan& p, long long n_rays, int K, cons
   a.bkgd = bkgd; a.g_radiance = g_radiance; a.g_opacity = g_opacity; a.g_depth = g_depth;
   a.g_radiance_dot = g_radiance_dot; a.g_opacity_dot = g_opacity_dot;
   a.graw = graw; a.g_bkgd = g_bkgd; a.tangent = 1; a.raw_dot = raw_dot; a.graw_dot = graw_dot; a.gmax = gmax;
+  a.ray_offsets = ray_offsets;
   long long blocks = (n_rays + 3) / 4;
   if (blocks > 148 * 64) blocks = 148 * 64;
   ren_prof_begin(REN_K_COMPOSITE_BWD, st);
@@ -563,12 +648,13 @@ int ren_launch_composite_tan_bwd(const RenPlan& p, long long n_rays, int K, cons
 }
 
 int ren_launch_composite(const RenPlan& p, long long n_rays, int K, const float* o, const float* d,
-                         const float* jitter, const float* raw, const float* bkgd, float* radiance,
-                         float* opacity, float* depth, int* n_kept, cudaStream_t st) {
+                         const float* jitter, const int* ray_offsets, const float* raw, const float* bkgd,
+                         float* radiance, float* opacity, float* depth, int* n_kept, cudaStream_t st) {
   if (n_rays <= 0) return REN_OK;
   CompArgs a = {};
   a.p = p; a.n_rays = n_rays; a.K = K; a.rays_o = o; a.rays_d = d; a.jitter = jitter; a.raw = raw;
   a.bkgd = bkgd; a.radiance = radiance; a.opacity = opacity; a.depth = depth; a.n_kept = n_kept;
+  a.ray_offsets = ray_offsets;
   long long blocks = (n_rays + 3) / 4;
   if (blocks > 148 * 64) blocks = 148 * 64;
   ren_prof_begin(REN_K_COMPOSITE_FWD, st);
@@ -580,14 +666,14 @@ int ren_launch_composite(const RenPlan& p, long long n_rays, int K, const float*
 }
 
 int ren_launch_composite_bwd(const RenPlan& p, long long n_rays, int K, const float* o, const float* d,
-                             const float* jitter, const float* raw, const float* bkgd,
+                             const float* jitter, const int* ray_offsets, const float* raw, const float* bkgd,
                              const float* g_radiance, const float* g_opacity, const float* g_depth,
                              float* graw, float* g_bkgd, unsigned int* gmax, cudaStream_t st) {
   if (n_rays <= 0) return REN_OK;
   CompArgs a = {};
   a.p = p; a.n_rays = n_rays; a.K = K; a.rays_o = o; a.rays_d = d; a.jitter = jitter; a.raw = raw;
   a.bkgd = bkgd; a.g_radiance = g_radiance; a.g_opacity = g_opacity; a.g_depth = g_depth;
-  a.graw = graw; a.g_bkgd = g_bkgd; a.gmax = gmax;
+  a.graw = graw; a.g_bkgd = g_bkgd; a.gmax = gmax; a.ray_offsets = ray_offsets;
   long long blocks = (n_rays + 3) / 4;
   if (blocks > 148 * 64) blocks = 148 * 64;
   ren_prof_begin(REN_K_COMPOSITE_BWD, st);

@@ -39,6 +39,8 @@ struct RgArgs {
   int fp16;                    // Delta matrices are fp16 blocked, scaled by delta_scale(gmax) (tcgen05 engine)
   const unsigned int* gmax;
   const unsigned char* tile_live;   // per-128-sample-tile flags or NULL: dead tiles hold no data
+  const int* sample_idx;            // packed samples: dense index r*K + k of sample s, or NULL
+  long long n_samples;
   const float* rays_o;
   const float* rays_d;
   const float* rays_o_dot;
@@ -94,7 +96,7 @@ extern "C" __global__ void __launch_bounds__(RG_THREADS) ren_raygrad_kernel(cons
   __shared__ __align__(16) float As[16][RG_ROWS];        // Delta chunk, k-major
   __shared__ __align__(16) float Ws[16][64];             // weight chunk [k][enc col]
   const RenPlan& p = a.p;
-  const long long S = a.n_rays * a.K * (a.tangent ? 2 : 1);     // rows (value and d/dw rows counted separately)
+  const long long S = (a.sample_idx ? a.n_samples : a.n_rays * a.K) * (a.tangent ? 2 : 1);   // rows
   const int tid = threadIdx.x;
   const int ty = tid >> 4, tx = tid & 15;                // rows 4 ty .. 4 ty + 3; columns 4 tx .. (P), 2 tx .. (D)
   const float unscale = a.fp16 ? 1.f / delta_scale(a.gmax) : 1.f;
@@ -167,8 +169,9 @@ extern "C" __global__ void __launch_bounds__(RG_THREADS) ren_raygrad_kernel(cons
       const long long r0 = row0 + threadIdx.x * per;
       if (r0 < S) {
         const long long smp = r0 / per;
-        const long long r = smp / a.K;
-        const int k = (int)(smp - r * a.K);
+        const long long dense = a.sample_idx ? (long long)a.sample_idx[smp] : smp;
+        const long long r = dense / a.K;
+        const int k = (int)(dense - r * a.K);
         float o[3], d[3], od[3] = {0.f, 0.f, 0.f}, dd[3] = {0.f, 0.f, 0.f};
         for (int c = 0; c < 3; ++c) {
           o[c] = a.rays_o[r * 3 + c];
@@ -237,14 +240,16 @@ extern "C" __global__ void __launch_bounds__(RG_THREADS) ren_raygrad_kernel(cons
 int ren_launch_raygrad(const RenPlan& p, long long n_rays, int K, const float* o, const float* d,
                        const float* o_dot, const float* d_dot, const float* jitter, const float* params,
                        const void* delta, const void* delta_dot, int fp16, const unsigned int* gmax,
-                       const unsigned char* tile_live, float* g_rays, cudaStream_t st) {
+                       const unsigned char* tile_live, const int* sample_idx, long long n_samples, float* g_rays,
+                       cudaStream_t st) {
   if (n_rays <= 0) return REN_OK;
   RgArgs a;
-  a.tile_live = tile_live;
+  a.tile_live = tile_live; a.sample_idx = sample_idx; a.n_samples = n_samples;
   a.p = p; a.n_rays = n_rays; a.K = K; a.tangent = o_dot != nullptr ? 1 : 0; a.fp16 = fp16; a.gmax = gmax;
   a.rays_o = o; a.rays_d = d; a.rays_o_dot = o_dot; a.rays_d_dot = d_dot; a.jitter = jitter; a.g_rays = g_rays;
-  const long long S = n_rays * K * (a.tangent ? 2 : 1);          // rows
-  const long long Sm = fp16 ? n_rays * K : S;                    // rows of one delta matrix
+  const long long Ns = sample_idx ? n_samples : n_rays * K;      // samples
+  const long long S = Ns * (a.tangent ? 2 : 1);                  // rows
+  const long long Sm = fp16 ? Ns : S;                            // rows of one delta matrix
   const float* graw = fp16 ? nullptr : (const float*)delta + p.act_floats * ren_pad128(S);
   int n = 0;
   auto add = [&](const void* D, const void* Dd, int N, int ldd, int rowmajor, const float* W, int ldw, int enc) {

@@ -132,6 +132,8 @@ struct TcArgs {
   const unsigned char* stash_dot;   // dgrad pass 1: the tangent pass' stash (read)
   unsigned char* extra;             // dgrad: E matrices (fp16 blocked; written by pass 1, read by pass 2)
   const unsigned char* tile_live;   // per-tile flags (occupancy-grid marching) or NULL: dead tiles are skipped by all roles
+  const int* sample_idx;            // packed samples: dense index r*K + k of every emitted marching step, or NULL
+  long long n_samples;              // number of packed samples (when sample_idx != NULL)
 };
 
 __device__ __forceinline__ float ex2_ftz(float x) {
@@ -263,7 +265,7 @@ __global__ void __launch_bounds__(MODE == 0 ? TC_THREADS_FWD : TC_THREADS_BWD, 1
   const uint32_t bar_acc = sbase + SM_BAR + 288;            // [2] accumulator N-half h is complete
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + SM_TMEM_PTR);
   float* vec = reinterpret_cast<float*>(smem + SM_VEC);
-  const long long S = a.n_rays * a.K;
+  const long long S = a.sample_idx != nullptr ? a.n_samples : a.n_rays * a.K;
   const long long n_tiles = (S + TC_M - 1) / TC_M;
   const int C1 = 1 + p.C;
 
@@ -407,9 +409,10 @@ __global__ void __launch_bounds__(MODE == 0 ? TC_THREADS_FWD : TC_THREADS_BWD, 1
         const bool valid = sidx < S && !(a.dbg & 4);
         float o[3] = {0.f, 0.f, 0.f}, d[3] = {0.f, 0.f, 1.f}, z[3] = {0.f, 0.f, 0.f};
         bool selector = false, skipped = false;
+        const long long dense = (valid && a.sample_idx != nullptr) ? (long long)a.sample_idx[sidx] : sidx;
         if (valid) {
-          const long long r = sidx / a.K;
-          const int k = (int)(sidx - r * a.K);
+          const long long r = dense / a.K;
+          const int k = (int)(dense - r * a.K);
 #pragma unroll
           for (int c = 0; c < 3; ++c) {
             o[c] = a.rays_o[r * 3 + c];
@@ -427,8 +430,8 @@ __global__ void __launch_bounds__(MODE == 0 ? TC_THREADS_FWD : TC_THREADS_BWD, 1
         float zdot[3] = {0.f, 0.f, 0.f}, dzdot[3] = {0.f, 0.f, 0.f};
         if (TAN && valid) {
           // x = o + d tm, xdot = odot + ddot tm (the march carries no gradient); zdot = J_contract(x) xdot
-          const long long r = sidx / a.K;
-          const int k = (int)(sidx - r * a.K);
+          const long long r = dense / a.K;
+          const int k = (int)(dense - r * a.K);
           float t_min, t_max, t0, t1;
           ren_ray_range(p.f, p.r, o, d, a.jitter ? a.jitter[r] : 0.f, &t_min, &t_max);
           ren_march_to(p.r, t_min, k, &t0, &t1);
@@ -1034,7 +1037,7 @@ static void fill_args(TcArgs& a, const RenPlan& p, const TcProgram& P) {
 int ren_tc_launch_fwd(const RenPlan& p, long long n_rays, int K, const float* o, const float* d,
                       const float* o_dot, const float* d_dot, const void* stash_val,
                       const float* jitter, const float* params, void* stash, float* raw, const unsigned char* tile_live,
-                      void* ws, size_t ws_bytes, cudaStream_t st) {
+                      const int* sample_idx, long long n_samples, void* ws, size_t ws_bytes, cudaStream_t st) {
   TcProgram P;
   build_forward(p, P);
   unsigned char* pack; float* vec; StageOp* prog;
@@ -1049,7 +1052,8 @@ int ren_tc_launch_fwd(const RenPlan& p, long long n_rays, int K, const float* o,
   a.pack = pack; a.vec = vec; a.prog = prog; a.n_ops = P.n_ops; a.stash = (unsigned char*)stash; a.raw = raw;
   a.tan = o_dot != nullptr ? 1 : 0; a.rays_o_dot = o_dot; a.rays_d_dot = d_dot;
   a.stash_val = (const unsigned char*)stash_val; a.tile_live = tile_live;
-  const long long n_tiles = (n_rays * K + TC_M - 1) / TC_M;
+  a.sample_idx = sample_idx; a.n_samples = n_samples;
+  const long long n_tiles = ((sample_idx ? n_samples : n_rays * K) + TC_M - 1) / TC_M;
   if (a.tan) return launch_chain<0, true, 1>(a, n_tiles, REN_K_FIELD_FWD, st);     // the tangent pass always stashes
   return stash ? launch_chain<0, true, 0>(a, n_tiles, REN_K_FIELD_FWD, st)
                : launch_chain<0, false, 0>(a, n_tiles, REN_K_FIELD_FWD, st);

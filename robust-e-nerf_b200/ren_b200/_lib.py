@@ -17,7 +17,7 @@ DENSITY_ACT = {"shifted_trunc_exp": 0, "softplus": 1, "shifted_softplus": 2}
 RADIANCE_ACT = {"softplus": 0, "sigmoid": 1}
 CONTRACTION = {"aabb": 0, "sphere": 1, "tanh": 2}
 ERROR_FN = {"l1": 0, "mse": 1, "mape": 2}
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 
 class RenFieldDesc(C.Structure):
@@ -29,6 +29,10 @@ class RenFieldDesc(C.Structure):
         ("radiance_activation", C.c_int32), ("contraction", C.c_int32),
         ("aabb", C.c_float * 6),
     ]
+
+
+class RenPacked(C.Structure):
+    _fields_ = [("n_samples", C.c_int64), ("sample_idx", C.c_void_p), ("ray_offsets", C.c_void_p)]
 
 
 class RenRenderDesc(C.Structure):
@@ -58,15 +62,21 @@ _SIGNATURES = {
     "ren_workspace_bytes": (C.c_int, [C.POINTER(RenFieldDesc), C.POINTER(RenRenderDesc), C.c_int64,
                                       C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_size_t)]),
     "ren_render_forward": (C.c_int, [C.POINTER(RenFieldDesc), C.POINTER(RenRenderDesc), C.c_int64,
-                                     C.c_int32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_size_t,
-                                     _P, C.c_size_t, _P]),
+                                     C.c_int32, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.POINTER(RenPacked), _P,
+                                     C.c_size_t, _P, C.c_size_t, _P]),
+    "ren_resolve_engine": (C.c_int, [C.POINTER(RenFieldDesc), C.POINTER(RenRenderDesc), C.POINTER(C.c_int32)]),
+    "ren_march_workspace_bytes": (C.c_int, [C.c_int64, C.POINTER(C.c_size_t)]),
+    "ren_march_count": (C.c_int, [C.POINTER(RenFieldDesc), C.POINTER(RenRenderDesc), C.c_int64, C.c_int32,
+                                  _P, _P, _P, _P, _P, C.c_size_t, _P]),
+    "ren_march_fill": (C.c_int, [C.POINTER(RenFieldDesc), C.POINTER(RenRenderDesc), C.c_int64, C.c_int32,
+                                 _P, _P, _P, _P, _P, _P]),
     "ren_density_workspace_bytes": (C.c_int, [C.POINTER(RenFieldDesc), C.POINTER(RenRenderDesc), C.c_int64,
                                               C.POINTER(C.c_size_t)]),
     "ren_field_density": (C.c_int, [C.POINTER(RenFieldDesc), C.POINTER(RenRenderDesc), C.c_int64, _P, _P, _P, _P,
                                     C.c_size_t, _P]),
     "ren_render_backward": (C.c_int, [C.POINTER(RenFieldDesc), C.POINTER(RenRenderDesc), C.c_int64,
-                                      C.c_int32, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P,
-                                      _P, _P, _P, C.c_size_t, _P]),
+                                      C.c_int32, _P, _P, _P, _P, _P, _P, _P, _P, C.POINTER(RenPacked), _P,
+                                      C.c_size_t, _P, _P, _P, _P, C.c_size_t, _P]),
     "ren_tangent_stash_bytes": (C.c_int, [C.POINTER(RenFieldDesc), C.POINTER(RenRenderDesc), C.c_int64,
                                           C.c_int32, C.POINTER(C.c_size_t)]),
     "ren_tangent_workspace_bytes": (C.c_int, [C.POINTER(RenFieldDesc), C.POINTER(RenRenderDesc),
@@ -74,11 +84,11 @@ _SIGNATURES = {
                                               C.POINTER(C.c_size_t)]),
     "ren_render_tangent_forward": (C.c_int, [C.POINTER(RenFieldDesc), C.POINTER(RenRenderDesc), C.c_int64,
                                              C.c_int32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
-                                             _P, _P, C.c_size_t, _P, C.c_size_t, _P]),
+                                             _P, C.POINTER(RenPacked), _P, C.c_size_t, _P, C.c_size_t, _P]),
     "ren_render_tangent_backward": (C.c_int, [C.POINTER(RenFieldDesc), C.POINTER(RenRenderDesc),
                                               C.c_int64, C.c_int32, _P, _P, _P, _P, _P, _P, _P, _P, _P,
-                                              _P, _P, _P, _P, C.c_size_t, _P, _P, _P, _P, C.c_size_t,
-                                              _P]),
+                                              _P, _P, _P, C.POINTER(RenPacked), _P, C.c_size_t, _P, _P, _P, _P,
+                                              C.c_size_t, _P]),
     "ren_event_rays": (C.c_int, [C.c_int64, _P, _P, _P, _P, _P, _P, _P, C.c_int64, _P, _P, _P, _P,
                                  C.c_int32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "ren_trajectory": (C.c_int, [C.c_int64, _P, C.c_int64, _P, _P, _P, _P, _P, _P]),
@@ -235,3 +245,30 @@ def tangent_workspace_bytes(fdesc, rdesc, n_rays, K, has_stash, for_backward):
     check(load().ren_tangent_workspace_bytes(C.byref(fdesc), C.byref(rdesc), n_rays, K, int(has_stash),
                                              int(for_backward), C.byref(n)), "ren_tangent_workspace_bytes")
     return int(n.value)
+
+
+def resolved_engine(fdesc, rdesc):
+    e = C.c_int32(0)
+    check(load().ren_resolve_engine(C.byref(fdesc), C.byref(rdesc), C.byref(e)), "ren_resolve_engine")
+    return int(e.value)
+
+
+def march_pack(fdesc, rdesc, n_rays, K, o, d, jitter):
+    """Packed march of one render call: (RenPacked, keep-alive tensors).  One host sync (the sample count), like
+    nerfacc's packed ray_marching."""
+    import torch
+    lib = load()
+    nb = C.c_size_t(0)
+    check(lib.ren_march_workspace_bytes(n_rays, C.byref(nb)), "ren_march_workspace_bytes")
+    ws = torch.empty((int(nb.value),), device=o.device, dtype=torch.uint8)
+    offsets = torch.empty((n_rays + 1,), device=o.device, dtype=torch.int32)
+    check(lib.ren_march_count(C.byref(fdesc), C.byref(rdesc), n_rays, K, ptr(o), ptr(d), ptr(jitter), ptr(offsets),
+                              ptr(ws), ws.numel(), stream_ptr()), "ren_march_count")
+    n = int(offsets[-1].item())
+    idx = torch.empty((max(n, 1),), device=o.device, dtype=torch.int32)
+    if n > 0:
+        check(lib.ren_march_fill(C.byref(fdesc), C.byref(rdesc), n_rays, K, ptr(o), ptr(d), ptr(jitter), ptr(offsets),
+                                 ptr(idx), stream_ptr()), "ren_march_fill")
+    pk = RenPacked()
+    pk.n_samples, pk.sample_idx, pk.ray_offsets = n, idx.data_ptr(), offsets.data_ptr()
+    return pk, (idx, offsets)

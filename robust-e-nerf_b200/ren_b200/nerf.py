@@ -156,21 +156,25 @@ class RenderFunction(torch.autograd.Function):
         opacity = torch.empty((B,), device=dev, dtype=torch.float32)
         depth = torch.empty((B,), device=dev, dtype=torch.float32)
         n_kept = torch.empty((B,), device=dev, dtype=torch.int32)
+        # occupancy grid on the tcgen05 engine: march first, run the field on the emitted samples only
+        packed, keep = owner._march_pack(fdesc, rdesc, B, K, o, d, jitter)
+        nS, nK = (max(int(packed.n_samples), 1), 1) if packed is not None else (B, K)
         stash = None
         stash_n = 0
         if need_grad:
-            stash_n = _lib.stash_bytes(fdesc, rdesc, B, K)
+            stash_n = _lib.stash_bytes(fdesc, rdesc, nS, nK)
             stash = torch.empty((stash_n,), device=dev, dtype=torch.uint8)
-        ws_n = _lib.workspace_bytes(fdesc, rdesc, B, K, need_grad, False)
+        ws_n = _lib.workspace_bytes(fdesc, rdesc, nS, nK, need_grad, False)
         ws = torch.empty((ws_n,), device=dev, dtype=torch.uint8)
         _lib.check(lib.ren_render_forward(
             C.byref(fdesc), C.byref(rdesc), B, K, _lib.ptr(o), _lib.ptr(d), _lib.ptr(jitter),
             _lib.ptr(flat), _lib.ptr(bkgd), _lib.ptr(radiance), _lib.ptr(opacity), _lib.ptr(depth),
-            _lib.ptr(n_kept), _lib.ptr(stash), stash_n, _lib.ptr(ws), ws.numel(),
-            _lib.stream_ptr()), "ren_render_forward")
+            _lib.ptr(n_kept), None if packed is None else C.byref(packed), _lib.ptr(stash), stash_n, _lib.ptr(ws),
+            ws.numel(), _lib.stream_ptr()), "ren_render_forward")
         if need_grad:
             ctx.owner = owner
             ctx.descs = (fdesc, rdesc, K)
+            ctx.packed, ctx.packed_keep = packed, keep
             ctx.save_for_backward(o, d, jitter if jitter is not None else torch.empty(0, device=dev),
                                   bkgd if bkgd is not None else torch.empty(0, device=dev), stash,
                                   flat)
@@ -193,7 +197,9 @@ class RenderFunction(torch.autograd.Function):
         bkgd = bkgd if ctx.has_bkgd else None
         g_flat = torch.zeros_like(flat)
         g_bkgd = torch.zeros_like(bkgd) if bkgd is not None else None
-        ws_n = _lib.workspace_bytes(fdesc, rdesc, B, K, True, True)
+        packed = ctx.packed
+        nS, nK = (max(int(packed.n_samples), 1), 1) if packed is not None else (B, K)
+        ws_n = _lib.workspace_bytes(fdesc, rdesc, nS, nK, True, True)
         ws = torch.empty((ws_n,), device=dev, dtype=torch.uint8)
         cg = lambda t: None if t is None else t.contiguous().float()
         g_rad, g_op, g_depth = cg(g_rad), cg(g_op), cg(g_depth)
@@ -201,8 +207,8 @@ class RenderFunction(torch.autograd.Function):
         _lib.check(lib.ren_render_backward(
             C.byref(fdesc), C.byref(rdesc), B, K, _lib.ptr(o), _lib.ptr(d), _lib.ptr(jitter),
             _lib.ptr(flat), _lib.ptr(bkgd), _lib.ptr(g_rad), _lib.ptr(g_op), _lib.ptr(g_depth),
-            _lib.ptr(stash), stash.numel(), _lib.ptr(g_flat), _lib.ptr(g_bkgd), _lib.ptr(g_rays),
-            _lib.ptr(ws), ws.numel(), _lib.stream_ptr()), "ren_render_backward")
+            None if packed is None else C.byref(packed), _lib.ptr(stash), stash.numel(), _lib.ptr(g_flat),
+            _lib.ptr(g_bkgd), _lib.ptr(g_rays), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()), "ren_render_backward")
         grads = owner._split_flat(g_flat)
         g_o = g_rays[:, 0:3] if ctx.ray_grad else None
         g_d = g_rays[:, 3:6] if ctx.ray_grad else None
@@ -242,21 +248,24 @@ class RenderTangentFunction(torch.autograd.Function):
         opacity_dot = torch.empty((B,), device=dev, dtype=torch.float32)
         depth = torch.empty((B,), device=dev, dtype=torch.float32)
         n_kept = torch.empty((B,), device=dev, dtype=torch.int32)
+        packed, keep = owner._march_pack(fdesc, rdesc, B, K, o, d, jitter)
+        nS, nK = (max(int(packed.n_samples), 1), 1) if packed is not None else (B, K)
         stash, stash_n = None, 0
         if need_grad:
-            stash_n = _lib.tangent_stash_bytes(fdesc, rdesc, B, K)
+            stash_n = _lib.tangent_stash_bytes(fdesc, rdesc, nS, nK)
             stash = torch.empty((stash_n,), device=dev, dtype=torch.uint8)
-        ws = torch.empty((_lib.tangent_workspace_bytes(fdesc, rdesc, B, K, need_grad, False),),
+        ws = torch.empty((_lib.tangent_workspace_bytes(fdesc, rdesc, nS, nK, need_grad, False),),
                          device=dev, dtype=torch.uint8)
         _lib.check(lib.ren_render_tangent_forward(
             C.byref(fdesc), C.byref(rdesc), B, K, _lib.ptr(o), _lib.ptr(d), _lib.ptr(o_dot),
             _lib.ptr(d_dot), _lib.ptr(jitter), _lib.ptr(flat), _lib.ptr(bkgd), _lib.ptr(radiance),
             _lib.ptr(opacity), _lib.ptr(depth), _lib.ptr(radiance_dot), _lib.ptr(opacity_dot),
-            _lib.ptr(n_kept), _lib.ptr(stash), stash_n, _lib.ptr(ws), ws.numel(), _lib.stream_ptr()),
-            "ren_render_tangent_forward")
+            _lib.ptr(n_kept), None if packed is None else C.byref(packed), _lib.ptr(stash), stash_n, _lib.ptr(ws),
+            ws.numel(), _lib.stream_ptr()), "ren_render_tangent_forward")
         if need_grad:
             ctx.owner = owner
             ctx.descs = (fdesc, rdesc, K)
+            ctx.packed, ctx.packed_keep = packed, keep
             empty = torch.empty(0, device=dev)
             ctx.save_for_backward(o, d, o_dot, d_dot, jitter if jitter is not None else empty,
                                   bkgd if bkgd is not None else empty, stash, flat)
@@ -278,7 +287,9 @@ class RenderTangentFunction(torch.autograd.Function):
         bkgd = bkgd if ctx.has_bkgd else None
         g_flat = torch.zeros_like(flat)
         g_bkgd = torch.zeros_like(bkgd) if bkgd is not None else None
-        ws = torch.empty((_lib.tangent_workspace_bytes(fdesc, rdesc, B, K, True, True),), device=dev,
+        packed = ctx.packed
+        nS, nK = (max(int(packed.n_samples), 1), 1) if packed is not None else (B, K)
+        ws = torch.empty((_lib.tangent_workspace_bytes(fdesc, rdesc, nS, nK, True, True),), device=dev,
                          dtype=torch.uint8)
         cg = lambda t: None if t is None else t.contiguous().float()
         g_rad, g_op, g_depth, g_rad_dot, g_op_dot = (cg(t) for t in (g_rad, g_op, g_depth, g_rad_dot, g_op_dot))
@@ -286,9 +297,10 @@ class RenderTangentFunction(torch.autograd.Function):
         _lib.check(lib.ren_render_tangent_backward(
             C.byref(fdesc), C.byref(rdesc), B, K, _lib.ptr(o), _lib.ptr(d), _lib.ptr(o_dot),
             _lib.ptr(d_dot), _lib.ptr(jitter), _lib.ptr(flat), _lib.ptr(bkgd), _lib.ptr(g_rad),
-            _lib.ptr(g_op), _lib.ptr(g_depth), _lib.ptr(g_rad_dot), _lib.ptr(g_op_dot), _lib.ptr(stash),
-            stash.numel(), _lib.ptr(g_flat), _lib.ptr(g_bkgd), _lib.ptr(g_rays), _lib.ptr(ws),
-            ws.numel(), _lib.stream_ptr()), "ren_render_tangent_backward")
+            _lib.ptr(g_op), _lib.ptr(g_depth), _lib.ptr(g_rad_dot), _lib.ptr(g_op_dot),
+            None if packed is None else C.byref(packed), _lib.ptr(stash), stash.numel(), _lib.ptr(g_flat),
+            _lib.ptr(g_bkgd), _lib.ptr(g_rays), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()),
+            "ren_render_tangent_backward")
         grads = owner._split_flat(g_flat)
         gr = [g_rays[:, 3 * i:3 * i + 3] if ctx.ray_grad else None for i in range(4)]
         return (None, None, gr[0], gr[1], gr[2], gr[3], None, g_bkgd) + tuple(grads)
@@ -495,6 +507,16 @@ class NeRF(torch.nn.Module):
             self._desc_cache[key] = hit
         _lib.set_occupancy(hit[1], None if self.occupancy_grid is None else self.occupancy_grid.binary_u8())
         return hit
+
+    packed_march = True      # occupancy grid + tcgen05 engine: run the field on the emitted samples only
+
+    def _march_pack(self, fdesc, rdesc, n_rays, K, o, d, jitter):
+        """(RenPacked, keep-alive tensors) when the render goes through the packed march, else (None, None)."""
+        if self.occupancy_grid is None or not self.packed_march or n_rays == 0:
+            return None, None
+        if _lib.resolved_engine(fdesc, rdesc) == _lib.REN_ENGINE["simt_fp32"]:
+            return None, None
+        return _lib.march_pack(fdesc, rdesc, n_rays, K, o, d, jitter)
 
     def query_density(self, x):
         """`VanillaNeRFRadianceField.query_density` (external/mlp.py:344-348) at free points (n,3) -> (n,)."""

@@ -29,7 +29,7 @@ def test_header_symbols_exported(built_lib):
 def test_binding_covers_header(built_lib):
     from ren_b200 import _lib
     assert _lib.exported_symbols() == _declared_symbols()
-    assert _lib.load().ren_version() == 3
+    assert _lib.load().ren_version() == 4
 
 
 @pytest.mark.parametrize("kw", [
@@ -99,7 +99,7 @@ def test_invalid_arguments_fail_loudly(built_lib):
     # null pointers are rejected before any launch
     r = _lib.make_render_desc(near_plane=0.5, far_plane=4.5, render_step_size=4 / 128)
     rc = lib.ren_render_forward(C.byref(f), C.byref(r), 8, 128, None, None, None, None, None, None, None,
-                                None, None, None, 0, None, 0, None)
+                                None, None, None, None, 0, None, 0, None)
     assert rc == 1
 
 
@@ -115,7 +115,8 @@ def test_sizes(built_lib):
     assert _lib.workspace_bytes(f, r, 1024, 128, False, False) >= 4 * S * 2
     # tcgen05 engine (auto for the 8x256 network): fp16 stash, fp32 raw
     r = _lib.make_render_desc(near_plane=0.5, far_plane=4.5, render_step_size=4 / 128, engine="auto")
-    assert _lib.stash_bytes(f, r, 1024, 128) == S * (2 * (acts + 64 + 32) + 4 * 2)
+    # ... plus one live-tile byte per 128 samples (occupancy-grid marching), padded to 256
+    assert _lib.stash_bytes(f, r, 1024, 128) == S * (2 * (acts + 64 + 32) + 4 * 2) + S // 128
     assert _lib.workspace_bytes(f, r, 1024, 128, True, True) >= S * (2 * acts + 4 * 2)
     # a shape the tcgen05 engine does not cover falls back to fp32 under auto and is refused when forced
     f64 = _lib.make_field_desc(net_depth=4, net_width=64)

@@ -147,10 +147,12 @@ def test_training_with_occupancy_grid(built_lib, dataset_dir):
         assert k in sd, k
 
 
-def test_dead_tile_skipping_matches_masked_march(built_lib, dataset_dir):
-    """A sparse grid over long rays (512 marching steps): the tcgen05 engine skips every 128-step tile that emits
-    no sample (forward, both dgrad passes, weight gradients, ray gradients); results must equal the fp32 engine,
-    which evaluates and masks every step -- value render, tangent render and all gradients."""
+@pytest.mark.parametrize("packed", [True, False])
+def test_sparse_grid_matches_masked_march(packed, built_lib, dataset_dir):
+    """A sparse grid over long rays (512 marching steps).  The tcgen05 engine either packs the emitted samples
+    (ren_march_count / ren_march_fill, the nerfacc layout) or, on the dense layout, skips every 128-step tile that
+    emits no sample; both must equal the fp32 engine, which evaluates and masks every step -- value render,
+    tangent render, MLP and ray gradients."""
     import time
     grid = torch.zeros(16, 16, 16, dtype=torch.bool)
     gen = torch.Generator().manual_seed(8)
@@ -164,6 +166,7 @@ def test_dead_tile_skipping_matches_masked_march(built_lib, dataset_dir):
         m.nerf.render_step_size.fill_(4.0 / 512)
         m.nerf.far_plane = 0.5 + 512.5 * (4.0 / 512)
         m.nerf._desc_cache.clear()
+        m.nerf.packed_march = packed
         m.nerf.occupancy_grid._binary = grid.cuda()
         oc, dc = o.cuda().requires_grad_(True), d.cuda().requires_grad_(True)
         odc, ddc = od.cuda().requires_grad_(True), dd.cuda().requires_grad_(True)
@@ -180,6 +183,6 @@ def test_dead_tile_skipping_matches_masked_march(built_lib, dataset_dir):
                             ("mlp grads", a[3], b[3], 5e-3), ("d loss/d o", a[4], b[4], 1e-2),
                             ("d loss/d d_dot", a[5], b[5], 1e-2)):
         nw = H.rel_err(x, y, floor=1e-9)[0]
-        print(f"[dead tiles] {name}: tcgen05 vs fp32 normwise={nw:.2e}")
+        print(f"[sparse grid packed={packed}] {name}: tcgen05 vs fp32 normwise={nw:.2e}")
         assert nw < bar, name
-    print(f"[dead tiles] kept {int(a[2].sum())} of {192 * 512} steps; tcgen05 {a[6] * 1e3:.1f} ms, fp32 {b[6] * 1e3:.1f} ms")
+    print(f"[sparse grid packed={packed}] kept {int(a[2].sum())} of {192 * 512} steps; tcgen05 {a[6] * 1e3:.1f} ms, fp32 {b[6] * 1e3:.1f} ms")
