@@ -186,3 +186,20 @@ def test_sparse_grid_matches_masked_march(packed, built_lib, dataset_dir):
         print(f"[sparse grid packed={packed}] {name}: tcgen05 vs fp32 normwise={nw:.2e}")
         assert nw < bar, name
     print(f"[sparse grid packed={packed}] kept {int(a[2].sum())} of {192 * 512} steps; tcgen05 {a[6] * 1e3:.1f} ms, fp32 {b[6] * 1e3:.1f} ms")
+
+
+@pytest.mark.parametrize("packed", [True, False])
+def test_empty_grid_renders_background(packed, built_lib, dataset_dir):
+    """No occupied cell at all (the state of a fresh nerfacc grid before its first update): zero samples, the
+    render is the background, gradients reach the background only."""
+    m, g = _model(dataset_dir, "auto", "sphere", res=8)
+    m.nerf.packed_march = packed
+    m.nerf.occupancy_grid._binary = torch.zeros(8, 8, 8, dtype=torch.bool).cuda()
+    o, d, u = _rays(33, 5)
+    rad, opac, depth, spp = m.nerf(o.cuda(), d.cuda(), u.cuda())
+    bk = float(m.nerf.background())
+    assert float(spp) == 0.0 and float(opac.abs().max()) == 0.0
+    assert torch.allclose(rad, torch.full_like(rad, bk))
+    rad.sum().backward()
+    assert float(m.nerf.parametrizations.render_bkgd.original.grad.abs().sum()) > 0
+    assert all(float(p.grad.abs().sum()) == 0.0 for p in m.nerf.mlp_parameters())
