@@ -89,8 +89,8 @@ typedef struct RenRenderDesc {
   /* nerfacc.OccupancyGrid binary grid (models/nerf.py:98-102, external/utils.py:106-119): device pointer to
    * occ_res[0]*occ_res[1]*occ_res[2] bytes (0 / 1), index (ix*res_y + iy)*res_z + iz over the contracted unit
    * cube of the field's aabb / contraction; NULL = every cell occupied.  Marching steps whose midpoint falls
-   * in an unoccupied cell emit no sample.  Supported for the sphere / tanh contractions (nerfacc advances by
-   * voxel traversal instead of fixed steps for `aabb`, which needs the packed-sample marcher). */
+   * in an unoccupied cell emit no sample.  All three contractions: for `aabb` nerfacc leaves an empty voxel in
+   * whole marching steps, so its samples are the same lattice steps this per-step test keeps. */
   const uint8_t* occ_binary;
   int32_t occ_res[3];
   int32_t reserved;

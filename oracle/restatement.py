@@ -329,9 +329,9 @@ def render(params, cfg: FieldConfig, rcfg: RenderConfig, o, d, jitter, bkgd=None
     t0, t1, alive = march(cfg, rcfg, o.detach(), d.detach(), jitter)
     K = t0.shape[1]
     if grid_binary is not None and K > 0:
-        # marching steps whose midpoint lies in an unoccupied cell emit no sample (non-aabb grid types advance by
-        # fixed steps, so the surviving samples stay on the same lattice)
-        assert cfg.contraction != "aabb"
+        # marching steps whose midpoint lies in an unoccupied cell emit no sample.  sphere / tanh grids advance by
+        # fixed steps; for aabb nerfacc's advance_to_next_voxel moves the midpoint by whole steps until it has left
+        # the empty voxel -- either way the surviving samples stay on the same lattice.
         alive = alive & grid_occupied(cfg, grid_binary, sample_positions(o.detach(), d.detach(), t0, t1))
     if K == 0:
         keep = alive

@@ -238,11 +238,14 @@ static int validate_render(const RenRenderDesc* r) {
 }
 // nerfacc skips unoccupied space by voxel traversal for the `aabb` grid type: sample positions leave the
 // fixed-step lattice the dense layout assumes
+// Occupancy grid: every contraction is marched on the fixed-step lattice with a per-step cell test.  For `aabb`
+// nerfacc skips empty voxels by stepping the midpoint in whole dt units until it leaves the voxel
+// (advance_to_next_voxel), so its surviving samples are exactly the lattice steps whose midpoint cell is occupied.
 static int check_occupancy(const RenFieldDesc* f, const RenRenderDesc* r) {
-  if (r->occ_binary != nullptr && f->contraction == REN_CONTRACT_AABB) {
-    ren_set_error("occupancy-grid skipping with contraction_type aabb needs the packed-sample marcher; "
-                  "sphere / tanh contractions are supported");
-    return REN_E_UNSUPPORTED;
+  (void)f;
+  if (r->occ_binary != nullptr && (r->occ_res[0] < 1 || r->occ_res[1] < 1 || r->occ_res[2] < 1)) {
+    ren_set_error("occupancy grid: bad resolution (%d, %d, %d)", r->occ_res[0], r->occ_res[1], r->occ_res[2]);
+    return REN_E_INVALID;
   }
   return REN_OK;
 }

@@ -348,9 +348,8 @@ class NeRF(torch.nn.Module):
             else (lambda k, dflt: getattr(occ_grid_config, k, dflt))
         self.occ_grid_enabled = bool(cfg_get("enabled", True)) and occ_grid_config is not None
         self.occupancy_grid = None
-        if self.occ_grid_enabled and self.contraction != "aabb":
+        if self.occ_grid_enabled:
             self.occupancy_grid = OccupancyGrid(aabb, cfg_get("resolution", 128), self.contraction)
-        self._warned_aabb_grid = False
         self.near_plane = near_plane
         self.far_plane = far_plane
         self.register_buffer("render_step_size", torch.tensor(render_step_size, dtype=torch.float32),
@@ -536,15 +535,11 @@ class NeRF(torch.nn.Module):
 
     @torch.no_grad()
     def update_occ_grid(self, step, T_wc_position, generator=None):
-        """models/nerf.py:170-204.  sphere / tanh contractions: the nerfacc occupancy-grid update, with the density
-        sweep over the sampled cells on the field kernels.  `aabb` contraction (nerfacc skips empty voxels by DDA
-        traversal there, SURVEY.md section 8f #1) and `occ_grid.enabled: false` keep every cell occupied."""
+        """models/nerf.py:170-204: the nerfacc occupancy-grid update, with the density sweep over the sampled cells
+        on the field kernels.  `occ_grid.enabled: false` keeps every cell occupied.  (For `aabb` nerfacc skips empty
+        voxels by whole marching steps, so the kept samples are the lattice steps in occupied cells -- the same
+        per-step test the sphere / tanh grids use.)"""
         if self.occupancy_grid is None:
-            if self.occ_grid_enabled and not self._warned_aabb_grid:
-                import warnings
-                warnings.warn("ren_b200: occupancy-grid skipping is not implemented for contraction_type 'aabb'; "
-                              "every marching step is evaluated (a superset of the reference's samples)")
-                self._warned_aabb_grid = True
             return None
         cfg = self.occ_grid_config
         get = (lambda k: cfg[k]) if isinstance(cfg, dict) else (lambda k: getattr(cfg, k))
