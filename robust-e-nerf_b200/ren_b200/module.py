@@ -543,12 +543,15 @@ class RobustENeRF(LightningModule):
                 "lr_scheduler": {"scheduler": scheduler, "interval": _get(sch_cfg, "interval")}}
 
     # -------------------------------------------------------------- evaluation render
-    def set_eval_stage(self, name, intrinsics, img_height, img_width):
-        """Registers `{name}_intrinsics_inv` / `{name}_img_pixel_pos` exactly as the reference's
-        constructor does from its PosedImage datasets (robust_e_nerf.py:100-147); `name` is
+    def set_eval_stage(self, name, intrinsics, img_height, img_width, min_normalized_pixel_value=0.0,
+                       max_normalized_pixel_value=1.0):
+        """Registers `{name}_intrinsics_inv` / `{name}_img_pixel_pos` and the target value range exactly as
+        the reference's constructor does from its PosedImage datasets (robust_e_nerf.py:97-147); `name` is
         "val" or "test".  The datasets themselves (views/transforms_*.json, PNG targets) are
         SURVEY.md section 8f #3."""
         assert name in ("val", "test")
+        setattr(self, f"{name}_min_normalized_pixel_value", float(min_normalized_pixel_value))
+        setattr(self, f"{name}_max_normalized_pixel_value", float(max_normalized_pixel_value))
         dev = self.train_intrinsics_inv.device
         k = torch.as_tensor(intrinsics, dtype=torch.float32)
         self.register_buffer(f"{name}_intrinsics_inv", torch.linalg.inv(k).to(dev), persistent=False)
@@ -575,11 +578,66 @@ class RobustENeRF(LightningModule):
         if not hasattr(self, f"{name}_intrinsics_inv"):
             raise RuntimeError(f"call set_eval_stage({name!r}, intrinsics, height, width) first: the posed-image "
                                "datasets that provide them are SURVEY.md section 8f #3")
-        return {"intrinsics_inv": getattr(self, f"{name}_intrinsics_inv"),
-                "img_pixel_pos": getattr(self, f"{name}_img_pixel_pos")}
+        return {"name": name, "intrinsics_inv": getattr(self, f"{name}_intrinsics_inv"),
+                "img_pixel_pos": getattr(self, f"{name}_img_pixel_pos"),
+                "min_normalized_pixel_value": getattr(self, f"{name}_min_normalized_pixel_value"),
+                "max_normalized_pixel_value": getattr(self, f"{name}_max_normalized_pixel_value")}
+
+    @staticmethod
+    @torch.no_grad()
+    def align_log_intensity(pred_intensity_img, target_intensity_img):
+        """robust_e_nerf.py:636-683: the event-only reconstruction is affine-ambiguous in log intensity, so the
+        prediction is mapped through the per-channel least-squares `scale * log(pred) + offset ~ log(target)`
+        (over all images of the epoch, float64) before any metric.  Images are (N, C, H, W).  The reference
+        materialises the (N*H*W, 2) design matrix on the CPU for `torch.linalg.lstsq`; here the same minimiser
+        comes from the five centred sums, on whatever device the images live on (a rank-deficient system -- a
+        constant prediction -- gets lstsq's minimum-norm solution).  Returns (aligned intensity, scale (C,),
+        offset (C,))."""
+        assert pred_intensity_img.shape == target_intensity_img.shape and pred_intensity_img.dim() == 4
+        p = pred_intensity_img.log().to(torch.float64)
+        t = target_intensity_img.log().to(torch.float64)
+        dims = (0, 2, 3)
+        pm, tm = p.mean(dims, keepdim=True), t.mean(dims, keepdim=True)
+        spp = ((p - pm) ** 2).sum(dims, keepdim=True)
+        spt = ((p - pm) * (t - tm)).sum(dims, keepdim=True)
+        degenerate = spp <= 0
+        scale = torch.where(degenerate, pm * tm / (pm * pm + 1), spt / spp.clamp(min=1e-300))
+        offset = torch.where(degenerate, tm / (pm * pm + 1), tm - scale * pm)
+        aligned = (scale * p + offset).to(target_intensity_img.dtype).exp()
+        return aligned, scale.reshape(-1), offset.reshape(-1)
+
+    @torch.no_grad()
+    def evaluation_epoch_end(self, outputs, stage):
+        """robust_e_nerf.py:589-696 up to the metrics this image can compute: merge the per-view outputs of
+        `evaluation_step`, align the predicted log intensities to the targets, then mean L1 and PSNR
+        (`loss_metric/metric.py:60-73`: PSNR per image with data_range = max - min of the target range).  SSIM and
+        LPIPS (torchmetrics / pretrained AlexNet, absent here) and the PNG dumps stay out.  Returns the metrics
+        and the aligned images."""
+        pred = torch.stack([o["pred_intensity_img"] for o in outputs])
+        target = torch.stack([o["target_intensity_img"] for o in outputs]).to(pred.device)
+        if not self.has_bayer_filter:                                   # (N, H, W) -> (N, 1, H, W)
+            pred, target = pred.unsqueeze(1), target.unsqueeze(1)
+        aligned, scale, offset = self.align_log_intensity(pred, target)
+        rng = stage["max_normalized_pixel_value"] - stage["min_normalized_pixel_value"]
+        l1 = torch.stack([(a - b).abs().mean() for a, b in zip(aligned, target)]).mean()
+        mse = ((aligned - target) ** 2).mean(dim=(1, 2, 3))
+        psnr = (10.0 * torch.log10(rng ** 2 / mse)).mean()
+        name = stage.get("name", "eval")
+        self.log(f"{name}/l1", l1, prog_bar=True, rank_zero_only=True)
+        self.log(f"{name}/psnr", psnr, prog_bar=True, rank_zero_only=True)
+        return {"l1": l1, "psnr": psnr, "log_intensity_scale": scale, "log_intensity_offset": offset,
+                "pred_intensity_img": aligned}
+
+    def validation_epoch_end(self, outputs):
+        """robust_e_nerf.py:573-579."""
+        return self.evaluation_epoch_end(outputs, self._eval_stage("val"))
+
+    def test_epoch_end(self, outputs):
+        """robust_e_nerf.py:581-587."""
+        return self.evaluation_epoch_end(outputs, self._eval_stage("test"))
 
     def validation_step(self, batch, batch_index):
-        """robust_e_nerf.py:519-524.  Image metrics / PNG dumps (`*_epoch_end`) stay out of scope."""
+        """robust_e_nerf.py:519-524."""
         return self.evaluation_step(batch, batch_index, self._eval_stage("val"))
 
     def test_step(self, batch, batch_index):

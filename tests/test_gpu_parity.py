@@ -497,6 +497,11 @@ def test_full_frame_evaluation_render(built_lib, dataset_dir):
     m.nerf.test_chunk_size = 50000
     again = m.test_step(batch, 0)["pred_intensity_img"]
     assert torch.equal(full, again)
+    # epoch end: a target that is an affine map of the prediction in log space is recovered exactly
+    target = torch.exp(0.8 * full.log() - 0.2).clamp(1e-6, 1.0)
+    outs = [{"pred_intensity_img": full, "target_intensity_img": target, "sample_id": None}] * 2
+    res = m.test_epoch_end(outs)
+    assert abs(float(res["log_intensity_scale"][0]) - 0.8) < 1e-3 and float(res["psnr"]) > 60 and float(res["l1"]) < 1e-4
 
 
 def test_adam_matches_torch(built_lib):

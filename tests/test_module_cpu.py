@@ -138,3 +138,34 @@ def test_device_sampler_distributions():
     s.batch_size = 17                                          # dynamic batch size
     assert next(s)["event"]["end_ts"].shape == (1, 17)
     assert float(trunc_normal(0, 1, (10,), 0.5, 0.25, dtype=torch.float64).max()) <= 1
+
+
+def test_affine_log_intensity_alignment():
+    """`align_log_intensity` vs the reference's formulation (robust_e_nerf.py:641-674): lstsq over the
+    (N*H*W, 2) design matrix [log pred | 1] per channel, float64."""
+    import numpy as np
+    from ren_b200 import RobustENeRF
+    gen = torch.Generator().manual_seed(0)
+    target = torch.rand(3, 2, 12, 16, generator=gen) * 0.9 + 0.05
+    # an affine distortion in log space + noise, different per channel
+    a = torch.tensor([0.7, 1.6]).view(1, 2, 1, 1)
+    b = torch.tensor([-0.4, 0.9]).view(1, 2, 1, 1)
+    pred = torch.exp((target.log() - b) / a + 0.01 * torch.randn(target.shape, generator=gen))
+    aligned, scale, offset = RobustENeRF.align_log_intensity(pred, target)
+    for c in range(2):
+        A = np.stack([pred[:, c].log().double().numpy().ravel(), np.ones(3 * 12 * 16)], axis=1)
+        x, *_ = np.linalg.lstsq(A, target[:, c].log().double().numpy().ravel(), rcond=None)
+        assert abs(float(scale[c]) - x[0]) < 1e-10 and abs(float(offset[c]) - x[1]) < 1e-10
+        want = np.exp((A @ x).astype(np.float32)).reshape(3, 12, 16)
+        assert np.allclose(aligned[:, c].numpy(), want, rtol=1e-6, atol=0)
+    assert torch.allclose(scale, a.reshape(-1).double(), atol=0.05)
+    # exact affine relation -> exact recovery
+    pred = torch.exp(2.0 * target.log() + 0.3)
+    aligned, scale, offset = RobustENeRF.align_log_intensity(pred, target)
+    assert torch.allclose(aligned, target, rtol=1e-5) and torch.allclose(scale, torch.full((2,), 0.5).double())
+    # a constant prediction: lstsq's minimum-norm solution of the rank-1 system
+    pred = torch.full_like(target, 0.5)
+    _, scale, offset = RobustENeRF.align_log_intensity(pred, target)
+    A = np.stack([np.full(3 * 12 * 16, float(torch.tensor(0.5).log())), np.ones(3 * 12 * 16)], axis=1)
+    x, *_ = np.linalg.lstsq(A, target[:, 0].log().double().numpy().ravel(), rcond=None)
+    assert abs(float(scale[0]) - x[0]) < 1e-9 and abs(float(offset[0]) - x[1]) < 1e-9
