@@ -194,6 +194,7 @@ class DiffLossFunction(torch.autograd.Function):
         return loss, log_i0, log_i1, n_valid
 
     @staticmethod
+    @torch.autograd.function.once_differentiable
     def backward(ctx, g_loss, _a, _b, _c):
         g_c0, g_c1, c1, ts_diff, start, end_ts = ctx.saved_tensors
         g_ev = None
@@ -218,6 +219,7 @@ class RayChainFunction(torch.autograd.Function):
         return o.clone(), d.clone(), o_dot.clone(), d_dot.clone()
 
     @staticmethod
+    @torch.autograd.function.once_differentiable
     def backward(ctx, g_o, g_d, g_odot, g_ddot):
         o_dot, d_dot, d_ddot, dw_dt = ctx.saved_tensors
         g_w = torch.zeros_like(dw_dt)

@@ -522,3 +522,16 @@ def test_adam_matches_torch(built_lib):
                                              0.01, 0.9, 0.999, 1e-8, 1e-6, 1.0, step, _lib.stream_ptr()),
                    "ren_adam_step")
     assert H.rel_err(p, ref)[1] < 1e-6
+
+
+def test_render_function_refuses_double_backward(built_lib, dataset_dir):
+    """The reference takes d logI / d t with autograd.grad(create_graph=True) (utils/autograd.py:4-34); the fused
+    render is once differentiable and must say so instead of returning a silent zero second derivative."""
+    g = H.load_golden("step_8x256")
+    m = H.build_product(g, dataset_dir, "cuda")
+    o = torch.tensor([[3.0, 0.0, 0.2]], device="cuda").repeat(8, 1).requires_grad_(True)
+    d = torch.nn.functional.normalize(-o.detach() + 0.1 * torch.randn(8, 3, device="cuda"), dim=-1)
+    rad, _, _, _ = m.nerf.render_raw(o, d, torch.rand(8, device="cuda"))
+    (go,) = torch.autograd.grad(rad.sum(), o, create_graph=True)
+    with pytest.raises(RuntimeError, match="once_differentiable|differentiate twice"):
+        go.sum().backward()
