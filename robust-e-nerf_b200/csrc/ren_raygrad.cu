@@ -11,6 +11,8 @@
 // reduces it to d loss / d (o, d); tangent mode (rows = (value, d/dw) pairs) also needs the second
 // derivative of the contraction, taken with hyper-dual numbers, and returns
 // d loss / d (o, d, o_dot, d_dot).
+#include <stdlib.h>
+
 #include "ren_tc.cuh"
 #include "ren_dual.cuh"
 
@@ -235,6 +237,13 @@ extern "C" __global__ void __launch_bounds__(RG_THREADS) ren_raygrad_kernel(cons
   }
 }
 
+int ren_tc_raygrad_supported(const RenPlan& p);      // ren_tc_raygrad.cu: tcgen05 version over the fp16 deltas
+int ren_tc_launch_raygrad(const RenPlan& p, long long n_rays, int K, const float* o, const float* d,
+                          const float* o_dot, const float* d_dot, const float* jitter, const float* params,
+                          const void* delta, const void* delta_dot, const unsigned int* gmax,
+                          const unsigned char* tile_live, const int* sample_idx, long long n_samples, float* g_rays,
+                          cudaStream_t st);
+
 // fp32 engine: delta = fp32 blocked delta workspace (mats mirror of the stash) followed by graw [rows][1+C];
 // tcgen05 engine (fp16 != 0): delta / delta_dot = fp16 blocked delta matrices of the value / d/dw rows
 int ren_launch_raygrad(const RenPlan& p, long long n_rays, int K, const float* o, const float* d,
@@ -243,6 +252,9 @@ int ren_launch_raygrad(const RenPlan& p, long long n_rays, int K, const float* o
                        const unsigned char* tile_live, const int* sample_idx, long long n_samples, float* g_rays,
                        cudaStream_t st) {
   if (n_rays <= 0) return REN_OK;
+  if (fp16 && ren_tc_raygrad_supported(p) && getenv("REN_RAYGRAD_SIMT") == nullptr)
+    return ren_tc_launch_raygrad(p, n_rays, K, o, d, o_dot, d_dot, jitter, params, delta, delta_dot, gmax, tile_live,
+                                 sample_idx, n_samples, g_rays, st);
   RgArgs a;
   a.tile_live = tile_live; a.sample_idx = sample_idx; a.n_samples = n_samples;
   a.p = p; a.n_rays = n_rays; a.K = K; a.tangent = o_dot != nullptr ? 1 : 0; a.fp16 = fp16; a.gmax = gmax;

@@ -14,6 +14,8 @@
 // The sigma / radiance head gradients (N = 1..3) are a bandwidth-bound SIMT pass.
 #include <string.h>
 
+#include <mutex>
+
 #include "ren_tc.cuh"
 
 #define WG_THREADS 192
@@ -202,8 +204,12 @@ struct HeadArgs {
 };
 
 extern "C" __global__ void __launch_bounds__(256) ren_tc_head_wgrad(const HeadArgs a) {
-  const int which = blockIdx.y;
-  const int N = a.N[which], groups = N >> 3, nch = a.n_ch[which];
+  // selected with ?: -- a runtime index into the parameter arrays would move them to local memory
+  const bool w1 = blockIdx.y != 0;
+  const int N = w1 ? a.N[1] : a.N[0], groups = N >> 3, nch = w1 ? a.n_ch[1] : a.n_ch[0];
+  const unsigned char* hmat = w1 ? a.h[1] : a.h[0];
+  const int g_col = w1 ? a.g_col[1] : a.g_col[0];
+  const int w_off = w1 ? a.w_off[1] : a.w_off[0], b_off = w1 ? a.b_off[1] : a.b_off[0];
   const int lane = threadIdx.x & 31;
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -218,7 +224,7 @@ extern "C" __global__ void __launch_bounds__(256) ren_tc_head_wgrad(const HeadAr
     for (int j = 0; j < 8; ++j) acc[c][j] = 0.f;
   for (long long t = warp / groups; t < a.n_tiles; t += tstride) {
     if (a.tile_live != nullptr && !__ldg(a.tile_live + t)) continue;
-    const uint4* blk = reinterpret_cast<const uint4*>(a.h[which]) + ((size_t)t * groups + fg) * 128;
+    const uint4* blk = reinterpret_cast<const uint4*>(hmat) + ((size_t)t * groups + fg) * 128;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int sl = lane * 4 + i;
@@ -226,30 +232,53 @@ extern "C" __global__ void __launch_bounds__(256) ren_tc_head_wgrad(const HeadAr
       if (s >= a.S) continue;
       float f[8];
       unpack8(__ldg(blk + sl), f);
-      for (int c = 0; c < nch; ++c) {
-        const float g = __ldg(a.graw + s * a.C1 + a.g_col[which] + c);
-        bsum[c] += g;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[c][j] = fmaf(g, f[j], acc[c][j]);
+      for (int c = 0; c < 3; ++c) {                     // static indices keep acc[][] in registers
+        if (c < nch) {
+          const float g = __ldg(a.graw + s * a.C1 + g_col + c);
+          bsum[c] += g;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[c][j] = fmaf(g, f[j], acc[c][j]);
+        }
       }
     }
   }
-  for (int c = 0; c < nch; ++c) {
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    if (c >= nch) continue;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       float v = acc[c][j];
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if (lane == 0) atomicAdd(a.g_params + a.w_off[which] + c * N + fg * 8 + j, v * a.h_scale);
+      if (lane == 0) atomicAdd(a.g_params + w_off + c * N + fg * 8 + j, v * a.h_scale);
     }
     float b = bsum[c];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) b += __shfl_xor_sync(0xffffffffu, b, o);
-    if (lane == 0 && fg == 0 && a.b_off[which] >= 0) atomicAdd(a.g_params + a.b_off[which] + c, b);
+    if (lane == 0 && fg == 0 && b_off >= 0) atomicAdd(a.g_params + b_off + c, b);
   }
 }
 
 // ------------------------------------------------------------------ host side
+// The head gradients (two skinny reductions over the stash, no shared memory) run on a side stream next to the
+// HBM-bound main kernel: fork / join with events on the caller's stream, one side stream per device.
+struct WgSide { cudaStream_t s; cudaEvent_t fork, join; bool ok; };
+static WgSide* wg_side(int dev) {
+  static WgSide side[64];
+  static std::mutex mu;
+  if (dev < 0 || dev >= 64) return nullptr;
+  std::lock_guard<std::mutex> lk(mu);
+  WgSide& w = side[dev];
+  if (!w.ok) {
+    if (cudaStreamCreateWithFlags(&w.s, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&w.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&w.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    w.ok = true;
+  }
+  return &w;
+}
+
 // with_bias = 0: the tangent rows of the tangent render (d/dw activations carry no bias)
 int ren_tc_launch_wgrad(const RenPlan& p, long long S, const void* stash, const void* delta,
                         const float* graw, const unsigned int* gmax, float* g_params, int with_bias,
@@ -302,12 +331,6 @@ int ren_tc_launch_wgrad(const RenPlan& p, long long S, const void* stash, const 
   const int grid = n_jobs < sms ? n_jobs : sms;
   cudaError_t e = cudaFuncSetAttribute(ren_tc_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, SMW_TOTAL);
   if (e != cudaSuccess) { ren_set_error("tc wgrad smem attr: %s", cudaGetErrorString(e)); return REN_E_CUDA; }
-  ren_prof_begin(REN_K_WGRAD, st);
-  ren_tc_wgrad<<<grid, WG_THREADS, SMW_TOTAL, st>>>(a);
-  ren_prof_end(REN_K_WGRAD, st);
-  e = cudaGetLastError();
-  if (e != cudaSuccess) { ren_set_error("tc wgrad launch: %s", cudaGetErrorString(e)); return REN_E_CUDA; }
-
   HeadArgs h;
   memset(&h, 0, sizeof(h));
   h.h[0] = (const unsigned char*)stash + tcs_mat(p, S, last_trunk); h.N[0] = p.W;
@@ -316,10 +339,22 @@ int ren_tc_launch_wgrad(const RenPlan& p, long long S, const void* stash, const 
   h.w_off[1] = p.rgb_w; h.b_off[1] = with_bias ? p.rgb_b : -1; h.n_ch[1] = p.C; h.g_col[1] = 1;
   h.graw = graw; h.C1 = 1 + p.C; h.S = S; h.n_tiles = a.n_tiles; h.g_params = g_params; h.h_scale = kap;
   h.tile_live = tile_live;
-  ren_prof_begin(REN_K_WGRAD, st);
-  ren_tc_head_wgrad<<<dim3(sms * 2, 2), 256, 0, st>>>(h);
-  ren_prof_end(REN_K_WGRAD, st);
+  WgSide* side = wg_side(dev);
+  if (side == nullptr) { ren_set_error("tc wgrad: side stream: %s", cudaGetErrorString(cudaGetLastError())); return REN_E_CUDA; }
+  cudaEventRecord(side->fork, st);
+  cudaStreamWaitEvent(side->s, side->fork, 0);
+  ren_prof_begin(REN_K_WGRAD, side->s);
+  ren_tc_head_wgrad<<<dim3(sms * 2, 2), 256, 0, side->s>>>(h);
+  ren_prof_end(REN_K_WGRAD, side->s);
   e = cudaGetLastError();
   if (e != cudaSuccess) { ren_set_error("tc head wgrad launch: %s", cudaGetErrorString(e)); return REN_E_CUDA; }
+  cudaEventRecord(side->join, side->s);
+  ren_prof_begin(REN_K_WGRAD, st);
+  ren_tc_wgrad<<<grid, WG_THREADS, SMW_TOTAL, st>>>(a);
+  ren_prof_end(REN_K_WGRAD, st);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) { ren_set_error("tc wgrad launch: %s", cudaGetErrorString(e)); return REN_E_CUDA; }
+
+  cudaStreamWaitEvent(st, side->join, 0);
   return REN_OK;
 }

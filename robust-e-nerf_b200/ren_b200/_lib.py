@@ -272,3 +272,16 @@ def march_pack(fdesc, rdesc, n_rays, K, o, d, jitter):
     pk = RenPacked()
     pk.n_samples, pk.sample_idx, pk.ray_offsets = n, idx.data_ptr(), offsets.data_ptr()
     return pk, (idx, offsets)
+
+
+def refuse_double_backward():
+    """First statement of every autograd.Function.backward here: grad mode is on inside a backward only under
+    `create_graph=True`, i.e. when the caller wants to differentiate the fused kernels a second time (the
+    reference does so for d log I / d t, utils/autograd.py:4-34).  They are once differentiable -- say so instead
+    of handing back gradients that silently carry no graph; `NeRF.render_tangent_raw` is the supported route."""
+    import torch
+    if torch.is_grad_enabled():
+        raise RuntimeError("ren_b200: the fused render is once differentiable (create_graph=True is not supported); "
+                           "use NeRF.render_tangent_raw / RobustENeRF.training_step for the log-intensity-gradient "
+                           "loss")
+

@@ -194,8 +194,8 @@ class DiffLossFunction(torch.autograd.Function):
         return loss, log_i0, log_i1, n_valid
 
     @staticmethod
-    @torch.autograd.function.once_differentiable
     def backward(ctx, g_loss, _a, _b, _c):
+        _lib.refuse_double_backward()
         g_c0, g_c1, c1, ts_diff, start, end_ts = ctx.saved_tensors
         g_ev = None
         if ctx.needs_input_grad[4]:
@@ -219,8 +219,8 @@ class RayChainFunction(torch.autograd.Function):
         return o.clone(), d.clone(), o_dot.clone(), d_dot.clone()
 
     @staticmethod
-    @torch.autograd.function.once_differentiable
     def backward(ctx, g_o, g_d, g_odot, g_ddot):
+        _lib.refuse_double_backward()
         o_dot, d_dot, d_ddot, dw_dt = ctx.saved_tensors
         g_w = torch.zeros_like(dw_dt)
         if g_o is not None:
@@ -483,9 +483,10 @@ class RobustENeRF(LightningModule):
             self.log("train/refractory_period", self.refractory_period.refractory_period)
         self.log("train/batch_size", B)
         self.log("train/mean_num_samples_per_ray", mean_spp)
-        self.log("train/mean_ray_occ_rate", sum((op > 0).float().mean() for op in opac_all) / len(opac_all))
+        occ_rate = sum((op > 0).float().mean() for op in opac_all) / len(opac_all)
+        self.log("train/mean_ray_occ_rate", occ_rate)
         if self.render_bkgd is None:
-            self.log("train/mean_valid_rate", sum((op > 0).float().mean() for op in opac_all) / len(opac_all))
+            self.log("train/mean_valid_rate", occ_rate)
         else:
             self.log("train/mean_valid_rate", torch.ones((), device=dev))
         self.last = dict(start_log_intensity=log_i0, end_log_intensity=log_i1, n_valid=n_valid,

@@ -186,8 +186,8 @@ class RenderFunction(torch.autograd.Function):
         return radiance, opacity, depth, n_kept
 
     @staticmethod
-    @torch.autograd.function.once_differentiable
     def backward(ctx, g_rad, g_op, g_depth, _g_kept):
+        _lib.refuse_double_backward()
         lib = _lib.load()
         o, d, jitter, bkgd, stash, flat = ctx.saved_tensors
         fdesc, rdesc, K = ctx.descs
@@ -277,8 +277,8 @@ class RenderTangentFunction(torch.autograd.Function):
         return radiance, opacity, depth, radiance_dot, opacity_dot, n_kept
 
     @staticmethod
-    @torch.autograd.function.once_differentiable
     def backward(ctx, g_rad, g_op, g_depth, g_rad_dot, g_op_dot, _g_kept):
+        _lib.refuse_double_backward()
         lib = _lib.load()
         o, d, o_dot, d_dot, jitter, bkgd, stash, flat = ctx.saved_tensors
         fdesc, rdesc, K = ctx.descs

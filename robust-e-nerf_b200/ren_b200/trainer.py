@@ -33,9 +33,33 @@ class FlatTrainer:
             # the torch optimiser keeps the small (scalar) groups only
             self.mlp_group["params"] = []
 
+    def _flat_mlp_grad(self):
+        """The fused backward hands out the MLP gradients as views of ONE flat buffer in parameter order
+        (`NeRF._split_flat`); autograd keeps those views as `.grad`.  Returns that buffer as a (n,) view when
+        this is still the case (one copy instead of one per parameter), else None."""
+        g0 = self.mlp_params[0].grad
+        if g0 is None or g0.dtype != torch.float32:
+            return None
+        base, off = g0.untyped_storage().data_ptr(), g0.storage_offset()
+        for p in self.mlp_params:
+            g = p.grad
+            if (g is None or g.dtype != torch.float32 or not g.is_contiguous() or g.storage_offset() != off
+                    or g.untyped_storage().data_ptr() != base):
+                return None
+            off += g.numel()
+        n = off - g0.storage_offset()
+        return torch.empty(0, dtype=torch.float32, device=g0.device).set_(
+            g0.untyped_storage(), g0.storage_offset(), (n,), (1,))
+
     def _gather_grads(self):
         off = 0
-        for p in self.mlp_params + self.small_params:
+        params = self.mlp_params + self.small_params
+        flat = self._flat_mlp_grad()
+        if flat is not None:
+            self.gbuf[:flat.numel()].copy_(flat)
+            off = flat.numel()
+            params = self.small_params
+        for p in params:
             n = p.numel()
             if p.grad is None:
                 self.gbuf[off:off + n].zero_()

@@ -104,3 +104,8 @@ def test_raw_events_to_training_steps(built_lib, dataset_dir):
         losses.append(float(tr.step(batch, i)))
     assert all(np.isfinite(losses)), losses
     assert int(m.logged["train/batch_size"]) == 512
+    # the trainer reads the MLP gradients as the one flat buffer the fused backward wrote
+    flat = tr._flat_mlp_grad()
+    assert flat is not None
+    assert torch.equal(flat, torch.cat([p.grad.reshape(-1) for p in m.nerf.mlp_parameters()]))
+    assert torch.equal(tr.gbuf[:flat.numel()], flat)

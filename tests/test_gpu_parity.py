@@ -532,6 +532,8 @@ def test_render_function_refuses_double_backward(built_lib, dataset_dir):
     o = torch.tensor([[3.0, 0.0, 0.2]], device="cuda").repeat(8, 1).requires_grad_(True)
     d = torch.nn.functional.normalize(-o.detach() + 0.1 * torch.randn(8, 3, device="cuda"), dim=-1)
     rad, _, _, _ = m.nerf.render_raw(o, d, torch.rand(8, device="cuda"))
-    (go,) = torch.autograd.grad(rad.sum(), o, create_graph=True)
-    with pytest.raises(RuntimeError, match="once_differentiable|differentiate twice"):
-        go.sum().backward()
+    with pytest.raises(RuntimeError, match="once differentiable"):
+        torch.autograd.grad(rad.sum(), o, create_graph=True)
+    rad, _, _, _ = m.nerf.render_raw(o, d, torch.rand(8, device="cuda"))
+    (go,) = torch.autograd.grad(rad.sum(), o)                     # the ordinary first-order gradient still works
+    assert bool(torch.isfinite(go).all())
