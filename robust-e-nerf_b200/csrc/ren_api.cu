@@ -86,6 +86,7 @@ void ren_prof_begin(int kind, cudaStream_t st) {
   g_prof_open = e;
   (void)kind;
 }
+void ren_prof_count() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 void ren_prof_end(int kind, cudaStream_t st) {
   if (!g_timing.load(std::memory_order_relaxed) || g_prof_open == nullptr) return;
   cudaEvent_t e;

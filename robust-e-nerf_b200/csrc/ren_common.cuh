@@ -309,5 +309,6 @@ enum { REN_K_FIELD_FWD = 0, REN_K_FIELD_DGRAD, REN_K_WGRAD, REN_K_COMPOSITE_FWD,
        REN_K_EVENT, REN_K_LOSS, REN_K_ADAM, REN_K_PACK, REN_K_COUNT };
 void ren_prof_begin(int kind, cudaStream_t st);   // counts the launch; records an event when timing is on
 void ren_prof_end(int kind, cudaStream_t st);
+void ren_prof_count();                            // counts a launch that runs beside a timed one (no events)
 int ren_build_plan(const RenFieldDesc* f, const RenRenderDesc* r, RenPlan* plan);
 void ren_set_error(const char* fmt, ...);

@@ -679,8 +679,10 @@ __global__ void __launch_bounds__(MODE == 0 ? TC_THREADS_FWD : TC_THREADS_BWD, 1
             lo16[j8 * 4 + 0] = lo.x; lo16[j8 * 4 + 1] = lo.y; lo16[j8 * 4 + 2] = lo.z; lo16[j8 * 4 + 3] = lo.w;
             if (out_mat != nullptr) *reinterpret_cast<uint4*>(out_mat + j8 * 2048) = hi;
             if (MODE == 1 && PASS == 1 && st.epi == EPI_D_ACT && st.out_mat >= 0) {
-              uint4 eh, el;
-              split8(e8, &eh, &el);
+              uint4 eh;                               // fp16 only: the value-adjoint pass adds E in fp32
+              __half2* e2 = reinterpret_cast<__half2*>(&eh);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) e2[j] = __floats2half2_rn(e8[2 * j], e8[2 * j + 1]);
               *reinterpret_cast<uint4*>(a.extra + tcs_mat(p, S, st.out_mat) + tile_off + j8 * 2048) = eh;
             }
           }

@@ -343,9 +343,8 @@ int ren_tc_launch_wgrad(const RenPlan& p, long long S, const void* stash, const 
   if (side == nullptr) { ren_set_error("tc wgrad: side stream: %s", cudaGetErrorString(cudaGetLastError())); return REN_E_CUDA; }
   cudaEventRecord(side->fork, st);
   cudaStreamWaitEvent(side->s, side->fork, 0);
-  ren_prof_begin(REN_K_WGRAD, side->s);
+  ren_prof_count();
   ren_tc_head_wgrad<<<dim3(sms * 2, 2), 256, 0, side->s>>>(h);
-  ren_prof_end(REN_K_WGRAD, side->s);
   e = cudaGetLastError();
   if (e != cudaSuccess) { ren_set_error("tc head wgrad launch: %s", cudaGetErrorString(e)); return REN_E_CUDA; }
   cudaEventRecord(side->join, side->s);
