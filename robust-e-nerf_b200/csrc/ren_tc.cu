@@ -49,6 +49,10 @@
 #define SM_D_HI 32768      // direction encoding [128 x 32]
 #define SM_D_LO 40960
 #define SM_ENC_BYTES 49152 // one encoding buffer; two of them (the prologue warps run one tile ahead)
+// dgrad has no encodings: the same 96 KB stage the activation stash of the NEXT half-epilogue (cp.async, one
+// 16-byte slot per epilogue thread and 8-feature group): two activation buffers + one for the tangent / E matrix
+#define SM_DSTAGE_ACT 0        // [2][4][512] x 16 B
+#define SM_DSTAGE_AUX 65536    // [4][512] x 16 B
 #define SM_RING (2 * SM_ENC_BYTES)
 #define SM_CHUNK_BYTES 8192          // one [128 x 16] hi|lo weight chunk (one K step of one N-half)
 #define SM_STAGE_BYTES (TC_STAGE_KS * SM_CHUNK_BYTES)
@@ -179,7 +183,19 @@ __device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t (&r)[16])
       "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
 }
+__device__ __forceinline__ void tc_st4(uint32_t taddr, const uint4& v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(v.x), "r"(v.y),
+               "r"(v.z), "r"(v.w)
+               : "memory");
+}
 __device__ __forceinline__ void tc_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// 16-byte asynchronous global -> shared copy (no register staging), group commit / wait
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // One out-of-line accurate sine keeps the kernel small (84 inlined sinf bodies were ~100 KB of
 // SASS and stalled the epilogue warps on instruction fetch).
@@ -543,6 +559,11 @@ __global__ void __launch_bounds__(MODE == 0 ? TC_THREADS_FWD : TC_THREADS_BWD, 1
         if (lane == 0) mbar_arrive(bar_a);
       }
 
+      // dgrad: staging state of the activation-stash copies (this thread's 16-byte slots)
+      const uint32_t d_stage = sbase + (uint32_t)((warp - 2) * 32 + lane) * 16u;
+      const unsigned char* d_stage_gen = smem + ((warp - 2) * 32 + lane) * 16;
+      uint32_t d_buf = 0u;
+      bool d_have = false;
       // ---- one epilogue per GEMM step and N-half
       for (int g = 0; g < a.n_steps; ++g) {
         const TcStep& st = a.steps[g];
@@ -551,16 +572,34 @@ __global__ void __launch_bounds__(MODE == 0 ? TC_THREADS_FWD : TC_THREADS_BWD, 1
           const int n0 = 128 * h + 32 * cg;            // first of this thread's 32 features
           // byte offset of this thread's first 8-feature group inside a blocked fp16 matrix of width N
           const size_t tile_off = (size_t)tile * (size_t)(st.N >> 3) * 2048 + (size_t)m * 16 + (size_t)(n0 >> 3) * 2048;
-          uint4 act[4], aux[4];
+          uint4 act[4];
+          bool staged_next = false;
           if (MODE == 1 && st.epi == EPI_D_ACT && valid) {
-            // prefetch this thread's slice of the activation stash while the MMAs run
-            const unsigned char* am = a.stash + tcs_mat(p, S, st.act_mat) + tile_off;
+            // this thread's slice of the activation stash arrives through shared memory: the copy for THIS
+            // half-epilogue was issued during the previous one (a whole epilogue of lead time, no registers
+            // held across the accumulator wait); issue the next one now
+            if (!d_have) {
+              const unsigned char* am = a.stash + tcs_mat(p, S, st.act_mat) + tile_off;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) act[i] = __ldg(reinterpret_cast<const uint4*>(am + i * 2048));
+              for (int i = 0; i < 4; ++i) cp_async16(d_stage + SM_DSTAGE_ACT + d_buf * 32768 + i * 8192, am + i * 2048);
+              cp_async_commit();
+            }
             if (PASS) {
               const unsigned char* xm = (PASS == 1 ? a.stash_dot : a.extra) + tcs_mat(p, S, st.act_mat) + tile_off;
 #pragma unroll
-              for (int i = 0; i < 4; ++i) aux[i] = __ldg(reinterpret_cast<const uint4*>(xm + i * 2048));
+              for (int i = 0; i < 4; ++i) cp_async16(d_stage + SM_DSTAGE_AUX + i * 8192, xm + i * 2048);
+              cp_async_commit();
+            }
+            const int g2 = h + 1 < nh ? g : g + 1, h2 = h + 1 < nh ? h + 1 : 0;
+            if (g2 < a.n_steps && a.steps[g2].epi == EPI_D_ACT) {
+              const TcStep& s2 = a.steps[g2];
+              const unsigned char* am = a.stash + tcs_mat(p, S, s2.act_mat) + (size_t)tile * (size_t)(s2.N >> 3) * 2048 +
+                                        (size_t)m * 16 + (size_t)((128 * h2 + 32 * cg) >> 3) * 2048;
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                cp_async16(d_stage + SM_DSTAGE_ACT + (d_buf ^ 1u) * 32768 + i * 8192, am + i * 2048);
+              cp_async_commit();
+              staged_next = true;
             }
           }
           if (MODE == 0 && TAN && st.epi != EPI_F_LINEAR && valid) {
@@ -585,6 +624,9 @@ __global__ void __launch_bounds__(MODE == 0 ? TC_THREADS_FWD : TC_THREADS_BWD, 1
           tc_ld16(tcol, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
           tc_ld16(tcol + 16, *reinterpret_cast<uint32_t(*)[16]>(&r[16]));
           tc_ld_wait();
+          if (MODE == 1 && st.epi == EPI_D_ACT && valid) {
+            if (staged_next) cp_async_wait<1>(); else cp_async_wait<0>();   // all but the copy for the next half
+          }
           unsigned char* out_mat = nullptr;        // already offset to this thread's row / first group
           if (MODE == 0) {
             if (STASH && st.out_mat >= 0) out_mat = a.stash + tcs_mat(p, S, st.out_mat) + tile_off;
@@ -592,7 +634,6 @@ __global__ void __launch_bounds__(MODE == 0 ? TC_THREADS_FWD : TC_THREADS_BWD, 1
             out_mat = a.delta + tcs_mat(p, S, st.out_mat) + tile_off;
           }
           const float* bias = (MODE == 0 && st.bias_idx >= 0) ? vec + VEC_BIAS + st.bias_idx * 256 + n0 : nullptr;
-          uint32_t hi16[16], lo16[16];
           // the common case (hidden softplus layer of the value pass) as ONE flat pass over the thread's 32
           // columns: 32 independent bias -> ex2 -> lg2 chains in flight instead of 8
           const bool flat = MODE == 0 && !TAN && st.epi == EPI_F_HIDDEN && a.softplus && !(a.dbg & 1);
@@ -660,8 +701,8 @@ __global__ void __launch_bounds__(MODE == 0 ? TC_THREADS_FWD : TC_THREADS_BWD, 1
             } else {
               float av[8], xv[8];
               if (st.epi == EPI_D_ACT) {
-                unpack8(act[j8], av);
-                if (PASS) unpack8(aux[j8], xv);
+                unpack8(*reinterpret_cast<const uint4*>(d_stage_gen + SM_DSTAGE_ACT + d_buf * 32768 + j8 * 8192), av);
+                if (PASS) unpack8(*reinterpret_cast<const uint4*>(d_stage_gen + SM_DSTAGE_AUX + j8 * 8192), xv);
               }
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
@@ -675,8 +716,12 @@ __global__ void __launch_bounds__(MODE == 0 ? TC_THREADS_FWD : TC_THREADS_BWD, 1
             }
             uint4 hi, lo;
             split8(y, &hi, &lo);
-            hi16[j8 * 4 + 0] = hi.x; hi16[j8 * 4 + 1] = hi.y; hi16[j8 * 4 + 2] = hi.z; hi16[j8 * 4 + 3] = hi.w;
-            lo16[j8 * 4 + 0] = lo.x; lo16[j8 * 4 + 1] = lo.y; lo16[j8 * 4 + 2] = lo.z; lo16[j8 * 4 + 3] = lo.w;
+            // every accumulator column of this thread is already in registers: the packed operand goes back over
+            // them group by group (keeps 32 registers free compared with one 16-column store at the end)
+            if (st.write_a) {
+              tc_st4(tcol + j8 * 4, hi);
+              tc_st4(tcol + 16 + j8 * 4, lo);
+            }
             if (out_mat != nullptr) *reinterpret_cast<uint4*>(out_mat + j8 * 2048) = hi;
             if (MODE == 1 && PASS == 1 && st.epi == EPI_D_ACT && st.out_mat >= 0) {
               uint4 eh;                               // fp16 only: the value-adjoint pass adds E in fp32
@@ -686,9 +731,11 @@ __global__ void __launch_bounds__(MODE == 0 ? TC_THREADS_FWD : TC_THREADS_BWD, 1
               *reinterpret_cast<uint4*>(a.extra + tcs_mat(p, S, st.out_mat) + tile_off + j8 * 2048) = eh;
             }
           }
+          if (MODE == 1 && st.epi == EPI_D_ACT && valid) {
+            d_have = staged_next;
+            if (staged_next) d_buf ^= 1u;
+          }
           if (st.write_a) {
-            tc_st16(tcol, hi16);
-            tc_st16(tcol + 16, lo16);
             tc_st_wait();
             tc_fence_before();
             __syncwarp();
