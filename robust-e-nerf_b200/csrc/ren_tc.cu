@@ -42,6 +42,9 @@
 #define TC_STAGES 3            // ring stages of up to TC_STAGE_KS K steps (32 KB)
 #define TC_STAGE_KS 4
 #define TC_MAX_STEPS 20
+#ifndef FLAT_AHEAD
+#define FLAT_AHEAD 1            // softplus groups (of 8 columns) computed ahead of the split / store of a group
+#endif
 
 // shared-memory map (bytes)
 #define SM_P_HI 0          // positional encoding [128 x 64] hi (K-major core matrices)
@@ -637,20 +640,27 @@ __global__ void __launch_bounds__(MODE == 0 ? TC_THREADS_FWD : TC_THREADS_BWD, 1
           // the common case (hidden softplus layer of the value pass) as ONE flat pass over the thread's 32
           // columns: 32 independent bias -> ex2 -> lg2 chains in flight instead of 8
           const bool flat = MODE == 0 && !TAN && st.epi == EPI_F_HIDDEN && a.softplus && !(a.dbg & 1);
-          if (flat) {
+          // software pipeline: the MUFU chains of group j8 + FLAT_AHEAD are issued before the split / stores of
+          // group j8, so the special-function pipe and the ALU work overlap inside every warp
+          auto sp8 = [&](int j8) {
 #pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
+            for (int j4 = 2 * j8; j4 < 2 * j8 + 2; ++j4) {
               const float4 b4 = *reinterpret_cast<const float4*>(bias + j4 * 4);
               r[j4 * 4 + 0] = __float_as_uint(softplus_log2(__uint_as_float(r[j4 * 4 + 0]) + b4.x));
               r[j4 * 4 + 1] = __float_as_uint(softplus_log2(__uint_as_float(r[j4 * 4 + 1]) + b4.y));
               r[j4 * 4 + 2] = __float_as_uint(softplus_log2(__uint_as_float(r[j4 * 4 + 2]) + b4.z));
               r[j4 * 4 + 3] = __float_as_uint(softplus_log2(__uint_as_float(r[j4 * 4 + 3]) + b4.w));
             }
+          };
+          if (flat) {
+#pragma unroll
+            for (int j8 = 0; j8 < FLAT_AHEAD; ++j8) sp8(j8);
           }
 #pragma unroll
           for (int j8 = 0; j8 < 4; ++j8) {
             float y[8];
             float e8[8];
+            if (flat && j8 + FLAT_AHEAD < 4) sp8(j8 + FLAT_AHEAD);
             if (flat) {
 #pragma unroll
               for (int j = 0; j < 8; ++j) y[j] = __uint_as_float(r[j8 * 8 + j]);

@@ -537,3 +537,38 @@ def test_render_function_refuses_double_backward(built_lib, dataset_dir):
     rad, _, _, _ = m.nerf.render_raw(o, d, torch.rand(8, device="cuda"))
     (go,) = torch.autograd.grad(rad.sum(), o)                     # the ordinary first-order gradient still works
     assert bool(torch.isfinite(go).all())
+
+
+@pytest.mark.parametrize("tangent", [False, True])
+def test_tcgen05_ray_gradient_matches_fp32_kernel(tangent, built_lib, dataset_dir, monkeypatch):
+    """Same tcgen05 engine, same fp16 deltas: the tcgen05 ray-gradient kernel (ren_tc_raygrad) against the fp32
+    register-blocked one (REN_RAYGRAD_SIMT=1 selects it) -- d loss / d (o, d[, o_dot, d_dot])."""
+    g = H.load_golden("step_8x256_gain2")
+    m = H.build_product(g, dataset_dir, "cuda")
+    gen = torch.Generator().manual_seed(5)
+    B = 300                                             # ragged last tile: 300 * 128 samples is a tile multiple, so
+    o = torch.randn(B, 3, generator=gen)                # also run a ray count that is not
+    o = 3 * o / o.norm(dim=-1, keepdim=True)
+    d = torch.nn.functional.normalize(-o + 0.3 * torch.randn(B, 3, generator=gen), dim=-1)
+    od, dd = 0.05 * torch.randn(B, 3, generator=gen), 0.05 * torch.randn(B, 3, generator=gen)
+    u = torch.rand(B, generator=gen)
+    wts = torch.randn(B, generator=gen).cuda()
+    out = {}
+    for mode in ("tc", "simt"):
+        if mode == "simt":
+            monkeypatch.setenv("REN_RAYGRAD_SIMT", "1")
+        else:
+            monkeypatch.delenv("REN_RAYGRAD_SIMT", raising=False)
+        leaves = [t.clone().cuda().requires_grad_(True) for t in (o, d, od, dd)]
+        if tangent:
+            rad, opac, _, rad_dot, opac_dot, _ = m.nerf.render_tangent_raw(*leaves, u.cuda())
+            loss = (rad[:, 0] * wts).sum() + (rad_dot[:, 0] * wts).sum() + opac_dot.sum()
+        else:
+            rad, opac, _, _ = m.nerf.render_raw(leaves[0], leaves[1], u.cuda())
+            loss = (rad[:, 0] * wts).sum() + opac.sum()
+        loss.backward()
+        out[mode] = [t.grad.clone() for t in leaves[:4 if tangent else 2]]
+    for a, b, name in zip(out["tc"], out["simt"], ("o", "d", "o_dot", "d_dot")):
+        nw = H.rel_err(a, b, floor=1e-9)[0]
+        print(f"[ray gradient tangent={tangent}] d loss / d {name}: tcgen05 vs fp32 kernel normwise={nw:.2e}")
+        assert nw < 1e-4 and float(b.abs().max()) > 0
