@@ -62,7 +62,30 @@ class ClockSampler(threading.Thread):
         self.stop_flag = threading.Event()
         self.rows = []
 
+    def _run_nvml(self):
+        """NVML directly (nvidia_ml_py): sub-millisecond samples instead of one nvidia-smi process per sample."""
+        import pynvml as N
+        N.nvmlInit()
+        h = N.nvmlDeviceGetHandleByIndex(self.gpu)
+        get_reasons = getattr(N, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            N.nvmlDeviceGetCurrentClocksThrottleReasons
+        mx = N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM)
+        bits = ((0x8, 4), (0x40, 5), (0x20, 6), (0x4, 7))       # hw_slowdown, hw_thermal, sw_thermal, sw_power_cap
+        while not self.stop_flag.is_set():
+            sm = N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)
+            r = int(get_reasons(h))
+            row = [str(self.gpu), str(sm), str(mx), "0", "", "", "", ""]
+            for bit, col in bits:
+                row[col] = "Active" if r & bit else "Not Active"
+            self.rows.append(row)
+            self.stop_flag.wait(0.01)
+
     def run(self):
+        try:
+            self._run_nvml()
+            return
+        except Exception:
+            pass
         while not self.stop_flag.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
