@@ -21,6 +21,21 @@ for eng in ("auto", "simt_fp32"):
     loss.backward()
     torch.cuda.synchronize()
     print(eng, float(loss))
+# occupancy-grid marching: packed samples (tcgen05) and the masked dense march (fp32)
+for eng in ("auto", "simt_fp32"):
+    g2 = dict(g)
+    g2["fcfg"] = dict(g["fcfg"], contraction="sphere")
+    cfg = H.product_config(g2)
+    cfg["nerf"]["occ_grid"] = dict(resolution=8, occ_thre=1e-2, ema_decay=0.95, warmup_steps=256, n=16, enabled=True)
+    from ren_b200 import RobustENeRF
+    m = RobustENeRF(dataset_directory=root, engine=eng, **cfg).cuda().train()
+    m.nerf.occupancy_grid._binary = (torch.rand(8, 8, 8, generator=torch.Generator().manual_seed(4)) > 0.6).cuda()
+    o = torch.tensor([[3.0, 0.1, 0.2]]).repeat(19, 1).cuda().requires_grad_(True)
+    d = torch.nn.functional.normalize(-o.detach() + 0.3 * torch.randn(19, 3, device="cuda"), dim=-1).requires_grad_(True)
+    rad, opac, depth, spp = m.nerf(o, d, torch.rand(19, device="cuda"))
+    (rad.sum() + opac.sum()).backward()
+    torch.cuda.synchronize()
+    print(eng, "grid render", float(spp))
 from ren_b200 import events as E
 raw = EP.synth_raw_events(20000, 31, 17, seed=2)
 q, mi = E._run(raw, {"img_width": 31, "img_height": 17}, "cuda")
