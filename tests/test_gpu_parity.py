@@ -546,8 +546,8 @@ def test_tcgen05_ray_gradient_matches_fp32_kernel(tangent, built_lib, dataset_di
     g = H.load_golden("step_8x256_gain2")
     m = H.build_product(g, dataset_dir, "cuda")
     gen = torch.Generator().manual_seed(5)
-    B = 300                                             # ragged last tile: 300 * 128 samples is a tile multiple, so
-    o = torch.randn(B, 3, generator=gen)                # also run a ray count that is not
+    B = 300                                             # (ragged last tiles: the packed-sample tests in
+    o = torch.randn(B, 3, generator=gen)                # test_occupancy_gpu.py and the 37-ray goldens)
     o = 3 * o / o.norm(dim=-1, keepdim=True)
     d = torch.nn.functional.normalize(-o + 0.3 * torch.randn(B, 3, generator=gen), dim=-1)
     od, dd = 0.05 * torch.randn(B, 3, generator=gen), 0.05 * torch.randn(B, 3, generator=gen)
