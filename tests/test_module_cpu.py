@@ -169,3 +169,25 @@ def test_affine_log_intensity_alignment():
     A = np.stack([np.full(3 * 12 * 16, float(torch.tensor(0.5).log())), np.ones(3 * 12 * 16)], axis=1)
     x, *_ = np.linalg.lstsq(A, target[:, 0].log().double().numpy().ravel(), rcond=None)
     assert abs(float(scale[0]) - x[0]) < 1e-9 and abs(float(offset[0]) - x[1]) < 1e-9
+
+
+def test_dynamic_batch_size_follows_the_reference_rule(built_lib, dataset_dir):
+    """robust_e_nerf.py:907-950: new batch = int(per-GPU ray-sample budget / mean samples per ray), written to the
+    datamodule's event dataset and its normalised-timestamp samplers; with gradient accumulation only on the
+    second-to-last micro-batch."""
+    from types import SimpleNamespace as NS
+    _, m = _model(dataset_dir, "step_plumbing")
+    samplers = [NS(size=7), NS(size=7), NS(size=7)]
+    dm = NS(train_dataset=NS(batch_size=7), train_normalized_sampler=NS(datasets=samplers))
+    m.trainer = NS(accumulate_grad_batches=1, datamodule=dm)
+    budget = m.train_ray_sample_batch_size
+    out = m.update_train_batch_size(torch.tensor(37.5), 0)
+    assert float(out) == 37.5
+    assert dm.train_dataset.batch_size == int(budget / 37.5) and all(s.size == int(budget / 37.5) for s in samplers)
+    # accumulation over 4 micro-batches: only index 2 (mod 4) resizes
+    m.trainer.accumulate_grad_batches = 4
+    for idx, expect_change in ((0, False), (1, False), (2, True), (3, False), (6, True)):
+        dm.train_dataset.batch_size = -1
+        m.update_train_batch_size(torch.tensor(100.0), idx)
+        assert (dm.train_dataset.batch_size == int(budget / 100.0)) == expect_change, idx
+    m.trainer = None
