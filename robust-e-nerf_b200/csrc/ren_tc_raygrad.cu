@@ -371,9 +371,12 @@ int ren_tc_launch_raygrad(const RenPlan& p, long long n_rays, int K, const float
   const long long S = sample_idx ? n_samples : n_rays * K;
   int n = 0, b_off = 0;
   auto add = [&](const RenLayer& L, int col0, int enc) {
-    RgtSrc& s = a.src[n++];
-    s.d_off = (long long)tcs_mat(p, S, L.mat); s.N = L.N; s.enc = enc; s.w_off = L.w_off + col0; s.ldw = L.K0 + L.K1;
-    s.b_off = b_off;
+    if (n < RGT_MAX_SRC) {
+      RgtSrc& s = a.src[n];
+      s.d_off = (long long)tcs_mat(p, S, L.mat); s.N = L.N; s.enc = enc; s.w_off = L.w_off + col0; s.ldw = L.K0 + L.K1;
+      s.b_off = b_off;
+    }
+    ++n;
     b_off += (L.N >> 4) * (enc == 1 ? REN_PE_MAX : REN_DE_MAX) * 64;
   };
   for (int i = 0; i < p.D; ++i) {
