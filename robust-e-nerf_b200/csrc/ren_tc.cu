@@ -8,15 +8,18 @@
 // activation ever touches shared memory and the two 128-column halves of a layer pipeline against
 // the tensor pipe: while the epilogue warps convert N-half 0, the MMAs of N-half 1 run, and the
 // next layer's K-half-0 MMAs start as soon as half 0 is converted.
-//   warp 0       weight producer: pre-packed fp16 (hi|lo) weight chunks, L2 -> 4 x 32 KB shared-memory
+//   warp 0       weight producer: pre-packed fp16 (hi|lo) weight chunks, L2 -> 3 x 32 KB shared-memory
 //                ring with 1-D bulk TMA (cp.async.bulk + mbarrier tx bytes)
 //   warp 1       MMA issuer: one thread issues tcgen05.mma kind::f16, M=128, K=16; A from TMEM
 //                (activations) or shared memory (positional / direction encodings).  The first K-half
 //                of a layer uses N=256 MMAs, the last K-half runs per N-half (N=128) so that
 //                accumulator half 0 completes -- and its epilogue starts -- a quarter layer early
-//   warps 2-17   prologue (march, contraction, 84 sines -> encodings in shared memory) + epilogues.
-//                Lane quadrant = warp % 4 (TMEM access rule); the 4 warps of a quadrant split the 128
-//                columns of a half 32 each and write their 32 packed columns back over their own.
+//   warps 2-17   epilogues.  Lane quadrant = warp % 4 (TMEM access rule); the 4 warps of a quadrant split
+//                the 128 columns of a half 32 each and write their 32 packed columns back over their own.
+//                dgrad: the activation-stash slices they need arrive by cp.async through the (idle)
+//                encoding buffers, issued one half-epilogue ahead
+//   warps 18-19  forward only: prologue (march, contraction, 84 sines -> encodings of the NEXT tile in the
+//                free one of two shared-memory buffers)
 // fp32-class accuracy from fp16 tensor cores: x = hi + lo; A*W ~= A_hi*W_hi + A_lo*W_hi + A_hi*W_lo
 // (3 MMAs per K step).  Single-pass fp16/bf16/TF32 misses the 1e-4 bar.
 //
