@@ -7,6 +7,7 @@ from . import _lib
 from .nerf import NeRF, RenderFunction
 from .module import (ContrastThreshold, DiffLossFunction, LinearTrajectory, RefractoryPeriod,
                      RobustENeRF)
+from .posed_images import PosedImage
 
 __all__ = ["NeRF", "RenderFunction", "RobustENeRF", "ContrastThreshold", "RefractoryPeriod",
-           "LinearTrajectory", "DiffLossFunction", "_lib"]
+           "LinearTrajectory", "DiffLossFunction", "PosedImage", "_lib"]

@@ -272,10 +272,43 @@ class RobustENeRF(LightningModule):
         self.trajectory = LinearTrajectory(camera_poses)
         self._load_model_component_state_dicts()
         self._freeze_model_components()
+        self._load_eval_stages(dataset_directory, eval_target)
         lw = _get(loss, "weight")
         for v in (lw.values() if isinstance(lw, dict) else vars(lw).values()):
             assert isinstance(v, (int, float)) and v >= 0                         # loss.py:16-20
         self._opt_state = None
+
+    def _load_eval_stages(self, dataset_directory, eval_target):
+        """robust_e_nerf.py:86-152: frame size, intrinsics and target value range of the validation / test
+        renders come from the posed target images (`event_view`: the training views for both stages;
+        `novel_view`: `transforms_val.json` / `transforms_test.json`).  A dataset without a `views` folder (the
+        synthetic benchmark streams) simply has no evaluation stage until `set_eval_stage` is called; like the
+        reference, a missing test split is not an error."""
+        from .posed_images import PosedImage
+        if set(eval_target) == {"event_view"}:
+            stages = {"val": "train", "test": "train"}
+        elif set(eval_target) == {"novel_view"}:
+            stages = {"val": "val", "test": "test"}
+        else:
+            raise NotImplementedError(eval_target)
+        if PosedImage.posed_img_folder_path(dataset_directory) is None:
+            return
+        loaded = {}
+        for name, stage in stages.items():
+            try:
+                if stage not in loaded:
+                    loaded[stage] = PosedImage(dataset_directory, stage, permutation_seed=None)
+            except FileNotFoundError:
+                if name == "val":
+                    raise
+                continue
+            self.set_eval_stage_from_dataset(name, loaded[stage])
+
+    def set_eval_stage_from_dataset(self, name, posed_images):
+        h, w = posed_images.posed_imgs.img.shape[-2:]
+        self.set_eval_stage(name, posed_images.posed_imgs.intrinsics, h, w,
+                            float(posed_images.min_normalized_pixel_value),
+                            float(posed_images.max_normalized_pixel_value))
 
     # -------------------------------------------------------------- builders
     def _build_nerf(self, camera_poses, gpus):
