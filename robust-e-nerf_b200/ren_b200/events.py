@@ -6,11 +6,13 @@ instead of two per-event Python loops).  SURVEY.md section 8(f) #3.
     events = queue_raw_events(root_directory, camera_calibration)          # == Event.queue_raw_events
     tau_max = extract_max_refractory_period(raw_events, camera_calibration)
     events = colorize_events(events, camera_calibration)
+    events = undistort_events(events, camera_calibration)                  # == Event.undistort_events
 
 File names / keys are the reference's (`raw_events.npz` {position (N,2) u16, timestamp (N,) i64 ns,
 polarity (N,) bool}, `camera_calibration.npz`, `events.pt`, `max_refractory_period.pt`).
 """
 import ctypes as C
+import math
 import os
 
 import numpy as np
@@ -92,4 +94,55 @@ def colorize_events(events, camera_calibration):
     x, y = events["position"][:, 0], events["position"][:, 1]
     events = dict(events)
     events["channel_idx"] = table[(y % 2) * 2 + (x % 2)]
+    return events
+
+
+def undistort_events(events, camera_calibration):
+    """`Event.undistort_events` (datasets.py:330-364): event pixel positions -> the ideal pinhole image with the
+    same intrinsics.  The reference calls `cv2.undistortPoints(..., P=K)` (plumb_bob: k1 k2 p1 p2) or
+    `cv2.fisheye.undistortPoints(..., P=K)` (equidistant: k1..k4) on the host; here the same fixed-point /
+    Newton iterations (OpenCV's published algorithms, float64 internally, float32 result) run as elementwise
+    tensor ops on whatever device holds the events.  Checked against OpenCV itself
+    (`tests/test_events_prep.py::test_undistort_events_matches_opencv`)."""
+    model = str(camera_calibration["distortion_model"])
+    params = np.asarray(camera_calibration["distortion_params"], dtype=np.float64).reshape(-1)
+    K = np.asarray(camera_calibration["intrinsics"], dtype=np.float64)
+    assert len(params) in (0, 4)
+    events = dict(events)
+    events["position"] = events["position"].to(torch.get_default_dtype())
+    if len(params) == 0:
+        return events
+    fx, fy, cx, cy = K[0, 0], K[1, 1], K[0, 2], K[1, 2]
+    p = events["position"].to(torch.float64)
+    x0, y0 = (p[:, 0] - cx) / fx, (p[:, 1] - cy) / fy
+    if model == "plumb_bob":
+        k1, k2, p1, p2 = params
+        x, y = x0.clone(), y0.clone()
+        for _ in range(5):                                   # cv::undistortPoints default: 5 fixed-point sweeps
+            r2 = x * x + y * y
+            icdist = 1.0 / (1.0 + (k2 * r2 + k1) * r2)
+            # a negative inverse distortion factor means the sweep left the model's valid range: keep the
+            # undistorted-as-is normalised point (OpenCV does the same)
+            bad = icdist < 0
+            dx = 2 * p1 * x * y + p2 * (r2 + 2 * x * x)
+            dy = p1 * (r2 + 2 * y * y) + 2 * p2 * x * y
+            x = torch.where(bad, x0, (x0 - dx) * icdist)
+            y = torch.where(bad, y0, (y0 - dy) * icdist)
+    elif model == "equidistant":
+        k1, k2, k3, k4 = params
+        theta_d = torch.sqrt(x0 * x0 + y0 * y0).clamp(-math.pi / 2, math.pi / 2)
+        theta = theta_d.clone()
+        active = theta_d > 1e-8
+        for _ in range(10):                                  # cv::fisheye::undistortPoints: Newton, <= 10 steps
+            t2 = theta * theta
+            t4, t6, t8 = t2 * t2, t2 * t2 * t2, t2 * t2 * t2 * t2
+            fix = (theta * (1 + k1 * t2 + k2 * t4 + k3 * t6 + k4 * t8) - theta_d) / \
+                  (1 + 3 * k1 * t2 + 5 * k2 * t4 + 7 * k3 * t6 + 9 * k4 * t8)
+            theta = torch.where(active, theta - fix, theta)
+            active = active & (fix.abs() >= 1e-8)
+        scale = torch.where(theta_d > 1e-8, torch.tan(theta) / theta_d.clamp(min=1e-300), torch.ones_like(theta))
+        x, y = x0 * scale, y0 * scale
+    else:
+        raise NotImplementedError(model)                     # "fov" is a TODO in the reference as well
+    events["position"] = torch.stack((x * fx + cx, y * fy + cy), dim=1).to(torch.float32)
     return events

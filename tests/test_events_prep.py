@@ -109,3 +109,54 @@ def test_raw_events_to_training_steps(built_lib, dataset_dir):
     assert flat is not None
     assert torch.equal(flat, torch.cat([p.grad.reshape(-1) for p in m.nerf.mlp_parameters()]))
     assert torch.equal(tr.gbuf[:flat.numel()], flat)
+
+
+def _undistort_cases():
+    K = np.array([[500.0, 0, 319.5], [0, 500.0, 239.5], [0, 0, 1]])
+    return K, [("plumb_bob", np.array([-0.3, 0.12, 0.001, -0.002])),
+               ("plumb_bob", np.array([0.2, -0.05, -0.003, 0.004])),
+               ("equidistant", np.array([0.05, -0.01, 0.002, -0.0003]))]
+
+
+def _opencv_undistort(model, src, K, D):
+    import cv2
+    if model == "plumb_bob":
+        return cv2.undistortPoints(src, K, D, P=K).squeeze(1)
+    return cv2.fisheye.undistortPoints(src[:, None, :], K, D, P=K).squeeze(1)
+
+
+def test_undistort_events_matches_opencv():
+    """`undistort_events` (datasets.py:330-364) against the OpenCV calls the reference makes, on every pixel of a
+    640 x 480 sensor: same iterations in float64 -> identical float32 positions on the CPU."""
+    from ren_b200 import events as E
+    K, cases = _undistort_cases()
+    xs, ys = np.meshgrid(np.arange(640), np.arange(480))
+    pos = torch.tensor(np.stack([xs.ravel(), ys.ravel()], 1).astype(np.int64))
+    for model, D in cases:
+        calib = {"distortion_model": np.array(model), "distortion_params": D, "intrinsics": K}
+        ev = {"position": pos, "end_ts": torch.zeros(len(pos), dtype=torch.int64)}
+        out = E.undistort_events(ev, calib)
+        assert out["position"].dtype == torch.float32 and out["end_ts"] is ev["end_ts"]
+        ref = _opencv_undistort(model, pos.to(torch.float32).numpy(), K, D)
+        assert np.array_equal(out["position"].numpy(), ref), model
+    # no distortion parameters: positions are only cast (datasets.py:339-344)
+    calib = {"distortion_model": np.array("plumb_bob"), "distortion_params": np.zeros(0), "intrinsics": K}
+    out = E.undistort_events({"position": pos}, calib)
+    assert out["position"].dtype == torch.float32 and torch.equal(out["position"], pos.float())
+    with pytest.raises(NotImplementedError):
+        E.undistort_events({"position": pos}, {"distortion_model": np.array("fov"),
+                                               "distortion_params": np.zeros(4), "intrinsics": K})
+
+
+@pytest.mark.gpu
+def test_undistort_events_on_device():
+    from ren_b200 import events as E
+    K, cases = _undistort_cases()
+    gen = np.random.default_rng(1)
+    pos = torch.tensor(np.stack([gen.integers(0, 640, 200000), gen.integers(0, 480, 200000)], 1).astype(np.int64))
+    for model, D in cases:
+        calib = {"distortion_model": np.array(model), "distortion_params": D, "intrinsics": K}
+        out = E.undistort_events({"position": pos.cuda()}, calib)["position"]
+        assert out.is_cuda
+        ref = _opencv_undistort(model, pos.to(torch.float32).numpy(), K, D)
+        assert float(np.abs(out.cpu().numpy() - ref).max()) < 1e-3          # fused multiply-adds on the device
