@@ -146,3 +146,46 @@ def undistort_events(events, camera_calibration):
         raise NotImplementedError(model)                     # "fov" is a TODO in the reference as well
     events["position"] = torch.stack((x * fx + cx, y * fy + cy), dim=1).to(torch.float32)
     return events
+
+
+class Event(torch.utils.data.Dataset):
+    """`datasets.Event` (datasets.py:14-131,366-373): the transformed events of a sequence -- the cached
+    `events.pt` when present, else raw events -> `queue_raw_events` -> `colorize_events` -> `undistort_events`
+    (all on `device`) -> cached in the reference's file and schema (CPU tensors: position (M,2) f32, start_ts /
+    end_ts / num_pos / num_neg (M,) i64 [, channel_idx (M,) u8]) -- optionally permuted with a seeded
+    `torch.randperm` as the reference does to emulate sparser event streams."""
+    CAMERA_CALIBRATION_FILENAME = "camera_calibration.npz"
+
+    def __init__(self, root_directory, permutation_seed, device="cuda"):
+        super().__init__()
+        path = os.path.join(root_directory, TF_EVENTS_FILENAME)
+        if os.path.isfile(path):
+            self.events = dict(torch.load(path))
+        else:
+            calib = self.load_camera_calibration(root_directory)
+            ev = queue_raw_events(root_directory, calib, device)
+            ev = undistort_events(colorize_events(ev, calib), calib)
+            self.events = {k: v.cpu() for k, v in ev.items()}
+            torch.save(self.events, path)
+        if permutation_seed is not None:
+            perm = torch.randperm(len(self), generator=torch.Generator().manual_seed(permutation_seed))
+            self.events = {k: v[perm] for k, v in self.events.items()}
+
+    @classmethod
+    def load_camera_calibration(cls, root_directory):
+        return np.load(os.path.join(root_directory, cls.CAMERA_CALIBRATION_FILENAME))
+
+    @staticmethod
+    def load_max_refractory_period(root_directory):
+        path = os.path.join(root_directory, MAX_REFRACTORY_PERIOD_FILENAME)
+        return torch.load(path) if os.path.isfile(path) else None
+
+    @staticmethod
+    def save_max_refractory_period(max_refractory_period, root_directory):
+        torch.save(max_refractory_period, os.path.join(root_directory, MAX_REFRACTORY_PERIOD_FILENAME))
+
+    def __getitem__(self, index):
+        return {k: v[index] for k, v in self.events.items()}
+
+    def __len__(self):
+        return len(self.events["position"])

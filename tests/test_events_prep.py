@@ -160,3 +160,34 @@ def test_undistort_events_on_device():
         assert out.is_cuda
         ref = _opencv_undistort(model, pos.to(torch.float32).numpy(), K, D)
         assert float(np.abs(out.cpu().numpy() - ref).max()) < 1e-3          # fused multiply-adds on the device
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_event_dataset_builds_and_caches_like_the_reference(tag, built_lib, tmp_path):
+    """`ren_b200.events.Event` from a raw stream: the cached `events.pt` holds what the unmodified reference's
+    queue + colorize produced (golden), positions cast to float32 (no distortion parameters), and a second
+    construction reads the cache; the seeded permutation is `torch.randperm`'s."""
+    from ren_b200 import events as E
+    g = np.load(GOLDEN)
+    w, h = (int(v) for v in g[f"{tag}_calib"])
+    np.savez(tmp_path / "raw_events.npz", **{k: g[f"{tag}_raw_{k}"] for k in ("position", "timestamp", "polarity")})
+    np.savez(tmp_path / "camera_calibration.npz", img_width=np.uint16(w), img_height=np.uint16(h),
+             bayer_pattern=g[f"{tag}_bayer"], distortion_model=np.array("plumb_bob"),
+             distortion_params=np.zeros(0), intrinsics=np.eye(3))
+    ds = E.Event(str(tmp_path), None)
+    assert os.path.isfile(tmp_path / "events.pt")
+    keys = [k[len(tag) + 3:] for k in g.files if k.startswith(f"{tag}_q_")]
+    assert sorted(ds.events) == sorted(keys)
+    for k in keys:
+        want = torch.from_numpy(g[f"{tag}_q_{k}"])
+        got = ds.events[k]
+        assert not got.is_cuda
+        if k == "position":
+            assert got.dtype == torch.float32 and torch.equal(got, want.float())
+        else:
+            assert got.dtype == want.dtype and torch.equal(got, want), k
+    again = E.Event(str(tmp_path), 9)                            # from the cache, permuted
+    perm = torch.randperm(len(ds), generator=torch.Generator().manual_seed(9))
+    assert torch.equal(again.events["end_ts"], ds.events["end_ts"][perm])
+    assert set(again[0]) == set(keys) and len(again) == len(ds)
