@@ -661,8 +661,32 @@ class RobustENeRF(LightningModule):
         name = stage.get("name", "eval")
         self.log(f"{name}/l1", l1, prog_bar=True, rank_zero_only=True)
         self.log(f"{name}/psnr", psnr, prog_bar=True, rank_zero_only=True)
+        log_dir = getattr(self.trainer, "log_dir", None)
+        if self.eval_save_pred_intensity_img and log_dir is not None and outputs[0].get("sample_id") is not None:
+            ids = torch.stack([o["sample_id"] for o in outputs]).reshape(len(outputs), -1)
+            self.save_pred_intensity_imgs(aligned, ids, stage, os.path.join(log_dir, self.PREDICTIONS_FOLDER_NAME))
         return {"l1": l1, "psnr": psnr, "log_intensity_scale": scale, "log_intensity_offset": offset,
                 "pred_intensity_img": aligned}
+
+    PREDICTIONS_FOLDER_NAME = "predictions"                          # robust_e_nerf.py:20-22
+    PREDICTION_FILE_EXTENSION = ".png"
+    PREDICTION_BIT_DEPTH = 8
+
+    def save_pred_intensity_imgs(self, pred_intensity_img, sample_id, stage, folder):
+        """robust_e_nerf.py:733-779: the aligned predictions (N, C, H, W), mapped from the target value range to
+        [0, 2^bits - 1], clipped, rounded and written as `<sample id>.png` (gray, or BGR for a colour sensor)."""
+        import cv2
+        top = 2 ** self.PREDICTION_BIT_DEPTH - 1
+        lo, hi = stage["min_normalized_pixel_value"], stage["max_normalized_pixel_value"]
+        img = (top * ((pred_intensity_img.detach().cpu() - lo) / (hi - lo)).clamp(min=0, max=1)).round()
+        img = img.numpy().astype(np.uint8 if self.PREDICTION_BIT_DEPTH == 8 else np.uint16).transpose(0, 2, 3, 1)
+        os.makedirs(folder, exist_ok=True)
+        names = ["".join(map(chr, row)).rstrip() for row in sample_id.tolist()]
+        for name, im in zip(names, img):
+            if self.has_bayer_filter:
+                im = cv2.cvtColor(im, cv2.COLOR_RGB2BGR)
+            cv2.imwrite(os.path.join(folder, name + self.PREDICTION_FILE_EXTENSION), im)
+        return names
 
     def validation_epoch_end(self, outputs):
         """robust_e_nerf.py:573-579."""

@@ -191,3 +191,29 @@ def test_dynamic_batch_size_follows_the_reference_rule(built_lib, dataset_dir):
         m.update_train_batch_size(torch.tensor(100.0), idx)
         assert (dm.train_dataset.batch_size == int(budget / 100.0)) == expect_change, idx
     m.trainer = None
+
+
+def test_epoch_end_writes_prediction_pngs(built_lib, dataset_dir, tmp_path):
+    """robust_e_nerf.py:733-779: aligned predictions -> 8-bit PNGs named by sample id under <log_dir>/predictions."""
+    import cv2
+    import numpy as np
+    from types import SimpleNamespace as NS
+    _, m = _model(dataset_dir, "step_plumbing")
+    m.eval_save_pred_intensity_img = True
+    m.trainer = NS(log_dir=str(tmp_path))
+    m.set_eval_stage("val", [[10.0, 0, 3.5], [0, 10.0, 2.5], [0, 0, 1]], 6, 8, 0.5 / 256, 1 - 0.5 / 256)
+    gen = torch.Generator().manual_seed(0)
+    target = torch.rand(2, 6, 8, generator=gen) * 0.9 + 0.05
+    pred = torch.exp(1.3 * target.log() + 0.2)                       # affine in log space: aligned == target
+    ids = [torch.tensor([ord(c) for c in name.ljust(16)]) for name in ("r_000", "r_001")]
+    outs = [{"pred_intensity_img": pred[i], "target_intensity_img": target[i], "sample_id": ids[i]} for i in range(2)]
+    res = m.validation_epoch_end(outs)
+    assert float(res["psnr"]) > 60
+    lo, hi = 0.5 / 256, 1 - 0.5 / 256
+    for i, name in enumerate(("r_000", "r_001")):
+        path = tmp_path / "predictions" / f"{name}.png"
+        assert path.is_file()
+        got = cv2.imread(str(path), cv2.IMREAD_UNCHANGED)
+        want = np.round(255 * np.clip((res["pred_intensity_img"][i, 0].numpy() - lo) / (hi - lo), 0, 1)).astype(np.uint8)
+        assert got.dtype == np.uint8 and got.shape == (6, 8) and np.array_equal(got, want)
+    m.trainer = None
