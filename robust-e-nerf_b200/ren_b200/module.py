@@ -642,6 +642,36 @@ class RobustENeRF(LightningModule):
         aligned = (scale * p + offset).to(target_intensity_img.dtype).exp()
         return aligned, scale.reshape(-1), offset.reshape(-1)
 
+    @staticmethod
+    @torch.no_grad()
+    def ssim(pred_img, target_img, data_range, kernel_size=11, sigma=1.5, k1=0.01, k2=0.03):
+        """Structural similarity as `torchmetrics.functional.ssim` of torchmetrics==0.6.2 computes it
+        (`loss_metric/metric.py:75-82`: defaults, `data_range = max_target_val`, mean over the map): 11 x 11
+        Gaussian window (sigma 1.5) applied per channel to reflect-padded images, the map cropped back by the pad
+        width, then averaged.  torchmetrics is absent here: restated from its published implementation, parity
+        unpinned; `tests/test_module_cpu.py::test_ssim_properties` checks it against an independent
+        scipy.ndimage evaluation of the same definition.  Images are (N, C, H, W)."""
+        assert pred_img.shape == target_img.shape and pred_img.dim() == 4
+        C_ = pred_img.shape[1]
+        c1, c2 = (k1 * data_range) ** 2, (k2 * data_range) ** 2
+        ax = torch.arange(kernel_size, dtype=pred_img.dtype, device=pred_img.device) - (kernel_size - 1) / 2
+        g = torch.exp(-(ax / sigma) ** 2 / 2)
+        g = g / g.sum()
+        kernel = (g[:, None] * g[None, :]).expand(C_, 1, kernel_size, kernel_size).contiguous()
+        pad = (kernel_size - 1) // 2
+        p = torch.nn.functional.pad(pred_img, (pad, pad, pad, pad), mode="reflect")
+        t = torch.nn.functional.pad(target_img, (pad, pad, pad, pad), mode="reflect")
+        n = p.shape[0]
+        out = torch.nn.functional.conv2d(torch.cat((p, t, p * p, t * t, p * t)), kernel, groups=C_)
+        mu_p, mu_t, e_pp, e_tt, e_pt = (out[i * n:(i + 1) * n] for i in range(5))
+        var_p, var_t, cov = e_pp - mu_p * mu_p, e_tt - mu_t * mu_t, e_pt - mu_p * mu_t
+        ssim_map = ((2 * mu_p * mu_t + c1) * (2 * cov + c2)) / ((mu_p * mu_p + mu_t * mu_t + c1) * (var_p + var_t + c2))
+        # the window is centred on every pixel of the ORIGINAL image after the valid convolution of the padded one;
+        # torchmetrics 0.6 additionally drops a pad-wide border of that map
+        if ssim_map.shape[-1] > 2 * pad and ssim_map.shape[-2] > 2 * pad:
+            ssim_map = ssim_map[..., pad:-pad, pad:-pad]
+        return ssim_map.mean()
+
     @torch.no_grad()
     def evaluation_epoch_end(self, outputs, stage):
         """robust_e_nerf.py:589-696 up to the metrics this image can compute: merge the per-view outputs of
@@ -658,14 +688,21 @@ class RobustENeRF(LightningModule):
         l1 = torch.stack([(a - b).abs().mean() for a, b in zip(aligned, target)]).mean()
         mse = ((aligned - target) ** 2).mean(dim=(1, 2, 3))
         psnr = (10.0 * torch.log10(rng ** 2 / mse)).mean()
+        h, w = aligned.shape[-2:]
+        ssim = None
+        if min(h, w) > 5:                                            # reflect padding needs pad < size
+            ssim = torch.stack([self.ssim(a[None], b[None], stage["max_normalized_pixel_value"])
+                                for a, b in zip(aligned, target)]).mean()
         name = stage.get("name", "eval")
         self.log(f"{name}/l1", l1, prog_bar=True, rank_zero_only=True)
         self.log(f"{name}/psnr", psnr, prog_bar=True, rank_zero_only=True)
+        if ssim is not None:
+            self.log(f"{name}/ssim", ssim, prog_bar=True, rank_zero_only=True)
         log_dir = getattr(self.trainer, "log_dir", None)
         if self.eval_save_pred_intensity_img and log_dir is not None and outputs[0].get("sample_id") is not None:
             ids = torch.stack([o["sample_id"] for o in outputs]).reshape(len(outputs), -1)
             self.save_pred_intensity_imgs(aligned, ids, stage, os.path.join(log_dir, self.PREDICTIONS_FOLDER_NAME))
-        return {"l1": l1, "psnr": psnr, "log_intensity_scale": scale, "log_intensity_offset": offset,
+        return {"l1": l1, "psnr": psnr, "ssim": ssim, "log_intensity_scale": scale, "log_intensity_offset": offset,
                 "pred_intensity_img": aligned}
 
     PREDICTIONS_FOLDER_NAME = "predictions"                          # robust_e_nerf.py:20-22

@@ -217,3 +217,33 @@ def test_epoch_end_writes_prediction_pngs(built_lib, dataset_dir, tmp_path):
         want = np.round(255 * np.clip((res["pred_intensity_img"][i, 0].numpy() - lo) / (hi - lo), 0, 1)).astype(np.uint8)
         assert got.dtype == np.uint8 and got.shape == (6, 8) and np.array_equal(got, want)
     m.trainer = None
+
+
+def test_ssim_properties():
+    """`RobustENeRF.ssim` (the torchmetrics 0.6.2 definition, restated): identity, symmetry, monotone in noise, and
+    equal to an independent scipy.ndimage evaluation of the same windowed statistics."""
+    import numpy as np
+    from scipy import ndimage
+    from ren_b200 import RobustENeRF
+    gen = torch.Generator().manual_seed(0)
+    x = torch.rand(2, 1, 40, 48, generator=gen, dtype=torch.float64)
+    assert abs(float(RobustENeRF.ssim(x, x, 1.0)) - 1.0) < 1e-12
+    noisy = [(x + s * torch.randn(x.shape, generator=gen, dtype=torch.float64)).clamp(0, 1) for s in (0.02, 0.1, 0.3)]
+    vals = [float(RobustENeRF.ssim(n, x, 1.0)) for n in noisy]
+    assert 1 > vals[0] > vals[1] > vals[2] > 0
+    assert abs(float(RobustENeRF.ssim(noisy[1], x, 1.0)) - float(RobustENeRF.ssim(x, noisy[1], 1.0))) < 1e-12
+    # independent evaluation: Gaussian-window means with mirror ("reflect" without edge repeat) boundaries
+    ax = np.arange(11) - 5.0
+    g = np.exp(-(ax / 1.5) ** 2 / 2)
+    g /= g.sum()
+    k = np.outer(g, g)
+    f = lambda a: ndimage.correlate(a, k, mode="mirror")
+    total = []
+    for i in range(2):
+        p, t = noisy[1][i, 0].numpy(), x[i, 0].numpy()
+        mp, mt = f(p), f(t)
+        vp, vt, cv = f(p * p) - mp * mp, f(t * t) - mt * mt, f(p * t) - mp * mt
+        c1, c2 = 0.01 ** 2, 0.03 ** 2
+        m = ((2 * mp * mt + c1) * (2 * cv + c2)) / ((mp * mp + mt * mt + c1) * (vp + vt + c2))
+        total.append(m[5:-5, 5:-5].mean())
+    assert abs(float(RobustENeRF.ssim(noisy[1], x, 1.0)) - float(np.mean(total))) < 1e-10
