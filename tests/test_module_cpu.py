@@ -247,3 +247,30 @@ def test_ssim_properties():
         m = ((2 * mp * mt + c1) * (2 * cv + c2)) / ((mp * mp + mt * mt + c1) * (vp + vt + c2))
         total.append(m[5:-5, 5:-5].mean())
     assert abs(float(RobustENeRF.ssim(noisy[1], x, 1.0)) - float(np.mean(total))) < 1e-10
+
+
+def test_trainer_flat_gradient_detection(built_lib, dataset_dir):
+    """`FlatTrainer._flat_mlp_grad`: the fused backward hands out the MLP gradients as views of one flat buffer;
+    the trainer copies that buffer once, and falls back to per-parameter copies when the views were replaced."""
+    from ren_b200.trainer import FlatTrainer
+    _, m = _model(dataset_dir, "step_plumbing")
+    tr = FlatTrainer(m, use_fused_adam=False)
+    params = m.nerf.mlp_parameters()
+    n = sum(p.numel() for p in params)
+    flat = torch.arange(n, dtype=torch.float32) * 1e-3
+    off = 0
+    for p in params:
+        p.grad = flat[off:off + p.numel()].view(p.shape)
+        off += p.numel()
+    got = tr._flat_mlp_grad()
+    assert got is not None and got.data_ptr() == flat.data_ptr() and torch.equal(got, flat)
+    tr._gather_grads()
+    assert torch.equal(tr.gbuf[:n], flat)
+    # one gradient replaced by a fresh tensor (e.g. a second backward accumulated out of place)
+    params[3].grad = params[3].grad.clone()
+    assert tr._flat_mlp_grad() is None
+    tr.gbuf.zero_()
+    tr._gather_grads()
+    assert torch.equal(tr.gbuf[:n], flat)                        # the per-parameter path gives the same vector
+    params[0].grad = None
+    assert tr._flat_mlp_grad() is None
