@@ -191,3 +191,15 @@ def test_event_dataset_builds_and_caches_like_the_reference(tag, built_lib, tmp_
     perm = torch.randperm(len(ds), generator=torch.Generator().manual_seed(9))
     assert torch.equal(again.events["end_ts"], ds.events["end_ts"][perm])
     assert set(again[0]) == set(keys) and len(again) == len(ds)
+
+
+def test_colorize_events_matches_reference_golden_on_cpu():
+    """`colorize_events` is plain tensor indexing: on the CPU against the reference's Bayer channel indices."""
+    from ren_b200 import events as E
+    g = np.load(GOLDEN)
+    pos = torch.from_numpy(g["b_q_position"])
+    out = E.colorize_events({"position": pos}, {"bayer_pattern": g["b_bayer"]})
+    assert out["channel_idx"].dtype == torch.uint8
+    assert torch.equal(out["channel_idx"], torch.from_numpy(g["b_q_channel_idx"]))
+    mono = E.colorize_events({"position": pos}, {"bayer_pattern": np.array("")})
+    assert "channel_idx" not in mono
