@@ -124,3 +124,18 @@ def test_sizes(built_lib):
     forced = _lib.make_render_desc(near_plane=0.5, far_plane=4.5, render_step_size=4 / 128, engine="tc_f16x3")
     with pytest.raises(RuntimeError, match="tcgen05"):
         _lib.stash_bytes(f64, forced, 8, 128)
+
+
+def test_header_is_plain_c(tmp_path):
+    """The boundary is a C ABI: the header compiles as C11 on its own (no C++ or torch types)."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    src = tmp_path / "use.c"
+    src.write_text('#include "ren_b200.h"\n'
+                   "int main(void) { RenFieldDesc f; RenRenderDesc r; RenPacked p; (void)f; (void)r; (void)p;\n"
+                   "  return REN_ABI_VERSION == 4 ? 0 : 1; }\n")
+    out = subprocess.run(["gcc", "-std=c11", "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"),
+                          str(src)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
