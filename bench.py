@@ -1,28 +1,41 @@
 #!/usr/bin/env python
 """bench.py -- ray-samples/s of the event-NeRF training hot path (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config 2|3|4|5] [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-A "step" is one `RobustENeRF.training_step` + backward + gradient all-reduce (N>1) + Adam on
-one synthetic event batch of BASELINE config 2: 4096 rays/GPU x 128 samples x 2 renders
-(= 1 048 576 ray-samples per GPU per step), 8-layer x 256-wide MLP.  One ray-sample = one
-(ray, sample) pair pushed through field + compositing in one render.
+A "step" is one `RobustENeRF.training_step` + backward + gradient all-reduce (N>1) + Adam on one
+synthetic event batch.  Workloads (BASELINE.json `configs`, shapes per SURVEY.md section 8d):
 
-  value     whole-job ray-samples/s, event batch already resident in HBM
-  e2e       same through the public API with HOST (pinned) batches: H2D copy of every batch
-            and a D2H read of the loss inside the timed region
-  roofline  dominant kernel (field forward) against the measured bf16 tensor peak:
-            1 186 304 algorithmic FLOP per ray-sample / CUDA-event time
-  cpu_baseline  the oracle port of the reference's own Python path on the host cores,
-            bounded sample of the same workload
+  2  (headline) 4096 rays/GPU x 128 samples x 2 renders, 8Lx256 MLP, l_diff, frozen C_p / tau
+  3  16384 rays x 128 samples x 3 renders (one in tangent mode), l_diff + l_grad, C_p and tau trainable
+  4  mocap-desk2-like: 8192 rays/GPU x 192 steps x 3 renders, aabb / near / far of the YAML, occupancy grid on
+  5  office-maze-like: 8192 rays/GPU x 256 steps x 3 renders, occupancy grid on
 
-`--impl reference` times that CPU path alone (the upstream reference has no CPU mode and
-cannot be installed here: nerfacc / tiny-cuda-nn are CUDA-only and absent).
+One ray-sample = one (ray, sample) pair pushed through field + compositing in one render; with an occupancy
+grid the emitted samples (what the reference's dynamic batch size counts) are reported next to the dense steps.
+
+  value     whole-job ray-samples/s, event batches already resident in HBM; the timed block of K steps is
+            repeated until >= 2 s of GPU time: median block (min / max in `blocks`)
+  e2e       same through the public API with HOST (pinned) batches: H2D copy of every batch and a D2H read of
+            the loss inside the timed region
+  roofline  dominant kernel (field forward) against the measured bf16 tensor peak: 1 186 304 algorithmic FLOP
+            per ray-sample / CUDA-event time
+  parity    the second half of BASELINE.json's metric: after the timed region, a fixed 128-ray subset of
+            batch 0 rendered by the CUDA path with the TRAINED weights vs the oracle on the same weights, rays
+            and jitter: per-ray log I (normwise, max-abs) and loss relative error
+  secondary (N=1, --config 2 only) short runs of configs 3, 4, 5 in the same JSON line
+  cpu_baseline  the oracle port of the reference's own Python path on the host cores, bounded sample
+
+`--impl reference` times that CPU path alone (the upstream reference has no CPU mode and cannot be installed
+here: nerfacc / tiny-cuda-nn are CUDA-only and absent) -- a PORT, not the reference.
 """
 import argparse
+import ctypes as C
 import json
+import math
 import os
+import statistics
 import subprocess
 import sys
 import tempfile
@@ -33,12 +46,30 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, "robust-e-nerf_b200"))
 sys.path.insert(0, ROOT)
 
-RAYS_PER_GPU = 4096
-N_SAMPLES = 128
-RENDERS = 2
-FLOP_PER_SAMPLE_FWD = 1_186_304
-WORKLOAD = ("config2: ficus-easy-like synthetic 640x480 event stream, 4096 rays/GPU x 128 samples x 2 "
-            "renders, 8Lx256 MLP, l_diff (mse), frozen Cp/tau, fwd+bwd+Adam")
+FLOP_PER_SAMPLE_FWD = 1_186_304          # 593 152 MAC, 8x256 MLP, C = 1
+MIN_TIMED_MS = 2000.0
+
+# rays per GPU, marching steps per ray, renders, l_grad weight, trainable sensor parameters, scene box
+CONFIGS = {
+    2: dict(name="config2: ficus-easy-like synthetic 640x480 event stream, 4096 rays/GPU x 128 samples x 2 renders, "
+                 "8Lx256 MLP, l_diff (mse), frozen Cp/tau, fwd+bwd+Adam",
+            rays=4096, n=128, renders=2, w_grad=0.0, trainable=False, aabb=(-1.5, -1.5, -1.5, 1.5, 1.5, 1.5),
+            near=0.5, far=None, span=4.0, grid=False),
+    3: dict(name="config3: ficus-hard-like, 16384 rays x 128 samples x 3 renders (2 value + 1 tangent), 8Lx256 MLP, "
+                 "l_diff + 1e-3 l_grad (mape), Cp and tau trainable from a poor init, fwd+bwd+Adam",
+            rays=16384, n=128, renders=3, w_grad=1e-3, trainable=True, aabb=(-1.5, -1.5, -1.5, 1.5, 1.5, 1.5),
+            near=0.5, far=None, span=4.0, grid=False),
+    4: dict(name="config4: mocap-desk2-like, 8192 rays/GPU x 192 marching steps x 3 renders, aabb / near / far of "
+                 "configs/train/mocap-desk2.yaml:38-48, sphere contraction, occupancy grid 128^3 on, l_diff + l_grad, "
+                 "Cp and tau trainable, fwd+bwd+Adam",
+            rays=8192, n=192, renders=3, w_grad=1e-3, trainable=True, aabb=(0.5, -2.1, 0.6, 2.0, -0.6, 1.6),
+            near=0.05, far=3.0, span=None, grid=True),
+    5: dict(name="config5: office-maze-like, 8192 rays/GPU x 256 marching steps x 3 renders, aabb / near / far of "
+                 "configs/train/office-maze.yaml:38-48, sphere contraction, occupancy grid 128^3 on, l_diff + l_grad, "
+                 "Cp and tau trainable, fwd+bwd+Adam",
+            rays=8192, n=256, renders=3, w_grad=1e-3, trainable=True, aabb=(-2.3, -3.2, 0.0, 1.7, 2.8, 3.0),
+            near=0.01, far=4.0, span=None, grid=True),
+}
 
 
 def peaks():
@@ -48,6 +79,20 @@ def peaks():
         return dict(tflops=p.get("bf16_tflops_sustained", p.get("bf16_tflops")), hbm=p["hbm_gbs"],
                     source="measured (MEASURED_PEAKS.json, bf16 sustained)")
     return dict(tflops=1400.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+def ncu_metrics():
+    """Tensor-pipe activity and DRAM bytes of the dominant kernel come from a COMMITTED ncu capture of this
+    command (profiles/r02_ncu_metrics.json names the report it was read from); absent file -> null fields."""
+    path = os.path.join(ROOT, "profiles", "r02_ncu_metrics.json")
+    if os.path.exists(path):
+        try:
+            d = json.load(open(path))
+            d["file"] = "profiles/r02_ncu_metrics.json"
+            return d
+        except Exception:
+            pass
+    return None
 
 
 class ClockSampler(threading.Thread):
@@ -109,7 +154,125 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(self.rows)}
 
 
-def cpu_oracle_rate(n_rays, steps, warmup, dataset_dir):
+# --------------------------------------------------------------------------- workload construction
+def scene_geometry(wc):
+    """Orbit centre / scale of the synthetic trajectory: the unit scene for configs 2-3, re-centred on the aabb
+    centre and scaled to its extent for the real-sequence boxes."""
+    a = wc["aabb"]
+    if tuple(a) == (-1.5, -1.5, -1.5, 1.5, 1.5, 1.5):
+        return (0.0, 0.0, 0.0), 1.0
+    center = tuple((a[i] + a[i + 3]) / 2 for i in range(3))
+    ext = max(a[i + 3] - a[i] for i in range(3))
+    return center, 0.3 * ext / 3.0            # orbit radius = 0.3 x the largest extent: the camera is inside
+
+
+def product_config(wc, world):
+    from ren_b200 import synthetic
+    if wc["span"] is not None:
+        cfg = synthetic.default_config(n_samples=wc["n"], aabb=wc["aabb"], near=wc["near"], span=wc["span"])
+    else:
+        step = (wc["far"] - wc["near"]) / (wc["n"] + 0.5)
+        cfg = synthetic.default_config(n_samples=wc["n"], aabb=wc["aabb"], near=wc["near"], span=step * wc["n"])
+    cfg["num_nodes"], cfg["gpus"] = 1, list(range(world))
+    cfg["loss"]["weight"]["log_intensity_grad"] = wc["w_grad"]
+    if wc["trainable"]:
+        cfg["contrast_threshold"]["freeze"] = False
+        cfg["refractory_period"]["freeze"] = False
+    if wc["grid"]:
+        cfg["nerf"]["occ_grid"] = dict(resolution=128, occ_thre=1e-2, ema_decay=0.95, warmup_steps=256, n=16,
+                                       enabled=True)
+    return cfg
+
+
+def build_model(wc, world, rank, dev, engine):
+    import torch
+    from ren_b200 import RobustENeRF, synthetic
+    root = os.path.join(tempfile.gettempdir(), f"ren_b200_bench_{rank}_{wc['n']}_{int(wc['grid'])}")
+    center, scale = scene_geometry(wc)
+    synthetic.write_dataset(root, center=center, scale=scale)
+    cfg = product_config(wc, world)
+    torch.manual_seed(0)
+    model = RobustENeRF(dataset_directory=root, engine=engine, **cfg).to(dev).train()
+    if wc["trainable"]:
+        with torch.no_grad():       # poor initialisation: ratio x1.5, tau x0.5 (SURVEY.md section 8d config 3)
+            ct = model.contrast_threshold.parametrizations.p2n_contrast_threshold_ratio
+            ct.original.copy_(ct[0].right_inverse(torch.tensor(1.5)))
+            rp = model.refractory_period.parametrizations._refractory_period
+            rp.original.copy_(rp[0].right_inverse(model.refractory_period.init_refractory_period.double() * 0.5))
+    return model, cfg, root
+
+
+def oracle_configs(cfg):
+    """oracle.restatement configs equivalent to a `synthetic.default_config` dict."""
+    from oracle import restatement as R
+    n, mlp, loss = cfg["nerf"], cfg["nerf"]["mlp"], cfg["loss"]
+    fcfg = R.FieldConfig(aabb=list(n["aabb"]), contraction=n["contraction_type"], net_depth=mlp["net_depth"],
+                         net_width=mlp["net_width"], skip_layer=mlp["skip_layer"],
+                         net_depth_condition=mlp["net_depth_condition"],
+                         net_width_condition=mlp["net_width_condition"])
+    rcfg = R.RenderConfig(near_plane=n["near_plane"], far_plane=n["far_plane"],
+                          render_step_size=n["render_step_size"], cone_angle=n["cone_angle"],
+                          early_stop_eps=n["early_stop_eps"], alpha_thre=n["alpha_thre"])
+    scfg = R.StepConfig(w_grad=loss["weight"]["log_intensity_grad"], w_diff=loss["weight"]["log_intensity_diff"],
+                        err_grad=loss["error_fn"]["log_intensity_grad"], err_diff=loss["error_fn"]["log_intensity_diff"],
+                        pw_grad=loss["param_weight"]["log_intensity_grad"],
+                        pw_diff=loss["param_weight"]["log_intensity_diff"],
+                        min_modeled_intensity=cfg["min_modeled_intensity"])
+    return fcfg, rcfg, scfg
+
+
+def parity_check(model, cfg, root, host_batch, host_jitter, dev, n_rays=128):
+    """CUDA path vs the oracle on the first `n_rays` rays of batch 0 with the model's CURRENT weights."""
+    import torch
+    from oracle import restatement as R
+    from oracle import synth as osynth
+    torch.set_num_threads(os.cpu_count() or 1)
+    sub = {k: {kk: vv[:, :n_rays].clone() for kk, vv in v.items()} for k, v in host_batch.items()}
+    jit = {k: v[:n_rays].clone() for k, v in host_jitter.items()}
+    grid = getattr(model.nerf, "occupancy_grid", None)
+    step0 = model.global_step
+    try:
+        model.global_step = None            # no occupancy-grid update inside the parity render
+    except AttributeError:
+        pass
+    with torch.no_grad():
+        loss = model.training_step({k: {kk: vv.to(dev) for kk, vv in v.items()} for k, v in sub.items()}, 0,
+                                   {k: v.to(dev) for k, v in jit.items()})
+    try:
+        model.global_step = step0
+    except AttributeError:
+        pass
+    got0, got1 = model.last["start_log_intensity"].double().cpu(), model.last["end_log_intensity"].double().cpu()
+    sd = model.state_dict()
+    params = {k[len("nerf.radiance_field."):]: v.detach().float().cpu() for k, v in sd.items()
+              if k.startswith("nerf.radiance_field.mlp.")}
+    scene = osynth.load_scene(root)
+    fcfg, rcfg, scfg = oracle_configs(cfg)
+    th_r = sd["contrast_threshold.parametrizations.p2n_contrast_threshold_ratio.original"].detach().cpu()
+    th_t = sd["refractory_period.parametrizations._refractory_period.original"].detach().cpu().clone()
+    if grid is not None:
+        return {"rays": n_rays, "note": "occupancy grid on: the oracle comparison of the grid path lives in "
+                                        "tests/test_occupancy_gpu.py", "loss": float(loss)}
+    if scfg.w_grad > 0:
+        out = R.training_step(params, fcfg, rcfg, scfg, scene, sub, jit, th_r, th_t)
+    else:
+        with torch.no_grad():
+            out = R.training_step(params, fcfg, rcfg, scfg, scene, sub, jit, th_r, th_t)
+    ref0, ref1 = out["start_log_intensity"].detach().double(), out["end_log_intensity"].detach().double()
+    got, ref = torch.cat((got0, got1)), torch.cat((ref0, ref1))
+    ref_loss = float(out["loss"].detach())
+    res = {"rays": n_rays, "weights": "after the timed training steps",
+           "logI_normwise": float((got - ref).norm() / ref.norm()), "logI_maxabs": float((got - ref).abs().max()),
+           "logI_std_over_rays": float(ref.std()),
+           "loss_rel_err": abs(float(loss) - ref_loss) / abs(ref_loss), "loss": float(loss), "oracle_loss": ref_loss,
+           "bar": 1e-4}
+    if scfg.w_grad > 0:
+        g, r = model.last_grad["log_intensity_grad"].double().cpu(), out["log_intensity_grad"].detach().double()
+        res["dlogI_dt_normwise"] = float((g - r).norm() / r.norm())
+    return res
+
+
+def cpu_oracle_rate(wc, n_rays, steps, warmup, dataset_dir):
     """Oracle port of the reference training step (fwd + bwd) on the host cores."""
     import torch
     from oracle import restatement as R
@@ -117,8 +280,8 @@ def cpu_oracle_rate(n_rays, steps, warmup, dataset_dir):
     torch.set_num_threads(os.cpu_count() or 1)
     scene = synth.load_scene(dataset_dir)
     fcfg = R.FieldConfig()
-    step = 4.0 / N_SAMPLES
-    rcfg = R.RenderConfig(near_plane=0.5, far_plane=0.5 + (N_SAMPLES + 0.5) * step, render_step_size=step)
+    step = 4.0 / wc["n"]
+    rcfg = R.RenderConfig(near_plane=0.5, far_plane=0.5 + (wc["n"] + 0.5) * step, render_step_size=step)
     scfg = R.StepConfig()
     params = {k: v.requires_grad_(True) for k, v in R.init_field_params(fcfg, seed=0).items()}
     batch, jitter = synth.make_batch(n_rays, scene["T_wc_timestamp"])
@@ -138,7 +301,7 @@ def cpu_oracle_rate(n_rays, steps, warmup, dataset_dir):
         if i >= warmup:
             times.append(dt)
     per_step = sum(times) / len(times)
-    return RENDERS * n_rays * N_SAMPLES / per_step, per_step, torch.get_num_threads(), loss
+    return wc["renders"] * n_rays * wc["n"] / per_step, per_step, torch.get_num_threads(), loss
 
 
 def run_reference(args):
@@ -146,18 +309,121 @@ def run_reference(args):
     if rank != 0:
         return
     from oracle import synth
+    wc = CONFIGS[2]
     root = synth.write_dataset(os.path.join(tempfile.gettempdir(), "ren_b200_bench_ref"))
     n_rays = 256
-    rate, per_step, cores, loss = cpu_oracle_rate(n_rays, args.steps, args.warmup, root)
-    sample = f"{n_rays} rays x {N_SAMPLES} samples x {RENDERS} renders per step (fwd+bwd, fp32, torch CPU)"
+    rate, per_step, cores, loss = cpu_oracle_rate(wc, n_rays, args.steps, args.warmup, root)
+    sample = (f"PORT of the reference path (oracle/restatement.py, torch CPU fp32): {n_rays} of the 4096 rays x "
+              f"{wc['n']} samples x {wc['renders']} renders per step (fwd+bwd)")
     print(json.dumps({
         "impl": "reference", "metric": "ray-samples/s", "value": rate, "unit": "ray-samples/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": {"workload": WORKLOAD, "sample": sample},
+        "data": "synthetic", "config": {"workload": wc["name"], "sample": sample},
         "cpu_baseline": {"value": rate, "unit": "ray-samples/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": rate, "unit": "ray-samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "loss": loss}))
+
+
+# --------------------------------------------------------------------------- product arm
+class Runner:
+    """One workload on this rank: model, trainer, resident + pinned host batches, timed blocks."""
+
+    def __init__(self, wc, args, rank, world, dev, graph):
+        import torch
+        from ren_b200 import synthetic
+        from ren_b200.trainer import FlatTrainer
+        self.wc, self.world, self.dev, self.rank = wc, world, dev, rank
+        self.model, self.cfg, self.root = build_model(wc, world, rank, dev, args.engine)
+        self.graph = bool(graph) and not wc["grid"]
+        self.trainer = FlatTrainer(self.model, world_size=world, cuda_graph=self.graph)
+        pose_ts = self.model.trajectory.T_wc_timestamp.cpu()
+        self.n_batches = 4
+        self.host = [synthetic.make_batch(wc["rays"], pose_ts, rank=rank, seed=1234 + 17 * i, pin=True)
+                     for i in range(self.n_batches)]
+        self.resident = [(synthetic.to_device(b, dev), {k: v.to(dev) for k, v in j.items()}) for b, j in self.host]
+        self.h2d = synthetic.batch_nbytes(self.host[0][0]) + sum(v.numel() * 4 for v in self.host[0][1].values())
+        self.it = 0
+        self.spp_sum = None
+        self.torch = torch
+
+    def sync_all(self):
+        import torch.distributed as dist
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier()
+            self.torch.cuda.synchronize()
+
+    def block(self, n_steps, e2e):
+        """K steps between two CUDA events (barrier + synchronize on both sides), max over ranks."""
+        import torch.distributed as dist
+        from ren_b200 import synthetic
+        torch = self.torch
+        self.sync_all()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        last = None
+        for _ in range(n_steps):
+            i = self.it
+            self.it += 1
+            if e2e:
+                hb, hj = self.host[i % self.n_batches]
+                batch = synthetic.to_device(hb, self.dev)
+                jit = {k: v.to(self.dev, non_blocking=True) for k, v in hj.items()}
+                last = float(self.trainer.step(batch, i, jit))            # D2H read of the loss
+            else:
+                batch, jit = self.resident[i % self.n_batches]
+                last = self.trainer.step(batch, i, jit)
+        b.record()
+        self.sync_all()
+        ms = a.elapsed_time(b)
+        if self.world > 1:
+            t = torch.tensor([ms], device=self.dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms, float(last)
+
+    def timed(self, n_steps, e2e, min_ms):
+        """Blocks of exactly `n_steps` steps, repeated until `min_ms` of GPU time: (median, [all], loss)."""
+        blocks, total, loss = [], 0.0, None
+        while True:
+            ms, loss = self.block(n_steps, e2e)
+            blocks.append(ms)
+            total += ms
+            if total >= min_ms or len(blocks) >= 200:
+                break
+        return statistics.median(blocks), blocks, loss
+
+    def mean_spp(self):
+        v = self.model.logged.get("train/mean_num_samples_per_ray")
+        return float(v) if v is not None else float(self.wc["n"])
+
+
+def run_secondary(cfg_id, args, rank, world, dev, graph):
+    """A short run of another BASELINE config (warm-up 3, then one block of 5 steps) for the same JSON line."""
+    wc = CONFIGS[cfg_id]
+    try:
+        r = Runner(wc, args, rank, world, dev, graph)
+        r.block(3, False)
+        if r.graph:
+            r.block(2, False)                       # first replay after the capture
+        ms, blocks, loss = r.timed(5, False, 0.0)
+        spp = r.mean_spp()
+        dense = wc["renders"] * wc["rays"] * wc["n"] * world
+        emitted = wc["renders"] * wc["rays"] * spp * world
+        out = {"config": cfg_id, "workload": wc["name"], "ms_per_step": ms / 5, "steps": 5,
+               "ray_samples_per_s": emitted * 5 / (ms * 1e-3), "dense_steps_per_s": dense * 5 / (ms * 1e-3),
+               "mean_samples_per_ray": spp, "loss": loss, "cuda_graph": r.graph}
+        try:
+            out["parity"] = parity_check(r.model, r.cfg, r.root, r.host[0][0], r.host[0][1], dev, 64)
+        except Exception as e:                      # the secondary record must not take the headline down
+            out["parity"] = {"error": repr(e)[:200]}
+        del r
+        import torch
+        torch.cuda.empty_cache()
+        return out
+    except Exception as e:
+        return {"config": cfg_id, "workload": wc["name"], "error": repr(e)[:300]}
 
 
 def run_ours(args):
@@ -173,127 +439,136 @@ def run_ours(args):
     import __graft_entry__ as G
     if not os.path.exists(G.LIB):
         G.build()
-    from ren_b200 import RobustENeRF, _lib, synthetic
-    from ren_b200.trainer import FlatTrainer
+    from ren_b200 import _lib
     lib = _lib.load()
-
-    root = os.path.join(tempfile.gettempdir(), f"ren_b200_bench_{rank}")
-    synthetic.write_dataset(root)
-    cfg = synthetic.default_config(n_samples=N_SAMPLES)
-    cfg["num_nodes"], cfg["gpus"] = 1, list(range(world))
-    torch.manual_seed(0)
-    model = RobustENeRF(dataset_directory=root, engine=args.engine, **cfg).to(dev).train()
-    trainer = FlatTrainer(model, world_size=world)
-    pose_ts = model.trajectory.T_wc_timestamp.cpu()
-    n_batches = 4
-    host = [synthetic.make_batch(RAYS_PER_GPU, pose_ts, rank=rank, seed=1234 + 17 * i, pin=True)
-            for i in range(n_batches)]
-    resident = [(synthetic.to_device(b, dev), {k: v.to(dev) for k, v in j.items()}) for b, j in host]
-    h2d = synthetic.batch_nbytes(host[0][0]) + sum(v.numel() * 4 for v in host[0][1].values())
-
-    def sync_all():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    def timed(n_steps, e2e):
-        sync_all()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        last = None
-        for i in range(n_steps):
-            if e2e:
-                hb, hj = host[i % n_batches]
-                batch = synthetic.to_device(hb, dev)
-                jit = {k: v.to(dev, non_blocking=True) for k, v in hj.items()}
-                last = float(trainer.step(batch, i, jit))            # D2H read of the loss
-            else:
-                batch, jit = resident[i % n_batches]
-                last = trainer.step(batch, i, jit)
-        b.record()
-        sync_all()
-        ms = a.elapsed_time(b)
-        if world > 1:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t)
-        return ms, float(last)
-
-    timed(args.warmup, False)
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    lib.ren_timing_enable(1)
-    for k in range(9):
-        import ctypes as C
-        lib.ren_timing_collect(k, C.byref(C.c_double()), C.byref(C.c_int64()))
-    launches0 = lib.ren_launch_count()
-    ms, loss = timed(args.steps, False)
-    launches = lib.ren_launch_count() - launches0
-    kern = {}
-    import ctypes as C
+    wc = CONFIGS[args.config]
+    graph = args.graph != "off"
+    run = Runner(wc, args, rank, world, dev, graph)
+    model, trainer = run.model, run.trainer
     names = ["field_fwd", "field_dgrad", "wgrad", "composite_fwd", "composite_bwd", "event_rays", "loss",
              "adam", "pack"]
+
+    # warm-up (eager: the first three steps are never captured), then the per-kernel CUDA-event split and the
+    # launch count of one eager step
+    run.block(max(args.warmup, 3), False)
+    lib.ren_timing_enable(1)
+    for k in range(len(names)):
+        lib.ren_timing_collect(k, C.byref(C.c_double()), C.byref(C.c_int64()))
+    trainer.cuda_graph = False
+    n_prof = 3
+    launches0 = lib.ren_launch_count()
+    run.block(n_prof, False)
+    launches_per_step = (lib.ren_launch_count() - launches0) / n_prof
+    kern = {}
     for k, nme in enumerate(names):
         tot, cnt = C.c_double(), C.c_int64()
         lib.ren_timing_collect(k, C.byref(tot), C.byref(cnt))
         if cnt.value:
             kern[nme] = {"ms_per_launch": tot.value / cnt.value, "launches": cnt.value,
-                         "ms_per_step": tot.value / args.steps}
+                         "ms_per_step": tot.value / n_prof}
     lib.ren_timing_enable(0)
-    timed(min(args.warmup, 2), True)
-    ms_e2e, _ = timed(args.steps, True)
+    trainer.cuda_graph = run.graph
+    graph_note = None
+    if run.graph:
+        try:
+            run.block(2, False)                     # capture + first replays, untimed
+        except Exception as e:                      # capture refused: stay eager and say so
+            graph_note = repr(e)[:200]
+            trainer.cuda_graph = run.graph = False
+            torch.cuda.synchronize()
+            run.block(1, False)
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms, blocks, loss = run.timed(args.steps, False, MIN_TIMED_MS)
+    run.block(min(args.warmup, 2), True)
+    ms_e2e, blocks_e2e, _ = run.timed(args.steps, True, MIN_TIMED_MS / 2)
     if rank == 0:
         sampler.stop_flag.set()
         sampler.join(timeout=2)
 
-    samples_per_step = RENDERS * RAYS_PER_GPU * N_SAMPLES * world
+    spp = run.mean_spp()
+    samples_per_step = wc["renders"] * wc["rays"] * spp * world
     value = samples_per_step * args.steps / (ms * 1e-3)
     e2e = samples_per_step * args.steps / (ms_e2e * 1e-3)
+
+    params_equal = None
+    if world > 1:
+        flat = model.nerf.flat_params()
+        chk = torch.stack((flat.double().sum(), flat.double().abs().sum(), flat.double().pow(2).sum()))
+        allc = [torch.empty_like(chk) for _ in range(world)]
+        dist.all_gather(allc, chk)
+        params_equal = all(bool(torch.equal(allc[0], c)) for c in allc)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
+
     pk = peaks()
-    engine_is_tc = model.nerf.engine != "simt_fp32"
+    engine = model.nerf.engine
+    engine_is_tc = engine != "simt_fp32"
+    ncu = ncu_metrics() if (engine_is_tc and args.config == 2) else None
     roof = None
     if "field_fwd" in kern:
-        per_launch_samples = RENDERS * RAYS_PER_GPU * N_SAMPLES
-        ach = per_launch_samples * FLOP_PER_SAMPLE_FWD / (kern["field_fwd"]["ms_per_launch"] * 1e-3) / 1e12
-        roof = {"bound": "tensor", "kernel": "field_fwd", "achieved": ach, "peak": pk["tflops"],
-                "unit": "TFLOP/s", "frac": ach / pk["tflops"],
-                # dram__bytes_read.sum + dram__bytes_write.sum of ren_tc_chain<0,1> for this exact launch shape
-                # (ncu --set full, profiles/r01_tc_v32_ncu_summary.txt); algorithmic = 5.1 KB stash per sample
-                "traffic": 5.391e9 if engine_is_tc else None, "traffic_unit": "bytes/launch",
-                "algorithmic_bytes": per_launch_samples * 5096,
-                "tensor_pipe_active_pct_ncu": 50.8 if engine_is_tc else None,
-                "peak_source": pk["source"], "samples_per_launch": per_launch_samples,
-                "flop_per_sample": FLOP_PER_SAMPLE_FWD,
-                "note": "fp16 hi/lo split executes 3 MMAs per algorithmic MMA: ceiling of frac is 1/3"}
+        per_launch_samples = wc["renders"] * wc["rays"] * wc["n"] if args.config == 2 else None
+        if per_launch_samples:
+            ach = per_launch_samples * FLOP_PER_SAMPLE_FWD / (kern["field_fwd"]["ms_per_launch"] * 1e-3) / 1e12
+            # ~100 B per ray per render (o, d, jitter in; C, O, D out) + the 2.38 MB of weights
+            alg = wc["renders"] * wc["rays"] * 100 + 595_586 * 4
+            roof = {"bound": "tensor", "kernel": "field_fwd (ren_tc_chain<0,1,0>)", "achieved": ach,
+                    "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"],
+                    "traffic": ncu.get("field_fwd_dram_bytes") if ncu else None, "traffic_unit": "bytes/launch",
+                    "algorithmic_bytes": alg,
+                    "stash_bytes": per_launch_samples * 5096,
+                    "tensor_pipe_active_pct_ncu": ncu.get("field_fwd_tensor_pipe_pct") if ncu else None,
+                    "ncu_source": ncu.get("source") if ncu else None,
+                    "peak_source": pk["source"], "samples_per_launch": per_launch_samples,
+                    "flop_per_sample": FLOP_PER_SAMPLE_FWD,
+                    "note": "fp16 hi/lo split executes 3 MMAs per algorithmic MMA: ceiling of frac is 1/3; "
+                            "traffic is the activation stash the training forward must write (stash_bytes), "
+                            "not algorithmic traffic"}
+    parity = None
+    try:
+        parity = parity_check(model, run.cfg, run.root, run.host[0][0], run.host[0][1], dev)
+    except Exception as e:
+        parity = {"error": repr(e)[:300]}
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         from oracle import synth as osynth
         oroot = osynth.write_dataset(os.path.join(tempfile.gettempdir(), "ren_b200_bench_ref"))
         n_rays = 256
-        rate, per_step, cores, _ = cpu_oracle_rate(n_rays, 2, 1, oroot)
+        rate, per_step, cores, _ = cpu_oracle_rate(CONFIGS[2], n_rays, 2, 1, oroot)
         cpu = {"value": rate, "unit": "ray-samples/s", "cores": cores, "kind": "port",
-               "sample": f"{n_rays} rays x {N_SAMPLES} samples x {RENDERS} renders per step, 2 timed steps "
-                         "(fwd+bwd, fp32, torch CPU oracle)"}
-    engine = model.nerf.engine
+               "sample": f"{n_rays} rays x 128 samples x 2 renders per step, 2 timed steps "
+                         "(fwd+bwd, fp32, torch CPU oracle port of the reference path)"}
+    h2d_bytes, graph_on, run_cfg = run.h2d, run.graph, None
+    secondary = None
+    if world == 1 and args.config == 2 and not args.no_secondary:
+        del run, trainer
+        torch.cuda.empty_cache()
+        secondary = [run_secondary(c, args, rank, world, dev, graph) for c in (3, 4, 5)]
     out = {
         "metric": "ray-samples/s", "value": value, "unit": "ray-samples/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32" if engine == "simt_fp32" else "f16x3-split operands, f32 accumulate (fwd); f32 (bwd)",
+        "dtype": "f32" if engine == "simt_fp32" else
+                 "fwd + dgrad: f16 hi/lo split operands (3 MMAs), f32 accumulate; wgrad: single f16 operands, "
+                 "f32 accumulate; geometry / compositing / loss / Adam f32 (timestamps f64)",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD, "engine": engine, "rays_per_gpu": RAYS_PER_GPU,
-                   "samples_per_ray": N_SAMPLES, "renders_per_step": RENDERS,
+        "config": {"workload": wc["name"], "config_id": args.config, "engine": engine, "rays_per_gpu": wc["rays"],
+                   "samples_per_ray": spp, "marching_steps_per_ray": wc["n"], "renders_per_step": wc["renders"],
+                   "cuda_graph": graph_on if graph_note is None else {"on": False, "capture_error": graph_note},
                    "l2": "per-step working set (activation stash ~11 GB) >> 126 MB L2; 4 rotating input batches",
                    "parallelism": f"dp{world}"},
-        "e2e": {"value": e2e, "unit": "ray-samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                "ms_per_step": ms_e2e / args.steps},
-        "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "kernels": kern,
+        "blocks": {"n": len(blocks), "steps_per_block": args.steps, "ms_per_step_median": ms / args.steps,
+                   "ms_per_step_min": min(blocks) / args.steps, "ms_per_step_max": max(blocks) / args.steps,
+                   "timed_ms_total": sum(blocks)},
+        "e2e": {"value": e2e, "unit": "ray-samples/s", "h2d_bytes_per_step": h2d_bytes,
+                "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps, "blocks": len(blocks_e2e)},
+        "gpu_launches": int(round(launches_per_step * args.steps)), "gpu_launches_per_step": launches_per_step,
+        "roofline": roof, "parity": parity, "cpu_baseline": cpu, "kernels": kern,
+        "params_equal_across_ranks": params_equal, "secondary": secondary,
         "clocks": sampler.summary(), "loss": loss,
     }
     print(json.dumps(out))
@@ -308,7 +583,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--engine", default="auto")
+    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS))
+    ap.add_argument("--graph", default="auto", choices=["auto", "off"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define REN_ABI_VERSION 4
+#define REN_ABI_VERSION 5
 
 enum {
   REN_OK = 0,
@@ -292,6 +292,12 @@ int ren_event_queue(int64_t n_events, int32_t img_width, int32_t img_height, con
 int ren_adam_step(int64_t n, float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
                   float lr, float beta1, float beta2, float eps, float weight_decay,
                   float grad_scale, int64_t step, void* stream);
+/* Same update with the 1-based step count read from device memory (`step`: (1) i64 device scalar the caller
+ * increments on the same stream), so that a CUDA graph capturing the whole training step stays valid across
+ * replays.  torch.optim.Adam(capturable=True) keeps its step on the device for the same reason. */
+int ren_adam_step_dev(int64_t n, float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
+                      float lr, float beta1, float beta2, float eps, float weight_decay,
+                      float grad_scale, const int64_t* step, void* stream);
 
 #ifdef __cplusplus
 }

@@ -469,3 +469,43 @@ extern "C" int ren_adam_step(int64_t n, float* params, const float* grads, float
   if (e != cudaSuccess) { ren_set_error("ren_adam_step launch: %s", cudaGetErrorString(e)); return REN_E_CUDA; }
   return REN_OK;
 }
+
+// Same update with the 1-based step count read from DEVICE memory, so that a captured CUDA graph of the whole
+// training step advances Adam's bias correction on every replay (the host only increments *step on the stream).
+extern "C" __global__ void ren_adam_dev_kernel(long long n, float* __restrict__ p, const float* __restrict__ g,
+                                               float* __restrict__ m, float* __restrict__ v, float lr,
+                                               float b1, float b2, float eps, float wd, float gscale,
+                                               const long long* __restrict__ step) {
+  __shared__ float s_bc[2];
+  if (threadIdx.x == 0) {
+    const double t = (double)*step;
+    s_bc[0] = (float)(1.0 - pow((double)b1, t));
+    s_bc[1] = (float)sqrt(1.0 - pow((double)b2, t));
+  }
+  __syncthreads();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float grad = g[i] * gscale;
+  const float param = p[i];
+  if (wd != 0.f) grad = fmaf(wd, param, grad);
+  const float mi = m[i] + (grad - m[i]) * (1.f - b1);
+  const float vi = v[i] * b2 + (1.f - b2) * grad * grad;
+  m[i] = mi;
+  v[i] = vi;
+  const float denom = sqrtf(vi) / s_bc[1] + eps;
+  p[i] = param - (lr / s_bc[0]) * (mi / denom);
+}
+
+extern "C" int ren_adam_step_dev(int64_t n, float* params, const float* grads, float* exp_avg,
+                                 float* exp_avg_sq, float lr, float beta1, float beta2, float eps,
+                                 float weight_decay, float grad_scale, const int64_t* step, void* stream) {
+  if (n <= 0 || step == nullptr) { ren_set_error("ren_adam_step_dev: bad arguments"); return REN_E_INVALID; }
+  ren_prof_begin(REN_K_ADAM, (cudaStream_t)stream);
+  ren_adam_dev_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      n, params, grads, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, grad_scale,
+      (const long long*)step);
+  ren_prof_end(REN_K_ADAM, (cudaStream_t)stream);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { ren_set_error("ren_adam_step_dev launch: %s", cudaGetErrorString(e)); return REN_E_CUDA; }
+  return REN_OK;
+}

@@ -17,7 +17,7 @@ DENSITY_ACT = {"shifted_trunc_exp": 0, "softplus": 1, "shifted_softplus": 2}
 RADIANCE_ACT = {"softplus": 0, "sigmoid": 1}
 CONTRACTION = {"aabb": 0, "sphere": 1, "tanh": 2}
 ERROR_FN = {"l1": 0, "mse": 1, "mape": 2}
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 
 class RenFieldDesc(C.Structure):
@@ -99,6 +99,8 @@ _SIGNATURES = {
                                   C.c_size_t, _P]),
     "ren_adam_step": (C.c_int, [C.c_int64, _P, _P, _P, _P, C.c_float, C.c_float, C.c_float,
                                 C.c_float, C.c_float, C.c_float, C.c_int64, _P]),
+    "ren_adam_step_dev": (C.c_int, [C.c_int64, _P, _P, _P, _P, C.c_float, C.c_float, C.c_float,
+                                    C.c_float, C.c_float, C.c_float, _P, _P]),
 }
 
 _lib = None

@@ -13,6 +13,7 @@ over the concatenated start|end rays, one `ren_event_diff_loss` launch; backward
 import ctypes as C
 import math
 import os
+import warnings
 
 import numpy as np
 import torch
@@ -110,14 +111,24 @@ class RefractoryPeriod(torch.nn.Module):
         super().__init__()
         calib = load_camera_calibration(dataset_directory)
         tau = torch.from_numpy(np.asarray(calib["refractory_period"]))
-        path = os.path.join(dataset_directory, "max_refractory_period.pt")
-        if not os.path.exists(path):
-            raise FileNotFoundError(
-                f"{path}: the cached maximum refractory period is produced by the event "
-                "preprocessing (robust_e_nerf/data/datasets.py:132-187; SURVEY.md section 8f #3)")
-        tau_max = torch.load(path)
+        # event_generation_params.py:101-114: the cached maximum refractory period, else extracted from the raw
+        # event stream (`ren_event_queue` on the current CUDA device) and cached for the next run
+        from . import events as _events
+        tau_max = _events.Event.load_max_refractory_period(dataset_directory)
+        if tau_max is None:
+            raw_path = os.path.join(dataset_directory, _events.RAW_EVENTS_FILENAME)
+            if not os.path.isfile(raw_path):
+                raise FileNotFoundError(
+                    f"{dataset_directory}: neither {_events.MAX_REFRACTORY_PERIOD_FILENAME} nor "
+                    f"{_events.RAW_EVENTS_FILENAME} (robust_e_nerf/data/datasets.py:97-130)")
+            tau_max = _events.extract_max_refractory_period(_events.load_raw_events(dataset_directory), calib)
+            _events.Event.save_max_refractory_period(tau_max, dataset_directory)
         if not (0 <= tau < tau_max):
+            warnings.warn(f"Calibrated refractory period ({tau}) >= Max. possible refractory period ({tau_max}).")
             tau = self.REDEFINED_CALIBRATED_REFRACTORY_PERIOD_FACTOR * tau_max
+            warnings.warn(f"Redefining calibrated refractory period to "
+                          f"{self.REDEFINED_CALIBRATED_REFRACTORY_PERIOD_FACTOR} of max. possible refractory "
+                          f"period ({tau}).")
         self.register_buffer("init_refractory_period", tau, persistent=False)
         self.register_buffer("max_refractory_period", tau_max, persistent=False)
         self.register_buffer(
@@ -188,20 +199,33 @@ class DiffLossFunction(torch.autograd.Function):
             _lib.ptr(o0), _lib.ptr(o1), _lib.ptr(ev_diff), _lib.ptr(ts_diff), _lib.ptr(start),
             _lib.ptr(end_ts), _lib.ptr(log_i0), _lib.ptr(log_i1), _lib.ptr(loss), _lib.ptr(n_valid),
             _lib.ptr(g_c0), _lib.ptr(g_c1), _lib.ptr(scratch), _lib.stream_ptr()), "ren_event_diff_loss")
-        ctx.save_for_backward(g_c0, g_c1, c1, ts_diff, start, end_ts)
+        ctx.save_for_backward(g_c0, g_c1, c1, ts_diff, start, end_ts, log_i0, log_i1, ev_diff, o0, o1, n_valid)
         ctx.imin = imin
+        ctx.error_fn = error_fn
+        ctx.all_valid = bool(all_valid)
         ctx.mark_non_differentiable(log_i0, log_i1, n_valid)
         return loss, log_i0, log_i1, n_valid
 
     @staticmethod
     def backward(ctx, g_loss, _a, _b, _c):
         _lib.refuse_double_backward()
-        g_c0, g_c1, c1, ts_diff, start, end_ts = ctx.saved_tensors
+        g_c0, g_c1, c1, ts_diff, start, end_ts, log_i0, log_i1, ev_diff, o0, o1, n_valid = ctx.saved_tensors
         g_ev = None
         if ctx.needs_input_grad[4]:
-            # d loss / d tgt = -(d loss / d L1) with L1 = log(c1 + imin); tgt = ts_diff*ev/(end-start)
-            dl1 = g_c1 * (c1 + ctx.imin)
-            g_ev = (-(dl1.double()) * ts_diff / (end_ts.double() - start)).float() * g_loss
+            # tgt = f32(ts_diff * ev / (end - start)).  l1 / mse depend on (pred - tgt) only, so
+            # d loss / d tgt = -(d loss / d L1) with L1 = log(c1 + imin); mape = |pred - tgt| / max(|tgt|, eps)
+            # has the target in the denominator as well (utils/modules.py:96)
+            dtgt_dev = ts_diff / (end_ts.double() - start)
+            g_tgt = -(g_c1 * (c1 + ctx.imin)).double()
+            if ctx.error_fn == "mape":
+                eps = 2.220446049250313e-16
+                tgt = (ev_diff.double() * dtgt_dev).float().double()
+                pred = (log_i1 - log_i0).double()
+                valid = torch.ones_like(o0, dtype=torch.bool) if ctx.all_valid else ((o0 > 0) | (o1 > 0))
+                extra = -(pred - tgt).abs() * torch.sign(tgt) / (tgt * tgt)
+                extra = torch.where(valid & (tgt.abs() > eps), extra, torch.zeros_like(extra))
+                g_tgt = g_tgt + extra / n_valid.double()
+            g_ev = (g_tgt * dtgt_dev * g_loss.double()).float()
         return (g_c0 * g_loss, g_c1 * g_loss, None, None, g_ev, None, None, None, None, None, None)
 
 
@@ -428,9 +452,7 @@ class RobustENeRF(LightningModule):
             assert v.shape[0] == B
         w_grad = self._loss_cfg("weight", "log_intensity_grad")
         w_diff = self._loss_cfg("weight", "log_intensity_diff")
-        if w_diff <= 0:
-            raise NotImplementedError("ren_b200 trains with the log-intensity-difference loss on "
-                                      "(every shipped config: configs/train/*.yaml:103-104)")
+        assert w_grad > 0 or w_diff > 0                                                   # loss.py:16-20
         tau_train = any(p.requires_grad for p in self.refractory_period.parameters()) and torch.is_grad_enabled()
         dev = event["start_ts"].device
         imin = self.hparams["min_modeled_intensity"]
@@ -439,9 +461,15 @@ class RobustENeRF(LightningModule):
         ev_diff = self.contrast_threshold(event["num_pos"], event["num_neg"])
         # b-d + raygen: [grad |] diff_start | diff_end
         nr = 3 if w_grad > 0 else 2
+        if w_diff <= 0:
+            # l_grad alone (:346-357): the gradient timestamp is drawn over the whole corrected interval
+            # [start + tau, end] -- the diff interval of normalised length 1 starting at 0
+            normalized = dict(normalized, ts_diff=torch.ones_like(normalized["ts_diff"]),
+                              diff_start_ts=torch.zeros_like(normalized["diff_start_ts"]))
         rays = self.event_rays(event, normalized, nr, jets=(w_grad > 0 or tau_train))
-        if self.global_step is not None:
-            self.nerf.update_occ_grid(self.global_step, self.trajectory.T_wc_position)   # :375-379
+        acc = getattr(self.trainer, "accumulate_grad_batches", 1) if self.trainer is not None else 1
+        if self.global_step is not None and batch_index % max(int(acc or 1), 1) == 0:     # :375-379
+            self.nerf.update_occ_grid(self.global_step, self.trajectory.T_wc_position)
         ro = [rays["o"][j] for j in range(nr)]
         rd = [rays["d"][j] for j in range(nr)]
         rod = [rays["o_dot"][j] if rays["o_dot"] is not None else None for j in range(nr)]
@@ -449,7 +477,7 @@ class RobustENeRF(LightningModule):
         start = rays["start"]
         if tau_train:
             # differentiable timestamps -> rays (d loss / d ts chains to tau)
-            start, ts = self._supervision_timestamps(event, normalized, w_grad > 0)
+            start, ts = self._supervision_timestamps(event, normalized, w_grad > 0)   # (normalised samples as above)
             for j in range(nr):
                 ro[j], rd[j], rod[j], rdd[j] = RayChainFunction.apply(
                     ts[j], rays["o"][j], rays["d"][j], rays["o_dot"][j], rays["d_dot"][j],
@@ -470,32 +498,35 @@ class RobustENeRF(LightningModule):
             rate = ev_diff / (event["end_ts"] - start)                                  # loss.py:38-41
             err = self._error(self._loss_cfg("error_fn", "log_intensity_grad"), log_i_grad, rate)
             valid_g = torch.ones_like(opac_g, dtype=torch.bool) if all_valid else opac_g > 0
-            losses["log_intensity_grad"] = err[valid_g].mean()
+            # masked mean without boolean indexing (no host sync); 0 / 0 = nan like `err[valid].mean()`
+            losses["log_intensity_grad"] = torch.where(valid_g, err, torch.zeros_like(err)).sum() / valid_g.sum()
             n_kept_all.append(n_kept)
             opac_all.append(opac_g)
             self.last_grad = dict(log_intensity_grad=log_i_grad, valid=valid_g, target=rate,
                                   log_intensity=torch.log(cg + imin))
         # f: both difference renders in one launch (start rays | end rays)
-        if jitter is None:
-            u = torch.rand((2 * B,), device=dev, dtype=torch.float32)
-        else:
-            u = torch.cat((jitter["diff_start"], jitter["diff_end"])).to(dev, torch.float32)
-        rad, opac, _depth, n_kept = self.nerf.render_raw(torch.cat((ro[nr - 2], ro[nr - 1])),
-                                                         torch.cat((rd[nr - 2], rd[nr - 1])), u)
-        n_kept_all += [n_kept[:B], n_kept[B:]]
-        opac_all += [opac[:B], opac[B:]]
-        if self.has_bayer_filter:
-            ch = event["channel_idx"].to(torch.int64).repeat(2).unsqueeze(-1)             # :887-890
-            c = rad.gather(1, ch).squeeze(-1)
-        else:
-            c = rad[:, 0]
-        c0, c1 = c[:B], c[B:]
-        o0, o1 = opac[:B], opac[B:]
-        # h-j: loss
-        loss_raw, log_i0, log_i1, n_valid = DiffLossFunction.apply(
-            c0, c1, o0, o1, ev_diff, rays["ts_diff"], rays["start"], event["end_ts"].contiguous(),
-            self._loss_cfg("error_fn", "log_intensity_diff"), all_valid, imin)
-        losses["log_intensity_diff"] = loss_raw
+        log_i0 = log_i1 = n_valid = opac = None
+        if w_diff > 0:
+            if jitter is None:
+                u = torch.rand((2 * B,), device=dev, dtype=torch.float32)
+            else:
+                u = torch.cat((jitter["diff_start"], jitter["diff_end"])).to(dev, torch.float32)
+            rad, opac, _depth, n_kept = self.nerf.render_raw(torch.cat((ro[nr - 2], ro[nr - 1])),
+                                                             torch.cat((rd[nr - 2], rd[nr - 1])), u)
+            n_kept_all += [n_kept[:B], n_kept[B:]]
+            opac_all += [opac[:B], opac[B:]]
+            if self.has_bayer_filter:
+                ch = event["channel_idx"].to(torch.int64).repeat(2).unsqueeze(-1)         # :887-890
+                c = rad.gather(1, ch).squeeze(-1)
+            else:
+                c = rad[:, 0]
+            c0, c1 = c[:B], c[B:]
+            o0, o1 = opac[:B], opac[B:]
+            # h-j: loss
+            loss_raw, log_i0, log_i1, n_valid = DiffLossFunction.apply(
+                c0, c1, o0, o1, ev_diff, rays["ts_diff"], rays["start"], event["end_ts"].contiguous(),
+                self._loss_cfg("error_fn", "log_intensity_diff"), all_valid, imin)
+            losses["log_intensity_diff"] = loss_raw
         mcr = 1 / self.contrast_threshold.mean_contrast_threshold
         pw = {None: 1.0, "mean_contrast_reciprocal": mcr, "mean_contrast_reciprocal_sq": mcr ** 2}
         train_loss = 0
@@ -674,13 +705,27 @@ class RobustENeRF(LightningModule):
 
     @torch.no_grad()
     def evaluation_epoch_end(self, outputs, stage):
-        """robust_e_nerf.py:589-696 up to the metrics this image can compute: merge the per-view outputs of
-        `evaluation_step`, align the predicted log intensities to the targets, then mean L1 and PSNR
-        (`loss_metric/metric.py:60-73`: PSNR per image with data_range = max - min of the target range).  SSIM and
-        LPIPS (torchmetrics / pretrained AlexNet, absent here) and the PNG dumps stay out.  Returns the metrics
-        and the aligned images."""
+        """robust_e_nerf.py:589-696: gather the per-view outputs of `evaluation_step` across ranks, and on the
+        global-zero rank align the predicted log intensities to the targets, then mean L1, PSNR
+        (`loss_metric/metric.py:60-73`: per image with data_range = max - min of the target range) and SSIM,
+        and dump the aligned predictions as PNGs.  LPIPS (pretrained AlexNet weights) is absent from this image.
+        Returns the metrics and the aligned images (None on the other ranks, like the reference's bare return)."""
         pred = torch.stack([o["pred_intensity_img"] for o in outputs])
         target = torch.stack([o["target_intensity_img"] for o in outputs]).to(pred.device)
+        ids = None
+        if outputs[0].get("sample_id") is not None:
+            ids = torch.stack([o["sample_id"] for o in outputs]).reshape(len(outputs), -1).to(pred.device)
+        # :591-606 gather & merge across devices (a sharded validation set under DDP)
+        distributed = torch.distributed.is_available() and torch.distributed.is_initialized() \
+            and torch.distributed.get_world_size() > 1
+        if distributed:
+            pred = self.all_gather(pred).flatten(0, 1)
+            target = self.all_gather(target).flatten(0, 1)
+            if ids is not None:
+                ids = self.all_gather(ids).flatten(0, 1)
+        log_dir = getattr(self.trainer, "log_dir", None)              # :613-616 (read on every rank)
+        if not getattr(self.trainer, "is_global_zero", True):         # :618-621
+            return None
         if not self.has_bayer_filter:                                   # (N, H, W) -> (N, 1, H, W)
             pred, target = pred.unsqueeze(1), target.unsqueeze(1)
         aligned, scale, offset = self.align_log_intensity(pred, target)
@@ -698,9 +743,8 @@ class RobustENeRF(LightningModule):
         self.log(f"{name}/psnr", psnr, prog_bar=True, rank_zero_only=True)
         if ssim is not None:
             self.log(f"{name}/ssim", ssim, prog_bar=True, rank_zero_only=True)
-        log_dir = getattr(self.trainer, "log_dir", None)
-        if self.eval_save_pred_intensity_img and log_dir is not None and outputs[0].get("sample_id") is not None:
-            ids = torch.stack([o["sample_id"] for o in outputs]).reshape(len(outputs), -1)
+        self.log(f"{name}/epoch", float(self.current_epoch), rank_zero_only=True)          # :690-696
+        if self.eval_save_pred_intensity_img and log_dir is not None and ids is not None:
             self.save_pred_intensity_imgs(aligned, ids, stage, os.path.join(log_dir, self.PREDICTIONS_FOLDER_NAME))
         return {"l1": l1, "psnr": psnr, "ssim": ssim, "log_intensity_scale": scale, "log_intensity_offset": offset,
                 "pred_intensity_img": aligned}

@@ -29,7 +29,7 @@ def test_header_symbols_exported(built_lib):
 def test_binding_covers_header(built_lib):
     from ren_b200 import _lib
     assert _lib.exported_symbols() == _declared_symbols()
-    assert _lib.load().ren_version() == 4
+    assert _lib.load().ren_version() == 5
 
 
 @pytest.mark.parametrize("kw", [
@@ -135,7 +135,7 @@ def test_header_is_plain_c(tmp_path):
     src = tmp_path / "use.c"
     src.write_text('#include "ren_b200.h"\n'
                    "int main(void) { RenFieldDesc f; RenRenderDesc r; RenPacked p; (void)f; (void)r; (void)p;\n"
-                   "  return REN_ABI_VERSION == 4 ? 0 : 1; }\n")
+                   "  return REN_ABI_VERSION == 5 ? 0 : 1; }\n")
     out = subprocess.run(["gcc", "-std=c11", "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"),
                           str(src)], capture_output=True, text=True)
     assert out.returncode == 0, out.stderr

@@ -35,10 +35,14 @@ class _ToyModule(torch.nn.Module):
         super().__init__()
         self.nerf = _ToyNeRF()
         self.scale = torch.nn.Parameter(torch.tensor(1.0))     # a "small" non-MLP parameter
+        # an f64 parameter like the refractory period (event_generation_params.py:126): its gradient must
+        # survive the fp32 all-reduce bucket (hi / lo pair)
+        self.tau = torch.nn.Parameter(torch.tensor(1.0 + 1e-9, dtype=torch.float64))
         self.global_step = 0
+        self.logged = {}
 
     def configure_optimizers(self):
-        opt = torch.optim.Adam([{"params": [], "lr": 0.1}, {"params": [], "lr": 1.0},
+        opt = torch.optim.Adam([{"params": [], "lr": 0.1}, {"params": [self.tau], "lr": 1.0},
                                 {"params": self.nerf.mlp_parameters(), "weight_decay": 1e-6},
                                 {"params": [self.scale]}], lr=0.01)
         sch = torch.optim.lr_scheduler.MultiStepLR(opt, milestones=[20], gamma=0.33)
@@ -47,7 +51,8 @@ class _ToyModule(torch.nn.Module):
     def training_step(self, batch, batch_index, jitter=None):
         x, y = batch
         pred = torch.nn.functional.linear(x, self.nerf.w, self.nerf.b) * self.scale
-        return ((pred - y) ** 2).mean()
+        self.logged["train/mean_num_samples_per_ray"] = torch.tensor(100.0 + float(x[0, 0]))
+        return ((pred.double() * self.tau - y) ** 2).mean()
 
 
 def _data(rank):
@@ -64,7 +69,11 @@ def _worker(rank, world, port, out):
     tr = FlatTrainer(model, world_size=world, use_fused_adam=False)
     for step in range(3):
         tr.step(_data(rank), step)
-    flat = torch.cat([p.detach().reshape(-1) for p in model.parameters()])
+    # the dynamic-batch scalar rode in the same all-reduce: cross-rank mean of the per-rank values
+    want = sum(100.0 + float(_data(r)[0][0, 0]) for r in range(world)) / world
+    assert abs(float(tr.mean_spp) - want) < 1e-4
+    tr.epoch_end()
+    flat = torch.cat([p.detach().reshape(-1).double() for p in model.parameters()])
     gathered = [torch.empty_like(flat) for _ in range(world)]
     dist.all_gather(gathered, flat)
     if rank == 0:
@@ -94,5 +103,24 @@ def test_flat_gradient_allreduce_world2(tmp_path, built_lib):
         for p, g0, g1 in zip(model.parameters(), grads[0], grads[1]):
             p.grad = (g0 + g1) / 2
         opt.step()
-    ref = torch.cat([p.detach().reshape(-1) for p in model.parameters()])
+    ref = torch.cat([p.detach().reshape(-1).double() for p in model.parameters()])
     assert torch.allclose(got[0], ref, rtol=1e-5, atol=1e-6)
+
+
+def test_f64_gradient_survives_the_fp32_bucket(built_lib):
+    """The refractory period's f64 gradient crosses the fp32 all-reduce vector as a (hi, lo) pair."""
+    sys.path.insert(0, os.path.join(ROOT, "robust-e-nerf_b200"))
+    from ren_b200.trainer import FlatTrainer
+    model = _ToyModule()
+    tr = FlatTrainer(model, world_size=1, use_fused_adam=False)
+    g = 1.2345678901234567e-7
+    model.tau.grad = torch.tensor(g, dtype=torch.float64)
+    model.scale.grad = torch.tensor(0.5)
+    for p in model.nerf.mlp_parameters():
+        p.grad = torch.zeros_like(p)
+    tr._gather_grads()
+    model.tau.grad = None
+    tr._scatter_small(0.5)
+    assert model.tau.grad.dtype == torch.float64
+    assert abs(float(model.tau.grad) - 0.5 * g) <= 1e-13 * g          # fp32 alone would be off by ~3e-8 * g
+    assert float(model.scale.grad) == 0.25
