@@ -48,6 +48,7 @@ sys.path.insert(0, ROOT)
 
 FLOP_PER_SAMPLE_FWD = 1_186_304          # 593 152 MAC, 8x256 MLP, C = 1
 MIN_TIMED_MS = 2000.0
+BENCH_LR = 5e-4
 
 # rays per GPU, marching steps per ray, renders, l_grad weight, trainable sensor parameters, scene box
 CONFIGS = {
@@ -174,6 +175,10 @@ def product_config(wc, world):
         step = (wc["far"] - wc["near"]) / (wc["n"] + 0.5)
         cfg = synthetic.default_config(n_samples=wc["n"], aabb=wc["aabb"], near=wc["near"], span=step * wc["n"])
     cfg["num_nodes"], cfg["gpus"] = 1, list(range(world))
+    # the synthetic events carry random polarities (there is nothing to converge to): at the YAML's lr 0.01 Adam
+    # drives the trunc-exp density to inf within a few hundred steps -- in the oracle as well.  A NeRF-MLP-sized
+    # lr keeps the benchmarked network finite for the whole run; the step's arithmetic does not depend on it.
+    cfg["optimizer"]["lr"]["default"] = BENCH_LR
     cfg["loss"]["weight"]["log_intensity_grad"] = wc["w_grad"]
     if wc["trainable"]:
         cfg["contrast_threshold"]["freeze"] = False
@@ -399,6 +404,17 @@ class Runner:
         return float(v) if v is not None else float(self.wc["n"])
 
 
+def release(run):
+    """Drop a Runner's CUDA graphs (their private memory pools) and cached blocks before the next workload."""
+    import gc
+    import torch
+    run.trainer._graphs.clear()
+    run.trainer = run.model = run.resident = None
+    gc.collect()
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+
+
 def run_secondary(cfg_id, args, rank, world, dev, graph):
     """A short run of another BASELINE config (warm-up 3, then one block of 5 steps) for the same JSON line."""
     wc = CONFIGS[cfg_id]
@@ -418,9 +434,7 @@ def run_secondary(cfg_id, args, rank, world, dev, graph):
             out["parity"] = parity_check(r.model, r.cfg, r.root, r.host[0][0], r.host[0][1], dev, 64)
         except Exception as e:                      # the secondary record must not take the headline down
             out["parity"] = {"error": repr(e)[:200]}
-        del r
-        import torch
-        torch.cuda.empty_cache()
+        release(r)
         return out
     except Exception as e:
         return {"config": cfg_id, "workload": wc["name"], "error": repr(e)[:300]}
@@ -545,8 +559,8 @@ def run_ours(args):
     h2d_bytes, graph_on, run_cfg = run.h2d, run.graph, None
     secondary = None
     if world == 1 and args.config == 2 and not args.no_secondary:
-        del run, trainer
-        torch.cuda.empty_cache()
+        del trainer
+        release(run)
         secondary = [run_secondary(c, args, rank, world, dev, graph) for c in (3, 4, 5)]
     out = {
         "metric": "ray-samples/s", "value": value, "unit": "ray-samples/s", "n_gpus": world,
@@ -559,6 +573,7 @@ def run_ours(args):
         "config": {"workload": wc["name"], "config_id": args.config, "engine": engine, "rays_per_gpu": wc["rays"],
                    "samples_per_ray": spp, "marching_steps_per_ray": wc["n"], "renders_per_step": wc["renders"],
                    "cuda_graph": graph_on if graph_note is None else {"on": False, "capture_error": graph_note},
+                   "adam_lr": BENCH_LR, "finite": bool(math.isfinite(loss)),
                    "l2": "per-step working set (activation stash ~11 GB) >> 126 MB L2; 4 rotating input batches",
                    "parallelism": f"dp{world}"},
         "blocks": {"n": len(blocks), "steps_per_block": args.steps, "ms_per_step_median": ms / args.steps,

@@ -16,7 +16,7 @@ def build_reference_model(dataset_dir, fcfg: FieldConfig, rcfg: RenderConfig, sc
                           learn_bkgd=False, freeze_ct=True, freeze_rp=True, seed=0,
                           train_eff_ray_sample_batch_size=1 << 20):
     """Instantiate the reference LightningModule with the YAML-equivalent hparams
-    (configs/train/synthetic.yaml:24-128) for `arch: mlp`."""
+    (configs/train/synthetic.yaml:24-128) for `arch: mlp` or `arch: ngp`."""
     ref = ref_loader.load_reference()
     from easydict import EasyDict
     import pytorch_lightning as pl
@@ -27,7 +27,20 @@ def build_reference_model(dataset_dir, fcfg: FieldConfig, rcfg: RenderConfig, sc
         near_plane=rcfg.near_plane, far_plane=rcfg.far_plane,
         render_step_size=rcfg.render_step_size, cone_angle=rcfg.cone_angle,
         early_stop_eps=rcfg.early_stop_eps, alpha_thre=rcfg.alpha_thre,
-        test_chunk_size=16384, arch="mlp", load_state_dict=False, freeze=False,
+        test_chunk_size=16384, arch=fcfg.arch, load_state_dict=False, freeze=False,
+        # configs/train/*.yaml:61-88
+        ngp=dict(
+            pos_encoding=dict(otype={"Hash": "HashGrid", "Dense": "DenseGrid", "Tiled": "TiledGrid"}[fcfg.grid_type],
+                              n_levels=fcfg.n_levels, n_features_per_level=fcfg.n_features_per_level,
+                              log2_hashmap_size=fcfg.log2_hashmap_size, base_resolution=fcfg.base_resolution,
+                              per_level_scale=fcfg.per_level_scale, interpolation="Linear"),
+            dir_encoding=dict(degree=fcfg.sh_degree),
+            mlp_base=dict(hidden_activation=fcfg.hidden_activation, density_activation=fcfg.density_activation,
+                          n_neurons=fcfg.base_n_neurons, n_hidden_layers=fcfg.base_n_hidden_layers,
+                          geo_feat_dim=fcfg.geo_feat_dim, weight_norm=False),
+            mlp_head=dict(hidden_activation=fcfg.head_hidden_activation or fcfg.hidden_activation,
+                          radiance_activation=fcfg.radiance_activation, n_neurons=fcfg.head_n_neurons,
+                          n_hidden_layers=fcfg.head_n_hidden_layers, weight_norm=False)),
         mlp=dict(net_depth=fcfg.net_depth, net_width=fcfg.net_width, skip_layer=fcfg.skip_layer,
                  net_depth_condition=fcfg.net_depth_condition,
                  net_width_condition=fcfg.net_width_condition,

@@ -41,6 +41,28 @@ class FieldConfig:
     radiance_activation: str = "softplus"   # | sigmoid (nerf.py:26-29)
     pos_deg: int = 10
     dir_deg: int = 4
+    # `arch: ngp` (robust_e_nerf/external/ngp.py:109-152, configs/train/*.yaml:61-88): multiresolution hash grid
+    # + SH directions + two small MLPs.  `hidden_activation` is mlp_base's, `head_hidden_activation` mlp_head's
+    # (None = the same); net_* / pos_deg / dir_deg above are unused.
+    arch: str = "mlp"                        # mlp | ngp
+    n_levels: int = 16
+    n_features_per_level: int = 2
+    log2_hashmap_size: int = 19
+    base_resolution: int = 16
+    per_level_scale: float = 1.4472692012786865
+    grid_type: str = "Hash"                  # Hash | Dense | Tiled  (otype HashGrid | DenseGrid | TiledGrid)
+    sh_degree: int = 4
+    base_n_neurons: int = 64
+    base_n_hidden_layers: int = 1
+    geo_feat_dim: int = 15
+    head_n_neurons: int = 64
+    head_n_hidden_layers: int = 2
+    head_hidden_activation: Optional[str] = None
+
+    def grid_meta(self):
+        from . import hashgrid
+        return hashgrid.grid_meta(self.n_levels, self.n_features_per_level, self.log2_hashmap_size,
+                                  self.base_resolution, self.per_level_scale, self.grid_type)
 
     @property
     def pos_dim(self):
@@ -52,7 +74,19 @@ class FieldConfig:
 
     def layer_shapes(self):
         """[(name, out, in)] in the reference's state-dict order
-        (external/mlp.py:56-76,143-186)."""
+        (external/mlp.py:56-76,143-186; `arch: ngp`: external/ngp.py:171-207 after the grid parameters)."""
+        if self.arch == "ngp":
+            shapes, in_f = [], self.n_levels * self.n_features_per_level
+            for i in range(self.base_n_hidden_layers):
+                shapes.append((f"mlp_base.1.hidden_layers.{i}", self.base_n_neurons, in_f))
+                in_f = self.base_n_neurons
+            shapes.append(("mlp_base.1.output_layer", 1 + self.geo_feat_dim, in_f))
+            in_f = self.sh_degree ** 2 + self.geo_feat_dim
+            for i in range(self.head_n_hidden_layers):
+                shapes.append((f"mlp_head.hidden_layers.{i}", self.head_n_neurons, in_f))
+                in_f = self.head_n_neurons
+            shapes.append(("mlp_head.output_layer", self.radiance_dim, in_f))
+            return shapes
         shapes = []
         in_f = self.pos_dim
         for i in range(self.net_depth):
@@ -85,6 +119,12 @@ class RenderConfig:
     stratified: bool = True
 
 
+def field_param_prefix(cfg: FieldConfig):
+    """State-dict prefix of the field's trainable tensors under `RobustENeRF`: `nerf.radiance_field.mlp.*` for
+    the vanilla field (external/mlp.py:266-299), `nerf.radiance_field.mlp_base.*` / `.mlp_head.*` for ngp."""
+    return "nerf.radiance_field.mlp_" if cfg.arch == "ngp" else "nerf.radiance_field.mlp."
+
+
 def init_field_params(cfg: FieldConfig, seed=0, dtype=torch.float32):
     """Default `nn.Linear` init (the reference passes hidden_init/output_init/
     bias_init = None, external/mlp.py:297-299): kaiming_uniform(a=sqrt(5)) weights,
@@ -93,6 +133,11 @@ def init_field_params(cfg: FieldConfig, seed=0, dtype=torch.float32):
     g_state = torch.random.get_rng_state()
     torch.manual_seed(seed)
     params = {}
+    if cfg.arch == "ngp":
+        # `tcnn.Encoding` is constructed first (external/ngp.py:166-170); the oracle shim draws its grid from
+        # torch's global generator (oracle/shims/tinycudann.py), then the Linear layers follow in order
+        from . import hashgrid
+        params["mlp_base.0.params"] = hashgrid.init_params(cfg.grid_meta()).to(dtype)
     for name, out_f, in_f in cfg.layer_shapes():
         lin = torch.nn.Linear(in_f, out_f)
         params[name + ".weight"] = lin.weight.detach().to(dtype).clone()
@@ -120,8 +165,11 @@ class _TruncExp(torch.autograd.Function):
         return g * torch.exp(torch.clamp(x, max=15))
 
 
-def hidden_act(cfg, x):
-    if cfg.hidden_activation == "softplus":
+def hidden_act(cfg, x, head=False):
+    kind = cfg.hidden_activation
+    if head and getattr(cfg, "head_hidden_activation", None) is not None:
+        kind = cfg.head_hidden_activation
+    if kind == "softplus":
         return softplus(x, 100.0)            # models/nerf.py:18
     return torch.relu(x)
 
@@ -227,8 +275,52 @@ def mlp_trunk(params, cfg, enc):
     return x
 
 
+def contract_unit_selector(cfg: FieldConfig, x):
+    """World -> [0,1]^3 and the in-box selector, as `NGPradianceField.query_density` applies them
+    (external/ngp.py:219-228; same contraction formulas as the mlp field, external/ngp.py:68-106)."""
+    aabb = torch.tensor(cfg.aabb, dtype=x.dtype)
+    a_min, a_max = aabb[:3], aabb[3:]
+    x = (x - a_min) / (a_max - a_min)
+    if cfg.contraction == "sphere":
+        x = x * 2 - 1
+        mag = x.norm(dim=-1, keepdim=True)
+        x = torch.where(mag > 1, (2 - 1 / mag) * (x / mag), x)
+        x = x / 4 + 0.5
+    elif cfg.contraction == "tanh":
+        x = (torch.tanh(x - 0.5) + 1) / 2
+    return x, ((x > 0.0) & (x < 1.0)).all(dim=-1)
+
+
+def ngp_base(params, cfg, x):
+    """`NGPradianceField.mlp_base` on world points (external/ngp.py:171-188,219-240): hash-grid features ->
+    MLP -> [density before activation | geometry features], and the selector."""
+    from . import hashgrid
+    u, selector = contract_unit_selector(cfg, x)
+    h = hashgrid.encode(u, params["mlp_base.0.params"], cfg.grid_meta())
+    for i in range(cfg.base_n_hidden_layers):
+        h = hidden_act(cfg, _linear(params, f"mlp_base.1.hidden_layers.{i}", h))
+    out = _linear(params, "mlp_base.1.output_layer", h)
+    return out[..., :1], out[..., 1:], selector
+
+
+def ngp_forward(params, cfg, x, d):
+    """`NGPradianceField.forward` (external/ngp.py:266-280): `_query_rgb` concatenates [SH(dir) | geometry
+    features] (:246-252) and mlp_head applies the radiance activation as its output activation (:189-207)."""
+    from . import hashgrid
+    raw_sigma, geo, selector = ngp_base(params, cfg, x)
+    h = torch.cat([hashgrid.sh_encode(d, cfg.sh_degree), geo], dim=-1)
+    for i in range(cfg.head_n_hidden_layers):
+        h = hidden_act(cfg, _linear(params, f"mlp_head.hidden_layers.{i}", h), head=True)
+    raw_rgb = _linear(params, "mlp_head.output_layer", h)
+    return radiance_act(cfg, raw_rgb), density_act(cfg, raw_sigma) * selector[..., None]
+
+
 def field_density(params, cfg, x):
-    """`VanillaNeRFRadianceField.query_density` (external/mlp.py:344-348)."""
+    """`VanillaNeRFRadianceField.query_density` (external/mlp.py:344-348) /
+    `NGPradianceField.query_density` (external/ngp.py:219-244)."""
+    if cfg.arch == "ngp":
+        raw_sigma, _, selector = ngp_base(params, cfg, x)
+        return density_act(cfg, raw_sigma) * selector[..., None]
     z, selector = contract_input_space(cfg, x)
     h = mlp_trunk(params, cfg, sinusoidal_encode(z, cfg.pos_deg))
     raw_sigma = _linear(params, "mlp.sigma_layer.output_layer", h)
@@ -238,6 +330,8 @@ def field_density(params, cfg, x):
 def field_forward(params, cfg, x, d):
     """`VanillaNeRFRadianceField.forward` (external/mlp.py:350-358) +
     `NerfMLP.forward` (:193-205)."""
+    if cfg.arch == "ngp":
+        return ngp_forward(params, cfg, x, d)
     z, selector = contract_input_space(cfg, x)
     h = mlp_trunk(params, cfg, sinusoidal_encode(z, cfg.pos_deg))
     raw_sigma = _linear(params, "mlp.sigma_layer.output_layer", h)
@@ -492,7 +586,7 @@ def training_step(params, cfg: FieldConfig, rcfg: RenderConfig, scfg: StepConfig
     scalars the reference logs plus per-ray intermediates."""
     ev = {k: v.squeeze(0) for k, v in batch["event"].items()}
     nz = {k: v.squeeze(0) for k, v in batch["normalized"].items()}
-    fdt = params["mlp.sigma_layer.output_layer.weight"].dtype
+    fdt = next(iter(params.values())).dtype
     out = {}
     # a2: contrast threshold (models/event_generation_params.py:59-84)
     C_n = scene["neg_contrast_threshold"].to(fdt)

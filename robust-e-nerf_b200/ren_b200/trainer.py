@@ -61,9 +61,14 @@ class FlatTrainer:
         self.cuda_graph = bool(cuda_graph)
         self._graphs = {}
         self._eager_steps = 0
+        self.stream = None
         if self.cuda_graph:
             for g in opt.param_groups:                  # torch Adam inside a graph needs capturable state
                 g["capturable"] = True
+            # every step -- eager warm-up and capture alike -- runs on ONE side stream: autograd's AccumulateGrad
+            # nodes are tied to the stream they were created on, and a capture must not make the legacy default
+            # stream depend on the capturing stream (cudaErrorStreamCaptureImplicit)
+            self.stream = torch.cuda.Stream(device=flat.device)
 
     # ------------------------------------------------------------------ gradient vector
     def _flat_mlp_grad(self):
@@ -173,11 +178,14 @@ class FlatTrainer:
 
     def step(self, batch, batch_index=0, jitter=None):
         m = self.model
-        if self.cuda_graph and jitter is not None and self._graphable() and self._eager_steps >= 3:
-            loss = self._graph_step(batch, batch_index, jitter)
+        if self.stream is not None:
+            caller = torch.cuda.current_stream()
+            self.stream.wait_stream(caller)             # the batch was produced on the caller's stream
+            with torch.cuda.stream(self.stream):
+                loss = self._dispatch(batch, batch_index, jitter)
+            caller.wait_stream(self.stream)             # loss / parameters are visible to the caller again
         else:
-            loss = self._step_body(batch, batch_index, jitter)
-            self._eager_steps += 1
+            loss = self._dispatch(batch, batch_index, jitter)
         self.step_count += 1
         if self.scheduler_interval == "step":
             self.scheduler.step()
@@ -186,6 +194,12 @@ class FlatTrainer:
         except AttributeError:      # Lightning: read-only, owned by the real Trainer
             pass
         return loss
+
+    def _dispatch(self, batch, batch_index, jitter):
+        if self.cuda_graph and jitter is not None and self._graphable() and self._eager_steps >= 3:
+            return self._graph_step(batch, batch_index, jitter)
+        self._eager_steps += 1
+        return self._step_body(batch, batch_index, jitter)
 
     def _graph_step(self, batch, batch_index, jitter):
         # learning rates are baked into the captured launches: a scheduler step re-captures
@@ -196,7 +210,7 @@ class FlatTrainer:
             static_j = {k: v.clone() for k, v in jitter.items()}
             graph = torch.cuda.CUDAGraph()
             torch.cuda.synchronize()
-            with torch.cuda.graph(graph):
+            with torch.cuda.graph(graph, stream=self.stream):
                 loss = self._step_body(static_b, batch_index, static_j)
             entry = (graph, static_b, static_j, loss)
             self._graphs[key] = entry

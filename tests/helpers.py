@@ -7,6 +7,7 @@ from oracle import restatement as R
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 GOLDEN_NAMES = ["step_plumbing", "step_8x256", "step_8x256_gain2", "step_aabb_cull"]
+NGP_GOLDEN_NAMES = ["step_ngp"]
 
 
 def load_golden(name):
@@ -26,6 +27,8 @@ def golden_params(g, dtype=torch.float32):
         for k in params:
             if k.endswith(".weight"):
                 params[k] = params[k] * g["weight_gain"]
+    if g.get("table_gain") is not None:
+        params["mlp_base.0.params"] = params["mlp_base.0.params"] * g["table_gain"]
     if g.get("sigma_bias_override") is not None:
         params["mlp.sigma_layer.output_layer.bias"].fill_(g["sigma_bias_override"])
     for k, (s, a) in g["weight_checksums"].items():

@@ -160,48 +160,60 @@ def test_config3_vs_oracle_2048_rays(built_lib, dataset_dir):
 
 @pytest.mark.parametrize("engine", ["simt_fp32", "auto"])
 def test_adam_trajectory_matches_oracle(engine, built_lib, dataset_dir):
-    """20 optimiser steps (B = 64 rays x 32 samples, 8x256, weights x2, Adam lr 0.01 + L2 1e-6 as
-    `configure_optimizers`, models/robust_e_nerf.py:782-813) of `FlatTrainer` against the oracle stepping
-    `torch.optim.Adam` on the same batches: the loss curve and the final weights.  This is what licenses the
-    tcgen05 backward's fp16 operands (dgrad fp16x3 split, weight gradients single fp16, fp32 accumulate)."""
+    """20 optimiser steps on one repeated batch (B = 64 rays x 32 samples, 8x256, weights x2, Adam lr 1e-3 + L2
+    1e-6 like `configure_optimizers`, models/robust_e_nerf.py:782-813): `FlatTrainer` against the oracle stepping
+    `torch.optim.Adam`, loss curve (which falls ~300x) and final weights.  The yardstick is the oracle's own
+    fp32-vs-fp64 trajectory gap: this is what licenses the tcgen05 backward's fp16 operands (dgrad fp16x3 split,
+    weight gradients single fp16, fp32 accumulate)."""
     from ren_b200.trainer import FlatTrainer
-    B, N, STEPS = 64, 32, 20
+    B, N, STEPS, LR = 64, 32, 20, 1e-3
     g = dict(H.load_golden("step_8x256_gain2"))
     step = 4.0 / N
     g["rcfg"] = dict(g["rcfg"], render_step_size=step, far_plane=0.5 + (N + 0.5) * step)
     g["learn_bkgd"] = False                        # MLP weights are the only trainable tensors
     scene = synth.load_scene(dataset_dir)
-    batches = [synth.make_batch(B, scene["T_wc_timestamp"], rank=0, seed=500 + i) for i in range(STEPS)]
+    b, j = synth.make_batch(B, scene["T_wc_timestamp"], rank=0, seed=500)
     m = H.build_product(g, dataset_dir, "cuda", engine)
+    m.hparams["optimizer"]["lr"]["default"] = LR
     tr = FlatTrainer(m)
-    got = []
-    for i, (b, j) in enumerate(batches):
-        cb, cj = _cuda_batch(b, j)
-        got.append(float(tr.step(cb, i, cj)))
-    # oracle
+    cb, cj = _cuda_batch(b, j)
+    got = [float(tr.step(cb, i, cj)) for i in range(STEPS)]
     fcfg, rcfg, scfg = H.golden_configs(g)
     torch.set_num_threads(os.cpu_count() or 8)
-    params = {k: v.clone().requires_grad_(True) for k, v in H.golden_params(g).items()}
-    opt = torch.optim.Adam(list(params.values()), lr=0.01, weight_decay=1e-6)
     tau_max = scene["max_refractory_period"]
-    th_r = torch.log(torch.expm1(torch.tensor(1.0)))
-    th_t = tau_max * torch.logit(scene["refractory_period"].double() / tau_max)
-    want = []
-    for b, j in batches:
-        opt.zero_grad()
-        out = R.training_step(params, fcfg, rcfg, scfg, scene, b, j, th_r, th_t.clone(), None)
-        out["loss"].backward()
-        opt.step()
-        want.append(float(out["loss"].detach()))
-    rel = max(abs(a - b) / abs(b) for a, b in zip(got, want))
-    sd = m.state_dict()
-    num = den = 0.0
-    for k, v in params.items():
-        w = sd["nerf.radiance_field." + k].double().cpu()
-        num += float((w - v.detach().double()).pow(2).sum())
-        den += float(v.detach().double().pow(2).sum())
-    nw = (num / den) ** 0.5
-    print(f"[adam trajectory / {engine}] loss {want[0]:.6f} -> {want[-1]:.6f}; worst loss rel over {STEPS} steps "
-          f"{rel:.2e}; final weights normwise {nw:.2e}")
-    assert want[-1] < want[0]                      # the oracle trajectory actually descends
-    assert rel < REL_BAR and nw < 1e-3
+
+    def oracle(dtype):
+        params = {k: v.clone().requires_grad_(True) for k, v in H.golden_params(g, dtype).items()}
+        sc = {k: (v.to(dtype) if v.is_floating_point() else v) for k, v in scene.items()}
+        opt = torch.optim.Adam(list(params.values()), lr=LR, weight_decay=1e-6)
+        th_r = torch.log(torch.expm1(torch.tensor(1.0, dtype=dtype)))
+        th_t = tau_max * torch.logit(scene["refractory_period"].double() / tau_max)
+        curve = []
+        for _ in range(STEPS):
+            opt.zero_grad()
+            out = R.training_step(params, fcfg, rcfg, scfg, sc, b, j, th_r, th_t.clone(), None)
+            out["loss"].backward()
+            opt.step()
+            curve.append(float(out["loss"].detach()))
+        return curve, params
+
+    want, params = oracle(torch.float32)
+    want64, params64 = oracle(torch.float64)
+
+    def weights_gap(a, bb):
+        num = sum(float((a[k].detach().double() - bb[k].detach().double()).pow(2).sum()) for k in a)
+        den = sum(float(bb[k].detach().double().pow(2).sum()) for k in a)
+        return (num / den) ** 0.5
+
+    sd = {k[len("nerf.radiance_field."):]: v.cpu() for k, v in m.state_dict().items()
+          if k.startswith("nerf.radiance_field.mlp.")}
+    rel = max(abs(a - c) / abs(c) for a, c in zip(got, want64))
+    rel32 = max(abs(a - c) / abs(c) for a, c in zip(want, want64))
+    nw, nw32 = weights_gap(sd, params64), weights_gap(params, params64)
+    print(f"[adam trajectory / {engine}] loss {want64[0]:.6f} -> {want64[-1]:.6f}; worst loss rel vs fp64 oracle over "
+          f"{STEPS} steps: cuda {rel:.2e}, fp32 oracle {rel32:.2e}; final weights normwise vs fp64 oracle: cuda "
+          f"{nw:.2e}, fp32 oracle {nw32:.2e}")
+    assert want64[-1] < 0.1 * want64[0]            # the trajectory really descends
+    # within 5x of the reference arithmetic's own fp32 noise on the same trajectory, or the absolute bars
+    assert rel < max(5 * rel32, REL_BAR), (rel, rel32)
+    assert nw < max(5 * nw32, 1e-3), (nw, nw32)

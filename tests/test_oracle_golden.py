@@ -23,24 +23,25 @@ def _run_restatement(g, dataset_dir):
     return out, params, th_b
 
 
-@pytest.mark.parametrize("name", H.GOLDEN_NAMES)
+@pytest.mark.parametrize("name", H.GOLDEN_NAMES + H.NGP_GOLDEN_NAMES)
 def test_restatement_matches_reference_golden(name, dataset_dir):
     g = H.load_golden(name)
     torch.set_num_threads(8)
     out, params, th_b = _run_restatement(g, dataset_dir)
+    prefix = R.field_param_prefix(H.golden_configs(g)[0])
     assert abs(float(out["loss"].detach()) - float(g["loss"])) <= 2e-6 * abs(float(g["loss"]))
     spp = float(g["logged"]["train/mean_num_samples_per_ray"])
     assert abs(float(out["mean_num_samples_per_ray"]) - spp) < 1e-5 * spp
     out["loss"].backward()
     checked = 0
     for k, gref in g["grads"].items():
-        if gref is None or not k.startswith("nerf.radiance_field.mlp."):
+        if gref is None or not k.startswith(prefix):
             continue
         got = params[k[len("nerf.radiance_field."):]].grad
         nw, _, _ = H.rel_err(got, gref)
         assert nw < 5e-4, (k, nw)
         checked += 1
-    assert checked >= 10
+    assert checked >= (9 if name in H.NGP_GOLDEN_NAMES else 10)
     if th_b is not None:
         gref = g["grads"]["nerf.parametrizations.render_bkgd.original"]
         assert H.rel_err(th_b.grad, gref)[0] < 5e-4
