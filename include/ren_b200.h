@@ -52,6 +52,10 @@ enum {
   REN_ENGINE_TC_F16X3 = 2,  /* tcgen05 kind::f16, split fp16 hi/lo operands, 3 MMAs (fp32-class accuracy) */
   REN_ENGINE_TC_F16 = 3     /* tcgen05 kind::f16, single pass (throughput mode; misses the 1e-4 bar) */
 };
+/* models/nerf.py:104-167 `arch` */
+enum { REN_ARCH_MLP = 0, REN_ARCH_NGP = 1 };
+/* tiny-cuda-nn grid encodings (`otype` in the configs/train YAMLs, line 63: HashGrid | DenseGrid | TiledGrid) */
+enum { REN_GRID_HASH = 0, REN_GRID_DENSE = 1, REN_GRID_TILED = 2 };
 /* loss_metric/loss.py:16-30 error functions */
 enum { REN_ERR_L1 = 0, REN_ERR_MSE = 1, REN_ERR_MAPE = 2 };
 
@@ -71,6 +75,24 @@ typedef struct RenFieldDesc {
   int32_t radiance_activation;/* REN_RADIANCE_* */
   int32_t contraction;        /* REN_CONTRACT_* */
   float aabb[6];              /* xmin,ymin,zmin,xmax,ymax,zmax (external/mlp.py:269) */
+  /* `arch: ngp` -- `NGPradianceField.__init__` (external/ngp.py:109-207) + the `model.nerf.ngp` YAML block
+   * (configs/train/mocap-desk2.yaml:61-88): multiresolution grid encoding of the contracted position
+   * (tiny-cuda-nn `Encoding`, interpolation Linear), real spherical harmonics of the raw direction
+   * (external/sh_encoder.py:15-193), mlp_base grid -> [density | geo_feat_dim features], mlp_head
+   * [SH | features] -> radiance.  With arch = REN_ARCH_NGP the fields above are read as: net_depth / net_width =
+   * mlp_base n_hidden_layers / n_neurons, net_depth_condition / net_width_condition = mlp_head
+   * n_hidden_layers (>= 1) / n_neurons, hidden_activation = both MLPs'; skip_layer, pos_deg, dir_deg unused.
+   * All zero (arch = REN_ARCH_MLP) for the vanilla field. */
+  int32_t arch;               /* REN_ARCH_* */
+  int32_t grid_type;          /* REN_GRID_* */
+  int32_t grid_levels;        /* n_levels (16), <= 32 */
+  int32_t grid_features;      /* n_features_per_level (2): 1, 2, 4 or 8; levels * features <= 64 */
+  int32_t grid_log2_hashmap_size; /* (19) */
+  int32_t grid_base_resolution;   /* (16) */
+  float grid_per_level_scale;     /* (1.4472692) */
+  int32_t sh_degree;          /* dir_encoding.degree (4), 1..4 */
+  int32_t geo_feat_dim;       /* (15), 1..63 */
+  int32_t reserved_ngp;
 } RenFieldDesc;
 
 /* `NeRF.__init__` rendering options (models/nerf.py:31-48) as consumed by
@@ -118,14 +140,21 @@ int64_t ren_launch_count(void);
 int ren_timing_enable(int32_t on);
 int ren_timing_collect(int32_t kind, double* total_ms, int64_t* count);
 
-/* Number of fp32 elements of the flat MLP parameter buffer. */
+/* Number of fp32 elements of the flat parameter buffer (arch ngp: grid parameters first, then the MLPs). */
 int ren_param_count(const RenFieldDesc* f, int64_t* n_params);
+
+/* arch ngp: number of grid parameters (= `tcnn.Encoding.params.numel()`, state-dict key
+ * `radiance_field.mlp_base.0.params`, external/ngp.py:166-188) at the head of the flat buffer; 0 for arch mlp.
+ * Per level l: scale_l = fp32(2^(l log2 per_level_scale) base_resolution - 1), resolution ceil(scale_l) + 1,
+ * entries min(roundup8(resolution^3), 2^log2_hashmap_size) (Hash), entry = features floats. */
+int ren_grid_param_count(const RenFieldDesc* f, int64_t* n_grid_params);
 
 /* Layout of the flat buffer: for layer l (state-dict order: base.hidden_layers.0..D-1,
  * sigma_layer.output_layer, bottleneck_layer.output_layer, rgb_layer.hidden_layers.*,
  * rgb_layer.output_layer; external/mlp.py:56-76,143-186) writes weight offset, bias
  * offset, out and in features.  Returns the number of layers via *n_layers; arrays may
- * be NULL to query the count. */
+ * be NULL to query the count.  arch ngp: mlp_base.1.hidden_layers.*, mlp_base.1.output_layer,
+ * mlp_head.hidden_layers.*, mlp_head.output_layer (external/ngp.py:171-207), offsets after the grid. */
 int ren_param_layout(const RenFieldDesc* f, int32_t* n_layers, int64_t* w_off, int64_t* b_off,
                      int32_t* out_features, int32_t* in_features);
 

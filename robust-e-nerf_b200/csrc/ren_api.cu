@@ -9,7 +9,7 @@
 // engines
 int ren_simt_launch_fwd(const RenPlan& p, long long n_rays, int K, const float* o, const float* d,
                         const float* o_dot, const float* d_dot, const float* jitter, const float* params,
-                        float* stash, float* raw, cudaStream_t st);
+                        float* stash, float* raw, const RenNgp* ngp, cudaStream_t st);
 int ren_simt_launch_dgrad(const RenPlan& p, long long S, const float* params, const float* stash,
                           const float* graw, float* delta, int tangent, cudaStream_t st);
 int ren_simt_launch_wgrad(const RenPlan& p, long long S, const float* stash, const float* delta,
@@ -29,7 +29,7 @@ int ren_launch_raygrad(const RenPlan& p, long long n_rays, int K, const float* o
                        const float* o_dot, const float* d_dot, const float* jitter, const float* params,
                        const void* delta, const void* delta_dot, int fp16, const unsigned int* gmax,
                        const unsigned char* tile_live, const int* sample_idx, long long n_samples, float* g_rays,
-                       cudaStream_t st);
+                       const RenNgp* ngp, cudaStream_t st);
 int ren_launch_composite(const RenPlan& p, long long n_rays, int K, const float* o, const float* d,
                          const float* jitter, const int* ray_offsets, const float* raw, const float* bkgd,
                          float* radiance, float* opacity, float* depth, int* n_kept, cudaStream_t st);
@@ -40,6 +40,10 @@ int ren_launch_composite_bwd(const RenPlan& p, long long n_rays, int K, const fl
                              const float* jitter, const int* ray_offsets, const float* raw, const float* bkgd,
                              const float* g_radiance, const float* g_opacity, const float* g_depth,
                              float* graw, float* g_bkgd, unsigned int* gmax, cudaStream_t st);
+// arch ngp (ren_ngp.cu)
+int ren_build_grid(const RenFieldDesc* f, RenGrid* g, long long* n_entries);
+int ren_ngp_pack(const RenPlan& p, const float* flat, float* kparams, cudaStream_t st);
+int ren_ngp_unpack_grads(const RenPlan& p, const float* g_kparams, float* g_flat, cudaStream_t st);
 // tcgen05 engine (ren_tc.cu)
 int ren_tc_supported(const RenPlan& p);
 size_t ren_tc_fwd_workspace_bytes(const RenPlan& p);
@@ -130,6 +134,15 @@ static int validate_field(const RenFieldDesc* f) {
   if (f->net_depth_condition < 0 || f->net_depth_condition > REN_MAX_COND) { ren_set_error("net_depth_condition %d outside [0,%d]", f->net_depth_condition, REN_MAX_COND); return REN_E_INVALID; }
   if (f->net_depth_condition > 0 && (f->net_width_condition < 16 || f->net_width_condition % 16)) { ren_set_error("net_width_condition %d must be a positive multiple of 16", f->net_width_condition); return REN_E_INVALID; }
   if (f->radiance_dim < 1 || f->radiance_dim > 3) { ren_set_error("radiance_dim %d outside [1,3]", f->radiance_dim); return REN_E_INVALID; }
+  if (f->arch != REN_ARCH_MLP && f->arch != REN_ARCH_NGP) { ren_set_error("arch id %d out of range", f->arch); return REN_E_INVALID; }
+  if (f->arch == REN_ARCH_NGP) {
+    if (f->net_depth_condition < 1) { ren_set_error("arch ngp: mlp_head needs at least one hidden layer"); return REN_E_UNSUPPORTED; }
+    if (f->sh_degree < 1 || f->sh_degree > 4) { ren_set_error("arch ngp: sh degree %d outside [1,4]", f->sh_degree); return REN_E_UNSUPPORTED; }
+    if (f->geo_feat_dim < 1 || f->geo_feat_dim > 63) { ren_set_error("arch ngp: geo_feat_dim %d outside [1,63]", f->geo_feat_dim); return REN_E_UNSUPPORTED; }
+    RenGrid g;
+    int grc = ren_build_grid(f, &g, nullptr);
+    if (grc) return grc;
+  } else
   if (f->pos_deg < 0 || f->pos_deg > 10 || f->dir_deg < 0 || f->dir_deg > 4) { ren_set_error("encoder degrees (%d,%d) outside [0,10]x[0,4]", f->pos_deg, f->dir_deg); return REN_E_INVALID; }
   if (f->skip_layer < 0) { ren_set_error("skip_layer must be >= 0 (0 = none)"); return REN_E_INVALID; }
   if (f->hidden_activation < 0 || f->hidden_activation > 1 || f->density_activation < 0 || f->density_activation > 2 ||
@@ -152,6 +165,20 @@ int ren_build_plan(const RenFieldDesc* f, const RenRenderDesc* r, RenPlan* p) {
   p->W = f->net_width; p->WC = f->net_depth_condition > 0 ? f->net_width_condition : f->net_width;
   p->C = f->radiance_dim;
   p->PE = 3 * (1 + 2 * f->pos_deg); p->DE = 3 * (1 + 2 * f->dir_deg);
+  p->arch = f->arch; p->WB = p->W; p->geo = 0; p->n_grid = 0;
+  const bool ngp = f->arch == REN_ARCH_NGP;
+  const int skip = ngp ? 0 : f->skip_layer;
+  if (ngp) {
+    RenGrid g;
+    long long entries = 0;
+    rc = ren_build_grid(f, &g, &entries);
+    if (rc) return rc;
+    p->PE = g.n_levels * g.F;                 // grid features take the place of the positional encoding
+    p->DE = f->sh_degree * f->sh_degree;      // spherical harmonics that of the direction encoding
+    p->geo = f->geo_feat_dim;
+    p->WB = (f->geo_feat_dim + 7) & ~7;
+    p->n_grid = entries * g.F;
+  }
   int off = 0, mat = 0;
   long long moff = 0;
   int in0 = p->PE, in1 = 0;  // input of the next trunk layer: main width, extra width
@@ -165,7 +192,7 @@ int ren_build_plan(const RenFieldDesc* f, const RenRenderDesc* r, RenPlan* p) {
     L.mat = mat; p->mat_width[mat] = L.N; p->mat_off[mat] = moff; moff += L.N; ++mat;
     first = false;
     in0 = p->W;
-    in1 = (f->skip_layer > 0 && i % f->skip_layer == 0 && i > 0) ? p->PE : 0;
+    in1 = (skip > 0 && i % skip == 0 && i > 0) ? p->PE : 0;
   }
   p->hid_K0 = in0; p->hid_K1 = in1;
   p->sig_w = off; off += p->hid_K0 + p->hid_K1;
@@ -173,12 +200,12 @@ int ren_build_plan(const RenFieldDesc* f, const RenRenderDesc* r, RenPlan* p) {
   {
     RenLayer& L = p->bott;
     L.K0 = p->hid_K0; L.K1 = p->hid_K1; L.src0 = 0; L.src1 = p->hid_K1 > 0 ? 1 : 0;
-    L.N = p->W; L.act = 0;
+    L.N = p->WB; L.act = 0;
     L.w_off = off; off += L.N * (L.K0 + L.K1);
     L.b_off = off; off += L.N;
     L.mat = mat; p->mat_width[mat] = L.N; p->mat_off[mat] = moff; moff += L.N; ++mat;
   }
-  int c0 = p->W, c1 = p->DE;
+  int c0 = p->WB, c1 = p->DE;
   for (int j = 0; j < p->CD; ++j) {
     RenLayer& L = p->cond[j];
     L.K0 = c0; L.K1 = c1; L.src0 = 0; L.src1 = c1 > 0 ? 2 : 0;
@@ -193,6 +220,18 @@ int ren_build_plan(const RenFieldDesc* f, const RenRenderDesc* r, RenPlan* p) {
   p->n_params = off;
   p->n_mats = mat;
   p->act_floats = moff;
+  p->n_flat = off;
+  if (ngp) {
+    // the reference's own tensors: grid, mlp_base (hidden, output (1 + geo, W)), mlp_head (hidden, output (C, WC))
+    long long n = p->n_grid;
+    int in = p->PE;
+    for (int i = 0; i < p->D; ++i) { n += (long long)p->W * in + p->W; in = p->W; }
+    n += (long long)(1 + p->geo) * p->W + (1 + p->geo);
+    in = p->DE + p->geo;
+    for (int j = 0; j < p->CD; ++j) { n += (long long)p->WC * in + p->WC; in = p->WC; }
+    n += (long long)p->C * p->WC + p->C;
+    p->n_flat = n;
+  }
   return REN_OK;
 }
 
@@ -200,7 +239,15 @@ extern "C" int ren_param_count(const RenFieldDesc* f, int64_t* n_params) {
   RenPlan p;
   int rc = ren_build_plan(f, nullptr, &p);
   if (rc) return rc;
-  if (n_params) *n_params = p.n_params;
+  if (n_params) *n_params = p.n_flat;
+  return REN_OK;
+}
+
+extern "C" int ren_grid_param_count(const RenFieldDesc* f, int64_t* n_grid_params) {
+  RenPlan p;
+  int rc = ren_build_plan(f, nullptr, &p);
+  if (rc) return rc;
+  if (n_grid_params) *n_grid_params = p.n_grid;
   return REN_OK;
 }
 
@@ -210,13 +257,25 @@ extern "C" int ren_param_layout(const RenFieldDesc* f, int32_t* n_layers, int64_
   int rc = ren_build_plan(f, nullptr, &p);
   if (rc) return rc;
   int n = 0;
-  auto put = [&](int wo, int bo, int outf, int inf) {
+  auto put = [&](long long wo, long long bo, int outf, int inf) {
     if (w_off) w_off[n] = wo;
     if (b_off) b_off[n] = bo;
     if (out_features) out_features[n] = outf;
     if (in_features) in_features[n] = inf;
     ++n;
   };
+  if (p.arch == REN_ARCH_NGP) {
+    long long o = p.n_grid;
+    auto lin = [&](int outf, int inf) { put(o, o + (long long)outf * inf, outf, inf); o += (long long)outf * inf + outf; };
+    int in = p.PE;
+    for (int i = 0; i < p.D; ++i) { lin(p.W, in); in = p.W; }
+    lin(1 + p.geo, p.W);
+    in = p.DE + p.geo;
+    for (int j = 0; j < p.CD; ++j) { lin(p.WC, in); in = p.WC; }
+    lin(p.C, p.WC);
+    if (n_layers) *n_layers = n;
+    return REN_OK;
+  }
   for (int i = 0; i < p.D; ++i) put(p.trunk[i].w_off, p.trunk[i].b_off, p.trunk[i].N, p.trunk[i].K0 + p.trunk[i].K1);
   put(p.sig_w, p.sig_b, 1, p.hid_K0 + p.hid_K1);
   put(p.bott.w_off, p.bott.b_off, p.bott.N, p.bott.K0 + p.bott.K1);
@@ -306,6 +365,48 @@ static int check_engine(const RenPlan& p, int engine) {
   }
   return REN_OK;
 }
+static inline void* align256(void* p) {
+  return (void*)(((uintptr_t)p + 255) & ~(uintptr_t)255);
+}
+
+// arch ngp: the kernels run on a kernel-side copy of the MLP parameters (ren_ngp.cu); both it and its gradient
+// live at the head of the caller's workspace
+struct NgpCtx {
+  bool on;
+  RenNgp ngp;
+  const float* kparams;     // what the field kernels read (== params for arch mlp)
+  float* g_kparams;         // backward: kernel-side gradient (== g_params for arch mlp)
+};
+static size_t ngp_ws_bytes(const RenPlan& p) {
+  return p.arch == REN_ARCH_NGP ? 2 * ((sizeof(float) * (size_t)p.n_params + 255) & ~(size_t)255) + 512 : 0;
+}
+static int ngp_prepare(const RenFieldDesc* f, const RenPlan& p, const float* params, float* g_params,
+                       void* workspace, size_t workspace_bytes, char** ws, size_t* ws_left, bool backward,
+                       cudaStream_t st, NgpCtx* c) {
+  c->on = p.arch == REN_ARCH_NGP;
+  c->kparams = params;
+  c->g_kparams = g_params;
+  if (!c->on) return REN_OK;
+  const size_t one = (sizeof(float) * (size_t)p.n_params + 255) & ~(size_t)255;
+  if (workspace == nullptr || *ws_left < 2 * one + 256) { ren_set_error("workspace too small for the ngp parameter copy"); return REN_E_WORKSPACE; }
+  float* kp = (float*)*ws;
+  float* gkp = (float*)(*ws + one);
+  *ws = (char*)align256(*ws + 2 * one);
+  *ws_left = workspace_bytes - (size_t)(*ws - (char*)workspace);
+  int rc = ren_build_grid(f, &c->ngp.grid, nullptr);
+  if (rc) return rc;
+  c->ngp.table = params;
+  c->ngp.g_table = g_params;
+  rc = ren_ngp_pack(p, params, kp, st);
+  if (rc) return rc;
+  c->kparams = kp;
+  if (backward) {
+    if (cudaMemsetAsync(gkp, 0, sizeof(float) * (size_t)p.n_params, st) != cudaSuccess) { ren_set_error("ngp gradient memset failed"); return REN_E_CUDA; }
+    c->g_kparams = gkp;
+  }
+  return REN_OK;
+}
+
 static size_t stash_bytes_for(const RenPlan& p, int engine, long long S) {
   return engine == REN_ENGINE_SIMT_FP32 ? sizeof(float) * (size_t)ren_stash_floats(p, S) : tcs_bytes(p, S);
 }
@@ -350,7 +451,7 @@ extern "C" int ren_workspace_bytes(const RenFieldDesc* f, const RenRenderDesc* r
                                             (size_t)(ren_pad128(S) >> 7) + 512) +
                            ren_tc_fwd_workspace_bytes(p);
   }
-  *bytes = n + 2048;
+  *bytes = n + 2048 + ngp_ws_bytes(p);
   return REN_OK;
 }
 
@@ -366,10 +467,6 @@ static int check_packed(const RenPacked* packed, int engine, int64_t n_rays, int
   }
   *S = packed->n_samples;
   return REN_OK;
-}
-
-static inline void* align256(void* p) {
-  return (void*)(((uintptr_t)p + 255) & ~(uintptr_t)255);
 }
 
 extern "C" int ren_render_forward(const RenFieldDesc* f, const RenRenderDesc* r, int64_t n_rays, int32_t K,
@@ -403,6 +500,9 @@ extern "C" int ren_render_forward(const RenFieldDesc* f, const RenRenderDesc* r,
   float* raw;
   char* ws = (char*)align256(workspace);
   size_t ws_left = workspace ? workspace_bytes - (size_t)(ws - (char*)workspace) : 0;
+  NgpCtx nc;
+  rc = ngp_prepare(f, p, params, nullptr, workspace, workspace_bytes, &ws, &ws_left, false, st, &nc);
+  if (rc) return rc;
   if (stash) {
     if (stash_bytes < stash_bytes_for(p, engine, S)) { ren_set_error("stash too small"); return REN_E_WORKSPACE; }
     raw = engine == REN_ENGINE_SIMT_FP32 ? (float*)stash + ren_stash_raw(p, S)
@@ -415,7 +515,8 @@ extern "C" int ren_render_forward(const RenFieldDesc* f, const RenRenderDesc* r,
     ws_left = workspace_bytes - (size_t)(ws - (char*)workspace);
   }
   if (engine == REN_ENGINE_SIMT_FP32)
-    rc = ren_simt_launch_fwd(p, n_rays, K, rays_o, rays_d, nullptr, nullptr, jitter, params, (float*)stash, raw, st);
+    rc = ren_simt_launch_fwd(p, n_rays, K, rays_o, rays_d, nullptr, nullptr, jitter, nc.kparams, (float*)stash, raw,
+                             nc.on ? &nc.ngp : nullptr, st);
   else {
     unsigned char* live = nullptr;
     if (r->occ_binary != nullptr && packed == nullptr) {   // dense layout: find the tiles that emit no sample at all
@@ -468,8 +569,11 @@ extern "C" int ren_render_backward(const RenFieldDesc* f, const RenRenderDesc* r
   const int* sample_idx = packed ? packed->sample_idx : nullptr;
   if (stash_bytes < stash_bytes_for(p, engine, S)) { ren_set_error("stash too small"); return REN_E_WORKSPACE; }
   char* ws = (char*)align256(workspace);
-  const size_t ws_left = workspace_bytes - (size_t)(ws - (char*)workspace);
+  size_t ws_left = workspace_bytes - (size_t)(ws - (char*)workspace);
   cudaStream_t st = (cudaStream_t)stream;
+  NgpCtx nc;
+  rc = ngp_prepare(f, p, params, g_params, workspace, workspace_bytes, &ws, &ws_left, true, st, &nc);
+  if (rc) return rc;
   if (engine == REN_ENGINE_SIMT_FP32) {
     const size_t need = sizeof(float) * (size_t)ren_delta_floats(p, S);
     if (ws_left < need) { ren_set_error("workspace too small for backward (%zu < %zu)", ws_left, need); return REN_E_WORKSPACE; }
@@ -480,14 +584,16 @@ extern "C" int ren_render_backward(const RenFieldDesc* f, const RenRenderDesc* r
     rc = ren_launch_composite_bwd(p, n_rays, K, rays_o, rays_d, jitter, nullptr, raw, bkgd, g_radiance, g_opacity,
                                   g_depth, graw, g_bkgd, nullptr, st);
     if (rc) return rc;
-    rc = ren_simt_launch_dgrad(p, S, params, st_f, graw, delta, 0, st);
+    rc = ren_simt_launch_dgrad(p, S, nc.kparams, st_f, graw, delta, 0, st);
     if (rc) return rc;
-    if (g_rays) {
-      rc = ren_launch_raygrad(p, n_rays, K, rays_o, rays_d, nullptr, nullptr, jitter, params, delta, nullptr, 0,
-                              nullptr, nullptr, nullptr, 0, g_rays, st);
+    if (g_rays || nc.on) {      // arch ngp: the same pass scatters the grid gradient
+      rc = ren_launch_raygrad(p, n_rays, K, rays_o, rays_d, nullptr, nullptr, jitter, nc.kparams, delta, nullptr, 0,
+                              nullptr, nullptr, nullptr, 0, g_rays, nc.on ? &nc.ngp : nullptr, st);
       if (rc) return rc;
     }
-    return ren_simt_launch_wgrad(p, S, st_f, delta, graw, g_params, 0, st);
+    rc = ren_simt_launch_wgrad(p, S, st_f, delta, graw, nc.g_kparams, 0, st);
+    if (rc) return rc;
+    return nc.on ? ren_ngp_unpack_grads(p, nc.g_kparams, g_params, st) : REN_OK;
   }
   const size_t need = tcd_bytes(p, S);
   if (ws_left < need + 1024) { ren_set_error("workspace too small for backward (%zu < %zu)", ws_left, need); return REN_E_WORKSPACE; }
@@ -511,7 +617,7 @@ extern "C" int ren_render_backward(const RenFieldDesc* f, const RenRenderDesc* r
   if (rc) return rc;
   if (g_rays) {
     rc = ren_launch_raygrad(p, n_rays, K, rays_o, rays_d, nullptr, nullptr, jitter, params, delta, nullptr, 1, gmax,
-                            live, sample_idx, S, g_rays, st);
+                            live, sample_idx, S, g_rays, nullptr, st);
     if (rc) return rc;
   }
   return ren_tc_launch_wgrad(p, S, stash, delta, graw, gmax, g_params, 1, live, st);
@@ -570,7 +676,7 @@ extern "C" int ren_tangent_workspace_bytes(const RenFieldDesc* f, const RenRende
     n = for_backward ? tct_bwd_bytes(p, S) + ren_tc_bwd_pack_bytes(p)
                      : (has_stash ? 0 : 2 * tcs_bytes(p, S) + 512) + ren_tc_fwd_workspace_bytes(p);
   }
-  *bytes = n + 2048;
+  *bytes = n + 2048 + ngp_ws_bytes(p);
   return REN_OK;
 }
 
@@ -599,6 +705,9 @@ extern "C" int ren_render_tangent_forward(const RenFieldDesc* f, const RenRender
   cudaStream_t st = (cudaStream_t)stream;
   char* ws = (char*)align256(workspace);
   size_t ws_left = workspace ? workspace_bytes - (size_t)(ws - (char*)workspace) : 0;
+  NgpCtx nc;
+  rc = ngp_prepare(f, p, params, nullptr, workspace, workspace_bytes, &ws, &ws_left, false, st, &nc);
+  if (rc) return rc;
   if (p.r.engine != REN_ENGINE_SIMT_FP32) {
     const size_t one = (tcs_bytes(p, S) + 255) & ~(size_t)255;
     char* sv;
@@ -641,7 +750,8 @@ extern "C" int ren_render_tangent_forward(const RenFieldDesc* f, const RenRender
     if (!workspace || ws_left < need) { ren_set_error("workspace too small for raw samples (%zu < %zu)", ws_left, need); return REN_E_WORKSPACE; }
     raw = (float*)ws;
   }
-  rc = ren_simt_launch_fwd(p, n_rays, K, rays_o, rays_d, rays_o_dot, rays_d_dot, jitter, params, (float*)stash, raw, st);
+  rc = ren_simt_launch_fwd(p, n_rays, K, rays_o, rays_d, rays_o_dot, rays_d_dot, jitter, nc.kparams, (float*)stash,
+                           raw, nc.on ? &nc.ngp : nullptr, st);
   if (rc) return rc;
   return ren_launch_composite_tan(p, n_rays, K, rays_o, rays_d, jitter, nullptr, raw, nullptr, bkgd, radiance, opacity,
                                   depth, radiance_dot, opacity_dot, n_kept, st);
@@ -669,8 +779,11 @@ extern "C" int ren_render_tangent_backward(const RenFieldDesc* f, const RenRende
   const int* ray_offsets = packed ? packed->ray_offsets : nullptr;
   const int* sample_idx = packed ? packed->sample_idx : nullptr;
   char* ws = (char*)align256(workspace);
-  const size_t ws_left = workspace_bytes - (size_t)(ws - (char*)workspace);
+  size_t ws_left = workspace_bytes - (size_t)(ws - (char*)workspace);
   cudaStream_t st = (cudaStream_t)stream;
+  NgpCtx nc;
+  rc = ngp_prepare(f, p, params, g_params, workspace, workspace_bytes, &ws, &ws_left, true, st, &nc);
+  if (rc) return rc;
   if (p.r.engine != REN_ENGINE_SIMT_FP32) {
     if (stash_bytes < 2 * tcs_bytes(p, S) + 512) { ren_set_error("stash too small"); return REN_E_WORKSPACE; }
     const size_t need = tct_bwd_bytes(p, S);
@@ -706,7 +819,7 @@ extern "C" int ren_render_tangent_backward(const RenFieldDesc* f, const RenRende
     if (rc) return rc;
     if (g_rays) {
       rc = ren_launch_raygrad(p, n_rays, K, rays_o, rays_d, rays_o_dot, rays_d_dot, jitter, params, delta_val,
-                              delta_dot, 1, gmax, live, sample_idx, S, g_rays, st);
+                              delta_dot, 1, gmax, live, sample_idx, S, g_rays, nullptr, st);
       if (rc) return rc;
     }
     rc = ren_tc_launch_wgrad(p, S, sv, delta_val, graw_val, gmax, g_params, 1, live, st);
@@ -724,14 +837,16 @@ extern "C" int ren_render_tangent_backward(const RenFieldDesc* f, const RenRende
   rc = ren_launch_composite_tan_bwd(p, n_rays, K, rays_o, rays_d, jitter, nullptr, raw, nullptr, bkgd, g_radiance,
                                     g_opacity, g_depth, g_radiance_dot, g_opacity_dot, graw, nullptr, g_bkgd, nullptr, st);
   if (rc) return rc;
-  rc = ren_simt_launch_dgrad(p, S2, params, st_f, graw, delta, 1, st);
+  rc = ren_simt_launch_dgrad(p, S2, nc.kparams, st_f, graw, delta, 1, st);
   if (rc) return rc;
-  if (g_rays) {
-    rc = ren_launch_raygrad(p, n_rays, K, rays_o, rays_d, rays_o_dot, rays_d_dot, jitter, params, delta, nullptr, 0,
-                            nullptr, nullptr, nullptr, 0, g_rays, st);
+  if (g_rays || nc.on) {
+    rc = ren_launch_raygrad(p, n_rays, K, rays_o, rays_d, rays_o_dot, rays_d_dot, jitter, nc.kparams, delta, nullptr, 0,
+                            nullptr, nullptr, nullptr, 0, g_rays, nc.on ? &nc.ngp : nullptr, st);
     if (rc) return rc;
   }
-  return ren_simt_launch_wgrad(p, S2, st_f, delta, graw, g_params, 1, st);
+  rc = ren_simt_launch_wgrad(p, S2, st_f, delta, graw, nc.g_kparams, 1, st);
+  if (rc) return rc;
+  return nc.on ? ren_ngp_unpack_grads(p, nc.g_kparams, g_params, st) : REN_OK;
 }
 
 // ------------------------------------------------------------------ density at free points
@@ -766,7 +881,7 @@ extern "C" int ren_density_workspace_bytes(const RenFieldDesc* f, const RenRende
   size_t ws = 0;
   int rc = ren_workspace_bytes(f, &rr, n_points, 1, 0, 0, &ws);
   if (rc) return rc;
-  *bytes = ws + sizeof(float) * 3 * (size_t)(n_points + 64) + 1024;
+  *bytes = ws + sizeof(float) * 3 * (size_t)(n_points + 64) + 1024;     // (ren_workspace_bytes counts the ngp copy)
   return REN_OK;
 }
 extern "C" int ren_field_density(const RenFieldDesc* f, const RenRenderDesc* r, int64_t n_points, const float* points,
@@ -790,6 +905,9 @@ extern "C" int ren_field_density(const RenFieldDesc* f, const RenRenderDesc* r, 
   cudaStream_t st = (cudaStream_t)stream;
   char* ws = (char*)align256(workspace);
   size_t ws_left = workspace_bytes - (size_t)(ws - (char*)workspace);
+  NgpCtx nc;
+  rc = ngp_prepare(f, p, params, nullptr, workspace, workspace_bytes, &ws, &ws_left, false, st, &nc);
+  if (rc) return rc;
   const size_t zero_bytes = sizeof(float) * 3 * (size_t)n_points;
   const size_t raw_bytes = sizeof(float) * (size_t)((1 + p.C) * ren_pad128(n_points));
   if (ws_left < zero_bytes + raw_bytes + 512) { ren_set_error("ren_field_density: workspace too small"); return REN_E_WORKSPACE; }
@@ -799,7 +917,8 @@ extern "C" int ren_field_density(const RenFieldDesc* f, const RenRenderDesc* r, 
   char* rest = (char*)align256((char*)raw + raw_bytes);
   ws_left = workspace_bytes - (size_t)(rest - (char*)workspace);
   if (engine == REN_ENGINE_SIMT_FP32)
-    rc = ren_simt_launch_fwd(p, n_points, 1, points, zeros, nullptr, nullptr, nullptr, params, nullptr, raw, st);
+    rc = ren_simt_launch_fwd(p, n_points, 1, points, zeros, nullptr, nullptr, nullptr, nc.kparams, nullptr, raw,
+                             nc.on ? &nc.ngp : nullptr, st);
   else
     rc = ren_tc_launch_fwd(p, n_points, 1, points, zeros, nullptr, nullptr, nullptr, nullptr, params, nullptr, raw,
                            nullptr, nullptr, 0, rest, ws_left, st);

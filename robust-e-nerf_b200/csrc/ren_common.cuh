@@ -43,7 +43,34 @@ struct RenPlan {
   int mat_width[REN_MAX_TRUNK + 1 + REN_MAX_COND];
   long long mat_off[REN_MAX_TRUNK + 1 + REN_MAX_COND];  // prefix of widths (floats per sample)
   long long act_floats;      // sum of widths
-  int n_params;
+  int n_params;              // arch mlp: the flat parameter buffer; arch ngp: the kernel-side MLP buffer (below)
+  // arch ngp (ren_ngp.cu): the kernels run on a kernel-side copy of the MLP parameters laid out like the vanilla
+  // topology (trunk = mlp_base hidden layers, sigma head = row 0 of mlp_base's output layer, bottleneck = its
+  // geo-feature rows padded to WB, condition layers = mlp_head with input [features | SH]); the caller's flat
+  // buffer keeps the reference's state-dict layout [grid | mlp_base | mlp_head]
+  int arch, WB;              // WB: bottleneck width (W for arch mlp, geo_feat_dim rounded up to 8 for ngp)
+  int geo;                   // geo_feat_dim
+  long long n_grid;          // grid parameters at the head of the caller's flat buffer
+  long long n_flat;          // elements of the caller's flat buffer
+};
+
+// arch ngp: multiresolution grid of tiny-cuda-nn (grid.h: grid_scale / grid_resolution / offset table)
+#define REN_MAX_LEVELS 32
+struct RenGridLevel {
+  float scale;               // fp32(2^(l log2 per_level_scale) base_resolution - 1), evaluated in double on the host
+  uint32_t res;              // ceil(scale) + 1
+  uint32_t entries;          // table entries of the level
+  uint32_t offset;           // first entry of the level
+};
+struct RenGrid {
+  int n_levels, F, type;
+  RenGridLevel lv[REN_MAX_LEVELS];
+};
+// what the NGP-aware kernels need besides the plan (NULL for arch mlp)
+struct RenNgp {
+  RenGrid grid;
+  const float* table;        // grid parameters (caller's flat buffer + 0)
+  float* g_table;            // their gradient (accumulated), backward only
 };
 
 // Stash layout (floats), S = n_rays*K samples:
@@ -302,7 +329,107 @@ __device__ __forceinline__ void ren_encode_tangent(const float* x, const float* 
   for (int j = 3 + 6 * deg; j < padded; ++j) store(j, 0.f);
 }
 
-#endif  // __CUDACC__
+#endif  // __CUDACC__ (geometry)
+
+// ------------------------------------------------------------------ arch ngp
+// `coherent_prime_hash` / `grid_index` of tiny-cuda-nn (grid.h): dense index while the stride fits the level's
+// table, else the prime hash; always modulo the table size.
+__host__ __device__ inline uint32_t ren_grid_index(const RenGridLevel& lv, int type, uint32_t x, uint32_t y,
+                                                   uint32_t z) {
+  uint32_t stride = 1, index = 0;
+  const uint32_t c[3] = {x, y, z};
+  for (int dim = 0; dim < 3 && stride <= lv.entries; ++dim) {
+    index += c[dim] * stride;
+    stride *= lv.res;
+  }
+  if (type == REN_GRID_HASH && lv.entries < stride) index = (x * 1u) ^ (y * 2654435761u) ^ (z * 805459861u);
+  return index % lv.entries;
+}
+#ifdef __CUDACC__
+// Corner data of one level at unit position x: integer cell, fractional position (pos_fract with the identity
+// interpolant: pos = fmaf(scale, x, 0.5f); floor; frac).
+struct RenCell { uint32_t g[3]; float f[3]; };
+__device__ __forceinline__ void ren_grid_cell(const RenGridLevel& lv, const float* x, RenCell& c) {
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const float pos = fmaf(lv.scale, x[a], 0.5f);
+    const float fl = floorf(pos);
+    c.g[a] = (uint32_t)(int)fl;
+    c.f[a] = pos - fl;
+  }
+}
+// trilinear weight of corner `corner` and its derivative data: a[dim] = f or 1 - f, s[dim] = +1 / -1
+__device__ __forceinline__ void ren_corner(const RenCell& c, int corner, float* a, float* s, uint32_t* g) {
+#pragma unroll
+  for (int dim = 0; dim < 3; ++dim) {
+    const bool up = (corner >> dim) & 1;
+    a[dim] = up ? c.f[dim] : 1.f - c.f[dim];
+    s[dim] = up ? 1.f : -1.f;
+    g[dim] = c.g[dim] + (up ? 1u : 0u);
+  }
+}
+// enc[l*F + j] = sum_corners w T[idx][j]  (kernel_grid of tiny-cuda-nn);  xdot != NULL: d enc / d w instead,
+// with the weights' derivative along xdot (d frac / d x = scale)
+template <typename Store>
+__device__ __forceinline__ void ren_grid_encode(const RenGrid& G, const float* __restrict__ table, const float* x,
+                                                const float* xdot, Store store) {
+  for (int l = 0; l < G.n_levels; ++l) {
+    const RenGridLevel lv = G.lv[l];
+    RenCell c;
+    ren_grid_cell(lv, x, c);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+    for (int corner = 0; corner < 8; ++corner) {
+      float a[3], s[3];
+      uint32_t g[3];
+      ren_corner(c, corner, a, s, g);
+      float w;
+      if (xdot == nullptr) {
+        w = a[0] * a[1] * a[2];
+      } else {
+        w = lv.scale * (s[0] * xdot[0] * a[1] * a[2] + s[1] * xdot[1] * a[0] * a[2] + s[2] * xdot[2] * a[0] * a[1]);
+      }
+      const float* t = table + ((size_t)lv.offset + ren_grid_index(lv, G.type, g[0], g[1], g[2])) * G.F;
+      if (G.F == 2) {
+        const float2 v = __ldg(reinterpret_cast<const float2*>(t));
+        acc[0] = fmaf(w, v.x, acc[0]);
+        acc[1] = fmaf(w, v.y, acc[1]);
+      } else {
+        for (int j = 0; j < G.F; ++j) acc[j] = fmaf(w, __ldg(t + j), acc[j]);
+      }
+    }
+    for (int j = 0; j < G.F; ++j) store(l * G.F + j, acc[j]);
+  }
+}
+#endif
+
+// real spherical harmonics of the raw direction, degree <= 4 (external/sh_encoder.py:27-85), on any number type
+template <class T>
+__host__ __device__ inline void ren_sh_t(const T* d, int degree, T* out) {
+  const T x = d[0], y = d[1], z = d[2];
+  const T xy = x * y, xz = x * z, yz = y * z, x2 = x * x, y2 = y * y, z2 = z * z;
+  out[0] = T(0.28209479177387814f);
+  if (degree <= 1) return;
+  out[1] = T(-0.48860251190291987f) * y;
+  out[2] = T(0.48860251190291987f) * z;
+  out[3] = T(-0.48860251190291987f) * x;
+  if (degree <= 2) return;
+  out[4] = T(1.0925484305920792f) * xy;
+  out[5] = T(-1.0925484305920792f) * yz;
+  out[6] = T(0.94617469575755997f) * z2 - T(0.31539156525251999f);
+  out[7] = T(-1.0925484305920792f) * xz;
+  out[8] = T(0.54627421529603959f) * x2 - T(0.54627421529603959f) * y2;
+  if (degree <= 3) return;
+  out[9] = T(0.59004358992664352f) * y * (T(-3.0f) * x2 + y2);
+  out[10] = T(2.8906114426405538f) * xy * z;
+  out[11] = T(0.45704579946446572f) * y * (T(1.0f) - T(5.0f) * z2);
+  out[12] = T(0.3731763325901154f) * z * (T(5.0f) * z2 - T(3.0f));
+  out[13] = T(0.45704579946446572f) * x * (T(1.0f) - T(5.0f) * z2);
+  out[14] = T(1.4453057213202769f) * z * (x2 - y2);
+  out[15] = T(0.59004358992664352f) * x * (T(-1.0f) * x2 + T(3.0f) * y2);
+}
 
 // host side (ren_api.cu)
 enum { REN_K_FIELD_FWD = 0, REN_K_FIELD_DGRAD, REN_K_WGRAD, REN_K_COMPOSITE_FWD, REN_K_COMPOSITE_BWD,

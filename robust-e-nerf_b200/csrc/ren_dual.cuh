@@ -107,9 +107,9 @@ __host__ __device__ inline J2 j2_cos(J2 a) { return j2_apply(a, cosf(a.v), -sinf
 // VanillaNeRFRadianceField.contract_input_space (external/mlp.py:321-335) with
 // contract_to_unisphere / contract_tanh (external/ngp.py:68-106): p -> z = 2 pi (x_hat - 1/2).
 #include "../../include/ren_b200.h"
+// p -> x_hat in the unit cube (what `NGPradianceField.query_density` feeds the grid encoding, external/ngp.py:219-228)
 template <class T>
-__host__ __device__ inline void ren_contract_t(const RenFieldDesc& f, const T* p, T* z) {
-  T x[3];
+__host__ __device__ inline void ren_contract_unit_t(const RenFieldDesc& f, const T* p, T* x) {
   for (int a = 0; a < 3; ++a) x[a] = (p[a] - T(f.aabb[a])) / T(f.aabb[3 + a] - f.aabb[a]);
   if (f.contraction == REN_CONTRACT_SPHERE) {
     for (int a = 0; a < 3; ++a) x[a] = x[a] * T(2.f) - T(1.f);
@@ -122,5 +122,10 @@ __host__ __device__ inline void ren_contract_t(const RenFieldDesc& f, const T* p
   } else if (f.contraction == REN_CONTRACT_TANH) {
     for (int a = 0; a < 3; ++a) x[a] = (t_tanh(x[a] - T(0.5f)) + T(1.f)) * T(0.5f);
   }
+}
+template <class T>
+__host__ __device__ inline void ren_contract_t(const RenFieldDesc& f, const T* p, T* z) {
+  T x[3];
+  ren_contract_unit_t<T>(f, p, x);
   for (int a = 0; a < 3; ++a) z[a] = T(6.283185307179586f) * (x[a] - T(0.5f));
 }

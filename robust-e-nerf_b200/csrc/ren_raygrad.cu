@@ -12,6 +12,7 @@
 // derivative of the contraction, taken with hyper-dual numbers, and returns
 // d loss / d (o, d, o_dot, d_dot).
 #include <stdlib.h>
+#include <string.h>
 
 #include "ren_tc.cuh"
 #include "ren_dual.cuh"
@@ -48,8 +49,83 @@ struct RgArgs {
   const float* rays_o_dot;
   const float* rays_d_dot;
   const float* jitter;
-  float* g_rays;    // [n_rays][6] (value) or [n_rays][12] (tangent)
+  float* g_rays;    // [n_rays][6] (value) or [n_rays][12] (tangent); arch ngp: may be NULL (grid gradient only)
+  // arch ngp: the positional encoding is the grid (its reverse also scatters the grid gradient), the direction
+  // encoding the spherical harmonics of the raw direction
+  RenGrid grid;
+  const float* table;
+  float* g_table;
 };
+
+// arch ngp: reverse of one sample through grid + SH encoders.  gvP / gtP: d loss / d (grid features, their d/dw);
+// gvD / gtD: same for the SH features.  Scatters the grid gradient; returns d loss / d (x_hat, x_hat_dot) and
+// d loss / d (d, d_dot) of the SH branch when `rays` is set.
+__device__ __forceinline__ void ngp_enc_backward(const RgArgs& a, const float* xu, const float* xudot,
+                                                 const float* d, const float* dd, const float* gvP,
+                                                 const float* gtP, const float* gvD, const float* gtD, bool rays,
+                                                 float* gxu, float* gxud, float* gd, float* gdd) {
+  const bool tan = a.tangent != 0;
+  const RenGrid& G = a.grid;
+  for (int c = 0; c < 3; ++c) gxu[c] = gxud[c] = gd[c] = gdd[c] = 0.f;
+  for (int l = 0; l < G.n_levels; ++l) {
+    const RenGridLevel lv = G.lv[l];
+    RenCell cell;
+    ren_grid_cell(lv, xu, cell);
+    const float* gv = gvP + l * G.F;
+    const float* gt = gtP + l * G.F;
+    bool any = false;
+    for (int j = 0; j < G.F; ++j) any = any || gv[j] != 0.f || (tan && gt[j] != 0.f);
+    if (!any) continue;
+#pragma unroll
+    for (int corner = 0; corner < 8; ++corner) {
+      float w3[3], s3[3];
+      uint32_t g3[3];
+      ren_corner(cell, corner, w3, s3, g3);
+      const float w = w3[0] * w3[1] * w3[2];
+      const float dw[3] = {lv.scale * s3[0] * w3[1] * w3[2], lv.scale * s3[1] * w3[0] * w3[2],
+                           lv.scale * s3[2] * w3[0] * w3[1]};
+      const float wdot = tan ? dw[0] * xudot[0] + dw[1] * xudot[1] + dw[2] * xudot[2] : 0.f;
+      const size_t e = ((size_t)lv.offset + ren_grid_index(lv, G.type, g3[0], g3[1], g3[2])) * G.F;
+      float A = 0.f, B = 0.f;
+      for (int j = 0; j < G.F; ++j) {
+        const float t = rays ? __ldg(a.table + e + j) : 0.f;
+        A = fmaf(t, gv[j], A);
+        if (tan) B = fmaf(t, gt[j], B);
+        atomicAdd(a.g_table + e + j, tan ? fmaf(wdot, gt[j], w * gv[j]) : w * gv[j]);
+      }
+      if (rays) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          gxu[k] = fmaf(dw[k], A, gxu[k]);
+          if (tan) {
+            gxud[k] = fmaf(dw[k], B, gxud[k]);
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+              if (j != k) gxu[k] = fmaf(lv.scale * lv.scale * s3[k] * s3[j] * w3[3 - k - j] * xudot[j], B, gxu[k]);
+          }
+        }
+      }
+    }
+  }
+  if (rays) {
+    const int n = a.p.DE;
+    for (int kk = 0; kk < 3; ++kk) {
+      HDual dh[3], out[16];
+      for (int c = 0; c < 3; ++c) dh[c] = HDual(d[c], c == kk ? 1.f : 0.f, dd[c], 0.f);
+      ren_sh_t<HDual>(dh, a.p.f.sh_degree, out);
+      float sv = 0.f, st = 0.f;
+      for (int j = 0; j < n; ++j) {
+        sv = fmaf(gvD[j], out[j].d1, sv);
+        if (tan) {
+          sv = fmaf(gtD[j], out[j].d12, sv);
+          st = fmaf(gtD[j], out[j].d1, st);
+        }
+      }
+      gd[kk] = sv;
+      gdd[kk] = st;
+    }
+  }
+}
 
 // d loss / d x and d loss / d xdot of one encoder from d loss / d enc (gv) and d loss / d enc_dot (gt)
 __device__ __forceinline__ void enc_backward(const float* x, const float* xdot, int deg, const float* gv,
@@ -194,6 +270,39 @@ extern "C" __global__ void __launch_bounds__(RG_THREADS) ren_raygrad_kernel(cons
         const float* gtP = gP[threadIdx.x * per + (per - 1)];
         const float* gvD = gD[threadIdx.x * per];
         const float* gtD = gD[threadIdx.x * per + (per - 1)];
+        if (p.arch == REN_ARCH_NGP) {
+          float xu[3], xudot[3] = {0.f, 0.f, 0.f};
+          ren_unit_position(p.f, o, d, t0, t1, xu);
+          if (a.tangent) {
+            Dual pd[3], xd[3];
+            for (int c = 0; c < 3; ++c) pd[c] = Dual(pos[c], xdot[c]);
+            ren_contract_unit_t<Dual>(p.f, pd, xd);
+            for (int c = 0; c < 3; ++c) xudot[c] = xd[c].d;
+          }
+          float gxu[3], gxud[3], gdir[3], gdird[3];
+          const bool rays = a.g_rays != nullptr;
+          ngp_enc_backward(a, xu, xudot, d, dd, gvP, gtP, gvD, gtD, rays, gxu, gxud, gdir, gdird);
+          if (rays) {
+            const int stride = a.tangent ? 12 : 6;
+            float* g = a.g_rays + r * stride;
+            for (int kk = 0; kk < 3; ++kk) {
+              HDual ph[3], xh[3];
+              for (int c = 0; c < 3; ++c) ph[c] = HDual(pos[c], c == kk ? 1.f : 0.f, xdot[c], 0.f);
+              ren_contract_unit_t<HDual>(p.f, ph, xh);
+              float sx = 0.f, sxd = 0.f;
+              for (int c = 0; c < 3; ++c) {
+                sx = fmaf(gxu[c], xh[c].d1, fmaf(gxud[c], xh[c].d12, sx));
+                sxd = fmaf(gxud[c], xh[c].d1, sxd);
+              }
+              atomicAdd(g + kk, sx);
+              atomicAdd(g + 3 + kk, fmaf(tm, sx, gdir[kk]));
+              if (a.tangent) {
+                atomicAdd(g + 6 + kk, sxd);
+                atomicAdd(g + 9 + kk, fmaf(tm, sxd, gdird[kk]));
+              }
+            }
+          }
+        } else {
         float gz[3], gzd[3], gdz[3], gdzd[3];
         float zdot[3] = {0.f, 0.f, 0.f};
         if (a.tangent) {
@@ -231,6 +340,7 @@ extern "C" __global__ void __launch_bounds__(RG_THREADS) ren_raygrad_kernel(cons
             atomicAdd(g + 9 + c, fmaf(tm, gxd[c], 3.141592653589793f * gdzd[c]));
           }
         }
+        }
       }
     }
     __syncthreads();
@@ -250,12 +360,19 @@ int ren_launch_raygrad(const RenPlan& p, long long n_rays, int K, const float* o
                        const float* o_dot, const float* d_dot, const float* jitter, const float* params,
                        const void* delta, const void* delta_dot, int fp16, const unsigned int* gmax,
                        const unsigned char* tile_live, const int* sample_idx, long long n_samples, float* g_rays,
-                       cudaStream_t st) {
+                       const RenNgp* ngp, cudaStream_t st) {
   if (n_rays <= 0) return REN_OK;
   if (fp16 && ren_tc_raygrad_supported(p) && getenv("REN_RAYGRAD_SIMT") == nullptr)
     return ren_tc_launch_raygrad(p, n_rays, K, o, d, o_dot, d_dot, jitter, params, delta, delta_dot, gmax, tile_live,
                                  sample_idx, n_samples, g_rays, st);
   RgArgs a;
+  static_assert(sizeof(RgArgs) <= 4000, "kernel parameter block too large");
+  memset(&a.grid, 0, sizeof(a.grid));
+  a.table = nullptr; a.g_table = nullptr;
+  if (p.arch == REN_ARCH_NGP) {
+    if (ngp == nullptr || ngp->g_table == nullptr) { ren_set_error("ray gradient: arch ngp without grid"); return REN_E_INVALID; }
+    a.grid = ngp->grid; a.table = ngp->table; a.g_table = ngp->g_table;
+  }
   a.tile_live = tile_live; a.sample_idx = sample_idx; a.n_samples = n_samples;
   a.p = p; a.n_rays = n_rays; a.K = K; a.tangent = o_dot != nullptr ? 1 : 0; a.fp16 = fp16; a.gmax = gmax;
   a.rays_o = o; a.rays_d = d; a.rays_o_dot = o_dot; a.rays_d_dot = d_dot; a.jitter = jitter; a.g_rays = g_rays;
@@ -293,7 +410,8 @@ int ren_launch_raygrad(const RenPlan& p, long long n_rays, int K, const float* o
   }
   if (n > RG_MAX_SRC) { ren_set_error("ray gradient: too many encoding consumers (%d)", n); return REN_E_UNSUPPORTED; }
   a.n_src = n;
-  cudaError_t e = cudaMemsetAsync(g_rays, 0, sizeof(float) * (size_t)n_rays * (a.tangent ? 12 : 6), st);
+  cudaError_t e = cudaSuccess;
+  if (g_rays != nullptr) e = cudaMemsetAsync(g_rays, 0, sizeof(float) * (size_t)n_rays * (a.tangent ? 12 : 6), st);
   if (e != cudaSuccess) { ren_set_error("ray gradient memset: %s", cudaGetErrorString(e)); return REN_E_CUDA; }
   long long blocks = (S + RG_ROWS - 1) / RG_ROWS;
   if (blocks > 148 * 32) blocks = 148 * 32;

@@ -13,6 +13,8 @@
 // same GEMMs push the activations AND their derivative along the ray's pose-interpolation weight
 // through the network (the reference gets d logI / d t by autograd with create_graph=True,
 // models/robust_e_nerf.py:394-398); stash / delta matrices simply have 2S rows.
+#include <string.h>
+
 #include "ren_common.cuh"
 #include "ren_dual.cuh"
 
@@ -32,6 +34,8 @@ struct FwdArgs {
   float* raw;       // [S][1+C] (inside stash when training, else workspace); tangent: [2S][1+C]
   const float* rays_o_dot;   // tangent mode: d o / d w, d d / d w per ray
   const float* rays_d_dot;
+  RenGrid grid;              // arch ngp: grid encoding of the contracted position instead of the sinusoidal one
+  const float* table;
 };
 
 struct DgradArgs {
@@ -267,6 +271,36 @@ __global__ void __launch_bounds__(NTHREADS, 1) ren_simt_field_fwd(const FwdArgs 
         skipped = !ren_occupied(p.f, p.r, o, d, t0, t1);  // unoccupied cell: the marcher emits no sample
         float dz[3] = {__fmul_rn(d[0], 3.141592653589793f), __fmul_rn(d[1], 3.141592653589793f),
                        __fmul_rn(d[2], 3.141592653589793f)};
+        if (p.arch == REN_ARCH_NGP) {
+          // external/ngp.py:219-252: grid features of the contracted unit position, spherical harmonics of the
+          // raw direction; the d/dw row takes the derivative of both along (odot + ddot tm, ddot)
+          float xu[3];
+          ren_unit_position(p.f, o, d, t0, t1, xu);
+          for (int j = 0; j < REN_PE_MAX; ++j) eP[j] = 0.f;
+          for (int j = 0; j < REN_DE_MAX; ++j) eD[j] = 0.f;
+          if (!tan_row) {
+            ren_grid_encode(a.grid, a.table, xu, nullptr, [&](int j, float v) { eP[j] = v; });
+            float sh[16];
+            ren_sh_t<float>(d, p.f.sh_degree, sh);
+            for (int j = 0; j < p.DE; ++j) eD[j] = sh[j];
+          } else {
+            const float tm = __fmul_rn(__fadd_rn(t0, t1), 0.5f);
+            Dual pd[3], xd[3], dd3[3], shd[16];
+            float xdot[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              const float od = a.rays_o_dot[r * 3 + c], ddc = a.rays_d_dot[r * 3 + c];
+              pd[c] = Dual(__fadd_rn(o[c], __fmul_rn(__fmul_rn(d[c], __fadd_rn(t0, t1)), 0.5f)), fmaf(ddc, tm, od));
+              dd3[c] = Dual(d[c], ddc);
+            }
+            ren_contract_unit_t<Dual>(p.f, pd, xd);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) xdot[c] = xd[c].d;
+            ren_grid_encode(a.grid, a.table, xu, xdot, [&](int j, float v) { eP[j] = v; });
+            ren_sh_t<Dual>(dd3, p.f.sh_degree, shd);
+            for (int j = 0; j < p.DE; ++j) eD[j] = shd[j].d;
+          }
+        } else
         if (!tan_row) {
           ren_encode(z, p.f.pos_deg, REN_PE_MAX, [&](int j, float v) { eP[j] = v; });
           ren_encode(dz, p.f.dir_deg, REN_DE_MAX, [&](int j, float v) { eD[j] = v; });
@@ -644,8 +678,15 @@ static int sm_count() {
 
 int ren_simt_launch_fwd(const RenPlan& p, long long n_rays, int K, const float* o, const float* d,
                         const float* o_dot, const float* d_dot, const float* jitter, const float* params,
-                        float* stash, float* raw, cudaStream_t st) {
+                        float* stash, float* raw, const RenNgp* ngp, cudaStream_t st) {
   FwdArgs a;
+  static_assert(sizeof(FwdArgs) <= 4000, "kernel parameter block too large");
+  memset(&a.grid, 0, sizeof(a.grid));
+  a.table = nullptr;
+  if (p.arch == REN_ARCH_NGP) {
+    if (ngp == nullptr) { ren_set_error("simt fwd: arch ngp without grid"); return REN_E_INVALID; }
+    a.grid = ngp->grid; a.table = ngp->table;
+  }
   a.p = p; a.n_rays = n_rays; a.K = K; a.rays_o = o; a.rays_d = d; a.jitter = jitter;
   a.params = params; a.stash = stash; a.raw = raw; a.rays_o_dot = o_dot; a.rays_d_dot = d_dot;
   const bool tan = o_dot != nullptr;

@@ -1007,7 +1007,7 @@ static int build_ops(TcProgram& P, int mode) {
 }
 
 int ren_tc_supported(const RenPlan& p) {
-  return p.W == 256 && p.WC == 128 && p.CD == 1 && p.hid_K1 == 0 && p.f.pos_deg == 10 && p.f.dir_deg == 4 &&
+  return p.arch == REN_ARCH_MLP && p.W == 256 && p.WC == 128 && p.CD == 1 && p.hid_K1 == 0 && p.f.pos_deg == 10 && p.f.dir_deg == 4 &&
          p.D >= 1 && p.D + 2 <= 12 && p.C <= 3 && p.trunk[0].K1 == 0;
 }
 

@@ -17,6 +17,8 @@ DENSITY_ACT = {"shifted_trunc_exp": 0, "softplus": 1, "shifted_softplus": 2}
 RADIANCE_ACT = {"softplus": 0, "sigmoid": 1}
 CONTRACTION = {"aabb": 0, "sphere": 1, "tanh": 2}
 ERROR_FN = {"l1": 0, "mse": 1, "mape": 2}
+ARCH = {"mlp": 0, "ngp": 1}
+GRID_TYPE = {"HashGrid": 0, "DenseGrid": 1, "TiledGrid": 2}
 ABI_VERSION = 5
 
 
@@ -28,6 +30,11 @@ class RenFieldDesc(C.Structure):
         ("hidden_activation", C.c_int32), ("density_activation", C.c_int32),
         ("radiance_activation", C.c_int32), ("contraction", C.c_int32),
         ("aabb", C.c_float * 6),
+        # arch ngp (include/ren_b200.h)
+        ("arch", C.c_int32), ("grid_type", C.c_int32), ("grid_levels", C.c_int32), ("grid_features", C.c_int32),
+        ("grid_log2_hashmap_size", C.c_int32), ("grid_base_resolution", C.c_int32),
+        ("grid_per_level_scale", C.c_float), ("sh_degree", C.c_int32), ("geo_feat_dim", C.c_int32),
+        ("reserved_ngp", C.c_int32),
     ]
 
 
@@ -53,6 +60,7 @@ _SIGNATURES = {
     "ren_timing_enable": (C.c_int, [C.c_int32]),
     "ren_timing_collect": (C.c_int, [C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "ren_param_count": (C.c_int, [C.POINTER(RenFieldDesc), C.POINTER(C.c_int64)]),
+    "ren_grid_param_count": (C.c_int, [C.POINTER(RenFieldDesc), C.POINTER(C.c_int64)]),
     "ren_param_layout": (C.c_int, [C.POINTER(RenFieldDesc), C.POINTER(C.c_int32), C.POINTER(C.c_int64),
                                    C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "ren_samples_per_ray": (C.c_int, [C.POINTER(RenFieldDesc), C.POINTER(RenRenderDesc),
@@ -167,6 +175,45 @@ def make_field_desc(net_depth=8, net_width=256, skip_layer=4, net_depth_conditio
     for i, v in enumerate(aabb):
         d.aabb[i] = float(v)
     return d
+
+
+def make_ngp_field_desc(pos_encoding, dir_encoding, mlp_base, mlp_head, radiance_dim=1, contraction="sphere",
+                        aabb=(-1.5, -1.5, -1.5, 1.5, 1.5, 1.5)):
+    """RenFieldDesc of `arch: ngp` from the four YAML blocks (configs/train/*.yaml:61-88; plain dicts)."""
+    if pos_encoding.get("otype") not in GRID_TYPE:
+        raise NotImplementedError(f"pos_encoding.otype {pos_encoding.get('otype')!r}")
+    if pos_encoding.get("interpolation", "Linear") != "Linear":
+        raise NotImplementedError("ren_b200 implements `interpolation: Linear` of the grid encoding")
+    if mlp_base["hidden_activation"] != mlp_head["hidden_activation"]:
+        raise NotImplementedError("ren_b200 expects mlp_base and mlp_head to share the hidden activation "
+                                  "(every shipped config does)")
+    d = RenFieldDesc()
+    d.arch = ARCH["ngp"]
+    d.net_depth, d.net_width = int(mlp_base["n_hidden_layers"]), int(mlp_base["n_neurons"])
+    d.skip_layer = 0
+    d.net_depth_condition, d.net_width_condition = int(mlp_head["n_hidden_layers"]), int(mlp_head["n_neurons"])
+    d.radiance_dim = int(radiance_dim)
+    d.hidden_activation = HIDDEN_ACT[mlp_base["hidden_activation"]]
+    d.density_activation = DENSITY_ACT[mlp_base["density_activation"]]
+    d.radiance_activation = RADIANCE_ACT[mlp_head["radiance_activation"]]
+    d.contraction = CONTRACTION[contraction]
+    for i, v in enumerate(aabb):
+        d.aabb[i] = float(v)
+    d.grid_type = GRID_TYPE[pos_encoding["otype"]]
+    d.grid_levels = int(pos_encoding["n_levels"])
+    d.grid_features = int(pos_encoding["n_features_per_level"])
+    d.grid_log2_hashmap_size = int(pos_encoding.get("log2_hashmap_size", 19))
+    d.grid_base_resolution = int(pos_encoding["base_resolution"])
+    d.grid_per_level_scale = float(pos_encoding["per_level_scale"])
+    d.sh_degree = int(dir_encoding["degree"])
+    d.geo_feat_dim = int(mlp_base["geo_feat_dim"])
+    return d
+
+
+def grid_param_count(fdesc):
+    n = C.c_int64(0)
+    check(load().ren_grid_param_count(C.byref(fdesc), C.byref(n)), "ren_grid_param_count")
+    return int(n.value)
 
 
 def make_render_desc(near_plane=None, far_plane=None, render_step_size=1e-2, cone_angle=0.0,

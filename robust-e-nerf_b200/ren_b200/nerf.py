@@ -1,5 +1,6 @@
 """`NeRF` -- drop-in for the reference's `robust_e_nerf.models.nerf.NeRF`
-(robust_e_nerf/models/nerf.py:16-286) for `arch: mlp`, backed by libren_b200.so.
+(robust_e_nerf/models/nerf.py:16-286) for `arch: mlp` (tcgen05 engine) and `arch: ngp` (grid encoding + small
+MLPs on the fp32 engine), backed by libren_b200.so.
 
 Same constructor arguments, same `forward(ray_origin, ray_direction)` ->
 `(radiance, opacity, depth, mean_num_samples_per_ray)`, same `update_occ_grid`,
@@ -308,9 +309,19 @@ class RenderTangentFunction(torch.autograd.Function):
         return (None, None, gr[0], gr[1], gr[2], gr[3], None, g_bkgd) + tuple(grads)
 
 
+class _GridParams(torch.nn.Module):
+    """Stands where `tcnn.Encoding` stands in the reference's `mlp_base` Sequential
+    (robust_e_nerf/external/ngp.py:166-188): ONE flat fp32 parameter `params` (state-dict key
+    `radiance_field.mlp_base.0.params`), initialised U(-1e-4, 1e-4) like tiny-cuda-nn's grids."""
+
+    def __init__(self, n_params):
+        super().__init__()
+        self.params = torch.nn.Parameter((torch.rand(n_params) * 2 - 1) * 1e-4)
+
+
 class NeRF(torch.nn.Module):
-    """See module docstring.  `arch` must be "mlp" (the 8x256 network the north star
-    names); `arch: ngp` is SURVEY.md section 8(f) #4."""
+    """See module docstring.  `arch: mlp` is the 8x256 network the north star names; `arch: ngp`
+    (SURVEY.md section 8(f) #4, robust_e_nerf/external/ngp.py:109-280) is what the shipped configs select."""
 
     HIDDEN_ACTIVATIONS = ("softplus", "relu")                               # models/nerf.py:17-20
     DENSITY_ACTIVATIONS = ("shifted_trunc_exp", "softplus", "shifted_softplus")   # :21-25
@@ -334,10 +345,11 @@ class NeRF(torch.nn.Module):
         assert num_dim == 3, "ren_b200 renders 3-D scenes"
         assert radiance_dim > 0
         assert isinstance(opacity_eps, (int, float)) and opacity_eps > 0
-        if arch != "mlp":
-            raise NotImplementedError(
-                f"arch={arch!r}: ren_b200 implements the `mlp` architecture (SURVEY.md section 8f #4)")
-        if bool(_cfg_get(arch_config, "weight_norm")):
+        if arch not in ("mlp", "ngp"):
+            raise NotImplementedError(f"arch={arch!r}")                      # models/nerf.py:166-167
+        self.arch = arch
+        sub = [arch_config] if arch == "mlp" else [_cfg_get(arch_config, "mlp_base"), _cfg_get(arch_config, "mlp_head")]
+        if any(bool(_cfg_get(c, "weight_norm")) for c in sub):
             raise NotImplementedError("weight_norm=True is not supported by ren_b200")
 
         self.register_buffer("aabb", torch.tensor(aabb, dtype=torch.float32), persistent=False)
@@ -381,6 +393,25 @@ class NeRF(torch.nn.Module):
             self.register_buffer("render_bkgd", render_bkgd, persistent=False)
 
         g = lambda k: _cfg_get(arch_config, k)
+        if arch == "ngp":
+            as_dict = lambda c: dict(c) if isinstance(c, dict) else {k: v for k, v in vars(c).items()}
+            blocks = {k: as_dict(g(k)) for k in ("pos_encoding", "dir_encoding", "mlp_base", "mlp_head")}
+            self.hidden_activation = blocks["mlp_base"]["hidden_activation"]
+            self.density_activation = blocks["mlp_base"]["density_activation"]
+            self.radiance_activation = blocks["mlp_head"]["radiance_activation"]
+            assert self.hidden_activation in self.HIDDEN_ACTIVATIONS
+            assert blocks["mlp_head"]["hidden_activation"] in self.HIDDEN_ACTIVATIONS
+            assert self.density_activation in self.DENSITY_ACTIVATIONS
+            assert self.radiance_activation in self.RADIANCE_ACTIVATIONS
+            self._fdesc = _lib.make_ngp_field_desc(radiance_dim=radiance_dim, contraction=self.contraction, aabb=aabb,
+                                                   **blocks)
+            self._layout = _lib.param_layout(self._fdesc)
+            self._n_params = _lib.param_count(self._fdesc)
+            self._n_grid = _lib.grid_param_count(self._fdesc)
+            self._build_ngp_tree(blocks)
+            self._desc_cache = {}
+            return
+        self._n_grid = 0
         self.hidden_activation = g("hidden_activation")
         self.density_activation = g("density_activation")
         self.radiance_activation = g("radiance_activation")
@@ -436,12 +467,47 @@ class NeRF(torch.nn.Module):
         self.radiance_field = rf
         self._flatten()
 
+    def _build_ngp_tree(self, blocks):
+        """Module tree with the reference's key names for `arch: ngp` (external/ngp.py:152-207):
+        `radiance_field.mlp_base.0.params` (grid), `mlp_base.1.{hidden_layers.i, output_layer}`,
+        `mlp_head.{hidden_layers.j, output_layer}`; grid first, then default `nn.Linear` inits in construction
+        order (the reference passes hidden_init / output_init / bias_init = None)."""
+        rf = _Holder()
+        rf.register_buffer("aabb", torch.tensor(self.aabb.tolist(), dtype=torch.float32))   # ngp.py:150
+        grid = _GridParams(self._n_grid)
+        base, head = _Holder(), _Holder()
+        base.hidden_layers = torch.nn.ModuleList()
+        head.hidden_layers = torch.nn.ModuleList()
+        n_base = int(blocks["mlp_base"]["n_hidden_layers"])
+        n_head = int(blocks["mlp_head"]["n_hidden_layers"])
+        assert len(self._layout) == n_base + 1 + n_head + 1
+        self._linears = []
+        for i, (w_off, b_off, out_f, in_f) in enumerate(self._layout):
+            lin = torch.nn.Linear(in_f, out_f)
+            self._linears.append(lin)
+            if i < n_base:
+                base.hidden_layers.append(lin)
+            elif i == n_base:
+                base.output_layer = lin
+            elif i < n_base + 1 + n_head:
+                head.hidden_layers.append(lin)
+            else:
+                head.output_layer = lin
+        rf.mlp_base = torch.nn.Sequential(grid, base)
+        rf.mlp_head = head
+        self.radiance_field = rf
+        object.__setattr__(self, "_grid", grid)          # alias, not a second registration of the module
+        self._flatten()
+
     def _flatten(self):
-        """(Re)pack every Linear's weight/bias into one flat buffer and re-point the
+        """(Re)pack the grid and every Linear's weight/bias into one flat buffer and re-point the
         parameters at views of it."""
         ref = self._linears[0].weight
         flat = torch.empty((self._n_params,), device=ref.device, dtype=torch.float32)
         with torch.no_grad():
+            if self._n_grid:
+                flat[:self._n_grid].copy_(self._grid.params.detach())
+                self._grid.params.data = flat[:self._n_grid]
             for lin, (w_off, b_off, out_f, in_f) in zip(self._linears, self._layout):
                 flat[w_off:w_off + out_f * in_f].copy_(lin.weight.detach().reshape(-1))
                 flat[b_off:b_off + out_f].copy_(lin.bias.detach())
@@ -452,6 +518,8 @@ class NeRF(torch.nn.Module):
     def _views_intact(self):
         base = self._flat.data_ptr()
         if self._flat.device != self._linears[0].weight.device:
+            return False
+        if self._n_grid and self._grid.params.data_ptr() != base:
             return False
         for lin, (w_off, b_off, _, _) in zip(self._linears, self._layout):
             if lin.weight.data_ptr() != base + 4 * w_off or lin.bias.data_ptr() != base + 4 * b_off:
@@ -466,13 +534,13 @@ class NeRF(torch.nn.Module):
         return self._flat
 
     def mlp_parameters(self):
-        out = []
+        out = [self._grid.params] if self._n_grid else []
         for lin in self._linears:
             out += [lin.weight, lin.bias]
         return out
 
     def _split_flat(self, g_flat):
-        grads = []
+        grads = [g_flat[:self._n_grid]] if self._n_grid else []
         for (w_off, b_off, out_f, in_f) in self._layout:
             grads.append(g_flat[w_off:w_off + out_f * in_f].view(out_f, in_f))
             grads.append(g_flat[b_off:b_off + out_f])

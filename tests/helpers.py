@@ -47,7 +47,19 @@ def product_config(g):
         occ_grid=dict(resolution=8, occ_thre=1e-2, ema_decay=0.95, warmup_steps=256, n=16, enabled=False),
         near_plane=r["near_plane"], far_plane=r["far_plane"], render_step_size=r["render_step_size"],
         cone_angle=r["cone_angle"], early_stop_eps=r["early_stop_eps"], alpha_thre=r["alpha_thre"],
-        test_chunk_size=16384, arch="mlp", load_state_dict=False, freeze=False,
+        test_chunk_size=16384, arch=f.get("arch", "mlp"), load_state_dict=False, freeze=False,
+        ngp=dict(
+            pos_encoding=dict(otype={"Hash": "HashGrid", "Dense": "DenseGrid", "Tiled": "TiledGrid"}[f.get("grid_type", "Hash")],
+                              n_levels=f.get("n_levels", 16), n_features_per_level=f.get("n_features_per_level", 2),
+                              log2_hashmap_size=f.get("log2_hashmap_size", 19), base_resolution=f.get("base_resolution", 16),
+                              per_level_scale=f.get("per_level_scale", 1.4472692012786865), interpolation="Linear"),
+            dir_encoding=dict(degree=f.get("sh_degree", 4)),
+            mlp_base=dict(hidden_activation=f["hidden_activation"], density_activation=f["density_activation"],
+                          n_neurons=f.get("base_n_neurons", 64), n_hidden_layers=f.get("base_n_hidden_layers", 1),
+                          geo_feat_dim=f.get("geo_feat_dim", 15), weight_norm=False),
+            mlp_head=dict(hidden_activation=f.get("head_hidden_activation") or f["hidden_activation"],
+                          radiance_activation=f["radiance_activation"], n_neurons=f.get("head_n_neurons", 64),
+                          n_hidden_layers=f.get("head_n_hidden_layers", 2), weight_norm=False)),
         mlp=dict(net_depth=f["net_depth"], net_width=f["net_width"], skip_layer=f["skip_layer"],
                  net_depth_condition=f["net_depth_condition"],
                  net_width_condition=f["net_width_condition"],

@@ -111,9 +111,35 @@ def test_unsupported_configurations_raise(built_lib, dataset_dir):
     from ren_b200 import NeRF
     g = H.load_golden("step_8x256")
     cfg = H.product_config(g)["nerf"]
-    with pytest.raises(NotImplementedError):
-        NeRF(cfg["aabb"], "sphere", cfg["occ_grid"], 0.5, 4.5, 0.03, None, 0.0, 0.0, 0.0, 16384, "ngp",
+    with pytest.raises(NotImplementedError):                      # models/nerf.py:166-167
+        NeRF(cfg["aabb"], "sphere", cfg["occ_grid"], 0.5, 4.5, 0.03, None, 0.0, 0.0, 0.0, 16384, "tensorf",
              arch_config=cfg["mlp"])
+    with pytest.raises(NotImplementedError):                      # weight_norm (external/mlp.py:301-319)
+        NeRF(cfg["aabb"], "sphere", cfg["occ_grid"], 0.5, 4.5, 0.03, None, 0.0, 0.0, 0.0, 16384, "mlp",
+             arch_config=dict(cfg["mlp"], weight_norm=True))
+    ngp = H.product_config(H.load_golden("step_ngp"))["nerf"]["ngp"]
+    with pytest.raises(NotImplementedError):                      # grid interpolation other than Linear
+        NeRF(cfg["aabb"], "sphere", cfg["occ_grid"], 0.5, 4.5, 0.03, None, 0.0, 0.0, 0.0, 16384, "ngp",
+             arch_config=dict(ngp, pos_encoding=dict(ngp["pos_encoding"], interpolation="Smoothstep")))
+
+
+def test_ngp_module_tree_matches_the_reference_keys(built_lib, dataset_dir):
+    """`arch: ngp`: state-dict keys / shapes of the reference's `NGPradianceField` (external/ngp.py:152-207) and
+    the oracle's seeded initial weights (same construction order: grid, mlp_base, mlp_head)."""
+    g = H.load_golden("step_ngp")
+    from ren_b200 import RobustENeRF
+    from oracle import restatement as R
+    torch.manual_seed(g["weight_seed"])
+    m = RobustENeRF(dataset_directory=dataset_dir, **H.product_config(g))
+    want = {k for k in g["grads"] if k.startswith("nerf.radiance_field.")}
+    have = {k for k, _ in m.named_parameters() if k.startswith("nerf.radiance_field.")}
+    assert want == have
+    init = R.init_field_params(H.golden_configs(g)[0], seed=g["weight_seed"])
+    sd = m.state_dict()
+    for k, v in init.items():
+        assert torch.equal(sd["nerf.radiance_field." + k], v), k
+    groups = m.configure_optimizers()["optimizer"].param_groups
+    assert len(groups[2]["params"]) == len(init)               # grid + MLPs all carry the L2 weight decay
 
 
 def test_device_sampler_distributions():
