@@ -50,7 +50,8 @@ enum {
   REN_ENGINE_AUTO = 0,    /* tcgen05 when the network shape is covered, else SIMT */
   REN_ENGINE_SIMT_FP32 = 1, /* fp32 FFMA tiles: parity baseline, any shape */
   REN_ENGINE_TC_F16X3 = 2,  /* tcgen05 kind::f16, split fp16 hi/lo operands, 3 MMAs (fp32-class accuracy) */
-  REN_ENGINE_TC_F16 = 3     /* tcgen05 kind::f16, single pass (throughput mode; misses the 1e-4 bar) */
+  REN_ENGINE_TC_F16 = 3,    /* tcgen05 kind::f16, single pass (throughput mode; misses the 1e-4 bar) */
+  REN_ENGINE_TC_F16A = 4    /* tcgen05 kind::f16, activations single fp16, weights split hi/lo: 2 MMAs */
 };
 /* models/nerf.py:104-167 `arch` */
 enum { REN_ARCH_MLP = 0, REN_ARCH_NGP = 1 };

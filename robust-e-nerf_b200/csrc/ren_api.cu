@@ -289,7 +289,7 @@ static int validate_render(const RenRenderDesc* r) {
   if (r == nullptr) { ren_set_error("null RenRenderDesc"); return REN_E_INVALID; }
   if (!(r->render_step_size > 0.f)) { ren_set_error("render_step_size must be > 0"); return REN_E_INVALID; }
   if (r->cone_angle < 0.f) { ren_set_error("cone_angle must be >= 0"); return REN_E_INVALID; }
-  if (r->engine < 0 || r->engine > 3) { ren_set_error("engine id out of range"); return REN_E_INVALID; }
+  if (r->engine < 0 || r->engine > 4) { ren_set_error("engine id out of range"); return REN_E_INVALID; }
   if (r->occ_binary != nullptr && (r->occ_res[0] < 1 || r->occ_res[1] < 1 || r->occ_res[2] < 1)) {
     ren_set_error("occupancy grid resolution must be positive");
     return REN_E_INVALID;

@@ -115,7 +115,8 @@ struct TcArgs {
   RenPlan p;
   TcStep steps[TC_MAX_STEPS];
   int n_steps;
-  int split3;
+  int split3;                    // operand precision: 0 single fp16 pass; 1 A and W split hi/lo (3 MMAs); 2 TMEM-resident
+                                 // activations single fp16, weights split (2 MMAs; the shared-memory encodings keep 3)
   int softplus;                  // hidden activation is softplus(beta=100) (log2-domain epilogue)
   int dbg;                       // timing experiments only (env REN_TC_DBG): 1 no epilogue math, 2 no MMAs, 4 no sines
   long long n_rays;
@@ -344,7 +345,7 @@ __global__ void __launch_bounds__(MODE == 0 ? TC_THREADS_FWD : TC_THREADS_BWD, 1
       const uint4* prog = reinterpret_cast<const uint4*>(smem + SM_PROG);
       uint32_t it = 0, n_p = 0, n_a0 = 0, n_a1 = 0;
       const uint32_t idesc128 = umma_idesc(128, 0, 0), idesc256 = umma_idesc(256, 0, 0);
-      const uint32_t split3 = a.split3, nomma = a.dbg & 2;
+      const uint32_t split3 = a.split3 != 0, a_lo = a.split3 == 1, nomma = a.dbg & 2;
       // low words of the shared-memory descriptors are linear in the address (all < 256 KB)
       const uint32_t ring_lo = ((sbase + SM_RING) >> 4) & 0x3FFFu;
       const uint32_t smem_lo = ((sbase >> 4) & 0x3FFFu) | (128u << 16);      // encodings: K-core stride 2048 B
@@ -397,7 +398,7 @@ __global__ void __launch_bounds__(MODE == 0 ? TC_THREADS_FWD : TC_THREADS_BWD, 1
                   const uint64_t db_hi = mk_desc(b_lo32 + kl * chunk16);
                   tc_mma_f16_ts(d_addr, a_hi, db_hi, idesc, acc);
                   if (split3) {
-                    tc_mma_f16_ts(d_addr, a_hi + a_ld, db_hi, idesc, 1u);
+                    if (a_lo) tc_mma_f16_ts(d_addr, a_hi + a_ld, db_hi, idesc, 1u);
                     tc_mma_f16_ts(d_addr, a_hi, mk_desc(b_lo32 + kl * chunk16 + (chunk16 >> 1)), idesc, 1u);
                   }
                   acc = 1u;
@@ -484,6 +485,7 @@ __global__ void __launch_bounds__(MODE == 0 ? TC_THREADS_FWD : TC_THREADS_BWD, 1
     }
   } else {
     // ===================== epilogue warps =====================
+    const bool a_single = a.split3 != 1;     // the activations go back to tensor memory as single fp16 values
     const int q = warp & 3;                  // TMEM lane quadrant this warp may access
     const int cg = (warp - 2) >> 2;          // column group 0..3: 32 of the 128 columns of a half
     const int m = q * 32 + lane;             // row of the tile == TMEM lane
@@ -547,7 +549,7 @@ __global__ void __launch_bounds__(MODE == 0 ? TC_THREADS_FWD : TC_THREADS_BWD, 1
             if (!valid) e[j] = 0.f;
           }
           uint4 hi, lo;
-          split8(y, &hi, &lo);
+          if (a_single) { pack8(y, &hi); lo = make_uint4(0u, 0u, 0u, 0u); } else split8(y, &hi, &lo);
           hi16[j8 * 4 + 0] = hi.x; hi16[j8 * 4 + 1] = hi.y; hi16[j8 * 4 + 2] = hi.z; hi16[j8 * 4 + 3] = hi.w;
           lo16[j8 * 4 + 0] = lo.x; lo16[j8 * 4 + 1] = lo.y; lo16[j8 * 4 + 2] = lo.z; lo16[j8 * 4 + 3] = lo.w;
           *reinterpret_cast<uint4*>(dm + j8 * 2048) = hi;
@@ -558,7 +560,7 @@ __global__ void __launch_bounds__(MODE == 0 ? TC_THREADS_FWD : TC_THREADS_BWD, 1
         }
         const uint32_t tcol = tmem_lane + (uint32_t)(st0.a_col + 32 * cg);
         tc_st16(tcol, hi16);
-        tc_st16(tcol + 16, lo16);
+        if (!a_single) tc_st16(tcol + 16, lo16);
         tc_st_wait();
         tc_fence_before();
         __syncwarp();
@@ -728,12 +730,12 @@ __global__ void __launch_bounds__(MODE == 0 ? TC_THREADS_FWD : TC_THREADS_BWD, 1
               }
             }
             uint4 hi, lo;
-            split8(y, &hi, &lo);
+            if (a_single) pack8(y, &hi); else split8(y, &hi, &lo);
             // every accumulator column of this thread is already in registers: the packed operand goes back over
             // them group by group (keeps 32 registers free compared with one 16-column store at the end)
             if (st.write_a) {
               tc_st4(tcol + j8 * 4, hi);
-              tc_st4(tcol + 16 + j8 * 4, lo);
+              if (!a_single) tc_st4(tcol + 16 + j8 * 4, lo);
             }
             if (out_mat != nullptr) *reinterpret_cast<uint4*>(out_mat + j8 * 2048) = hi;
             if (MODE == 1 && PASS == 1 && st.epi == EPI_D_ACT && st.out_mat >= 0) {
@@ -1089,7 +1091,8 @@ static void fill_args(TcArgs& a, const RenPlan& p, const TcProgram& P) {
   a.p = p;
   for (int i = 0; i < P.n_steps; ++i) a.steps[i] = P.steps[i];
   a.n_steps = P.n_steps;
-  a.split3 = p.r.engine == REN_ENGINE_TC_F16 ? 0 : 1;
+  a.split3 = p.r.engine == REN_ENGINE_TC_F16 ? 0 : (p.r.engine == REN_ENGINE_TC_F16A ? 2 : 1);
+  if (const char* sp = getenv("REN_TC_SPLIT")) a.split3 = atoi(sp);      // precision experiments
   a.softplus = p.f.hidden_activation == REN_HIDDEN_SOFTPLUS100 ? 1 : 0;
   const char* dbg = getenv("REN_TC_DBG");
   a.dbg = dbg ? atoi(dbg) : 0;

@@ -131,6 +131,16 @@ __device__ __forceinline__ void split8(const float* y, uint4* hi, uint4* lo) {
   *hi = make_uint4(h[0], h[1], h[2], h[3]);
   *lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
+// 8 values -> 16 B of fp16 (round to nearest)
+__device__ __forceinline__ void pack8(const float* y, uint4* hi) {
+  uint32_t h[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __half2 hh = __floats2half2_rn(y[2 * i], y[2 * i + 1]);
+    h[i] = *reinterpret_cast<const uint32_t*>(&hh);
+  }
+  *hi = make_uint4(h[0], h[1], h[2], h[3]);
+}
 // power-of-two scale that brings max |graw| to ~16 (fp16 headroom 2^12 above, 2^28 below)
 __device__ __forceinline__ float delta_scale(const unsigned int* gmax) {
   const float mx = __uint_as_float(*gmax);

@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libren_b200.so")
 
-REN_ENGINE = {"auto": 0, "simt_fp32": 1, "tc_f16x3": 2, "tc_f16": 3}
+REN_ENGINE = {"auto": 0, "simt_fp32": 1, "tc_f16x3": 2, "tc_f16": 3, "tc_f16a": 4}
 HIDDEN_ACT = {"softplus": 0, "relu": 1}
 DENSITY_ACT = {"shifted_trunc_exp": 0, "softplus": 1, "shifted_softplus": 2}
 RADIANCE_ACT = {"softplus": 0, "sigmoid": 1}
