@@ -495,9 +495,9 @@ def run_ours(args):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ms, blocks, loss = run.timed(args.steps, False, MIN_TIMED_MS)
+    ms, blocks, loss = run.timed(args.steps, False, args.min_ms)
     run.block(min(args.warmup, 2), True)
-    ms_e2e, blocks_e2e, _ = run.timed(args.steps, True, MIN_TIMED_MS / 2)
+    ms_e2e, blocks_e2e, _ = run.timed(args.steps, True, args.min_ms / 2)
     if rank == 0:
         sampler.stop_flag.set()
         sampler.join(timeout=2)
@@ -600,6 +600,8 @@ def main():
     ap.add_argument("--engine", default="auto")
     ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS))
     ap.add_argument("--graph", default="auto", choices=["auto", "off"])
+    ap.add_argument("--min-ms", type=float, default=MIN_TIMED_MS,
+                    help="repeat the timed block until this much GPU time (profiler runs pass 0)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true")
     args = ap.parse_args()

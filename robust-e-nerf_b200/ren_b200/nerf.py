@@ -384,9 +384,10 @@ class NeRF(torch.nn.Module):
             self._bkgd_mode = "parameter"
             holder = _Holder()
             holder.render_bkgd = _Holder()
-            # parametrize stores right_inverse(init): softplus(original) == ones (utils/modules.py:46-54)
+            # parametrize stores right_inverse(init): softplus(original) == ones, with the reference's own
+            # formula log(exp(x) - 1) (utils/modules.py:46-54) so that the initial value is bit-identical
             holder.render_bkgd.original = torch.nn.Parameter(
-                torch.log(torch.expm1(torch.ones(radiance_dim))))
+                torch.log(torch.exp(torch.ones(radiance_dim)) - 1))
             self.parametrizations = holder          # key: parametrizations.render_bkgd.original
         else:
             self._bkgd_mode = "buffer"
@@ -590,6 +591,8 @@ class NeRF(torch.nn.Module):
     def query_density(self, x):
         """`VanillaNeRFRadianceField.query_density` (external/mlp.py:344-348) at free points (n,3) -> (n,)."""
         lib = _lib.load()
+        if not x.is_cuda:
+            raise RuntimeError("ren_b200 evaluates the field on CUDA tensors only (no CPU fallback)")
         x = x.detach().contiguous().float()
         n = x.shape[0]
         fdesc, rdesc, _ = self._descs()
