@@ -178,7 +178,7 @@ class RenderFunction(torch.autograd.Function):
             ctx.packed, ctx.packed_keep = packed, keep
             ctx.save_for_backward(o, d, jitter if jitter is not None else torch.empty(0, device=dev),
                                   bkgd if bkgd is not None else torch.empty(0, device=dev), stash,
-                                  flat)
+                                  flat, *params)
             ctx.has_jitter = jitter is not None
             ctx.has_bkgd = bkgd is not None
             ctx.n_params = len(params)
@@ -188,9 +188,21 @@ class RenderFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_rad, g_op, g_depth, _g_kept):
-        _lib.refuse_double_backward()
+        if torch.is_grad_enabled():
+            # create_graph=True: the caller will differentiate this gradient again -- the reference does so for
+            # d log I / d t (utils/autograd.py:4-34, models/robust_e_nerf.py:394-398).  The gradient with respect
+            # to the rays then becomes a differentiable op of its own (RenderRayGradFunction).
+            o, d, jitter, bkgd = ctx.saved_tensors[:4]
+            params = ctx.saved_tensors[6:]
+            if ctx.packed is not None:
+                raise RuntimeError("ren_b200: create_graph=True through the packed occupancy-grid march is not "
+                                   "supported; use RobustENeRF.training_step (tangent render)")
+            res = RenderRayGradFunction.apply(ctx.owner, ctx.descs, o, d, jitter if ctx.has_jitter else None,
+                                              bkgd if ctx.has_bkgd else None, g_rad, g_op, g_depth, *params)
+            # (g_o, g_d) carry a graph; the parameter / background gradients are returned as plain values
+            return (None, None, res[0], res[1], None, res[2] if ctx.has_bkgd else None) + tuple(res[3:])
         lib = _lib.load()
-        o, d, jitter, bkgd, stash, flat = ctx.saved_tensors
+        o, d, jitter, bkgd, stash, flat = ctx.saved_tensors[:6]
         fdesc, rdesc, K = ctx.descs
         owner = ctx.owner
         B = o.shape[0]
@@ -215,6 +227,102 @@ class RenderFunction(torch.autograd.Function):
         g_o = g_rays[:, 0:3] if ctx.ray_grad else None
         g_d = g_rays[:, 3:6] if ctx.ray_grad else None
         return (None, None, g_o, g_d, None, g_bkgd) + tuple(grads)
+
+
+class RenderRayGradFunction(torch.autograd.Function):
+    """d (sum_rays g_rad . C + g_op O) / d (o, d) as a differentiable op -- what `autograd.grad(log_intensity, ts,
+    create_graph=True)` needs from the render when the reference's own `training_step` runs on `ren_b200.NeRF`
+    (the NeRF-level plug of INTEGRATION.md section 1 with the log-intensity-gradient loss on).
+
+    forward : one ordinary reverse pass (`ren_render_backward` with ray gradients).
+    backward: for cotangents (v_o, v_d) of (g_o, g_d), the scalar  sum v_o . g_o + v_d . g_d  is the directional
+              derivative of  sum g_rad . C + g_op O  along (o_dot, d_dot) = (v_o, v_d), i.e.
+              sum g_rad . C_dot + g_op O_dot  of the TANGENT render: its gradient with respect to the parameters and
+              rays is `ren_render_tangent_backward` with (g_rad, g_op) as the upstream of (C_dot, O_dot), and with
+              respect to (g_rad, g_op) it is (C_dot, O_dot) itself.  No second-order kernel is needed.
+    inputs  : owner, descs, o, d, jitter|None, bkgd|None, g_rad (B,C), g_op (B)|None, g_depth|None, *params
+    outputs : g_o, g_d (B,3) [differentiable], then g_bkgd and the parameter gradients as plain values"""
+
+    @staticmethod
+    def forward(ctx, owner, descs, o, d, jitter, bkgd, g_rad, g_op, g_depth, *params):
+        lib = _lib.load()
+        fdesc, rdesc, K = descs
+        if g_depth is not None and bool((g_depth != 0).any()):
+            raise RuntimeError("ren_b200: create_graph=True with a depth gradient is not supported")
+        B, dev = o.shape[0], o.device
+        flat = owner.flat_params()
+        cg = lambda t: None if t is None else t.detach().contiguous().float()
+        o_, d_, g_rad_, g_op_ = cg(o), cg(d), cg(g_rad), cg(g_op)
+        jit, bk = cg(jitter), cg(bkgd)
+        # value pass with a stash, then its reverse with ray gradients
+        C_ = owner.radiance_dim
+        outs = [torch.empty((B, C_), device=dev), torch.empty((B,), device=dev), torch.empty((B,), device=dev)]
+        n_kept = torch.empty((B,), device=dev, dtype=torch.int32)
+        stash_n = _lib.stash_bytes(fdesc, rdesc, B, K)
+        stash = torch.empty((stash_n,), device=dev, dtype=torch.uint8)
+        ws = torch.empty((_lib.workspace_bytes(fdesc, rdesc, B, K, True, False),), device=dev, dtype=torch.uint8)
+        _lib.check(lib.ren_render_forward(
+            C.byref(fdesc), C.byref(rdesc), B, K, _lib.ptr(o_), _lib.ptr(d_), _lib.ptr(jit), _lib.ptr(flat),
+            _lib.ptr(bk), _lib.ptr(outs[0]), _lib.ptr(outs[1]), _lib.ptr(outs[2]), _lib.ptr(n_kept), None,
+            _lib.ptr(stash), stash_n, _lib.ptr(ws), ws.numel(), _lib.stream_ptr()), "ren_render_forward")
+        g_flat = torch.zeros_like(flat)
+        g_bk = torch.zeros_like(bk) if bk is not None else None
+        g_rays = torch.empty((B, 6), device=dev, dtype=torch.float32)
+        ws = torch.empty((_lib.workspace_bytes(fdesc, rdesc, B, K, True, True),), device=dev, dtype=torch.uint8)
+        _lib.check(lib.ren_render_backward(
+            C.byref(fdesc), C.byref(rdesc), B, K, _lib.ptr(o_), _lib.ptr(d_), _lib.ptr(jit), _lib.ptr(flat),
+            _lib.ptr(bk), _lib.ptr(g_rad_), _lib.ptr(g_op_), None, None, _lib.ptr(stash), stash.numel(),
+            _lib.ptr(g_flat), _lib.ptr(g_bk), _lib.ptr(g_rays), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()),
+            "ren_render_backward")
+        ctx.owner, ctx.descs = owner, descs
+        empty = torch.empty(0, device=dev)
+        ctx.save_for_backward(o_, d_, jit if jit is not None else empty, bk if bk is not None else empty,
+                              g_rad_, g_op_ if g_op_ is not None else empty)
+        ctx.flags = (jit is not None, bk is not None, g_op_ is not None)
+        ctx.n_params = len(params)
+        plain = (g_bk if g_bk is not None else torch.zeros(0, device=dev),) + tuple(owner._split_flat(g_flat))
+        ctx.mark_non_differentiable(*plain)
+        return (g_rays[:, 0:3].contiguous(), g_rays[:, 3:6].contiguous()) + plain
+
+    @staticmethod
+    def backward(ctx, v_o, v_d, *_plain):
+        _lib.refuse_double_backward()
+        lib = _lib.load()
+        owner = ctx.owner
+        fdesc, rdesc, K = ctx.descs
+        o, d, jit, bk, g_rad, g_op = ctx.saved_tensors
+        has_jit, has_bk, has_gop = ctx.flags
+        jit = jit if has_jit else None
+        bk = bk if has_bk else None
+        g_op = g_op if has_gop else None
+        B, dev = o.shape[0], o.device
+        C_ = owner.radiance_dim
+        zero3 = lambda t: torch.zeros((B, 3), device=dev) if t is None else t.contiguous().float()
+        v_o, v_d = zero3(v_o), zero3(v_d)
+        flat = owner.flat_params()
+        rad, rad_dot = torch.empty((B, C_), device=dev), torch.empty((B, C_), device=dev)
+        opac, opac_dot, depth = (torch.empty((B,), device=dev) for _ in range(3))
+        n_kept = torch.empty((B,), device=dev, dtype=torch.int32)
+        stash_n = _lib.tangent_stash_bytes(fdesc, rdesc, B, K)
+        stash = torch.empty((stash_n,), device=dev, dtype=torch.uint8)
+        ws = torch.empty((_lib.tangent_workspace_bytes(fdesc, rdesc, B, K, True, False),), device=dev, dtype=torch.uint8)
+        _lib.check(lib.ren_render_tangent_forward(
+            C.byref(fdesc), C.byref(rdesc), B, K, _lib.ptr(o), _lib.ptr(d), _lib.ptr(v_o), _lib.ptr(v_d),
+            _lib.ptr(jit), _lib.ptr(flat), _lib.ptr(bk), _lib.ptr(rad), _lib.ptr(opac), _lib.ptr(depth),
+            _lib.ptr(rad_dot), _lib.ptr(opac_dot), _lib.ptr(n_kept), None, _lib.ptr(stash), stash_n, _lib.ptr(ws),
+            ws.numel(), _lib.stream_ptr()), "ren_render_tangent_forward")
+        g_flat = torch.zeros_like(flat)
+        g_bk = torch.zeros_like(bk) if bk is not None else None
+        g_rays = torch.empty((B, 12), device=dev, dtype=torch.float32)
+        ws = torch.empty((_lib.tangent_workspace_bytes(fdesc, rdesc, B, K, True, True),), device=dev, dtype=torch.uint8)
+        _lib.check(lib.ren_render_tangent_backward(
+            C.byref(fdesc), C.byref(rdesc), B, K, _lib.ptr(o), _lib.ptr(d), _lib.ptr(v_o), _lib.ptr(v_d),
+            _lib.ptr(jit), _lib.ptr(flat), _lib.ptr(bk), None, None, None, _lib.ptr(g_rad), _lib.ptr(g_op), None,
+            _lib.ptr(stash), stash.numel(), _lib.ptr(g_flat), _lib.ptr(g_bk), _lib.ptr(g_rays), _lib.ptr(ws),
+            ws.numel(), _lib.stream_ptr()), "ren_render_tangent_backward")
+        grads = owner._split_flat(g_flat)
+        return (None, None, g_rays[:, 0:3], g_rays[:, 3:6], None, g_bk, rad_dot, opac_dot if has_gop else None,
+                None) + tuple(grads)
 
 
 class RenderTangentFunction(torch.autograd.Function):
