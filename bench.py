@@ -24,7 +24,8 @@ grid the emitted samples (what the reference's dynamic batch size counts) are re
   parity    the second half of BASELINE.json's metric: after the timed region, a fixed 128-ray subset of
             batch 0 rendered by the CUDA path with the TRAINED weights vs the oracle on the same weights, rays
             and jitter: per-ray log I (normwise, max-abs) and loss relative error
-  secondary (N=1, --config 2 only) short runs of configs 3, 4, 5 in the same JSON line
+  secondary (N=1, --config 2 only) short runs of configs 3, 4, 5 (and of config 4's shape with `arch: ngp`) in the
+            same JSON line
   cpu_baseline  the oracle port of the reference's own Python path on the host cores, bounded sample
 
 `--impl reference` times that CPU path alone (the upstream reference has no CPU mode and cannot be installed
@@ -70,7 +71,21 @@ CONFIGS = {
                  "Cp and tau trainable, fwd+bwd+Adam",
             rays=8192, n=256, renders=3, w_grad=1e-3, trainable=True, aabb=(-2.3, -3.2, 0.0, 1.7, 2.8, 3.0),
             near=0.01, far=4.0, span=None, grid=True),
+    # not a BASELINE config (its metric names the 8Lx256 MLP): the architecture the reference's YAMLs select
+    6: dict(name="config4 shape with `arch: ngp` (configs/train/mocap-desk2.yaml:56-88: 16-level 2^19 hash grid, SH-4, "
+                 "64-wide softplus MLPs) on the fp32 engine: 8192 rays/GPU x 192 marching steps x 3 renders, occupancy "
+                 "grid 128^3 on, l_diff + l_grad, Cp and tau trainable, fwd+bwd+Adam",
+            rays=8192, n=192, renders=3, w_grad=1e-3, trainable=True, aabb=(0.5, -2.1, 0.6, 2.0, -0.6, 1.6),
+            near=0.05, far=3.0, span=None, grid=True, arch="ngp"),
 }
+NGP_BLOCK = dict(
+    pos_encoding=dict(otype="HashGrid", n_levels=16, n_features_per_level=2, log2_hashmap_size=19,
+                      base_resolution=16, per_level_scale=1.4472692012786865, interpolation="Linear"),
+    dir_encoding=dict(degree=4),
+    mlp_base=dict(hidden_activation="softplus", density_activation="shifted_trunc_exp", n_neurons=64,
+                  n_hidden_layers=1, geo_feat_dim=15, weight_norm=False),
+    mlp_head=dict(hidden_activation="softplus", radiance_activation="softplus", n_neurons=64, n_hidden_layers=2,
+                  weight_norm=False))
 
 
 def peaks():
@@ -183,6 +198,9 @@ def product_config(wc, world):
     if wc["trainable"]:
         cfg["contrast_threshold"]["freeze"] = False
         cfg["refractory_period"]["freeze"] = False
+    if wc.get("arch") == "ngp":
+        cfg["nerf"]["arch"] = "ngp"
+        cfg["nerf"]["ngp"] = NGP_BLOCK
     if wc["grid"]:
         cfg["nerf"]["occ_grid"] = dict(resolution=128, occ_thre=1e-2, ema_decay=0.95, warmup_steps=256, n=16,
                                        enabled=True)
@@ -255,9 +273,9 @@ def parity_check(model, cfg, root, host_batch, host_jitter, dev, n_rays=128):
     fcfg, rcfg, scfg = oracle_configs(cfg)
     th_r = sd["contrast_threshold.parametrizations.p2n_contrast_threshold_ratio.original"].detach().cpu()
     th_t = sd["refractory_period.parametrizations._refractory_period.original"].detach().cpu().clone()
-    if grid is not None:
-        return {"rays": n_rays, "note": "occupancy grid on: the oracle comparison of the grid path lives in "
-                                        "tests/test_occupancy_gpu.py", "loss": float(loss)}
+    if grid is not None or cfg["nerf"]["arch"] != "mlp":
+        return {"rays": n_rays, "note": "occupancy grid on / arch ngp: the oracle comparisons of these paths live in "
+                                        "tests/test_occupancy_gpu.py and tests/test_ngp_gpu.py", "loss": float(loss)}
     if scfg.w_grad > 0:
         out = R.training_step(params, fcfg, rcfg, scfg, scene, sub, jit, th_r, th_t)
     else:
@@ -561,7 +579,7 @@ def run_ours(args):
     if world == 1 and args.config == 2 and not args.no_secondary:
         del trainer
         release(run)
-        secondary = [run_secondary(c, args, rank, world, dev, graph) for c in (3, 4, 5)]
+        secondary = [run_secondary(c, args, rank, world, dev, graph) for c in (3, 4, 5, 6)]
     out = {
         "metric": "ray-samples/s", "value": value, "unit": "ray-samples/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
@@ -598,7 +616,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--engine", default="auto")
-    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS))
+    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS))   # 6: config-4 shape, arch ngp
     ap.add_argument("--graph", default="auto", choices=["auto", "off"])
     ap.add_argument("--min-ms", type=float, default=MIN_TIMED_MS,
                     help="repeat the timed block until this much GPU time (profiler runs pass 0)")

@@ -299,6 +299,14 @@ class RenderRayGradFunction(torch.autograd.Function):
         C_ = owner.radiance_dim
         zero3 = lambda t: torch.zeros((B, 3), device=dev) if t is None else t.contiguous().float()
         v_o, v_d = zero3(v_o), zero3(v_d)
+        # everything below is linear in each ray's (v_o, v_d): run the tangent kernels on per-ray directions of
+        # unit size (the tcgen05 engine keeps tangent activations in fp16) and move the scale into the upstream
+        # gradients / back onto the outputs
+        scale = torch.maximum(v_o.abs().amax(dim=1), v_d.abs().amax(dim=1)).clamp(min=1e-30)
+        v_o, v_d = v_o / scale[:, None], v_d / scale[:, None]
+        g_rad = (g_rad * scale[:, None]).contiguous()
+        if has_gop:
+            g_op = (g_op * scale).contiguous()
         flat = owner.flat_params()
         rad, rad_dot = torch.empty((B, C_), device=dev), torch.empty((B, C_), device=dev)
         opac, opac_dot, depth = (torch.empty((B,), device=dev) for _ in range(3))
@@ -321,8 +329,8 @@ class RenderRayGradFunction(torch.autograd.Function):
             _lib.ptr(stash), stash.numel(), _lib.ptr(g_flat), _lib.ptr(g_bk), _lib.ptr(g_rays), _lib.ptr(ws),
             ws.numel(), _lib.stream_ptr()), "ren_render_tangent_backward")
         grads = owner._split_flat(g_flat)
-        return (None, None, g_rays[:, 0:3], g_rays[:, 3:6], None, g_bk, rad_dot, opac_dot if has_gop else None,
-                None) + tuple(grads)
+        return (None, None, g_rays[:, 0:3], g_rays[:, 3:6], None, g_bk, rad_dot * scale[:, None],
+                opac_dot * scale if has_gop else None, None) + tuple(grads)
 
 
 class RenderTangentFunction(torch.autograd.Function):

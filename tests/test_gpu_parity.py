@@ -624,3 +624,40 @@ def test_nerf_level_plug_serves_the_gradient_loss(engine, built_lib, dataset_dir
     for k, v in params.items():
         worst = max(worst, _grad_cmp(k, named["nerf.radiance_field." + k].grad, v.grad, cos_bar=0.999, nw_bar=3e-2))
     print(f"  worst parameter-gradient normwise rel = {worst:.2e}")
+
+
+@pytest.mark.parametrize("err_diff", ["l1", "mse", "mape"])
+def test_contrast_threshold_gradient_for_every_error_fn(err_diff, built_lib, dataset_dir):
+    """Unfrozen contrast threshold: d loss / d (p2n ratio) flows through the TARGET of the difference loss
+    (loss_metric/loss.py:38-41,64-74).  For l1 / mse the target only enters through (pred - target); MAPE also
+    divides by |target| (utils/modules.py:96) -- `DiffLossFunction.backward` must carry that term."""
+    B, N = 64, 32
+    g = dict(H.load_golden("step_8x256_gain2"))
+    step = 4.0 / N
+    g["rcfg"] = dict(g["rcfg"], render_step_size=step, far_plane=0.5 + (N + 0.5) * step)
+    g["scfg"] = dict(g["scfg"], err_diff=err_diff, pw_diff=None)
+    g["freeze_ct"] = False
+    g["learn_bkgd"] = False
+    scene = synth.load_scene(dataset_dir)
+    batch, jitter = synth.make_batch(B, scene["T_wc_timestamp"], rank=7, seed=321)
+    m = H.build_product(g, dataset_dir, "cuda", "simt_fp32")
+    th0 = torch.log(torch.expm1(torch.tensor(1.3)))
+    with torch.no_grad():
+        m.contrast_threshold.parametrizations.p2n_contrast_threshold_ratio.original.copy_(th0)
+    loss = m.training_step({k: {kk: vv.cuda() for kk, vv in v.items()} for k, v in batch.items()}, 0,
+                           {k: v.cuda() for k, v in jitter.items()})
+    loss.backward()
+    fcfg, rcfg, scfg = H.golden_configs(g)
+    tau_max = scene["max_refractory_period"]
+    params = {k: v.double() for k, v in H.golden_params(g).items()}
+    sc = {k: (v.double() if v.is_floating_point() else v) for k, v in scene.items()}
+    th_r = th0.double().clone().requires_grad_(True)
+    out = R.training_step(params, fcfg, rcfg, scfg, sc, batch, jitter, th_r,
+                          tau_max * torch.logit(scene["refractory_period"].double() / tau_max))
+    out["loss"].backward()
+    got = float(m.contrast_threshold.parametrizations.p2n_contrast_threshold_ratio.original.grad)
+    want = float(th_r.grad)
+    print(f"[{err_diff}] loss cuda={float(loss):.7f} fp64 oracle={float(out['loss']):.7f}; "
+          f"d loss / d theta_ratio cuda={got:.6e} oracle={want:.6e}")
+    assert abs(float(loss) - float(out["loss"])) <= 1e-4 * abs(float(out["loss"]))
+    assert abs(got - want) <= 2e-3 * abs(want) + 1e-9
