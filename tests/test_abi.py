@@ -139,3 +139,37 @@ def test_header_is_plain_c(tmp_path):
     out = subprocess.run(["gcc", "-std=c11", "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"),
                           str(src)], capture_output=True, text=True)
     assert out.returncode == 0, out.stderr
+
+
+@pytest.mark.parametrize("kw", [
+    dict(), dict(n_levels=8, log2_hashmap_size=12, base_resolution=4, per_level_scale=1.6),
+    dict(n_levels=16, log2_hashmap_size=22, base_resolution=32, per_level_scale=1.3819),
+    dict(grid_type="Dense", n_levels=4, base_resolution=8, per_level_scale=2.0, n_features_per_level=4),
+    dict(grid_type="Tiled", n_levels=6, base_resolution=16, per_level_scale=1.5, n_features_per_level=1),
+])
+def test_ngp_grid_and_layout_match_the_oracle(built_lib, kw):
+    """`arch: ngp` host arithmetic: the per-level table sizes (tiny-cuda-nn's offset table) and the flat parameter
+    layout (grid, mlp_base, mlp_head in state-dict order) agree with the oracle's restatement."""
+    from ren_b200 import _lib
+    fcfg = R.FieldConfig(arch="ngp", **kw)
+    meta = fcfg.grid_meta()
+    otype = {"Hash": "HashGrid", "Dense": "DenseGrid", "Tiled": "TiledGrid"}[fcfg.grid_type]
+    desc = _lib.make_ngp_field_desc(
+        pos_encoding=dict(otype=otype, n_levels=fcfg.n_levels, n_features_per_level=fcfg.n_features_per_level,
+                          log2_hashmap_size=fcfg.log2_hashmap_size, base_resolution=fcfg.base_resolution,
+                          per_level_scale=fcfg.per_level_scale, interpolation="Linear"),
+        dir_encoding=dict(degree=fcfg.sh_degree),
+        mlp_base=dict(hidden_activation="softplus", density_activation="shifted_trunc_exp", n_neurons=64,
+                      n_hidden_layers=1, geo_feat_dim=15),
+        mlp_head=dict(hidden_activation="softplus", radiance_activation="softplus", n_neurons=64, n_hidden_layers=2))
+    assert _lib.grid_param_count(desc) == meta["n_params"]
+    layout = _lib.param_layout(desc)
+    shapes = fcfg.layer_shapes()
+    assert len(layout) == len(shapes)
+    off = meta["n_params"]
+    for (w_off, b_off, out_f, in_f), (_, o, i) in zip(layout, shapes):
+        assert (out_f, in_f) == (o, i) and w_off == off
+        off += o * i
+        assert b_off == off
+        off += o
+    assert _lib.param_count(desc) == off
