@@ -58,7 +58,14 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+// The suspend-time hint lets the hardware park the thread until the phase completes (or the hint expires) instead
+// of returning after the short default window: without it the wait loops of the chain kernel re-issued
+// try_wait + branch every ~125 cycles (a quarter of all executed instructions, ncu r02).
+#ifndef REN_MBAR_HINT_NS
+#define REN_MBAR_HINT_NS 20000
+#endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+#if REN_MBAR_HINT_NS == 0
   asm volatile(
       "{\n"
       ".reg .pred P1;\n"
@@ -68,6 +75,17 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "bra WAIT_LOOP;\n"
       "DONE:\n"
       "}\n" ::"r"(bar), "r"(parity) : "memory");
+#else
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n"
+      "@P1 bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}\n" ::"r"(bar), "r"(parity), "r"((uint32_t)REN_MBAR_HINT_NS) : "memory");
+#endif
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),

@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libren_b200.so")
+# REN_B200_LIB selects another build of the same library (A/B timing of kernel variants); default: the in-tree one
+LIB_PATH = os.environ.get("REN_B200_LIB") or os.path.join(_HERE, "lib", "libren_b200.so")
 
 REN_ENGINE = {"auto": 0, "simt_fp32": 1, "tc_f16x3": 2, "tc_f16": 3, "tc_f16a": 4}
 HIDDEN_ACT = {"softplus": 0, "relu": 1}
