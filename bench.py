@@ -533,8 +533,7 @@ def run_ours(args):
         dist.all_gather(allc, chk)
         params_equal = all(bool(torch.equal(allc[0], c)) for c in allc)
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        leave(world)
         return
 
     pk = peaks()
@@ -604,9 +603,20 @@ def run_ours(args):
         "params_equal_across_ranks": params_equal, "secondary": secondary,
         "clocks": sampler.summary(), "loss": loss,
     }
-    print(json.dumps(out))
+    print(json.dumps(out), flush=True)
+    leave(world)
+
+
+def leave(world):
+    """Multi-rank exit without communicator teardown: every collective of the run has completed on every rank (the
+    last one is the parameter-checksum all-gather), and `destroy_process_group` with captured graphs that hold
+    NCCL kernels still alive was seen to hang at 8 ranks.  torchrun only needs exit code 0 from every rank."""
     if world > 1:
-        dist.destroy_process_group()
+        import torch
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():

@@ -262,7 +262,13 @@ def sinusoidal_encode(x, max_deg):
 
 
 def _linear(params, name, x):
-    return F.linear(x, params[name + ".weight"], params[name + ".bias"])
+    """`nn.Linear`, or its `torch.nn.utils.weight_norm` form (`weight_g`, `weight_v`: external/mlp.py:301-319,
+    external/ngp.py:209-217) when the parameter dict carries those keys."""
+    if name + ".weight_g" in params:
+        w = torch._weight_norm(params[name + ".weight_v"], params[name + ".weight_g"], 0)
+    else:
+        w = params[name + ".weight"]
+    return F.linear(x, w, params[name + ".bias"])
 
 
 def mlp_trunk(params, cfg, enc):

@@ -144,7 +144,7 @@ class RenderFunction(torch.autograd.Function):
         C_ = owner.radiance_dim
         ray_grad = bool(want_grad) and (ctx.needs_input_grad[2] or ctx.needs_input_grad[3])
         fdesc, rdesc, K = owner._descs()
-        flat = owner.flat_params()
+        flat = owner._flat_for(params)
         need_grad = bool(want_grad) and (ray_grad or any(ctx.needs_input_grad[5:]))
         dev = o.device
         o = o.contiguous().float()
@@ -250,7 +250,7 @@ class RenderRayGradFunction(torch.autograd.Function):
         if g_depth is not None and bool((g_depth != 0).any()):
             raise RuntimeError("ren_b200: create_graph=True with a depth gradient is not supported")
         B, dev = o.shape[0], o.device
-        flat = owner.flat_params()
+        flat = owner._flat_for(params)
         cg = lambda t: None if t is None else t.detach().contiguous().float()
         o_, d_, g_rad_, g_op_ = cg(o), cg(d), cg(g_rad), cg(g_op)
         jit, bk = cg(jitter), cg(bkgd)
@@ -279,6 +279,7 @@ class RenderRayGradFunction(torch.autograd.Function):
         ctx.save_for_backward(o_, d_, jit if jit is not None else empty, bk if bk is not None else empty,
                               g_rad_, g_op_ if g_op_ is not None else empty)
         ctx.flags = (jit is not None, bk is not None, g_op_ is not None)
+        ctx.flat = flat
         ctx.n_params = len(params)
         plain = (g_bk if g_bk is not None else torch.zeros(0, device=dev),) + tuple(owner._split_flat(g_flat))
         ctx.mark_non_differentiable(*plain)
@@ -307,7 +308,7 @@ class RenderRayGradFunction(torch.autograd.Function):
         g_rad = (g_rad * scale[:, None]).contiguous()
         if has_gop:
             g_op = (g_op * scale).contiguous()
-        flat = owner.flat_params()
+        flat = ctx.flat
         rad, rad_dot = torch.empty((B, C_), device=dev), torch.empty((B, C_), device=dev)
         opac, opac_dot, depth = (torch.empty((B,), device=dev) for _ in range(3))
         n_kept = torch.empty((B,), device=dev, dtype=torch.int32)
@@ -352,7 +353,7 @@ class RenderTangentFunction(torch.autograd.Function):
         C_ = owner.radiance_dim
         ray_grad = bool(want_grad) and any(ctx.needs_input_grad[2:6])
         fdesc, rdesc, K = owner._descs()
-        flat = owner.flat_params()
+        flat = owner._flat_for(params)
         need_grad = bool(want_grad) and (ray_grad or any(ctx.needs_input_grad[7:]))
         dev = o.device
         o, d, o_dot, d_dot = (t.contiguous().float() for t in (o, d, o_dot, d_dot))
@@ -465,8 +466,12 @@ class NeRF(torch.nn.Module):
             raise NotImplementedError(f"arch={arch!r}")                      # models/nerf.py:166-167
         self.arch = arch
         sub = [arch_config] if arch == "mlp" else [_cfg_get(arch_config, "mlp_base"), _cfg_get(arch_config, "mlp_head")]
-        if any(bool(_cfg_get(c, "weight_norm")) for c in sub):
-            raise NotImplementedError("weight_norm=True is not supported by ren_b200")
+        wn = [bool(_cfg_get(c, "weight_norm")) for c in sub]
+        if any(wn) and not all(wn):
+            raise NotImplementedError("ren_b200 applies weight_norm to mlp_base and mlp_head together or not at all")
+        # external/mlp.py:301-319, external/ngp.py:209-217: `torch.nn.utils.weight_norm` on every Linear
+        # (state-dict keys `weight_g` / `weight_v`); the kernels see the effective weights g v / |v|
+        self.weight_norm = all(wn)
 
         self.register_buffer("aabb", torch.tensor(aabb, dtype=torch.float32), persistent=False)
         self.contraction_type = contraction_type
@@ -582,6 +587,7 @@ class NeRF(torch.nn.Module):
                 setattr(getattr(mlp, head), leaf, lin)
         rf.mlp = mlp
         self.radiance_field = rf
+        self._apply_weight_norm()
         self._flatten()
 
     def _build_ngp_tree(self, blocks):
@@ -614,11 +620,39 @@ class NeRF(torch.nn.Module):
         rf.mlp_head = head
         self.radiance_field = rf
         object.__setattr__(self, "_grid", grid)          # alias, not a second registration of the module
+        self._apply_weight_norm()
         self._flatten()
+
+    def _apply_weight_norm(self):
+        if self.weight_norm:
+            for lin in self._linears:
+                torch.nn.utils.weight_norm(lin)
+
+    def _flat_effective(self):
+        """weight_norm: the flat buffer of EFFECTIVE parameters as a differentiable function of
+        (weight_g, weight_v, bias) [and the grid]: autograd carries the render's flat gradient back to them."""
+        parts = [self._grid.params] if self._n_grid else []
+        for lin in self._linears:
+            parts.append(torch._weight_norm(lin.weight_v, lin.weight_g, 0).reshape(-1))
+            parts.append(lin.bias)
+        return torch.cat(parts).float()
+
+    def _render_params(self):
+        return [self._flat_effective()] if self.weight_norm else self.mlp_parameters()
+
+    def _flat_for(self, params):
+        """The flat parameter buffer a render call reads: the caller's effective-weight tensor under weight_norm,
+        else the buffer the named parameters are views of."""
+        if self.weight_norm:
+            return params[0].detach().contiguous()
+        return self.flat_params()
 
     def _flatten(self):
         """(Re)pack the grid and every Linear's weight/bias into one flat buffer and re-point the
         parameters at views of it."""
+        if self.weight_norm:
+            self._flat = None                      # parameters are (g, v, bias) leaves: no shared buffer
+            return
         ref = self._linears[0].weight
         flat = torch.empty((self._n_params,), device=ref.device, dtype=torch.float32)
         with torch.no_grad():
@@ -646,6 +680,9 @@ class NeRF(torch.nn.Module):
     def flat_params(self):
         """The flat fp32 parameter buffer (rebuilt if `.to()` / `load_state_dict` moved
         the parameters)."""
+        if self.weight_norm:
+            with torch.no_grad():
+                return self._flat_effective().contiguous()
         if not self._views_intact():
             self._flatten()
         return self._flat
@@ -653,10 +690,12 @@ class NeRF(torch.nn.Module):
     def mlp_parameters(self):
         out = [self._grid.params] if self._n_grid else []
         for lin in self._linears:
-            out += [lin.weight, lin.bias]
+            out += [lin.weight_g, lin.weight_v, lin.bias] if self.weight_norm else [lin.weight, lin.bias]
         return out
 
     def _split_flat(self, g_flat):
+        if self.weight_norm:
+            return [g_flat]                        # one input (the effective flat buffer), one gradient
         grads = [g_flat[:self._n_grid]] if self._n_grid else []
         for (w_off, b_off, out_f, in_f) in self._layout:
             grads.append(g_flat[w_off:w_off + out_f * in_f].view(out_f, in_f))
@@ -764,7 +803,7 @@ class NeRF(torch.nn.Module):
         if not self.training:
             jitter = None
         return RenderFunction.apply(self, torch.is_grad_enabled(), o, d, jitter, self.background(),
-                                    *self.mlp_parameters())
+                                    *self._render_params())
 
     def render_tangent_raw(self, o, d, o_dot, d_dot, jitter=None):
         """Render + derivative along the pose interpolation weight: (radiance (B,C), opacity (B),
@@ -774,7 +813,7 @@ class NeRF(torch.nn.Module):
         if not self.training:
             jitter = None
         return RenderTangentFunction.apply(self, torch.is_grad_enabled(), o, d, o_dot, d_dot, jitter,
-                                           self.background(), *self.mlp_parameters())
+                                           self.background(), *self._render_params())
 
     def forward(self, ray_origin, ray_direction, jitter=None):
         """models/nerf.py:230-286.  `jitter` (optional, (N,) in [0,1)) injects the per-ray

@@ -36,9 +36,12 @@ class FlatTrainer:
         self.mlp_params = model.nerf.mlp_parameters()
         self.small_params = [p for i, g in enumerate(opt.param_groups) if i != 2 for p in g["params"]
                              if p.requires_grad]
-        self.use_fused_adam = use_fused_adam and all(p.requires_grad for p in self.mlp_params)
+        # the fused Adam runs on the flat buffer the parameters are views of; under weight_norm they are separate
+        # (weight_g, weight_v, bias) leaves and torch's Adam takes them
+        self.use_fused_adam = use_fused_adam and all(p.requires_grad for p in self.mlp_params) \
+            and not getattr(model.nerf, "weight_norm", False)
         flat = model.nerf.flat_params()
-        self.n_mlp = flat.numel()
+        self.n_mlp = sum(p.numel() for p in self.mlp_params)
         # small parameters: fp32 ones take one slot per element, f64 ones a (hi, lo) pair
         self._small_slots = []
         off = self.n_mlp
@@ -48,8 +51,8 @@ class FlatTrainer:
             off += p.numel() * width
         self.spp_slot = off
         self.gbuf = torch.zeros(off + 1, device=flat.device, dtype=torch.float32)
-        self.exp_avg = torch.zeros_like(flat)
-        self.exp_avg_sq = torch.zeros_like(flat)
+        self.exp_avg = torch.zeros_like(flat) if self.use_fused_adam else None
+        self.exp_avg_sq = torch.zeros_like(flat) if self.use_fused_adam else None
         self.step_count = 0
         self.epoch = 0
         self.mean_spp = None                            # device scalar: cross-rank mean samples per ray

@@ -661,3 +661,47 @@ def test_contrast_threshold_gradient_for_every_error_fn(err_diff, built_lib, dat
           f"d loss / d theta_ratio cuda={got:.6e} oracle={want:.6e}")
     assert abs(float(loss) - float(out["loss"])) <= 1e-4 * abs(float(out["loss"]))
     assert abs(got - want) <= 2e-3 * abs(want) + 1e-9
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_weight_norm_training_step_matches_oracle(engine, built_lib, dataset_dir):
+    """`weight_norm: true`: the kernels run on the effective weights g v / |v|, autograd carries the flat gradient
+    back to (weight_g, weight_v, bias): loss, log I and those gradients vs the oracle on the same leaves."""
+    B, N = 48, 32
+    g = dict(H.load_golden("step_8x256_gain2"))
+    step = 4.0 / N
+    g["rcfg"] = dict(g["rcfg"], render_step_size=step, far_plane=0.5 + (N + 0.5) * step)
+    g["learn_bkgd"] = False
+    scene = synth.load_scene(dataset_dir)
+    batch, jitter = synth.make_batch(B, scene["T_wc_timestamp"], rank=8, seed=77)
+    from ren_b200 import RobustENeRF
+    cfg = H.product_config(g)
+    cfg["nerf"]["mlp"]["weight_norm"] = True
+    torch.manual_seed(0)
+    m = RobustENeRF(dataset_directory=dataset_dir, engine=engine, **cfg)
+    with torch.no_grad():                      # a non-trivial (g, v): scale v, double g
+        for lin in m.nerf._linears:
+            lin.weight_v.mul_(0.7)
+            lin.weight_g.mul_(2.0)
+    m = m.cuda().train()
+    loss = m.training_step({k: {kk: vv.cuda() for kk, vv in v.items()} for k, v in batch.items()}, 0,
+                           {k: v.cuda() for k, v in jitter.items()})
+    loss.backward()
+    fcfg, rcfg, scfg = H.golden_configs(g)
+    params = {k[len("nerf.radiance_field."):]: v.detach().cpu().clone().requires_grad_(True)
+              for k, v in m.state_dict().items() if k.startswith("nerf.radiance_field.mlp.")}
+    assert any(k.endswith("weight_g") for k in params)
+    tau_max = scene["max_refractory_period"]
+    torch.set_num_threads(8)
+    out = R.training_step(params, fcfg, rcfg, scfg, scene, batch, jitter, torch.log(torch.expm1(torch.tensor(1.0))),
+                          tau_max * torch.logit(scene["refractory_period"].double() / tau_max))
+    out["loss"].backward()
+    rel = abs(float(loss) - float(out["loss"])) / abs(float(out["loss"]))
+    nw, ma, _ = H.rel_err(m.last["end_log_intensity"], out["end_log_intensity"])
+    print(f"[weight_norm / {engine}] loss rel={rel:.2e} logI normwise={nw:.2e} maxabs={ma:.2e}")
+    assert rel < REL_BAR and nw < REL_BAR and ma < 3e-4
+    named = dict(m.named_parameters())
+    worst = 0.0
+    for k, v in params.items():
+        worst = max(worst, _grad_cmp(k, named["nerf.radiance_field." + k].grad, v.grad, cos_bar=0.999, nw_bar=2e-2))
+    print(f"  worst (g, v, bias) gradient normwise rel = {worst:.2e}")

@@ -114,13 +114,39 @@ def test_unsupported_configurations_raise(built_lib, dataset_dir):
     with pytest.raises(NotImplementedError):                      # models/nerf.py:166-167
         NeRF(cfg["aabb"], "sphere", cfg["occ_grid"], 0.5, 4.5, 0.03, None, 0.0, 0.0, 0.0, 16384, "tensorf",
              arch_config=cfg["mlp"])
-    with pytest.raises(NotImplementedError):                      # weight_norm (external/mlp.py:301-319)
-        NeRF(cfg["aabb"], "sphere", cfg["occ_grid"], 0.5, 4.5, 0.03, None, 0.0, 0.0, 0.0, 16384, "mlp",
-             arch_config=dict(cfg["mlp"], weight_norm=True))
     ngp = H.product_config(H.load_golden("step_ngp"))["nerf"]["ngp"]
     with pytest.raises(NotImplementedError):                      # grid interpolation other than Linear
         NeRF(cfg["aabb"], "sphere", cfg["occ_grid"], 0.5, 4.5, 0.03, None, 0.0, 0.0, 0.0, 16384, "ngp",
              arch_config=dict(ngp, pos_encoding=dict(ngp["pos_encoding"], interpolation="Smoothstep")))
+
+
+@pytest.mark.parametrize("name", ["step_8x256", "step_ngp"])
+def test_weight_norm_keys_and_effective_weights(name, built_lib, dataset_dir):
+    """`weight_norm: true` (external/mlp.py:301-319, external/ngp.py:209-217): `weight_g` / `weight_v` state-dict
+    keys like `torch.nn.utils.weight_norm`, the effective weights equal the plain initialisation, the optimiser's
+    MLP group holds the (g, v, bias) leaves."""
+    from ren_b200 import RobustENeRF
+    g = H.load_golden(name)
+    cfg = H.product_config(g)
+    cfg_wn = H.product_config(g)
+    if name == "step_ngp":
+        cfg_wn["nerf"]["ngp"]["mlp_base"]["weight_norm"] = True
+        cfg_wn["nerf"]["ngp"]["mlp_head"]["weight_norm"] = True
+    else:
+        cfg_wn["nerf"]["mlp"]["weight_norm"] = True
+    torch.manual_seed(0)
+    plain = RobustENeRF(dataset_directory=dataset_dir, **cfg)
+    torch.manual_seed(0)
+    wn = RobustENeRF(dataset_directory=dataset_dir, **cfg_wn)
+    n_lin = len(plain.nerf._linears)
+    keys = set(wn.state_dict())
+    assert sum(k.endswith(".weight_g") for k in keys) == n_lin and sum(k.endswith(".weight_v") for k in keys) == n_lin
+    assert not any(k.endswith(".weight") for k in keys if "radiance_field" in k)
+    assert float((wn.nerf.flat_params() - plain.nerf.flat_params()).abs().max()) < 1e-6
+    groups = wn.configure_optimizers()["optimizer"].param_groups
+    assert len(groups[2]["params"]) == 3 * n_lin + (1 if name == "step_ngp" else 0)
+    flat = wn.nerf._flat_effective()
+    assert flat.requires_grad and flat.numel() == plain.nerf.flat_params().numel()
 
 
 def test_ngp_module_tree_matches_the_reference_keys(built_lib, dataset_dir):
