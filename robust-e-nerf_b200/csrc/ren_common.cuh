@@ -370,10 +370,11 @@ __device__ __forceinline__ void ren_corner(const RenCell& c, int corner, float* 
 }
 // enc[l*F + j] = sum_corners w T[idx][j]  (kernel_grid of tiny-cuda-nn);  xdot != NULL: d enc / d w instead,
 // with the weights' derivative along xdot (d frac / d x = scale)
+// levels l0, l0 + lstep, ... (lstep = 1: all of them; the fp32 engine's prologue spreads a row's levels over 4 threads)
 template <typename Store>
 __device__ __forceinline__ void ren_grid_encode(const RenGrid& G, const float* __restrict__ table, const float* x,
-                                                const float* xdot, Store store) {
-  for (int l = 0; l < G.n_levels; ++l) {
+                                                const float* xdot, Store store, int l0 = 0, int lstep = 1) {
+  for (int l = l0; l < G.n_levels; l += lstep) {
     const RenGridLevel lv = G.lv[l];
     RenCell c;
     ren_grid_cell(lv, x, c);

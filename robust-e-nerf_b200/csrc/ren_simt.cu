@@ -278,8 +278,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) ren_simt_field_fwd(const FwdArgs 
           ren_unit_position(p.f, o, d, t0, t1, xu);
           for (int j = 0; j < REN_PE_MAX; ++j) eP[j] = 0.f;
           for (int j = 0; j < REN_DE_MAX; ++j) eD[j] = 0.f;
+          // the grid features are filled in by all 256 threads after this block (4 threads per row): leave the
+          // unit position (and its derivative along w) in shared memory
+          float* gx = s.misc + TM + tid * 7;
+          gx[0] = xu[0]; gx[1] = xu[1]; gx[2] = xu[2];
+          gx[3] = 0.f; gx[4] = 0.f; gx[5] = 0.f;
+          gx[6] = tan_row ? 2.f : 1.f;
           if (!tan_row) {
-            ren_grid_encode(a.grid, a.table, xu, nullptr, [&](int j, float v) { eP[j] = v; });
             float sh[16];
             ren_sh_t<float>(d, p.f.sh_degree, sh);
             for (int j = 0; j < p.DE; ++j) eD[j] = sh[j];
@@ -295,8 +300,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ren_simt_field_fwd(const FwdArgs 
             }
             ren_contract_unit_t<Dual>(p.f, pd, xd);
 #pragma unroll
-            for (int c = 0; c < 3; ++c) xdot[c] = xd[c].d;
-            ren_grid_encode(a.grid, a.table, xu, xdot, [&](int j, float v) { eP[j] = v; });
+            for (int c = 0; c < 3; ++c) { xdot[c] = xd[c].d; gx[3 + c] = xdot[c]; }
             ren_sh_t<Dual>(dd3, p.f.sh_degree, shd);
             for (int j = 0; j < p.DE; ++j) eD[j] = shd[j].d;
           }
@@ -325,16 +329,37 @@ __global__ void __launch_bounds__(NTHREADS, 1) ren_simt_field_fwd(const FwdArgs 
         if (a.stash) {
           float* gP = a.stash + ren_stash_encp(p, S);
           float* gD = a.stash + ren_stash_encd(p, S);
-          for (int j = 0; j < REN_PE_MAX; ++j) gP[ren_blk(sidx, j, REN_PE_MAX)] = eP[j];
+          if (p.arch != REN_ARCH_NGP)
+            for (int j = 0; j < REN_PE_MAX; ++j) gP[ren_blk(sidx, j, REN_PE_MAX)] = eP[j];
           for (int j = 0; j < REN_DE_MAX; ++j) gD[ren_blk(sidx, j, REN_DE_MAX)] = eD[j];
         }
       } else {
         for (int j = 0; j < REN_PE_MAX; ++j) eP[j] = 0.f;
         for (int j = 0; j < REN_DE_MAX; ++j) eD[j] = 0.f;
+        if (p.arch == REN_ARCH_NGP) s.misc[TM + tid * 7 + 6] = 0.f;
       }
       sel[tid] = skipped ? 2.f : (selector ? 1.f : 0.f);
     }
     __syncthreads();
+    if (p.arch == REN_ARCH_NGP) {
+      // grid features: row = tid & 63, levels (tid >> 6), (tid >> 6) + 4, ...  (128 gathers per row spread over 4 threads)
+      const int row = tid & (TM - 1), lg = tid >> 6;
+      const float* gx = s.misc + TM + row * 7;
+      const float mode = gx[6];
+      if (mode != 0.f) {
+        const float xu[3] = {gx[0], gx[1], gx[2]}, xd[3] = {gx[3], gx[4], gx[5]};
+        float* eP = s.encP + row * REN_PE_MAX;
+        float* gP = a.stash ? a.stash + ren_stash_encp(p, S) : nullptr;
+        const long long sidx = s0 + row;
+        ren_grid_encode(a.grid, a.table, xu, mode == 2.f ? xd : nullptr, [&](int j, float v) {
+          eP[j] = v;
+          if (gP) gP[ren_blk(sidx, j, REN_PE_MAX)] = v;
+        }, lg, NTHREADS / TM);
+        if (gP && lg == 0)
+          for (int j = p.PE; j < REN_PE_MAX; ++j) gP[ren_blk(sidx, j, REN_PE_MAX)] = 0.f;
+      }
+      __syncthreads();
+    }
     // ---- trunk
     float* cur = s.bufA;
     float* nxt = s.bufB;
@@ -579,9 +604,14 @@ struct WgradArgs {
 };
 #define WG_MC 16
 
-extern "C" __global__ void __launch_bounds__(NTHREADS, 2) ren_simt_wgrad(const WgradArgs a) {
-  __shared__ __align__(16) float Ds[2][WG_MC][128];
-  __shared__ __align__(16) float Hs[2][WG_MC][128];
+// NT: outputs per thread along n and k (8: 128 x 128 tiles; 4: 64 x 64 tiles for narrow networks such as the
+// 64-wide MLPs of `arch: ngp`, where a 128 x 128 tile would be 7/8 padding)
+template <int NT>
+__global__ void __launch_bounds__(NTHREADS, 2) ren_simt_wgrad(const WgradArgs a) {
+  constexpr int TW = 16 * NT;                 // tile width along n and along k
+  constexpr int PER = WG_MC * TW / NTHREADS;  // staged elements per thread and matrix
+  __shared__ __align__(16) float Ds[2][WG_MC][TW];
+  __shared__ __align__(16) float Hs[2][WG_MC][TW];
   const int tid = threadIdx.x;
   const int total_tiles = a.tile_prefix[a.n_problems];
   const int tile_id = blockIdx.x % total_tiles;
@@ -591,23 +621,25 @@ extern "C" __global__ void __launch_bounds__(NTHREADS, 2) ren_simt_wgrad(const W
   const WgradProblem& P = a.pr[pi];
   const int local = tile_id - a.tile_prefix[pi];
   const int tn = local / P.ntk, tk = local - tn * P.ntk;
-  const int n0 = tn * 128, k0 = tk * 128;
+  const int n0 = tn * TW, k0 = tk * TW;
   const long long per = ((a.S + a.splits - 1) / a.splits + 15) & ~15LL;
   const long long m_begin = (long long)split * per;
   const long long m_end = min(a.S, m_begin + per);
-  const int ty = tid >> 4, tx = tid & 15;  // ty: 16 groups of 8 n; tx: 16 groups of (4 + 4) k
-  float acc[8][8];
-  zero_acc(acc);
-  float bsum[8];
+  const int ty = tid >> 4, tx = tid & 15;  // ty: 16 groups of NT n; tx: 16 groups of 4 (+ 4) k
+  float acc[NT][NT];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) bsum[i] = 0.f;
-  // staging: 16 rows x 128 cols x 2 matrices = 4096 floats, 16 per thread
-  float dreg[8], hreg[8];
+  for (int i = 0; i < NT; ++i)
+#pragma unroll
+    for (int j = 0; j < NT; ++j) acc[i][j] = 0.f;
+  float bsum[NT];
+#pragma unroll
+  for (int i = 0; i < NT; ++i) bsum[i] = 0.f;
+  float dreg[PER], hreg[PER];
   auto fetch = [&](long long m0) {
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
+    for (int e = 0; e < PER; ++e) {
       const int idx = e * NTHREADS + tid;
-      const int mm = idx >> 7, cc = idx & 127;
+      const int mm = idx / TW, cc = idx % TW;
       const long long m = m0 + mm;
       dreg[e] = (m < m_end && n0 + cc < P.N)
                     ? __ldg(P.D + (P.d_rowmajor ? m * P.ldd + n0 + cc : ren_blk(m, n0 + cc, P.ldd))) : 0.f;
@@ -616,10 +648,10 @@ extern "C" __global__ void __launch_bounds__(NTHREADS, 2) ren_simt_wgrad(const W
   };
   auto commit = [&](int buf) {
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
+    for (int e = 0; e < PER; ++e) {
       const int idx = e * NTHREADS + tid;
-      Ds[buf][idx >> 7][idx & 127] = dreg[e];
-      Hs[buf][idx >> 7][idx & 127] = hreg[e];
+      Ds[buf][idx / TW][idx % TW] = dreg[e];
+      Hs[buf][idx / TW][idx % TW] = hreg[e];
     }
   };
   if (m_begin < m_end) {
@@ -633,18 +665,26 @@ extern "C" __global__ void __launch_bounds__(NTHREADS, 2) ren_simt_wgrad(const W
     if (more) fetch(m0 + WG_MC);
 #pragma unroll
     for (int mm = 0; mm < WG_MC; ++mm) {
-      float4 d0 = *reinterpret_cast<const float4*>(&Ds[buf][mm][ty * 8]);
-      float4 d1 = *reinterpret_cast<const float4*>(&Ds[buf][mm][ty * 8 + 4]);
-      float4 h0 = *reinterpret_cast<const float4*>(&Hs[buf][mm][tx * 4]);
-      float4 h1 = *reinterpret_cast<const float4*>(&Hs[buf][mm][64 + tx * 4]);
-      const float dv[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
-      const float hv[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+      float dv[NT], hv[NT];
+#pragma unroll
+      for (int i = 0; i < NT; i += 4) {
+        const float4 d4 = *reinterpret_cast<const float4*>(&Ds[buf][mm][ty * NT + i]);
+        dv[i] = d4.x; dv[i + 1] = d4.y; dv[i + 2] = d4.z; dv[i + 3] = d4.w;
+      }
+      {
+        const float4 h0 = *reinterpret_cast<const float4*>(&Hs[buf][mm][tx * 4]);
+        hv[0] = h0.x; hv[1] = h0.y; hv[2] = h0.z; hv[3] = h0.w;
+        if (NT == 8) {
+          const float4 h1 = *reinterpret_cast<const float4*>(&Hs[buf][mm][(TW / 2) + tx * 4]);
+          hv[NT - 4] = h1.x; hv[NT - 3] = h1.y; hv[NT - 2] = h1.z; hv[NT - 1] = h1.w;
+        }
+      }
       const bool brow = !(a.tangent && (mm & 1));    // m0 is a multiple of 16: row parity == mm parity
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < NT; ++i) {
         if (brow) bsum[i] += dv[i];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(dv[i], hv[j], acc[i][j]);
+        for (int j = 0; j < NT; ++j) acc[i][j] = fmaf(dv[i], hv[j], acc[i][j]);
       }
     }
     if (more) commit(buf ^ 1);
@@ -652,12 +692,12 @@ extern "C" __global__ void __launch_bounds__(NTHREADS, 2) ren_simt_wgrad(const W
     buf ^= 1;
   }
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int n = n0 + ty * 8 + i;
+  for (int i = 0; i < NT; ++i) {
+    const int n = n0 + ty * NT + i;
     if (n >= P.N) continue;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int k = k0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+    for (int j = 0; j < NT; ++j) {
+      const int k = k0 + (j < 4 ? tx * 4 + j : (TW / 2) + tx * 4 + (j - 4));
       if (k < P.Kc) atomicAdd(P.dW + (long long)n * P.ldw + k, acc[i][j]);
     }
     if (P.db != nullptr && tk == 0 && tx == 0) atomicAdd(P.db + n, bsum[i]);
@@ -735,6 +775,9 @@ int ren_simt_launch_wgrad(const RenPlan& p, long long S, const float* stash, con
   WgradArgs a;
   a.tangent = tangent;
   int np = 0;
+  // 64 x 64 output tiles when no layer is wider than 64 (arch ngp), else 128 x 128
+  const bool narrow = p.W <= 64 && p.WC <= 64 && p.PE <= 64 && p.DE <= 64;
+  const int tw = narrow ? 64 : 128;
   const float* encP = stash + ren_stash_encp(p, S);
   const float* encD = stash + ren_stash_encd(p, S);
   auto add = [&](const float* D, int ldd, int N, const float* H, int ldh, int Kc, float* dW, int ldw,
@@ -742,7 +785,7 @@ int ren_simt_launch_wgrad(const RenPlan& p, long long S, const float* stash, con
     WgradProblem& P = a.pr[np++];
     P.D = D; P.ldd = ldd; P.N = N; P.H = H; P.ldh = ldh; P.Kc = Kc; P.dW = dW; P.ldw = ldw; P.db = db;
     P.d_rowmajor = (D == graw || D == graw + 1) ? 1 : 0;
-    P.ntn = (N + 127) / 128; P.ntk = (Kc + 127) / 128;
+    P.ntn = (N + tw - 1) / tw; P.ntk = (Kc + tw - 1) / tw;
   };
   auto add_layer = [&](const RenLayer& L, const float* in_main, int ld_main) {
     const float* D = delta + ren_stash_mat(p, S, L.mat);
@@ -797,7 +840,8 @@ int ren_simt_launch_wgrad(const RenPlan& p, long long S, const float* stash, con
   a.splits = splits;
   a.S = S;
   ren_prof_begin(REN_K_WGRAD, st);
-  ren_simt_wgrad<<<(unsigned)(total * splits), NTHREADS, 0, st>>>(a);
+  if (narrow) ren_simt_wgrad<4><<<(unsigned)(total * splits), NTHREADS, 0, st>>>(a);
+  else ren_simt_wgrad<8><<<(unsigned)(total * splits), NTHREADS, 0, st>>>(a);
   ren_prof_end(REN_K_WGRAD, st);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { ren_set_error("simt wgrad launch: %s", cudaGetErrorString(e)); return REN_E_CUDA; }
