@@ -48,6 +48,32 @@
 #ifndef FLAT_AHEAD
 #define FLAT_AHEAD 1            // softplus groups (of 8 columns) computed ahead of the split / store of a group
 #endif
+// Straight-line epilogues of the common layer kinds (hidden softplus layer of the value pass; plain dgrad through a
+// hidden softplus layer): the per-group runtime tests of the generic loop (layer kind, operand precision, stash /
+// operand destinations, row validity) are decided once per half-epilogue.  0 = generic loop only (A/B builds).
+#ifndef REN_FLAT_FWD
+#define REN_FLAT_FWD 1
+#endif
+#ifndef REN_FLAT_BWD
+#define REN_FLAT_BWD 1
+#endif
+// Biases of the hidden softplus layers of the value pass as one more K step of the layer's GEMM instead of one
+// FADD (+ a quarter of a shared-memory load) per element in the epilogue, which is the limiter: A = a resident
+// [128 x 16] tile whose first column is 1, B = [N x 16] with the scaled bias (fp16 hi | lo) in its first column, two
+// MMAs (1 * b_hi + 1 * b_lo) that also initialise the accumulator.  Needs REN_FLAT_FWD.  0 = bias in the epilogue.
+#ifndef REN_BIAS_MMA
+#define REN_BIAS_MMA 0
+#endif
+#if REN_BIAS_MMA && !REN_FLAT_FWD
+#error "REN_BIAS_MMA needs REN_FLAT_FWD"
+#endif
+// Every N = 256 MMA of a layer's first K-half is issued as two N = 128 MMAs on the two accumulator halves,
+// interleaved, so that consecutive MMAs never accumulate into the same columns (same arithmetic, bit-identical
+// results; measured -1 % forward / -3 % dgrad once the issue loop runs on an elect.sync lane, +10 % before that,
+// when every extra tcgen05.mma cost a per-lane serialisation loop).  0 = one N = 256 MMA.
+#ifndef REN_WIDE_SPLIT
+#define REN_WIDE_SPLIT 1
+#endif
 
 // shared-memory map (bytes)
 #define SM_P_HI 0          // positional encoding [128 x 64] hi (K-major core matrices)
@@ -74,7 +100,9 @@
 #define SM_SEL (SM_PROG + TC_MAX_OPS * 32)              // selector flags of the two buffered tiles: float [2][128]
 #define SM_BAR (SM_SEL + 1024)
 #define SM_TMEM_PTR (SM_BAR + 320)
-#define SM_TOTAL (SM_BAR + 512)
+#define SM_ONES (SM_BAR + 512)                          // [128 x 16] fp16 K-major operand, column 0 = 1 (bias K step)
+#define SM_TOTAL (SM_ONES + 4096)
+#define OP_ONES 0x400u                                  // StageOp flag: A = the ones tile, B = the bias chunk
 
 #define LOG2E_100 144.26950408889634f      // 100 * log2(e)
 #define LN2_OVER_100 0.0069314718055994531f
@@ -95,6 +123,7 @@ struct TcStep {
   int rank1;      // dgrad: += g_sigma * w_sigma[n] before the activation derivative
   int sig_head;   // fwd: this epilogue also accumulates the sigma head
   float acc_scale;   // EPI_F_LINEAR: out = acc_scale * acc + bias (keeps the packed weights out of fp16 subnormals)
+  int bias_mma;      // fwd: the bias enters as the first K step of the GEMM (ones tile x bias chunk), not in the epilogue
   long long pack_off;   // byte offset of this step's weight chunks (in MMA issue order)
 };
 
@@ -107,7 +136,7 @@ struct StageOp {
   uint32_t a_addr;      // A of the first K step: TMEM column (a_smem = 0) or descriptor low word minus base (a_smem = 1)
   uint32_t a_lo_delta;  // from the hi to the lo part of A (TMEM columns / descriptor units)
   uint32_t flags;       // [0:2] K steps, [3] wide (N=256), [4] a_smem, [5] first MMA overwrites, [6:7] wait: 1 A-half 0,
-                        // 2 A-half 1, 3 encodings; [8:9] commit accumulator half (1, 2) after the stage
+                        // 2 A-half 1, 3 encodings; [8:9] commit accumulator half (1, 2) after the stage; [10] bias K step
   uint32_t pad0, pad1;
 };
 
@@ -310,6 +339,12 @@ __global__ void __launch_bounds__(MODE == 0 ? TC_THREADS_FWD : TC_THREADS_BWD, 1
   for (int i = threadIdx.x; i < VEC_FLOATS; i += blockDim.x) vec[i] = a.vec[i];
   for (int i = threadIdx.x; i < a.n_ops * 8; i += blockDim.x)
     reinterpret_cast<uint32_t*>(smem + SM_PROG)[i] = reinterpret_cast<const uint32_t*>(a.prog)[i];
+  if (MODE == 0 && REN_BIAS_MMA) {
+    // K core 0: row m = (1, 0, 0, 0, 0, 0, 0, 0); K core 1: zeros
+    for (int i = threadIdx.x; i < 2 * TC_M; i += blockDim.x)
+      reinterpret_cast<uint4*>(smem + SM_ONES)[i] = make_uint4(i < TC_M ? 0x00003C00u : 0u, 0u, 0u, 0u);
+    fence_proxy_async();          // read by the tensor core (async proxy)
+  }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(sbase + SM_TMEM_PTR) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -321,7 +356,7 @@ __global__ void __launch_bounds__(MODE == 0 ? TC_THREADS_FWD : TC_THREADS_BWD, 1
 
   if (warp == 0) {
     // ===================== weight producer =====================
-    if (lane == 0) {
+    if (REN_ONE_LANE()) {
       const uint4* prog = reinterpret_cast<const uint4*>(smem + SM_PROG);
       uint32_t it = 0;
       for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -341,7 +376,7 @@ __global__ void __launch_bounds__(MODE == 0 ? TC_THREADS_FWD : TC_THREADS_BWD, 1
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    if (REN_ONE_LANE()) {
       const uint4* prog = reinterpret_cast<const uint4*>(smem + SM_PROG);
       uint32_t it = 0, n_p = 0, n_a0 = 0, n_a1 = 0;
       const uint32_t idesc128 = umma_idesc(128, 0, 0), idesc256 = umma_idesc(256, 0, 0);
@@ -373,17 +408,35 @@ __global__ void __launch_bounds__(MODE == 0 ? TC_THREADS_FWD : TC_THREADS_BWD, 1
           const int cnt = (int)(flags & 7u);
           uint32_t acc = (flags & 32u) ? 0u : 1u;
           if (!nomma) {
-            if (flags & 16u) {
+            if (flags & OP_ONES) {
+              const uint64_t da = mk_desc(smem_lo + (uint32_t)(SM_ONES >> 4));
+              tc_mma_f16(d_addr, da, mk_desc(b_lo32), idesc, acc);
+              if (split3) tc_mma_f16(d_addr, da, mk_desc(b_lo32 + (chunk16 >> 1)), idesc, 1u);
+            } else if (flags & 16u) {
               const uint32_t a_lo32 = enc_lo + a0;
 #pragma unroll
               for (int kl = 0; kl < TC_STAGE_KS; ++kl) {
                 if (kl < cnt) {
-                  const uint64_t db_hi = mk_desc(b_lo32 + kl * chunk16);
                   const uint64_t da_hi = mk_desc(a_lo32 + kl * 256);
-                  tc_mma_f16(d_addr, da_hi, db_hi, idesc, acc);
-                  if (split3) {
-                    tc_mma_f16(d_addr, mk_desc(a_lo32 + kl * 256 + a_ld), db_hi, idesc, 1u);
-                    tc_mma_f16(d_addr, da_hi, mk_desc(b_lo32 + kl * chunk16 + (chunk16 >> 1)), idesc, 1u);
+                  if (REN_WIDE_SPLIT && wide) {
+                    // rows 128..255 of the [256 x 16] chunk start 2048 B into each K core
+                    const uint32_t bh = b_lo32 + kl * chunk16, bl = bh + (chunk16 >> 1);
+                    tc_mma_f16(d_addr, da_hi, mk_desc(bh), idesc128, acc);
+                    tc_mma_f16(d_addr + 128u, da_hi, mk_desc(bh + 128u), idesc128, acc);
+                    if (split3) {
+                      const uint64_t da_lo = mk_desc(a_lo32 + kl * 256 + a_ld);
+                      tc_mma_f16(d_addr, da_lo, mk_desc(bh), idesc128, 1u);
+                      tc_mma_f16(d_addr + 128u, da_lo, mk_desc(bh + 128u), idesc128, 1u);
+                      tc_mma_f16(d_addr, da_hi, mk_desc(bl), idesc128, 1u);
+                      tc_mma_f16(d_addr + 128u, da_hi, mk_desc(bl + 128u), idesc128, 1u);
+                    }
+                  } else {
+                    const uint64_t db_hi = mk_desc(b_lo32 + kl * chunk16);
+                    tc_mma_f16(d_addr, da_hi, db_hi, idesc, acc);
+                    if (split3) {
+                      tc_mma_f16(d_addr, mk_desc(a_lo32 + kl * 256 + a_ld), db_hi, idesc, 1u);
+                      tc_mma_f16(d_addr, da_hi, mk_desc(b_lo32 + kl * chunk16 + (chunk16 >> 1)), idesc, 1u);
+                    }
                   }
                   acc = 1u;
                 }
@@ -395,11 +448,25 @@ __global__ void __launch_bounds__(MODE == 0 ? TC_THREADS_FWD : TC_THREADS_BWD, 1
                 if (kl < cnt) {
                   // K step ks0 + kl (ks0 even): hi columns at +32 (kl/2) + 8 (kl%2), lo 16 further
                   const uint32_t a_hi = a_tm + (uint32_t)(32 * (kl >> 1) + 8 * (kl & 1));
-                  const uint64_t db_hi = mk_desc(b_lo32 + kl * chunk16);
-                  tc_mma_f16_ts(d_addr, a_hi, db_hi, idesc, acc);
-                  if (split3) {
-                    if (a_lo) tc_mma_f16_ts(d_addr, a_hi + a_ld, db_hi, idesc, 1u);
-                    tc_mma_f16_ts(d_addr, a_hi, mk_desc(b_lo32 + kl * chunk16 + (chunk16 >> 1)), idesc, 1u);
+                  if (REN_WIDE_SPLIT && wide) {
+                    const uint32_t bh = b_lo32 + kl * chunk16, bl = bh + (chunk16 >> 1);
+                    tc_mma_f16_ts(d_addr, a_hi, mk_desc(bh), idesc128, acc);
+                    tc_mma_f16_ts(d_addr + 128u, a_hi, mk_desc(bh + 128u), idesc128, acc);
+                    if (split3) {
+                      if (a_lo) {
+                        tc_mma_f16_ts(d_addr, a_hi + a_ld, mk_desc(bh), idesc128, 1u);
+                        tc_mma_f16_ts(d_addr + 128u, a_hi + a_ld, mk_desc(bh + 128u), idesc128, 1u);
+                      }
+                      tc_mma_f16_ts(d_addr, a_hi, mk_desc(bl), idesc128, 1u);
+                      tc_mma_f16_ts(d_addr + 128u, a_hi, mk_desc(bl + 128u), idesc128, 1u);
+                    }
+                  } else {
+                    const uint64_t db_hi = mk_desc(b_lo32 + kl * chunk16);
+                    tc_mma_f16_ts(d_addr, a_hi, db_hi, idesc, acc);
+                    if (split3) {
+                      if (a_lo) tc_mma_f16_ts(d_addr, a_hi + a_ld, db_hi, idesc, 1u);
+                      tc_mma_f16_ts(d_addr, a_hi, mk_desc(b_lo32 + kl * chunk16 + (chunk16 >> 1)), idesc, 1u);
+                    }
                   }
                   acc = 1u;
                 }
@@ -642,34 +709,106 @@ __global__ void __launch_bounds__(MODE == 0 ? TC_THREADS_FWD : TC_THREADS_BWD, 1
             out_mat = a.delta + tcs_mat(p, S, st.out_mat) + tile_off;
           }
           const float* bias = (MODE == 0 && st.bias_idx >= 0) ? vec + VEC_BIAS + st.bias_idx * 256 + n0 : nullptr;
-          // the common case (hidden softplus layer of the value pass) as ONE flat pass over the thread's 32
-          // columns: 32 independent bias -> ex2 -> lg2 chains in flight instead of 8
-          const bool flat = MODE == 0 && !TAN && st.epi == EPI_F_HIDDEN && a.softplus && !(a.dbg & 1);
-          // software pipeline: the MUFU chains of group j8 + FLAT_AHEAD are issued before the split / stores of
-          // group j8, so the special-function pipe and the ALU work overlap inside every warp
-          auto sp8 = [&](int j8) {
+          // the common case (hidden softplus layer of the value pass, split operands) as ONE flat pass over the
+          // thread's 32 columns: 32 independent bias -> ex2 -> lg2 chains in flight instead of 8, and no per-group
+          // tests of the layer kind / destinations.  Software pipeline: the MUFU chains of group j8 + FLAT_AHEAD are
+          // issued before the split / stores of group j8, so the special-function pipe and the ALU work overlap
+          // inside every warp
+          bool done = false;
+          if (REN_FLAT_FWD && MODE == 0 && !TAN) {
+            // (with REN_BIAS_MMA the host marks exactly these steps -- the bias is already in the accumulator)
+            if (REN_BIAS_MMA ? st.bias_mma != 0
+                             : (st.epi == EPI_F_HIDDEN && a.softplus && !a_single && !(a.dbg & 1) &&
+                                (!STASH || st.out_mat >= 0))) {
+              auto sp8 = [&](int j8) {
+#if REN_BIAS_MMA
 #pragma unroll
-            for (int j4 = 2 * j8; j4 < 2 * j8 + 2; ++j4) {
-              const float4 b4 = *reinterpret_cast<const float4*>(bias + j4 * 4);
-              r[j4 * 4 + 0] = __float_as_uint(softplus_log2(__uint_as_float(r[j4 * 4 + 0]) + b4.x));
-              r[j4 * 4 + 1] = __float_as_uint(softplus_log2(__uint_as_float(r[j4 * 4 + 1]) + b4.y));
-              r[j4 * 4 + 2] = __float_as_uint(softplus_log2(__uint_as_float(r[j4 * 4 + 2]) + b4.z));
-              r[j4 * 4 + 3] = __float_as_uint(softplus_log2(__uint_as_float(r[j4 * 4 + 3]) + b4.w));
+                for (int j = 8 * j8; j < 8 * j8 + 8; ++j) r[j] = __float_as_uint(softplus_log2(__uint_as_float(r[j])));
+#else
+#pragma unroll
+                for (int j4 = 2 * j8; j4 < 2 * j8 + 2; ++j4) {
+                  const float4 b4 = *reinterpret_cast<const float4*>(bias + j4 * 4);
+                  r[j4 * 4 + 0] = __float_as_uint(softplus_log2(__uint_as_float(r[j4 * 4 + 0]) + b4.x));
+                  r[j4 * 4 + 1] = __float_as_uint(softplus_log2(__uint_as_float(r[j4 * 4 + 1]) + b4.y));
+                  r[j4 * 4 + 2] = __float_as_uint(softplus_log2(__uint_as_float(r[j4 * 4 + 2]) + b4.z));
+                  r[j4 * 4 + 3] = __float_as_uint(softplus_log2(__uint_as_float(r[j4 * 4 + 3]) + b4.w));
+                }
+#endif
+              };
+#pragma unroll
+              for (int j8 = 0; j8 < FLAT_AHEAD; ++j8) sp8(j8);
+#pragma unroll
+              for (int j8 = 0; j8 < 4; ++j8) {
+                if (j8 + FLAT_AHEAD < 4) sp8(j8 + FLAT_AHEAD);
+                float y[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) y[j] = __uint_as_float(r[j8 * 8 + j]);
+                if (st.sig_head) {
+                  const float4 w0 = *reinterpret_cast<const float4*>(vec + VEC_WSIG + n0 + j8 * 8);
+                  const float4 w1 = *reinterpret_cast<const float4*>(vec + VEC_WSIG + n0 + j8 * 8 + 4);
+                  const float ww[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) head_acc[0] = fmaf(y[j], ww[j], head_acc[0]);
+                }
+                uint4 hi, lo;
+                split8(y, &hi, &lo);
+                tc_st4(tcol + j8 * 4, hi);                     // a hidden layer always feeds the next step
+                tc_st4(tcol + 16 + j8 * 4, lo);
+                if (STASH) *reinterpret_cast<uint4*>(out_mat + j8 * 2048) = hi;
+              }
+              done = true;
             }
-          };
-          if (flat) {
-#pragma unroll
-            for (int j8 = 0; j8 < FLAT_AHEAD; ++j8) sp8(j8);
           }
+          // plain dgrad through a hidden softplus layer: y = v (1 - 2^-g) = fma(-v, 2^-g, v) with g from the staged
+          // activation stash; one pass over the 32 columns, the ex2 chains of the next group ahead of the split / stores
+          // of this one.  Rows past the last sample (last tile only) write zero deltas (the weight-gradient kernel
+          // reads whole tiles); what they leave in tensor memory stays inside their own row of every later MMA
+          if (REN_FLAT_BWD && MODE == 1 && PASS == 0) {
+            if (st.epi == EPI_D_ACT && a.softplus && !a_single && st.out_mat >= 0 && !(a.dbg & 1)) {
+              const unsigned char* sa = d_stage_gen + SM_DSTAGE_ACT + d_buf * 32768;
+              const float* wsig = vec + VEC_WSIG + n0;
+              auto da8 = [&](int j8) {
+                float av[8];
+                unpack8(*reinterpret_cast<const uint4*>(sa + j8 * 8192), av);
+                if (st.rank1) {
+                  const float4 w0 = *reinterpret_cast<const float4*>(wsig + j8 * 8);
+                  const float4 w1 = *reinterpret_cast<const float4*>(wsig + j8 * 8 + 4);
+                  const float ww[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+                  for (int j = 0; j < 8; ++j)
+                    r[j8 * 8 + j] = __float_as_uint(fmaf(gs, ww[j], __uint_as_float(r[j8 * 8 + j])));
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const float v = __uint_as_float(r[j8 * 8 + j]);
+                  r[j8 * 8 + j] = __float_as_uint(fmaf(-v, ex2_ftz(-av[j]), v));
+                }
+              };
+              da8(0);
+#pragma unroll
+              for (int j8 = 0; j8 < 4; ++j8) {
+                if (j8 + 1 < 4) da8(j8 + 1);
+                float y[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) y[j] = __uint_as_float(r[j8 * 8 + j]);
+                uint4 hi, lo;
+                split8(y, &hi, &lo);
+                if (st.write_a) {
+                  tc_st4(tcol + j8 * 4, hi);
+                  tc_st4(tcol + 16 + j8 * 4, lo);
+                }
+                if (!valid) hi = make_uint4(0u, 0u, 0u, 0u);
+                *reinterpret_cast<uint4*>(out_mat + j8 * 2048) = hi;
+              }
+              done = true;
+            }
+          }
+          if (!done) {
 #pragma unroll
           for (int j8 = 0; j8 < 4; ++j8) {
             float y[8];
             float e8[8];
-            if (flat && j8 + FLAT_AHEAD < 4) sp8(j8 + FLAT_AHEAD);
-            if (flat) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) y[j] = __uint_as_float(r[j8 * 8 + j]);
-            } else if (MODE == 0 && TAN) {
+            if (MODE == 0 && TAN) {
               // d/dw rows: no bias; gdot = act'(pre) * (W gdot_prev) with act' from the value stash
               float av[8];
               if (st.epi != EPI_F_LINEAR) unpack8(act[j8], av);
@@ -746,6 +885,7 @@ __global__ void __launch_bounds__(MODE == 0 ? TC_THREADS_FWD : TC_THREADS_BWD, 1
               *reinterpret_cast<uint4*>(a.extra + tcs_mat(p, S, st.out_mat) + tile_off + j8 * 2048) = eh;
             }
           }
+          }   // !done
           if (MODE == 1 && st.epi == EPI_D_ACT && valid) {
             d_have = staged_next;
             if (staged_next) d_buf ^= 1u;
@@ -856,10 +996,20 @@ static void add_vec(TcProgram& P, int dst, int count, int n_valid, int w_off, fl
 
 // chunks of one step in MMA issue order: source (segment, K-half 0, K-half 1) -> N-half -> K step
 static void add_step_pack(TcProgram& P, TcStep& s, long long& off, int mode, int w_off, int ldw, int Ntrue,
-                          int main_col0, int main_K, float main_scale, int seg_col0, int seg_K, float seg_scale) {
+                          int main_col0, int main_K, float main_scale, int seg_col0, int seg_K, float seg_scale,
+                          int b_off = -1, float b_scale = 1.f) {
   s.pack_off = off;
   const int nh = s.N >> 7;
   const int last_src = step_last_src(s);
+  if (s.bias_mma) {
+    // one [N x 16] chunk whose k = 0 column is the scaled bias: the "weight" matrix is the bias vector itself
+    // (row stride 1, one true column)
+    PackJob& j = P.jobs[P.n_jobs++];
+    memset(&j, 0, sizeof(j));
+    j.dst_off = off; j.mode = 0; j.n0 = 0; j.Ntrue = Ntrue; j.n_ksteps = 1; j.rows = s.N;
+    j.w_off = b_off; j.ldw = 1; j.col0 = 0; j.k0 = 0; j.Ktrue = 1; j.scale = b_scale;
+    off += (long long)s.N * 64;
+  }
   for (int src = 0; src < 3; ++src) {
     const int nks = step_src_ksteps(s, src);
     if (nks == 0) continue;
@@ -876,7 +1026,9 @@ static void add_step_pack(TcProgram& P, TcStep& s, long long& off, int mode, int
   }
 }
 
-static void build_forward(const RenPlan& p, TcProgram& P) {
+// bias_mma: the hidden softplus layers take their bias as a K step of the GEMM -- exactly the steps the flat forward
+// epilogue handles (value pass, split operands; see fwd_bias_mma())
+static void build_forward(const RenPlan& p, TcProgram& P, bool bias_mma) {
   memset(&P, 0, sizeof(P));
   const bool sp = p.f.hidden_activation == REN_HIDDEN_SOFTPLUS100;
   const float cs = sp ? LOG2E_100 : 1.f, kap = sp ? LN2_OVER_100 : 1.f;
@@ -887,6 +1039,7 @@ static void build_forward(const RenPlan& p, TcProgram& P) {
     memset(&s, 0, sizeof(s));
     s.N = N; s.acc_col = acc; s.a_col = prev_acc; s.epi = epi; s.out_mat = L.mat; s.act_mat = -1;
     s.write_a = epi != EPI_F_LAST; s.bias_idx = P.n_steps;
+    s.bias_mma = (bias_mma && epi == EPI_F_HIDDEN && sp && N == 256 && L.mat >= 0) ? 1 : 0;
     int seg_col0 = 0, seg_K = 0, main_K = 0;
     if (L.src0 == 1) { s.a_k = 0; s.seg = 1; seg_col0 = 0; seg_K = L.K0; }          // first layer: encoding only
     else {
@@ -895,7 +1048,8 @@ static void build_forward(const RenPlan& p, TcProgram& P) {
     }
     const float main_scale = (out_scale * main_in_scale > 0.999f && out_scale * main_in_scale < 1.001f)
                                  ? 1.f : out_scale * main_in_scale;     // 100 log2e * ln2/100 == 1 exactly
-    add_step_pack(P, s, off, 0, L.w_off, L.K0 + L.K1, L.N, 0, main_K, main_scale, seg_col0, seg_K, out_scale);
+    add_step_pack(P, s, off, 0, L.w_off, L.K0 + L.K1, L.N, 0, main_K, main_scale, seg_col0, seg_K, out_scale,
+                  L.b_off, out_scale);
     add_vec(P, VEC_BIAS + P.n_steps * 256, 256, L.N, L.b_off, out_scale);
     ++P.n_steps;
     prev_acc = acc;
@@ -955,6 +1109,27 @@ __host__ __device__ inline int build_ops_impl(const TcStep* steps, int n_steps, 
     const int last_src = step_last_src(st);
     long long off = st.pack_off;
     bool fresh = true;
+    int moved_wait_src = -1;       // source whose first-op wait the bias op already carries
+    if (mode == 0 && st.bias_mma) {
+      if (n_ops >= TC_MAX_OPS) return -1;
+      StageOp& o = ops[n_ops++];
+      o.pad0 = 0; o.pad1 = 0;
+      o.pack_off = (uint32_t)off; o.bytes = (uint32_t)(st.N * 64);
+      off += st.N * 64;
+      o.d_col = (uint32_t)st.acc_col; o.a_addr = 0; o.a_lo_delta = 0;
+      uint32_t flags = 1u | (nh == 2 ? 8u : 0u) | 16u | 32u | OP_ONES;
+      // the accumulator region may only be overwritten once the step's first source could be issued (for the
+      // second step of a tile that is what orders it after the previous tile's last epilogue)
+      for (int src = 0; src < 3; ++src) {
+        if (step_src_ksteps(st, src) == 0) continue;
+        if (src > 0) flags |= (uint32_t)src << 6;
+        else if (g == 0) flags |= 3u << 6;
+        moved_wait_src = src;
+        break;
+      }
+      o.flags = flags;
+      fresh = false;
+    }
     for (int src = 0; src < 3; ++src) {
       const int nks = step_src_ksteps(st, src);
       if (nks == 0) continue;
@@ -981,7 +1156,7 @@ __host__ __device__ inline int build_ops_impl(const TcStep* steps, int n_steps, 
             o.a_lo_delta = 16u;
           }
           if (fresh && ks0 == 0) flags |= 32u;
-          if (ks0 == 0 && h == 0) {
+          if (ks0 == 0 && h == 0 && src != moved_wait_src) {
             if (src > 0) flags |= (uint32_t)src << 6;
             else if (mode == 0 && g == 0) flags |= 3u << 6;          // first stage of the tile: encodings ready
           }
@@ -1020,7 +1195,7 @@ static size_t program_bytes(const TcProgram& P) {
 size_t ren_tc_fwd_workspace_bytes(const RenPlan& p) {
   if (!ren_tc_supported(p)) return 0;
   TcProgram P;
-  build_forward(p, P);
+  build_forward(p, P, REN_BIAS_MMA != 0);      // the largest variant of the forward program
   return program_bytes(P);
 }
 size_t ren_tc_bwd_pack_bytes(const RenPlan& p) {
@@ -1085,17 +1260,28 @@ static int carve_pack(const TcProgram& P, void* ws, size_t ws_bytes, unsigned ch
   return REN_OK;
 }
 
+// operand precision, activation and the timing switches of a launch
+static void fill_modes(TcArgs& a, const RenPlan& p) {
+  a.split3 = p.r.engine == REN_ENGINE_TC_F16 ? 0 : (p.r.engine == REN_ENGINE_TC_F16A ? 2 : 1);
+  if (const char* sp = getenv("REN_TC_SPLIT")) a.split3 = atoi(sp);      // precision experiments
+  a.softplus = p.f.hidden_activation == REN_HIDDEN_SOFTPLUS100 ? 1 : 0;
+  const char* dbg = getenv("REN_TC_DBG");
+  a.dbg = dbg ? atoi(dbg) : 0;
+}
 static void fill_args(TcArgs& a, const RenPlan& p, const TcProgram& P) {
   static_assert(sizeof(TcArgs) <= 4000, "kernel parameter block too large");
   memset(&a, 0, sizeof(a));
   a.p = p;
   for (int i = 0; i < P.n_steps; ++i) a.steps[i] = P.steps[i];
   a.n_steps = P.n_steps;
-  a.split3 = p.r.engine == REN_ENGINE_TC_F16 ? 0 : (p.r.engine == REN_ENGINE_TC_F16A ? 2 : 1);
-  if (const char* sp = getenv("REN_TC_SPLIT")) a.split3 = atoi(sp);      // precision experiments
-  a.softplus = p.f.hidden_activation == REN_HIDDEN_SOFTPLUS100 ? 1 : 0;
-  const char* dbg = getenv("REN_TC_DBG");
-  a.dbg = dbg ? atoi(dbg) : 0;
+  fill_modes(a, p);
+}
+
+// The forward value pass with split operands runs the flat epilogue on its hidden softplus layers; with
+// REN_BIAS_MMA those layers take their bias through the GEMM (the tangent pass carries no biases; the reduced
+// precision modes and the timing switches keep the generic epilogue, which adds the bias itself)
+static bool fwd_bias_mma(const TcArgs& a, bool tan) {
+  return REN_BIAS_MMA != 0 && !tan && a.split3 == 1 && a.softplus && !(a.dbg & 1);
 }
 
 // o_dot / d_dot / stash_val != NULL: the tangent pass of the tangent render (stash = its own stash, raw = raw_dot)
@@ -1104,14 +1290,15 @@ int ren_tc_launch_fwd(const RenPlan& p, long long n_rays, int K, const float* o,
                       const float* jitter, const float* params, void* stash, float* raw, const unsigned char* tile_live,
                       const int* sample_idx, long long n_samples, void* ws, size_t ws_bytes, cudaStream_t st) {
   TcProgram P;
-  build_forward(p, P);
+  TcArgs a;
+  fill_modes(a, p);            // operand precision / timing switches decide which epilogue the hidden layers take
+  build_forward(p, P, fwd_bias_mma(a, o_dot != nullptr));
   unsigned char* pack; float* vec; StageOp* prog;
   if (build_ops(P, 0)) { ren_set_error("tc forward: stage program too long"); return REN_E_UNSUPPORTED; }
   int rc = carve_pack(P, ws, ws_bytes, &pack, &vec, &prog);
   if (rc) return rc;
   rc = run_pack(P, 0, params, pack, vec, prog, st);
   if (rc) return rc;
-  TcArgs a;
   fill_args(a, p, P);
   a.n_rays = n_rays; a.K = K; a.rays_o = o; a.rays_d = d; a.jitter = jitter;
   a.pack = pack; a.vec = vec; a.prog = prog; a.n_ops = P.n_ops; a.stash = (unsigned char*)stash; a.raw = raw;
@@ -1148,4 +1335,42 @@ int ren_tc_launch_dgrad(const RenPlan& p, long long S, const float* params, cons
   if (pass == 1) return launch_chain<1, false, 1>(a, n_tiles, REN_K_FIELD_DGRAD, st);
   if (pass == 2) return launch_chain<1, false, 2>(a, n_tiles, REN_K_FIELD_DGRAD, st);
   return launch_chain<1, false, 0>(a, n_tiles, REN_K_FIELD_DGRAD, st);
+}
+
+// ------------------------------------------------------------------ program dump (tests; no GPU needed)
+// The tile program of the chain kernel as the host builds it: steps (12 ints each: N, acc_col, a_col, a_k, seg,
+// epi, out_mat, act_mat, write_a, bias_idx, rank1 | sig_head << 8, bias_mma), stage ops (8 words each, the
+// device layout) and weight-pack jobs (12 int64 each: dst_off, mode, n0, Ntrue, n_ksteps, k0, Ktrue, rows, w_off,
+// ldw, col0, scale bits).  mode 0 forward (bias_mma: 0 / 1), 1 dgrad.  Not part of the C ABI in include/: internal.
+extern "C" int ren_tc_debug_program(const RenFieldDesc* f, const RenRenderDesc* r, int32_t mode, int32_t bias_mma,
+                                    int32_t* steps, int32_t* n_steps, uint32_t* ops, int32_t* n_ops, int64_t* jobs,
+                                    int32_t* n_jobs, int64_t* pack_bytes) {
+  RenPlan p;
+  int rc = ren_build_plan(f, r, &p);
+  if (rc) return rc;
+  if (!ren_tc_supported(p)) { ren_set_error("tc engine does not support this network"); return REN_E_UNSUPPORTED; }
+  TcProgram P;
+  if (mode == 0) build_forward(p, P, bias_mma != 0); else build_dgrad(p, P);
+  if (build_ops(P, mode)) { ren_set_error("stage program too long"); return REN_E_UNSUPPORTED; }
+  if (P.n_jobs > TC_MAX_PACK) { ren_set_error("too many pack jobs (%d)", P.n_jobs); return REN_E_INVALID; }
+  for (int i = 0; i < P.n_steps; ++i) {
+    const TcStep& s = P.steps[i];
+    const int v[12] = {s.N, s.acc_col, s.a_col, s.a_k, s.seg, s.epi, s.out_mat, s.act_mat, s.write_a, s.bias_idx,
+                       s.rank1 | (s.sig_head << 8), s.bias_mma};
+    for (int k = 0; k < 12; ++k) steps[12 * i + k] = v[k];
+  }
+  *n_steps = P.n_steps;
+  memcpy(ops, P.ops, sizeof(StageOp) * P.n_ops);
+  *n_ops = P.n_ops;
+  for (int i = 0; i < P.n_jobs; ++i) {
+    const PackJob& j = P.jobs[i];
+    uint32_t sb;
+    memcpy(&sb, &j.scale, 4);
+    const int64_t v[12] = {j.dst_off, j.mode, j.n0, j.Ntrue, j.n_ksteps, j.k0, j.Ktrue, j.rows, j.w_off, j.ldw,
+                           j.col0, (int64_t)sb};
+    for (int k = 0; k < 12; ++k) jobs[12 * i + k] = v[k];
+  }
+  *n_jobs = P.n_jobs;
+  *pack_bytes = P.pack_bytes;
+  return REN_OK;
 }

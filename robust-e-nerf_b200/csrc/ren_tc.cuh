@@ -92,6 +92,24 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
+// REN_ELECT: the single-thread roles (TMA producers, MMA issuers) run on a lane chosen with elect.sync (1) or on
+// lane 0 (0, the A/B baseline)
+#ifndef REN_ELECT
+#define REN_ELECT 1
+#endif
+// One lane of the (converged) warp; unlike `lane == 0`, ptxas knows the guarded region runs on exactly one thread, so
+// the uniform-register operands of tcgen05.mma / commit need no per-lane serialisation loop around every instruction
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n" : "=r"(pred));
+  return pred != 0u;
+}
+#define REN_ONE_LANE() (REN_ELECT ? elect_one() : lane == 0)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }

@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(RGT_THREADS, 1) ren_tc_raygrad(const RgtArgs a
 
   if (warp == 0) {
     // ===================== producer: delta tiles =====================
-    if (lane == 0) {
+    if (REN_ONE_LANE()) {
       uint32_t it = 0;
       for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         if (a.tile_live != nullptr && !__ldg(a.tile_live + tile)) continue;
@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(RGT_THREADS, 1) ren_tc_raygrad(const RgtArgs a
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    if (REN_ONE_LANE()) {
       uint32_t it = 0, n_t = 0;
       const uint32_t idesc_p = umma_idesc(REN_PE_MAX, 0, 0), idesc_d = umma_idesc(REN_DE_MAX, 0, 0);
       for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {

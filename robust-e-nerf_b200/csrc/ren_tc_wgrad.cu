@@ -87,7 +87,7 @@ extern "C" __global__ void __launch_bounds__(WG_THREADS, 1) ren_tc_wgrad(const W
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (REN_ONE_LANE()) {
       uint32_t it = 0;
       for (int job = blockIdx.x; job < n_jobs; job += gridDim.x) {
         const WgMat& mt = a.mats[job / a.splits];
@@ -108,7 +108,7 @@ extern "C" __global__ void __launch_bounds__(WG_THREADS, 1) ren_tc_wgrad(const W
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (REN_ONE_LANE()) {
       uint32_t it = 0, jn = 0;
       const uint32_t idesc_ones = umma_idesc(16, 1, 1);
       for (int job = blockIdx.x; job < n_jobs; job += gridDim.x) {
@@ -275,7 +275,7 @@ extern "C" __global__ void __launch_bounds__(W2_THREADS, 1) ren_tc_wgrad2(const 
 
   if (warp == 0) {
     // ===================== producer =====================
-    if (lane == 0) {
+    if (REN_ONE_LANE()) {
       uint32_t it = 0;
       for (int j = j0; j < j1; ++j) {
         const W2Job jb = a.jobs[j];
@@ -299,7 +299,7 @@ extern "C" __global__ void __launch_bounds__(W2_THREADS, 1) ren_tc_wgrad2(const 
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    if (REN_ONE_LANE()) {
       uint32_t it = 0, jn = 0;
       for (int j = j0; j < j1; ++j) {
         const W2Job jb = a.jobs[j];
