@@ -2,7 +2,8 @@
 # A/B builds of libren_b200.so that differ only in csrc/ren_tc.cu compile-time switches (the other objects are the
 # in-tree build's).  Usage: tools/build_variants.sh  ->  robust-e-nerf_b200/ren_b200/lib/variants/libren_b200_<tag>.so
 #   bias    : REN_BIAS_MMA=1 (hidden-layer biases as one more K step of the GEMM)
-#   wsplit  : REN_WIDE_SPLIT=1 (N = 256 MMAs issued as interleaved N = 128 pairs)
+#   nosplit : REN_WIDE_SPLIT=0 (one N = 256 MMA instead of an interleaved N = 128 pair)
+#   ahead2  : FLAT_AHEAD=2 (forward flat epilogue: softplus two groups ahead of the split / stores)
 #   nohint  : REN_MBAR_HINT_NS=0 (mbarrier waits spin instead of suspending)
 #   noelect : REN_ELECT=0 (single-thread roles on lane 0 instead of an elect.sync lane)
 #   generic : REN_FLAT_FWD=0 REN_FLAT_BWD=0 (generic epilogue loop only)
@@ -27,7 +28,8 @@ build() {  # tag, defines...: the three tcgen05 sources with the defines, everyt
       $objs $OTHERS -lcuda
 }
 build bias -DREN_BIAS_MMA=1 &
-build wsplit -DREN_WIDE_SPLIT=1 &
+build nosplit -DREN_WIDE_SPLIT=0 &
+build ahead2 -DFLAT_AHEAD=2 &
 build nohint -DREN_MBAR_HINT_NS=0 &
 build noelect -DREN_ELECT=0 &
 build generic -DREN_FLAT_FWD=0 -DREN_FLAT_BWD=0 &
