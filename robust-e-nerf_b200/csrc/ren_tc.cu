@@ -12,8 +12,12 @@
 //                ring with 1-D bulk TMA (cp.async.bulk + mbarrier tx bytes)
 //   warp 1       MMA issuer: one thread issues tcgen05.mma kind::f16, M=128, K=16; A from TMEM
 //                (activations) or shared memory (positional / direction encodings).  The first K-half
-//                of a layer uses N=256 MMAs, the last K-half runs per N-half (N=128) so that
-//                accumulator half 0 completes -- and its epilogue starts -- a quarter layer early
+//                of a layer covers both N-halves (N=256 operands, issued as interleaved N=128 pairs), the
+//                last K-half runs per N-half (N=128) so that accumulator half 0 completes -- and its
+//                epilogue starts -- a quarter layer early.  The thread is chosen with elect.sync
+//                (REN_ONE_LANE): under `lane == 0` ptxas wraps every tcgen05 / bulk-copy instruction in a
+//                per-lane serialisation loop and the single issuing thread, not the tensor pipe, sets the
+//                pace
 //   warps 2-17   epilogues.  Lane quadrant = warp % 4 (TMEM access rule); the 4 warps of a quadrant split
 //                the 128 columns of a half 32 each and write their 32 packed columns back over their own.
 //                dgrad: the activation-stash slices they need arrive by cp.async through the (idle)
@@ -88,7 +92,7 @@
 #define SM_RING (2 * SM_ENC_BYTES)
 #define SM_CHUNK_BYTES 8192          // one [128 x 16] hi|lo weight chunk (one K step of one N-half)
 #define SM_STAGE_BYTES (TC_STAGE_KS * SM_CHUNK_BYTES)
-#define SM_VEC (SM_RING + TC_STAGES * SM_STAGE_BYTES)   // 180224: float vectors (biases, head weights)
+#define SM_VEC (SM_RING + TC_STAGES * SM_STAGE_BYTES)   // 196608: float vectors (biases, head weights)
 #define VEC_BIAS 0                                      // [TC_MAX_STEPS][256] -> only n_steps used
 #define VEC_WSIG (12 * 256)
 #define VEC_WO (VEC_WSIG + 256)                         // [3][128]

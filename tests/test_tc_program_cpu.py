@@ -209,3 +209,25 @@ def test_tile_programs(built_lib, radiance_dim):
     # the layers that take the bias through the GEMM are the hidden trunk layers, and only in the forward program
     assert [s["bias_mma"] for s in S1] == [1] * 8 + [0, 0]
     assert [s["epi"] for s in S1] == [EPI_F_HIDDEN] * 8 + [EPI_F_LINEAR, EPI_F_LAST]
+
+
+def test_no_per_lane_serialisation_loops_in_the_tcgen05_kernels(built_lib):
+    """The single-thread roles (TMA producers, MMA issuers) are guarded by `elect.sync`: under `lane == 0` ptxas
+    wraps every instruction with uniform-register operands (tcgen05.mma, tcgen05.commit, bulk copies) in an
+    `ELECT ... BRA.U.ANY` loop over the active lanes -- 213 of them in ren_tc.o -- and the issuing thread becomes
+    the bottleneck of the tensor pipe (forward -9 %, dgrad -6 %).  Guard against a
+    regression by looking at the SASS of the objects the library was linked from."""
+    import os
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    obj_dir = os.path.join(G.PKG_DIR, "build")
+    for name in ("ren_tc.o", "ren_tc_wgrad.o", "ren_tc_raygrad.o"):
+        path = os.path.join(obj_dir, name)
+        if not os.path.exists(path):
+            pytest.skip("objects of the in-tree build not present")
+        sass = subprocess.run([cuobjdump, "-sass", path], capture_output=True, text=True, check=True).stdout
+        assert "UTCHMMA" in sass, name                      # tcgen05.mma is what these kernels issue
+        assert sass.count("BRA.U.ANY") == 0, f"{name}: per-lane serialisation loops around uniform-datapath instructions"
