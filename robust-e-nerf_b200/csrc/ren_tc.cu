@@ -78,6 +78,11 @@
 #ifndef REN_WIDE_SPLIT
 #define REN_WIDE_SPLIT 1
 #endif
+// Issue experiment (A/B builds only, off): operand set-up of an op hoisted above the issuer's barrier waits, which poll
+// without the suspend hint.  Same MMAs in the same order: bit-identical results.
+#ifndef REN_ISSUE_FAST
+#define REN_ISSUE_FAST 0
+#endif
 
 // shared-memory map (bytes)
 #define SM_P_HI 0          // positional encoding [128 x 64] hi (K-major core matrices)
@@ -399,10 +404,27 @@ __global__ void __launch_bounds__(MODE == 0 ? TC_THREADS_FWD : TC_THREADS_BWD, 1
           const int nx = (i + 1 < a.n_ops) ? i + 1 : 0;
           const uint4 p0 = prog[2 * nx], p1 = prog[2 * nx + 1];
           const uint32_t wt = (flags >> 6) & 3u;
+          const uint32_t s = it % TC_STAGES;
+#if REN_ISSUE_FAST
+          // everything the MMAs of this op need that does not depend on the hand-off is computed BEFORE the waits (the
+          // empty asm pins it there), and the issuer -- one thread -- polls its barriers without the suspend hint: the
+          // epilogue -> first-MMA hand-off is on the critical cycle of every layer
+          const bool wide = (flags & 8u) != 0u;
+          uint32_t idesc = wide ? idesc256 : idesc128;
+          const uint32_t chunk16 = wide ? 1024u : 512u;               // chunk bytes / 16
+          uint32_t b_lo32 = (ring_lo + s * (SM_STAGE_BYTES >> 4)) | ((wide ? 256u : 128u) << 16);
+          const int cnt = (int)(flags & 7u);
+          uint32_t acc = (flags & 32u) ? 0u : 1u;
+          asm volatile("" : "+r"(idesc), "+r"(b_lo32), "+r"(acc));
+          if (wt == 1u) { mbar_wait_spin(bar_a, n_a0 & 1u); ++n_a0; tc_fence_after(); }
+          else if (wt == 2u) { mbar_wait_spin(bar_a + 8, n_a1 & 1u); ++n_a1; tc_fence_after(); }
+          else if (wt == 3u) { mbar_wait_spin(bar_p + 8 * eb, (n_p >> 1) & 1u); tc_fence_after(); }
+          mbar_wait_spin(bar_full + 8 * s, (it / TC_STAGES) & 1u);
+          tc_fence_after();
+#else
           if (wt == 1u) { mbar_wait(bar_a, n_a0 & 1u); ++n_a0; tc_fence_after(); }
           else if (wt == 2u) { mbar_wait(bar_a + 8, n_a1 & 1u); ++n_a1; tc_fence_after(); }
           else if (wt == 3u) { mbar_wait(bar_p + 8 * eb, (n_p >> 1) & 1u); tc_fence_after(); }
-          const uint32_t s = it % TC_STAGES;
           mbar_wait(bar_full + 8 * s, (it / TC_STAGES) & 1u);
           tc_fence_after();
           const bool wide = (flags & 8u) != 0u;
@@ -411,6 +433,7 @@ __global__ void __launch_bounds__(MODE == 0 ? TC_THREADS_FWD : TC_THREADS_BWD, 1
           const uint32_t b_lo32 = (ring_lo + s * (SM_STAGE_BYTES >> 4)) | ((wide ? 256u : 128u) << 16);
           const int cnt = (int)(flags & 7u);
           uint32_t acc = (flags & 32u) ? 0u : 1u;
+#endif
           if (!nomma) {
             if (flags & OP_ONES) {
               const uint64_t da = mk_desc(smem_lo + (uint32_t)(SM_ONES >> 4));
