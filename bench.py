@@ -422,6 +422,37 @@ class Runner:
         return float(v) if v is not None else float(self.wc["n"])
 
 
+def forward_only_rate(run, n_rays=8192, iters=10):
+    """the forward-only (inference) rate beside the training rate -- a no-grad render of
+    `n_rays` rays through the public `NeRF.forward` with the weights the timed steps left behind (no stash is written),
+    CUDA events around `iters` calls after 3 warm-up calls.  Rays are the training rays of the resident batches' kind:
+    origins on the camera orbit, directions through the scene."""
+    torch = run.torch
+    dev = run.dev
+    g = torch.Generator(device=dev).manual_seed(4321)
+    o = torch.randn((n_rays, 3), device=dev, generator=g)
+    o = 3.0 * o / o.norm(dim=-1, keepdim=True)
+    d = torch.nn.functional.normalize(-o + 0.3 * torch.randn((n_rays, 3), device=dev, generator=g), dim=-1)
+    u = torch.rand((n_rays,), device=dev, generator=g)
+    nerf = run.model.nerf
+    with torch.no_grad():
+        for _ in range(3):
+            out = nerf(o, d, u)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(iters):
+            out = nerf(o, d, u)
+        b.record()
+        torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / iters
+    spp = float(out[3])
+    return {"rays": n_rays, "mean_samples_per_ray": spp, "ms_per_render": ms,
+            "ray_samples_per_s": n_rays * spp / (ms * 1e-3),
+            "tflops_algorithmic": n_rays * spp * FLOP_PER_SAMPLE_FWD / (ms * 1e-3) / 1e12,
+            "note": "no-grad NeRF.forward (march, encode, MLP, composite), no activation stash"}
+
+
 def release(run):
     """Drop a Runner's CUDA graphs (their private memory pools) and cached blocks before the next workload."""
     import gc
@@ -564,6 +595,12 @@ def run_ours(args):
         parity = parity_check(model, run.cfg, run.root, run.host[0][0], run.host[0][1], dev)
     except Exception as e:
         parity = {"error": repr(e)[:300]}
+    fwd_only = None
+    if world == 1:
+        try:
+            fwd_only = forward_only_rate(run)
+        except Exception as e:                      # an extra record must not take the headline down
+            fwd_only = {"error": repr(e)[:300]}
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         from oracle import synth as osynth
@@ -599,7 +636,7 @@ def run_ours(args):
         "e2e": {"value": e2e, "unit": "ray-samples/s", "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps, "blocks": len(blocks_e2e)},
         "gpu_launches": int(round(launches_per_step * args.steps)), "gpu_launches_per_step": launches_per_step,
-        "roofline": roof, "parity": parity, "cpu_baseline": cpu, "kernels": kern,
+        "roofline": roof, "parity": parity, "cpu_baseline": cpu, "kernels": kern, "forward_only": fwd_only,
         "params_equal_across_ranks": params_equal, "secondary": secondary,
         "clocks": sampler.summary(), "loss": loss,
     }
