@@ -590,6 +590,21 @@ def run_ours(args):
                     "note": "fp16 hi/lo split executes 3 MMAs per algorithmic MMA: ceiling of frac is 1/3; "
                             "traffic is the activation stash the training forward must write (stash_bytes), "
                             "not algorithmic traffic"}
+    # the HBM-bound kernel of the step beside the tensor-bound one: weight gradients read the activation stash and the
+    # deltas once each (DRAM bytes of the committed ncu capture, this run's CUDA-event time, measured copy peak)
+    roof_wgrad = None
+    try:
+        wk = (ncu or {}).get("kernels", {}).get("ren_tc_wgrad2")
+        if wk and "wgrad" in kern and args.config == 2:
+            gb = wk["dram_read_gb"] + wk["dram_write_gb"]
+            ach = gb / (kern["wgrad"]["ms_per_launch"] * 1e-3)
+            roof_wgrad = {"bound": "hbm", "kernel": "wgrad (ren_tc_wgrad2)", "achieved": ach, "peak": pk["hbm"],
+                          "unit": "GB/s", "frac": ach / pk["hbm"], "traffic": gb * 1e9, "traffic_unit": "bytes/launch",
+                          "algorithmic_bytes": per_launch_samples * 2 * 2 * 2432 if per_launch_samples else None,
+                          "note": "algorithmic bytes = fp16 stash + fp16 deltas of the 2432 hidden activations per "
+                                  "sample, read once each; traffic from the committed ncu capture"}
+    except Exception:
+        roof_wgrad = None
     parity = None
     try:
         parity = parity_check(model, run.cfg, run.root, run.host[0][0], run.host[0][1], dev)
@@ -637,6 +652,7 @@ def run_ours(args):
                 "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps, "blocks": len(blocks_e2e)},
         "gpu_launches": int(round(launches_per_step * args.steps)), "gpu_launches_per_step": launches_per_step,
         "roofline": roof, "parity": parity, "cpu_baseline": cpu, "kernels": kern, "forward_only": fwd_only,
+        "roofline_wgrad": roof_wgrad,
         "params_equal_across_ranks": params_equal, "secondary": secondary,
         "clocks": sampler.summary(), "loss": loss,
     }
