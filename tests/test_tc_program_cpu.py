@@ -231,3 +231,23 @@ def test_no_per_lane_serialisation_loops_in_the_tcgen05_kernels(built_lib):
         sass = subprocess.run([cuobjdump, "-sass", path], capture_output=True, text=True, check=True).stdout
         assert "UTCHMMA" in sass, name                      # tcgen05.mma is what these kernels issue
         assert sass.count("BRA.U.ANY") == 0, f"{name}: per-lane serialisation loops around uniform-datapath instructions"
+
+
+def test_schedule_model_reproduces_the_measured_operating_points():
+    """`tools/chain_model.py`: with the measured per-layer epilogue / tensor / hand-off cycles
+    the discrete-event model of the two-halves schedule lands on both measured tensor-pipe figures -- 52 % with the
+    lane-0 issuer's MMA time (8.4 k cycles per layer), 60 % with the elect.sync issuer -- and ranks the re-tilings."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location(
+        "chain_model", os.path.join(G.ROOT, "tools", "chain_model.py"))
+    cm = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(cm)
+    active = 5650.0                                    # measured tensor-pipe active cycles per 256-wide layer
+    today = cm.period([0.5, 0.5], 6200.0, 6500.0, 700.0, 700.0)
+    slow = cm.period([0.5, 0.5], 6200.0, 8400.0, 700.0, 700.0)
+    assert abs(active / today - 0.600) < 0.01          # profiles/r02_tc_step_ncu_summary_elect.txt: 60.0 %
+    assert abs(active / slow - 0.523) < 0.01           # profiles/r02_tc_step_ncu_summary.txt: 52.3 %
+    quarters = cm.period([0.25] * 4, 6200.0, 6500.0, 700.0, 700.0)
+    lopsided = cm.period([0.25, 0.75], 6200.0, 6500.0, 700.0, 700.0)
+    assert quarters < 0.9 * today < lopsided           # four quarters help, a 64 | 192 split does not
